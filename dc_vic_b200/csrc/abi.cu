@@ -1,0 +1,83 @@
+// extern "C" entry points that dispatch between the VQ kernels (see include/dcvic_b200.h).
+#include "vq_common.cuh"
+
+using namespace dcvic;
+
+extern "C" const char* dcvic_version(void) { return "dcvic_b200 0.1 (sm_100a)"; }
+
+extern "C" const char* dcvic_error_string(int code) {
+  switch (code) {
+    case DCVIC_OK: return "ok";
+    case DCVIC_ERR_BAD_ARG: return "bad argument (null pointer, non-positive size or misaligned buffer)";
+    case DCVIC_ERR_UNSUPPORTED: return "shape not supported by the sm_100a kernels";
+    case DCVIC_ERR_WORKSPACE: return "workspace missing or too small";
+    case DCVIC_ERR_CUDA: return "CUDA error while enqueuing";
+    case DCVIC_ERR_DEVICE: return "device is not sm_100";
+    default: return "unknown error";
+  }
+}
+
+static inline bool vq_narrow_ok(int D) { return D == 4 || D == 8; }
+
+extern "C" int dcvic_vq_path(int D, int K, int flags) {
+  if (D <= 0 || K <= 0) return DCVIC_ERR_BAD_ARG;
+  if (!(flags & DCVIC_VQ_FORCE_EXACT) && vq_tensor_supported(D, K)) return 2;
+  if (flags & DCVIC_VQ_FORCE_TENSOR) return DCVIC_ERR_UNSUPPORTED;
+  if (vq_narrow_ok(D) && !(flags & DCVIC_VQ_FORCE_EXACT)) return 0;
+  return D <= 1024 ? 1 : DCVIC_ERR_UNSUPPORTED;
+}
+
+extern "C" size_t dcvic_vq_workspace_bytes(int B, int D, int H, int W, int K) {
+  if (B <= 0 || D <= 0 || H <= 0 || W <= 0 || K <= 0) return 0;
+  if ((long long)B * H * W > 0x7fffffffLL) return 0;
+  return vq_workspace_layout(B, D, H * W, K).total;
+}
+
+extern "C" int dcvic_vq_forward(const float* z_nchw, const float* codebook, int B, int D, int H, int W, int K,
+                                float beta, int legacy, float* zq_nchw, int64_t* idx, float* loss, float* onehot,
+                                float* perplexity, int flags, void* workspace, size_t ws_bytes,
+                                dcvic_stream_t stream) {
+  DCVIC_CHECK_ARG(z_nchw && codebook && zq_nchw && idx && loss && workspace);
+  DCVIC_CHECK_ARG(B > 0 && D > 0 && H > 0 && W > 0 && K > 0);
+  if ((long long)B * H * W > 0x7fffffffLL || (long long)K * D > 0x7fffffffLL) return DCVIC_ERR_UNSUPPORTED;
+  const int path = dcvic_vq_path(D, K, flags);
+  if (path < 0) return path;
+  const int HW = H * W, N = B * HW;
+  const VqWorkspace w = vq_workspace_layout(B, D, HW, K);
+  if (ws_bytes < w.total) return DCVIC_ERR_WORKSPACE;
+  if (reinterpret_cast<uintptr_t>(workspace) & 255) return DCVIC_ERR_BAD_ARG;
+  char* ws = reinterpret_cast<char*>(workspace);
+  unsigned* counters = reinterpret_cast<unsigned*>(ws + w.off_counters);
+  float* ee = reinterpret_cast<float*>(ws + w.off_ee);
+  float* emax = reinterpret_cast<float*>(ws + w.off_emax);
+  double* partials = reinterpret_cast<double*>(ws + w.off_partials);
+  unsigned* hist = reinterpret_cast<unsigned*>(ws + w.off_hist);
+  int* cand = reinterpret_cast<int*>(ws + w.off_cand);
+  int* count = reinterpret_cast<int*>(ws + w.off_count);
+  __nv_bfloat16* cb16 = reinterpret_cast<__nv_bfloat16*>(ws + w.off_cb16);
+  cudaStream_t s = (cudaStream_t)stream;
+  int rc = DCVIC_OK;
+
+  if (path == 0) {
+    rc = vq_narrow_forward(z_nchw, codebook, B, D, HW, K, beta, legacy, zq_nchw, idx, loss, partials, counters, s);
+  } else {
+    if (!(flags & DCVIC_VQ_REUSE_PREP)) {
+      rc = vq_prepare_codebook(codebook, K, D, ee, emax, path == 2 ? cb16 : nullptr, w.dpad16, s);
+      if (rc) return rc;
+    }
+    if (path == 2) {
+      rc = vq_tensor_search(z_nchw, cb16, w.dpad16, emax, B, D, HW, K, cand, count, counters, s);
+      if (rc) return rc;
+      rc = vq_finish(z_nchw, codebook, ee, cand, kCandCap, count, B, D, HW, K, beta, legacy, zq_nchw, idx, loss,
+                     partials, counters, s);
+    } else {
+      rc = vq_exact_search(z_nchw, codebook, ee, B, D, HW, K, cand, s);
+      if (rc) return rc;
+      rc = vq_finish(z_nchw, codebook, ee, cand, 1, nullptr, B, D, HW, K, beta, legacy, zq_nchw, idx, loss, partials,
+                     counters, s);
+    }
+  }
+  if (rc) return rc;
+  if (onehot || perplexity) rc = vq_v1_extras(idx, N, K, onehot, perplexity, hist, counters, s);
+  return rc;
+}

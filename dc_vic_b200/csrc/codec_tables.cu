@@ -1,0 +1,44 @@
+// Host-side integer CDF construction for the entropy-coder tables (model-setup time, like the
+// reference's C++ extension): compressai==1.2.4 `_CXX.pmf_to_quantized_cdf`, reached from
+// EntropyModel._pmf_to_cdf <- EntropyBottleneck.update / GaussianConditional.update
+// (callers in iwa-shi/DC_VIC: src/models/comp_model/hyperprior_dc_vic_model.py:65-68).
+// Runs on the CPU in the reference too; this is not a fallback of a GPU path.
+#include "common.cuh"
+#include <cmath>
+#include <vector>
+
+extern "C" int dcvic_pmf_to_quantized_cdf(const float* pmf /*host*/, int n, int precision, int32_t* cdf /*host n+1*/) {
+  if (!pmf || !cdf || n < 1 || precision < 1 || precision > 30) return DCVIC_ERR_BAD_ARG;
+  for (int i = 0; i < n; ++i)
+    if (!std::isfinite(pmf[i]) || pmf[i] < 0.f) return DCVIC_ERR_BAD_ARG;
+  const uint64_t one = 1ull << precision;
+  std::vector<uint64_t> c((size_t)n + 1, 0);
+  uint64_t total = 0;
+  for (int i = 0; i < n; ++i) {
+    const float scaled = pmf[i] * (float)one;         // float product, then round half away from zero
+    c[i + 1] = (uint64_t)std::llround((double)scaled);
+    total += c[i + 1];
+  }
+  if (total == 0) return DCVIC_ERR_BAD_ARG;
+  uint64_t run = 0;
+  for (int i = 0; i <= n; ++i) {
+    run += (one * c[i]) / total;
+    c[i] = run;
+  }
+  c[n] = one;
+  for (int i = 0; i < n; ++i) {
+    if (c[i] != c[i + 1]) continue;
+    // zero-width symbol: take one count from the narrowest symbol that can spare it
+    uint64_t best_w = ~0ull;
+    int donor = -1;
+    for (int j = 0; j < n; ++j) {
+      const uint64_t w = c[j + 1] - c[j];
+      if (w > 1 && w < best_w) { best_w = w; donor = j; }
+    }
+    if (donor < 0) return DCVIC_ERR_UNSUPPORTED;
+    if (donor < i) for (int j = donor + 1; j <= i; ++j) c[j]--;
+    else           for (int j = i + 1; j <= donor; ++j) c[j]++;
+  }
+  for (int i = 0; i <= n; ++i) cdf[i] = (int32_t)c[i];
+  return DCVIC_OK;
+}

@@ -1,0 +1,590 @@
+// FP32 SIMT kernels of the VQ quantizer path (sm_100a):
+//   * codebook preparation (|e|^2, max|e|, BF16 copy with the -|e|^2/2 fold for the tensor search)
+//   * narrow fused forward   (e_dim 4 / 8: the codebooks DC-VIC itself uses, K=256..16384)
+//   * exact FP32 search      (any e_dim <= 1024, any K): register-tiled distance scan + argmin
+//   * finish                 (FP32 re-rank of candidates + gather + straight-through value + loss)
+//   * V1 extras              (one-hot rows, perplexity)
+//   * backward               (dz, dE scatter-add)
+//   * gather / one-hot feature
+// Reference semantics: taming/modules/vqvae/quantize.py:34-107, :271-329 (iwa-shi/DC_VIC).
+// Distances are formed as (sum z^2 + sum e^2) - 2 z.e in FP32; ties resolve to the lowest index.
+#include "vq_common.cuh"
+#include <float.h>
+
+namespace dcvic {
+
+// ------------------------------------------------------------------ codebook prepare
+// One warp per code.  ee[k] = sum_c fl(e^2) (lane-strided partials + xor tree), emax = max_k |e_k|
+// (atomicMax on the non-negative float's bit pattern), cb16[k][0..D) = bf16(e), cb16[k][D..D+3) =
+// three-way bf16 split of -ee/2, rest zero.
+__global__ void __launch_bounds__(256) vq_prepare_kernel(const float* __restrict__ E, int K, int D,
+                                                          float* __restrict__ ee, float* __restrict__ emax,
+                                                          __nv_bfloat16* __restrict__ cb16, int dpad16) {
+  const int lane = threadIdx.x & 31;
+  const int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (k >= K) return;
+  const float* row = E + (size_t)k * D;
+  float acc = 0.f;
+  for (int c = lane; c < D; c += 32) {
+    const float v = row[c];
+    acc = __fadd_rn(acc, __fmul_rn(v, v));
+    if (cb16) cb16[(size_t)k * dpad16 + c] = __float2bfloat16_rn(v);
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) {
+    ee[k] = acc;
+    atomicMax(reinterpret_cast<unsigned*>(emax), __float_as_uint(sqrtf(acc) * 1.0000002f));
+  }
+  if (cb16 && lane < kTcK16Pad) {
+    const float v = -0.5f * acc;
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    const float r1 = v - __bfloat162float(h);
+    const __nv_bfloat16 m = __float2bfloat16_rn(r1);
+    const float r2 = r1 - __bfloat162float(m);
+    const __nv_bfloat16 l = __float2bfloat16_rn(r2);
+    __nv_bfloat16 out = __float2bfloat16_rn(0.f);
+    if (lane == 0) out = h;
+    if (lane == 1) out = m;
+    if (lane == 2) out = l;
+    cb16[(size_t)k * dpad16 + D + lane] = out;
+  }
+}
+
+int vq_prepare_codebook(const float* codebook, int K, int D, float* ee, float* emax, __nv_bfloat16* cb16, int dpad16,
+                        cudaStream_t s) {
+  if (cudaMemsetAsync(emax, 0, sizeof(float), s) != cudaSuccess) return DCVIC_ERR_CUDA;
+  vq_prepare_kernel<<<ceil_div_i(K, 8), 256, 0, s>>>(codebook, K, D, ee, emax, cb16, dpad16);
+  return dcvic_launch_status();
+}
+
+// Shared tail: turn sum((e-z)^2) into the reference's loss scalar.
+__device__ __forceinline__ void write_loss(double total, long long numel, float beta, int legacy, float* loss) {
+  const float m = (float)(total / (double)numel);
+  *loss = legacy ? __fadd_rn(m, __fmul_rn(beta, m)) : __fadd_rn(__fmul_rn(beta, m), m);
+}
+
+// ------------------------------------------------------------------ narrow fused forward
+// One thread per token, token row in registers, codebook tile (+ |e|^2) in shared memory and
+// read as warp-wide broadcasts.  Reads z NCHW directly, writes z_q NCHW + idx + loss.
+template <int D>
+__global__ void __launch_bounds__(128) vq_narrow_kernel(const float* __restrict__ z, const float* __restrict__ E,
+                                                         int N, int HW, int K, int KT, float beta, int legacy,
+                                                         float* __restrict__ zq, int64_t* __restrict__ idx,
+                                                         float* __restrict__ loss, double* __restrict__ partials,
+                                                         unsigned* __restrict__ counters) {
+  extern __shared__ __align__(16) float smem_f[];
+  float* sE = smem_f;            // [KT][D]
+  float* sEE = smem_f + KT * D;  // [KT]
+  __shared__ double scratch[32];
+
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool valid = t < N;
+  const size_t base = valid ? ((size_t)(t / HW) * D * HW + (size_t)(t % HW)) : 0;
+  float zr[D];
+  float zz = 0.f;
+#pragma unroll
+  for (int c = 0; c < D; ++c) {
+    zr[c] = valid ? z[base + (size_t)c * HW] : 0.f;
+    zz = __fadd_rn(zz, __fmul_rn(zr[c], zr[c]));
+  }
+  float best = FLT_MAX;
+  int bi = 0;
+  for (int k0 = 0; k0 < K; k0 += KT) {
+    const int kt = min(KT, K - k0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < kt * D; i += blockDim.x) sE[i] = E[(size_t)k0 * D + i];
+    __syncthreads();
+    for (int k = threadIdx.x; k < kt; k += blockDim.x) {
+      float a = 0.f;
+#pragma unroll
+      for (int c = 0; c < D; ++c) a = __fadd_rn(a, __fmul_rn(sE[k * D + c], sE[k * D + c]));
+      sEE[k] = a;
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int k = 0; k < kt; ++k) {
+      float dot = __fmul_rn(zr[0], sE[k * D]);
+#pragma unroll
+      for (int c = 1; c < D; ++c) dot = fmaf(zr[c], sE[k * D + c], dot);
+      const float d = fmaf(-2.f, dot, __fadd_rn(zz, sEE[k]));
+      if (d < best) {
+        best = d;
+        bi = k0 + k;
+      }
+    }
+  }
+  float sq = 0.f;
+  if (valid) {
+#pragma unroll
+    for (int c = 0; c < D; ++c) {
+      const float e = E[(size_t)bi * D + c];
+      const float diff = __fsub_rn(e, zr[c]);
+      zq[base + (size_t)c * HW] = __fadd_rn(zr[c], diff);
+      sq = fmaf(diff, diff, sq);
+    }
+    idx[t] = (int64_t)bi;
+  }
+  const double bsum = block_sum((double)sq, scratch);
+  double total;
+  if (publish_and_elect_last(bsum, partials, counters + kCtrLoss, gridDim.x, blockIdx.x, scratch, &total)) {
+    if (threadIdx.x == 0) write_loss(total, (long long)N * D, beta, legacy, loss);
+  }
+}
+
+int vq_narrow_forward(const float* z, const float* E, int B, int D, int HW, int K, float beta, int legacy, float* zq,
+                      int64_t* idx, float* loss, double* partials, unsigned* counters, cudaStream_t s) {
+  const int N = B * HW;
+  const int KT = min(K, D == 4 ? 4096 : 2048);
+  const size_t smem = (size_t)KT * (D + 1) * sizeof(float);
+  const int grid = ceil_div_i(N, 128);
+  if (D == 4) {
+    cudaFuncSetAttribute(vq_narrow_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    vq_narrow_kernel<4><<<grid, 128, smem, s>>>(z, E, N, HW, K, KT, beta, legacy, zq, idx, loss, partials, counters);
+  } else if (D == 8) {
+    cudaFuncSetAttribute(vq_narrow_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    vq_narrow_kernel<8><<<grid, 128, smem, s>>>(z, E, N, HW, K, KT, beta, legacy, zq, idx, loss, partials, counters);
+  } else {
+    return DCVIC_ERR_UNSUPPORTED;
+  }
+  return dcvic_launch_status();
+}
+
+// ------------------------------------------------------------------ exact FP32 search
+// 128 tokens x 128 codes per CTA tile, 16-wide e_dim chunks through shared memory, 8x8 register
+// micro-tile per thread, dot products accumulated with sequential FMAs over e_dim, running
+// (min, argmin) per token across code tiles.  This is the reference-order FP32 path: it is the
+// product path for shapes the tensor search does not cover and the check for the ones it does.
+constexpr int XT = 128, XC = 128, XD = 16;
+
+__global__ void __launch_bounds__(256) vq_exact_kernel(const float* __restrict__ z, const float* __restrict__ E,
+                                                        const float* __restrict__ ee, int N, int D, int HW, int K,
+                                                        int* __restrict__ cand) {
+  __shared__ __align__(16) float As[XD][XT];   // [c][token]
+  __shared__ __align__(16) float Bs[XD][XC + 4];  // [c][code]
+  __shared__ float s_zz[XT];
+  __shared__ size_t s_base[XT];
+  __shared__ float s_bd[XT][17];
+  __shared__ int s_bk[XT][17];
+
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int t0 = blockIdx.x * XT;
+
+  if (tid < XT) {
+    const int t = t0 + tid;
+    size_t base = 0;
+    float zz = 0.f;
+    if (t < N) {
+      base = (size_t)(t / HW) * D * HW + (size_t)(t % HW);
+      for (int c = 0; c < D; ++c) {
+        const float v = z[base + (size_t)c * HW];
+        zz = __fadd_rn(zz, __fmul_rn(v, v));
+      }
+    }
+    s_base[tid] = base;
+    s_zz[tid] = zz;
+  }
+  __syncthreads();
+
+  float best[8];
+  int bk[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    best[i] = FLT_MAX;
+    bk[i] = 0x7fffffff;
+  }
+
+  for (int k0 = 0; k0 < K; k0 += XC) {
+    float acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+    for (int c0 = 0; c0 < D; c0 += XD) {
+      // z chunk: 16 x 128 floats, coalesced along tokens
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        const int li = tid + r * 256;
+        const int c = li >> 7, tk = li & 127;
+        const bool ok = (t0 + tk < N) && (c0 + c < D);
+        As[c][tk] = ok ? z[s_base[tk] + (size_t)(c0 + c) * HW] : 0.f;
+      }
+      // codebook chunk: 128 codes x 16 floats, stored transposed
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        const int li = tid + r * 256;
+        const int code = li >> 4, c = li & 15;
+        const bool ok = (k0 + code < K) && (c0 + c < D);
+        Bs[c][code] = ok ? E[(size_t)(k0 + code) * D + c0 + c] : 0.f;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int c = 0; c < XD; ++c) {
+        const float4 a0 = *reinterpret_cast<const float4*>(&As[c][ty * 4]);
+        const float4 a1 = *reinterpret_cast<const float4*>(&As[c][64 + ty * 4]);
+        const float4 b0 = *reinterpret_cast<const float4*>(&Bs[c][tx * 4]);
+        const float4 b1 = *reinterpret_cast<const float4*>(&Bs[c][64 + tx * 4]);
+        const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+      }
+      __syncthreads();
+    }
+    // fold this code tile into the running minima (ascending code order within the thread)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int code = k0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
+      if (code < K) {
+        const float e2 = ee[code];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int tk = (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+          const float d = fmaf(-2.f, acc[i][j], __fadd_rn(s_zz[tk], e2));
+          if (d < best[i] || (d == best[i] && code < bk[i])) {
+            best[i] = d;
+            bk[i] = code;
+          }
+        }
+      }
+    }
+  }
+  // cross-thread argmin per token (16 threads share a token)
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int tk = (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+    s_bd[tk][tx] = best[i];
+    s_bk[tk][tx] = bk[i];
+  }
+  __syncthreads();
+  if (tid < XT && t0 + tid < N) {
+    float d = s_bd[tid][0];
+    int k = s_bk[tid][0];
+    for (int j = 1; j < 16; ++j) {
+      const float dj = s_bd[tid][j];
+      const int kj = s_bk[tid][j];
+      if (dj < d || (dj == d && kj < k)) {
+        d = dj;
+        k = kj;
+      }
+    }
+    cand[t0 + tid] = k;
+  }
+}
+
+int vq_exact_search(const float* z, const float* E, const float* ee, int B, int D, int HW, int K, int* cand,
+                    cudaStream_t s) {
+  const int N = B * HW;
+  vq_exact_kernel<<<ceil_div_i(N, XT), 256, 0, s>>>(z, E, ee, N, D, HW, K, cand);
+  return dcvic_launch_status();
+}
+
+// ------------------------------------------------------------------ finish
+// 32 tokens x e_dim per CTA staged (transposed, padded) in shared memory so that both the NCHW
+// side (lanes = tokens) and the codebook side (lanes = channels) are coalesced.
+//   count == nullptr : one candidate per token at cand[t*cap]
+//   count[t] in [1,cap] : FP32 re-rank of cand[t*cap .. +count)
+//   count[t] <= 0 or > cap : candidate list overflowed -> full FP32 scan of the codebook for that token
+__global__ void __launch_bounds__(256) vq_finish_kernel(const float* __restrict__ z, const float* __restrict__ E,
+                                                         const float* __restrict__ ee, const int* __restrict__ cand,
+                                                         int cap, const int* __restrict__ count, int N, int D, int HW,
+                                                         int K, float beta, int legacy, float* __restrict__ zq,
+                                                         int64_t* __restrict__ idx, float* __restrict__ loss,
+                                                         double* __restrict__ partials,
+                                                         unsigned* __restrict__ counters) {
+  extern __shared__ __align__(16) float buf[];  // [D][33]
+  __shared__ double scratch[32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int t0 = blockIdx.x * kFinishTokens;
+  const int tl = t0 + lane;
+  const bool valid = tl < N;
+  const size_t base = valid ? ((size_t)(tl / HW) * D * HW + (size_t)(tl % HW)) : 0;
+
+  for (int c = wid; c < D; c += 8) buf[c * 33 + lane] = valid ? z[base + (size_t)c * HW] : 0.f;
+  __syncthreads();
+
+  float sq = 0.f;
+  for (int tok = wid; tok < kFinishTokens; tok += 8) {
+    const int t = t0 + tok;
+    if (t >= N) break;
+    int n = count ? count[t] : 1;
+    int best_k;
+    if (n == 1) {
+      best_k = cand[(size_t)t * cap];
+    } else {
+      float zzp = 0.f;
+      for (int c = lane; c < D; c += 32) {
+        const float v = buf[c * 33 + tok];
+        zzp = __fadd_rn(zzp, __fmul_rn(v, v));
+      }
+      const float zz = warp_sum(zzp);
+      float best_d = FLT_MAX;
+      best_k = 0x7fffffff;
+      const bool full = (n <= 0 || n > cap);
+      const int iters = full ? K : n;
+      for (int i = 0; i < iters; ++i) {
+        const int k = full ? i : cand[(size_t)t * cap + i];
+        const float* er = E + (size_t)k * D;
+        float dp = 0.f;
+        for (int c = lane; c < D; c += 32) dp = fmaf(buf[c * 33 + tok], er[c], dp);
+        const float dot = warp_sum(dp);
+        const float d = fmaf(-2.f, dot, __fadd_rn(zz, ee[k]));
+        if (d < best_d || (d == best_d && k < best_k)) {
+          best_d = d;
+          best_k = k;
+        }
+      }
+      if (lane == 0) {
+        if (full) atomicAdd(counters + kCtrOverflow, 1u);
+        else atomicAdd(counters + kCtrRerank, 1u);
+      }
+    }
+    best_k = min(max(best_k, 0), K - 1);
+    const float* er = E + (size_t)best_k * D;
+    for (int c = lane; c < D; c += 32) {
+      const float zv = buf[c * 33 + tok];
+      const float diff = __fsub_rn(er[c], zv);
+      buf[c * 33 + tok] = __fadd_rn(zv, diff);
+      sq = fmaf(diff, diff, sq);
+    }
+    if (lane == 0) idx[t] = (int64_t)best_k;
+  }
+  __syncthreads();
+  if (valid)
+    for (int c = wid; c < D; c += 8) zq[base + (size_t)c * HW] = buf[c * 33 + lane];
+
+  const double bsum = block_sum((double)sq, scratch);
+  double total;
+  if (publish_and_elect_last(bsum, partials, counters + kCtrLoss, gridDim.x, blockIdx.x, scratch, &total)) {
+    if (threadIdx.x == 0) write_loss(total, (long long)N * D, beta, legacy, loss);
+  }
+}
+
+int vq_finish(const float* z, const float* E, const float* ee, const int* cand, int cap, const int* count, int B, int D,
+              int HW, int K, float beta, int legacy, float* zq, int64_t* idx, float* loss, double* partials,
+              unsigned* counters, cudaStream_t s) {
+  const int N = B * HW;
+  const size_t smem = (size_t)D * 33 * sizeof(float);
+  if (smem > 200 * 1024) return DCVIC_ERR_UNSUPPORTED;
+  if (smem > 48 * 1024)
+    cudaFuncSetAttribute(vq_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  vq_finish_kernel<<<ceil_div_i(N, kFinishTokens), 256, smem, s>>>(z, E, ee, cand, cap, count, N, D, HW, K, beta,
+                                                                    legacy, zq, idx, loss, partials, counters);
+  return dcvic_launch_status();
+}
+
+// ------------------------------------------------------------------ V1 extras
+__global__ void __launch_bounds__(256) vq_onehot_rows_kernel(const int64_t* __restrict__ idx, int N, int K,
+                                                              float* __restrict__ onehot) {
+  // one warp per row; float4 stores when K % 4 == 0
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= N) return;
+  const int hot = (int)idx[row];
+  float* out = onehot + (size_t)row * K;
+  if ((K & 3) == 0) {
+    for (int c = lane * 4; c < K; c += 128) {
+      float4 v = make_float4(c == hot, c + 1 == hot, c + 2 == hot, c + 3 == hot);
+      stg_stream(reinterpret_cast<float4*>(out + c), v);
+    }
+  } else {
+    for (int c = lane; c < K; c += 32) out[c] = (c == hot) ? 1.f : 0.f;
+  }
+}
+
+__global__ void __launch_bounds__(256) vq_hist_kernel(const int64_t* __restrict__ idx, int N, int K,
+                                                       unsigned* __restrict__ hist) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
+    const int k = (int)idx[i];
+    if (k >= 0 && k < K) atomicAdd(hist + k, 1u);
+  }
+}
+
+__global__ void __launch_bounds__(256) vq_perplexity_kernel(const unsigned* __restrict__ hist, int N, int K,
+                                                             float* __restrict__ perplexity) {
+  __shared__ double scratch[32];
+  double acc = 0.0;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    const float p = (float)hist[k] / (float)N;  // torch.mean of a 0/1 fp32 column
+    acc += (double)(p * logf(p + 1e-10f));
+  }
+  const double s = block_sum(acc, scratch);
+  if (threadIdx.x == 0) *perplexity = expf(-(float)s);
+}
+
+int vq_v1_extras(const int64_t* idx, int N, int K, float* onehot, float* perplexity, unsigned* hist, unsigned* counters,
+                 cudaStream_t s) {
+  (void)counters;
+  if (onehot) {
+    vq_onehot_rows_kernel<<<ceil_div_i(N, 8), 256, 0, s>>>(idx, N, K, onehot);
+    if (dcvic_launch_status() != DCVIC_OK) return DCVIC_ERR_CUDA;
+  }
+  if (perplexity) {
+    if (cudaMemsetAsync(hist, 0, (size_t)K * sizeof(unsigned), s) != cudaSuccess) return DCVIC_ERR_CUDA;
+    vq_hist_kernel<<<min(ceil_div_i(N, 256), 4 * kNumSMs), 256, 0, s>>>(idx, N, K, hist);
+    vq_perplexity_kernel<<<1, 256, 0, s>>>(hist, N, K, perplexity);
+  }
+  return dcvic_launch_status();
+}
+
+// ------------------------------------------------------------------ backward
+// Same 32-token transposed tile as the finish kernel.  dz is written coalesced along tokens;
+// dE receives coalesced (lanes = channels) atomic adds.
+__global__ void __launch_bounds__(256) vq_backward_kernel(const float* __restrict__ g_zq,
+                                                           const float* __restrict__ g_loss,
+                                                           const float* __restrict__ z, const float* __restrict__ E,
+                                                           const int64_t* __restrict__ idx, int N, int D, int HW, int K,
+                                                           float coef_z, float coef_e, float* __restrict__ dz,
+                                                           float* __restrict__ dE) {
+  extern __shared__ __align__(16) float buf[];  // [D][33] z, then dz
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int t0 = blockIdx.x * kFinishTokens;
+  const int tl = t0 + lane;
+  const bool valid = tl < N;
+  const size_t base = valid ? ((size_t)(tl / HW) * D * HW + (size_t)(tl % HW)) : 0;
+  const float gl = g_loss ? *g_loss : 0.f;
+  const float scale = 2.f / ((float)N * (float)D);
+  const float az = gl * coef_z * scale, ae = gl * coef_e * scale;
+
+  for (int c = wid; c < D; c += 8) buf[c * 33 + lane] = valid ? z[base + (size_t)c * HW] : 0.f;
+  __syncthreads();
+  for (int tok = wid; tok < kFinishTokens; tok += 8) {
+    const int t = t0 + tok;
+    if (t >= N) break;
+    const int k = min(max((int)idx[t], 0), K - 1);
+    const float* er = E + (size_t)k * D;
+    for (int c = lane; c < D; c += 32) {
+      const float diff = buf[c * 33 + tok] - er[c];  // z - e
+      buf[c * 33 + tok] = az * diff;
+      if (dE) atomicAdd(dE + (size_t)k * D + c, -ae * diff);
+    }
+  }
+  __syncthreads();
+  if (valid && dz)
+    for (int c = wid; c < D; c += 8) {
+      const size_t o = base + (size_t)c * HW;
+      dz[o] = (g_zq ? g_zq[o] : 0.f) + buf[c * 33 + lane];
+    }
+}
+
+}  // namespace dcvic
+
+using namespace dcvic;
+
+extern "C" int dcvic_vq_backward(const float* g_zq, const float* g_loss, const float* z_nchw, const float* codebook,
+                                 const int64_t* idx, int B, int D, int H, int W, int K, float beta, int legacy,
+                                 float* dz, float* dE, dcvic_stream_t stream) {
+  DCVIC_CHECK_ARG(z_nchw && codebook && idx);
+  DCVIC_CHECK_ARG(B > 0 && D > 0 && H > 0 && W > 0 && K > 0);
+  DCVIC_CHECK_ARG(dz || dE);
+  if ((long long)B * H * W > 0x7fffffffLL) return DCVIC_ERR_UNSUPPORTED;
+  const size_t smem = (size_t)D * 33 * sizeof(float);
+  if (smem > 200 * 1024) return DCVIC_ERR_UNSUPPORTED;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int HW = H * W, N = B * HW;
+  if (dE && cudaMemsetAsync(dE, 0, (size_t)K * D * sizeof(float), s) != cudaSuccess) return DCVIC_ERR_CUDA;
+  // legacy: loss = mean((sg(zq)-z)^2) + beta*mean((zq-sg(z))^2): z gets coefficient 1, E gets beta
+  const float coef_z = legacy ? 1.f : beta, coef_e = legacy ? beta : 1.f;
+  if (smem > 48 * 1024)
+    cudaFuncSetAttribute(vq_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  vq_backward_kernel<<<ceil_div_i(N, kFinishTokens), 256, smem, s>>>(g_zq, g_loss, z_nchw, codebook, idx, N, D, HW, K,
+                                                                      coef_z, coef_e, dz, dE);
+  return dcvic_launch_status();
+}
+
+// ------------------------------------------------------------------ gather / one-hot feature
+namespace dcvic {
+
+__global__ void __launch_bounds__(256) vq_gather_nchw_kernel(const int64_t* __restrict__ idx,
+                                                              const float* __restrict__ E, int N, int D, int HW, int K,
+                                                              float* __restrict__ out, int* __restrict__ bad) {
+  extern __shared__ __align__(16) float buf[];  // [D][33]
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int t0 = blockIdx.x * kFinishTokens;
+  for (int tok = wid; tok < kFinishTokens; tok += 8) {
+    const int t = t0 + tok;
+    if (t >= N) break;
+    const long long raw = idx[t];
+    if ((raw < 0 || raw >= K) && lane == 0 && bad) atomicAdd(bad, 1);
+    const int k = (int)min(max(raw, 0LL), (long long)K - 1);
+    const float* er = E + (size_t)k * D;
+    for (int c = lane; c < D; c += 32) buf[c * 33 + tok] = er[c];
+  }
+  __syncthreads();
+  const int tl = t0 + lane;
+  if (tl < N) {
+    const size_t base = (size_t)(tl / HW) * D * HW + (size_t)(tl % HW);
+    for (int c = wid; c < D; c += 8) out[base + (size_t)c * HW] = buf[c * 33 + lane];
+  }
+}
+
+__global__ void __launch_bounds__(256) vq_gather_rows_kernel(const int64_t* __restrict__ idx,
+                                                              const float* __restrict__ E, long long N, int D, int K,
+                                                              float* __restrict__ out, int* __restrict__ bad) {
+  const int lane = threadIdx.x & 31;
+  const long long t = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (t >= N) return;
+  const long long raw = idx[t];
+  if ((raw < 0 || raw >= K) && lane == 0 && bad) atomicAdd(bad, 1);
+  const int k = (int)min(max(raw, 0LL), (long long)K - 1);
+  for (int c = lane; c < D; c += 32) out[(size_t)t * D + c] = E[(size_t)k * D + c];
+}
+
+// out[b][k][p] = (idx[b][p] == k): each thread owns 4 consecutive tokens of one (b,k) row.
+__global__ void __launch_bounds__(256) vq_onehot_nchw_kernel(const int64_t* __restrict__ idx, int B, int HW, int K,
+                                                              float* __restrict__ out) {
+  const int b = blockIdx.z;
+  const int k = blockIdx.y;
+  const int64_t* ib = idx + (size_t)b * HW;
+  float* ob = out + ((size_t)b * K + k) * HW;
+  const bool vec = ((HW & 3) == 0);
+  if (vec) {
+    for (int p = (blockIdx.x * blockDim.x + threadIdx.x) * 4; p < HW; p += gridDim.x * blockDim.x * 4) {
+      const longlong2 i01 = *reinterpret_cast<const longlong2*>(ib + p);
+      const longlong2 i23 = *reinterpret_cast<const longlong2*>(ib + p + 2);
+      float4 v = make_float4(i01.x == k, i01.y == k, i23.x == k, i23.y == k);
+      stg_stream(reinterpret_cast<float4*>(ob + p), v);
+    }
+  } else {
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < HW; p += gridDim.x * blockDim.x)
+      ob[p] = (ib[p] == k) ? 1.f : 0.f;
+  }
+}
+
+}  // namespace dcvic
+
+extern "C" int dcvic_codebook_gather(const int64_t* idx, const float* codebook, int B, int HW, int D, int K,
+                                     int to_nchw, float* out, int* bad_count, dcvic_stream_t stream) {
+  DCVIC_CHECK_ARG(idx && codebook && out);
+  DCVIC_CHECK_ARG(B > 0 && HW > 0 && D > 0 && K > 0);
+  if ((long long)B * HW > 0x7fffffffLL) return DCVIC_ERR_UNSUPPORTED;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int N = B * HW;
+  if (bad_count && cudaMemsetAsync(bad_count, 0, sizeof(int), s) != cudaSuccess) return DCVIC_ERR_CUDA;
+  if (to_nchw) {
+    const size_t smem = (size_t)D * 33 * sizeof(float);
+    if (smem > 200 * 1024) return DCVIC_ERR_UNSUPPORTED;
+    if (smem > 48 * 1024)
+      cudaFuncSetAttribute(vq_gather_nchw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    vq_gather_nchw_kernel<<<ceil_div_i(N, kFinishTokens), 256, smem, s>>>(idx, codebook, N, D, HW, K, out, bad_count);
+  } else {
+    vq_gather_rows_kernel<<<ceil_div_i(N, 8), 256, 0, s>>>(idx, codebook, N, D, K, out, bad_count);
+  }
+  return dcvic_launch_status();
+}
+
+extern "C" int dcvic_onehot_nchw(const int64_t* idx, int B, int HW, int K, float* out, dcvic_stream_t stream) {
+  DCVIC_CHECK_ARG(idx && out);
+  DCVIC_CHECK_ARG(B > 0 && HW > 0 && K > 0);
+  if (K > 65535 || B > 65535) return DCVIC_ERR_UNSUPPORTED;
+  const bool vec = ((HW & 3) == 0) && ((reinterpret_cast<uintptr_t>(idx) & 15) == 0) &&
+                   ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+  if (!vec && (HW & 3) == 0) return DCVIC_ERR_BAD_ARG;  // misaligned buffers with a vectorisable shape
+  const int per = 256 * 4;
+  dim3 grid(min(ceil_div_i(HW, per), 64), K, B);
+  vq_onehot_nchw_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(idx, B, HW, K, out);
+  return dcvic_launch_status();
+}

@@ -1,0 +1,275 @@
+"""B200-native VQGAN codebook quantizers with the reference's module interface.
+
+Mirrors (same ctor arguments, attribute / state-dict names, forward signatures, return tuples):
+
+* ``VectorQuantizer``   -- taming/modules/vqvae/quantize.py:9-107   (V1: one-hot + perplexity)
+* ``VectorQuantizer2``  -- taming/modules/vqvae/quantize.py:213-329 (the class DC-VIC uses via
+  ldm/models/autoencoder.py:6,39-41; ``sane_index_shape`` is set at
+  src/models/comp_model/hyperprior_vic_model.py:61)
+
+All arithmetic runs in hand-written CUDA behind the C ABI of ``include/dcvic_b200.h``
+(``dcvic_vq_forward`` / ``dcvic_vq_backward`` / ``dcvic_codebook_gather`` / ``dcvic_onehot_nchw``).
+There is no CPU or PyTorch fallback: CPU tensors raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+__all__ = ["VectorQuantizer", "VectorQuantizer2", "codebook_lookup", "onehot_feature", "swap_quantizer"]
+
+
+class _Workspace:
+    """Zero-initialised device scratch, cached per (device, stream, shape)."""
+
+    def __init__(self):
+        self._cache = {}
+
+    def get(self, key, nbytes: int, device) -> torch.Tensor:
+        stream = torch.cuda.current_stream(device).cuda_stream
+        k = (device.index, stream) + tuple(key)
+        buf = self._cache.get(k)
+        if buf is None or buf.numel() < nbytes:
+            buf = torch.zeros(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+            self._cache[k] = buf
+            return buf, True
+        return buf, False
+
+
+class _VQForward(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, z, weight, beta, legacy, want_v1, flags, owner):
+        _lib.require_cuda(z, weight)
+        if z.dim() != 4:
+            raise ValueError(f"expected z of shape [B, C, H, W], got {tuple(z.shape)}")
+        B, D, H, W = z.shape
+        K, D2 = weight.shape
+        if D != D2:
+            raise ValueError(f"z has {D} channels but the codebook has e_dim={D2}")
+        lib = _lib.load()
+        zc = z.detach().contiguous().float()
+        wc = weight.detach().contiguous().float()
+        N = B * H * W
+        with torch.cuda.device(z.device):
+            z_q = torch.empty_like(zc)
+            idx = torch.empty(N, dtype=torch.int64, device=z.device)
+            loss = torch.empty((), dtype=torch.float32, device=z.device)
+            onehot = torch.empty(N, K, dtype=torch.float32, device=z.device) if want_v1 else None
+            ppl = torch.empty((), dtype=torch.float32, device=z.device) if want_v1 else None
+            nbytes = lib.dcvic_vq_workspace_bytes(B, D, H, W, K)
+            if nbytes == 0:
+                raise RuntimeError("dcvic_vq_workspace_bytes rejected the shape")
+            ws, fresh = owner._ws.get((B, D, H, W, K), nbytes, z.device)
+            key = (wc.data_ptr(), weight._version, ws.data_ptr())
+            if owner._frozen and not fresh and owner._prep_key == key:
+                flags |= _lib.VQ_REUSE_PREP
+            rc = lib.dcvic_vq_forward(_lib.ptr(zc), _lib.ptr(wc), B, D, H, W, K, float(beta), int(bool(legacy)),
+                                      _lib.ptr(z_q), _lib.ptr(idx), _lib.ptr(loss), _lib.ptr(onehot), _lib.ptr(ppl),
+                                      int(flags), _lib.ptr(ws), ws.numel(), _lib.cur_stream())
+            _lib.check(rc, "dcvic_vq_forward")
+            owner._prep_key = key
+        ctx.save_for_backward(zc, wc, idx)
+        ctx.meta = (B, D, H, W, K, float(beta), bool(legacy))
+        ctx.mark_non_differentiable(idx)
+        if want_v1:
+            ctx.mark_non_differentiable(onehot, ppl)
+            return z_q, loss, idx, onehot, ppl
+        return z_q, loss, idx
+
+    @staticmethod
+    def backward(ctx, g_zq, g_loss, *unused):
+        zc, wc, idx = ctx.saved_tensors
+        B, D, H, W, K, beta, legacy = ctx.meta
+        lib = _lib.load()
+        need_z, need_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        with torch.cuda.device(zc.device):
+            dz = torch.empty_like(zc) if need_z else None
+            dE = torch.empty_like(wc) if need_w else None
+            if dz is None and dE is None:
+                return (None,) * 7
+            gz = g_zq.contiguous().float() if g_zq is not None else None
+            gl = g_loss.contiguous().float() if g_loss is not None else None
+            rc = lib.dcvic_vq_backward(_lib.ptr(gz), _lib.ptr(gl), _lib.ptr(zc), _lib.ptr(wc), _lib.ptr(idx),
+                                       B, D, H, W, K, beta, int(legacy), _lib.ptr(dz), _lib.ptr(dE),
+                                       _lib.cur_stream())
+            _lib.check(rc, "dcvic_vq_backward")
+        return dz, dE, None, None, None, None, None
+
+
+def codebook_lookup(indices: torch.Tensor, weight: torch.Tensor, nchw: bool = True) -> torch.Tensor:
+    """``embedding(indices)`` [+ 'b h w c -> b c h w'] in one gather kernel.
+
+    ``indices`` [B, H, W] (nchw=True -> [B, D, H, W]) or any shape (nchw=False -> [..., D]).
+    Mirrors vq_indices_to_latent (src/models/comp_model/hyperprior_vic_model.py:165-168).
+    """
+    _lib.require_cuda(indices, weight)
+    lib = _lib.load()
+    K, D = weight.shape
+    idx = indices.contiguous().long()
+    wc = weight.detach().contiguous().float()
+    with torch.cuda.device(weight.device):
+        bad = torch.zeros(1, dtype=torch.int32, device=weight.device)
+        if nchw:
+            if idx.dim() != 3:
+                raise ValueError("nchw lookup expects indices of shape [B, H, W]")
+            B, H, W = idx.shape
+            out = torch.empty(B, D, H, W, dtype=torch.float32, device=weight.device)
+            rc = lib.dcvic_codebook_gather(_lib.ptr(idx), _lib.ptr(wc), B, H * W, D, K, 1, _lib.ptr(out),
+                                           _lib.ptr(bad), _lib.cur_stream())
+        else:
+            n = idx.numel()
+            out = torch.empty(*idx.shape, D, dtype=torch.float32, device=weight.device)
+            rc = lib.dcvic_codebook_gather(_lib.ptr(idx), _lib.ptr(wc), 1, n, D, K, 0, _lib.ptr(out), _lib.ptr(bad),
+                                           _lib.cur_stream())
+        _lib.check(rc, "dcvic_codebook_gather")
+    return out
+
+
+def onehot_feature(indices_bhw: torch.Tensor, n_embed: int) -> torch.Tensor:
+    """``F.one_hot(idx, K).permute(0,3,1,2).float()`` (hyperprior_vic_model.py:268-271), one kernel."""
+    _lib.require_cuda(indices_bhw)
+    lib = _lib.load()
+    idx = indices_bhw.contiguous().long()
+    B, H, W = idx.shape
+    with torch.cuda.device(idx.device):
+        out = torch.empty(B, n_embed, H, W, dtype=torch.float32, device=idx.device)
+        rc = lib.dcvic_onehot_nchw(_lib.ptr(idx), B, H * W, int(n_embed), _lib.ptr(out), _lib.cur_stream())
+        _lib.check(rc, "dcvic_onehot_nchw")
+    return out
+
+
+class _QuantizerBase(nn.Module):
+    def _init_common(self, n_e, e_dim, beta):
+        self.n_e = n_e
+        self.e_dim = e_dim
+        self.beta = beta
+        self.embedding = nn.Embedding(self.n_e, self.e_dim)
+        self.embedding.weight.data.uniform_(-1.0 / self.n_e, 1.0 / self.n_e)
+        self._ws = _Workspace()
+        self._frozen = False
+        self._prep_key = None
+        self.search = "auto"   # "auto" | "exact" (FP32 SIMT scan) | "tensor" (tcgen05, error if unsupported)
+
+    def freeze_codebook(self, frozen: bool = True):
+        """Declare the codebook constant (DC-VIC always freezes the VQGAN,
+        src/trainer/rate_distortion_vq_code_trainer.py:62): |e|^2 and the BF16 copy used by the
+        tensor-core search are then prepared once and reused while ``weight._version`` is unchanged."""
+        self._frozen = bool(frozen)
+        self._prep_key = None
+        return self
+
+    def _flags(self) -> int:
+        return {"auto": 0, "exact": _lib.VQ_FORCE_EXACT, "tensor": _lib.VQ_FORCE_TENSOR}[self.search]
+
+    def search_path(self) -> str:
+        code = _lib.load().dcvic_vq_path(self.e_dim, self.n_e, self._flags())
+        return {0: "narrow-simt", 1: "exact-simt", 2: "tcgen05"}.get(code, f"unsupported({code})")
+
+
+class VectorQuantizer(_QuantizerBase):
+    """taming ``VectorQuantizer`` (quantize.py:9-107): returns
+    ``(z_q, loss, (perplexity, min_encodings[N,K], min_encoding_indices[N,1]))``."""
+
+    def __init__(self, n_e, e_dim, beta):
+        super().__init__()
+        self._init_common(n_e, e_dim, beta)
+
+    def forward(self, z):
+        z_q, loss, idx, onehot, ppl = _VQForward.apply(z, self.embedding.weight, self.beta, True, True,
+                                                       self._flags(), self)
+        return z_q, loss, (ppl, onehot, idx.unsqueeze(1))
+
+    def get_codebook_entry(self, indices, shape):
+        # shape specifying (batch, height, width, channel)
+        if shape is not None:
+            return codebook_lookup(indices.reshape(shape[0], shape[1], shape[2]), self.embedding.weight, nchw=True)
+        return codebook_lookup(indices.reshape(-1), self.embedding.weight, nchw=False)
+
+
+class VectorQuantizer2(_QuantizerBase):
+    """taming ``VectorQuantizer2`` (quantize.py:213-329): returns
+    ``(z_q, loss, (None, None, min_encoding_indices))``; indices are [N] or, with
+    ``sane_index_shape``, [B, H, W]."""
+
+    def __init__(self, n_e, e_dim, beta, remap=None, unknown_index="random", sane_index_shape=False, legacy=True):
+        super().__init__()
+        self._init_common(n_e, e_dim, beta)
+        self.legacy = legacy
+        self.remap = remap
+        if self.remap is not None:
+            self.register_buffer("used", torch.tensor(np.load(self.remap)))
+            self.re_embed = self.used.shape[0]
+            self.unknown_index = unknown_index  # "random" or "extra" or integer
+            if self.unknown_index == "extra":
+                self.unknown_index = self.re_embed
+                self.re_embed = self.re_embed + 1
+        else:
+            self.re_embed = n_e
+        self.sane_index_shape = sane_index_shape
+
+    # remap helpers (quantize.py:245-269): index bookkeeping, host-side torch ops, unused by DC-VIC
+    def remap_to_used(self, inds):
+        ishape = inds.shape
+        assert len(ishape) > 1
+        inds = inds.reshape(ishape[0], -1)
+        used = self.used.to(inds)
+        match = (inds[:, :, None] == used[None, None, ...]).long()
+        new = match.argmax(-1)
+        unknown = match.sum(2) < 1
+        if self.unknown_index == "random":
+            new[unknown] = torch.randint(0, self.re_embed, size=new[unknown].shape).to(device=new.device)
+        else:
+            new[unknown] = self.unknown_index
+        return new.reshape(ishape)
+
+    def unmap_to_all(self, inds):
+        ishape = inds.shape
+        assert len(ishape) > 1
+        inds = inds.reshape(ishape[0], -1)
+        used = self.used.to(inds)
+        if self.re_embed > self.used.shape[0]:  # extra token
+            inds[inds >= self.used.shape[0]] = 0
+        back = torch.gather(used[None, :][inds.shape[0] * [0], :], 1, inds)
+        return back.reshape(ishape)
+
+    def forward(self, z, temp=None, rescale_logits=False, return_logits=False):
+        assert temp is None or temp == 1.0, "Only for interface compatible with Gumbel"
+        assert rescale_logits is False, "Only for interface compatible with Gumbel"
+        assert return_logits is False, "Only for interface compatible with Gumbel"
+        z_q, loss, idx = _VQForward.apply(z, self.embedding.weight, self.beta, self.legacy, False, self._flags(), self)
+        if self.remap is not None:
+            idx = self.remap_to_used(idx.reshape(z.shape[0], -1)).reshape(-1, 1)
+        if self.sane_index_shape:
+            idx = idx.reshape(z_q.shape[0], z_q.shape[2], z_q.shape[3])
+        return z_q, loss, (None, None, idx)
+
+    def get_codebook_entry(self, indices, shape):
+        # shape specifying (batch, height, width, channel)
+        if self.remap is not None:
+            indices = self.unmap_to_all(indices.reshape(shape[0], -1)).reshape(-1)
+        if shape is not None:
+            return codebook_lookup(indices.reshape(shape[0], shape[1], shape[2]), self.embedding.weight, nchw=True)
+        return codebook_lookup(indices.reshape(-1), self.embedding.weight, nchw=False)
+
+    @classmethod
+    def from_reference(cls, ref: nn.Module) -> "VectorQuantizer2":
+        """Build from a taming ``VectorQuantizer2`` instance (same codebook tensor values)."""
+        new = cls(ref.n_e, ref.e_dim, ref.beta, remap=getattr(ref, "remap", None),
+                  unknown_index=getattr(ref, "unknown_index", "random"),
+                  sane_index_shape=getattr(ref, "sane_index_shape", False), legacy=getattr(ref, "legacy", True))
+        new.embedding.weight.data = ref.embedding.weight.data.clone()
+        new.embedding.weight.requires_grad_(ref.embedding.weight.requires_grad)
+        return new.to(ref.embedding.weight.device)
+
+
+def swap_quantizer(vq_model: nn.Module) -> nn.Module:
+    """``vq_model.quantize = VectorQuantizer2.from_reference(vq_model.quantize)`` -- the VQ plugin
+    boundary of DC-VIC is this attribute (ldm/models/autoencoder.py:39-41)."""
+    vq_model.quantize = VectorQuantizer2.from_reference(vq_model.quantize)
+    return vq_model

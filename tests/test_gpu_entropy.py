@@ -1,0 +1,224 @@
+"""GPU parity of the rate/entropy kernels against the CPU oracle (CompressAI 1.2.4 restatement;
+parity unpinned at that boundary, see oracle/entropy_oracle.py).  Tolerances (BASELINE.json):
+y_hat bit-exact; likelihoods and bpp within 1e-4 relative."""
+import numpy as np
+import pytest
+import torch
+
+import dc_vic_b200 as D
+from oracle import entropy_oracle as O
+from synth import entropy_inputs, entropy_inputs_init, noise_like
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+REL = 1e-4   # north-star tolerance on likelihoods / bpp
+
+
+def rel_err(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float(((a - b).abs() / b.abs().clamp_min(1e-30)).max())
+
+
+@pytest.mark.parametrize("q", [0, 1, 2, 3, 4])
+def test_gaussian_eval_c3_slice(q):
+    y, params = entropy_inputs(q, B=4, C=320, H=32, W=32)
+    ref = O.SteGaussianMeanScaleConditional(scale_bound=0.11)
+    ours = D.SteGaussianMeanScaleConditional(scale_bound=0.11).to(DEV)
+    with torch.no_grad():
+        yh_r, lk_r = ref(y, params, is_train=False)
+        yh, lk = ours(y.to(DEV), params.to(DEV), is_train=False)
+    assert torch.equal(yh.cpu(), yh_r)
+    assert rel_err(lk, lk_r) < REL
+    b_r, bpp_r = O.likelihood_to_bit(lk_r, 512 * 512 * 4)
+    b, bpp = D.likelihood_to_bit(lk, 512 * 512 * 4)
+    assert abs(float(b) - float(b_r)) <= REL * float(b_r) and abs(float(bpp) - float(bpp_r)) <= REL * float(bpp_r)
+    # FP64 closed form, reported through the assertion message
+    mu, sg = params.chunk(2, 1)
+    from scipy.stats import norm
+    s = sg.double().clamp_min(0.11)
+    v = (yh_r.double() - mu.double()).abs()
+    f64 = np.maximum(norm.cdf(((0.5 - v) / s).numpy()) - norm.cdf(((-0.5 - v) / s).numpy()), 1e-9)
+    e64 = np.abs(lk.double().cpu().numpy() - f64) / f64
+    assert e64.max() < 2e-4, f"vs FP64 closed form: {e64.max():.3e}"
+
+
+@pytest.mark.parametrize("cls", ["GaussianMeanScaleConditional", "SteGaussianMeanScaleConditional",
+                                 "GaussianScaleConditional"])
+def test_gaussian_train_with_explicit_noise(cls):
+    y, params = entropy_inputs(2, B=3, C=32, H=16, W=12)
+    if cls == "GaussianScaleConditional":
+        params = params.chunk(2, 1)[1].contiguous()
+    nz = noise_like(y, 202)
+    ref = getattr(O, cls)(scale_bound=0.11)
+    ours = getattr(D, cls)(scale_bound=0.11).to(DEV)
+    yr = y.clone().requires_grad_(True)
+    pr = params.clone().requires_grad_(True)
+    yh_r, lk_r = ref(yr, pr, is_train=True, noise=nz)
+    yo = y.to(DEV).requires_grad_(True)
+    po = params.to(DEV).requires_grad_(True)
+    yh, lk = ours(yo, po, is_train=True, noise=nz.to(DEV))
+    assert torch.equal(yh.detach().cpu(), yh_r.detach())
+    assert rel_err(lk, lk_r) < REL
+    g = torch.Generator().manual_seed(4)
+    w1, w2 = torch.randn(y.shape, generator=g), torch.randn(y.shape, generator=g)
+    (O.likelihood_to_bit(lk_r, 100)[1] + (yh_r * w1).sum() * 1e-3 + (lk_r * w2).sum()).backward()
+    (D.likelihood_to_bit(lk, 100)[1] + (yh * w1.to(DEV)).sum() * 1e-3 + (lk * w2.to(DEV)).sum()).backward()
+    for a, b in ((yo.grad, yr.grad), (po.grad, pr.grad)):
+        scale = float(b.abs().max())
+        assert float((a.cpu() - b).abs().max()) <= 2e-4 * scale + 1e-7
+
+
+def test_gaussian_q_init_bounds_and_nonvec_path():
+    y, params = entropy_inputs_init(B=3, C=5, H=7, W=9)       # n % 4 != 0 -> scalar kernel
+    ref = O.SteGaussianMeanScaleConditional(scale_bound=0.11)
+    ours = D.SteGaussianMeanScaleConditional(scale_bound=0.11).to(DEV)
+    nz = noise_like(y, 203)
+    for train in (False, True):
+        with torch.no_grad():
+            yh_r, lk_r = ref(y, params, is_train=train, noise=nz if train else None)
+            yh, lk = ours(y.to(DEV), params.to(DEV), is_train=train, noise=nz.to(DEV) if train else None)
+        assert torch.equal(yh.cpu(), yh_r)
+        assert rel_err(lk, lk_r) < REL
+        assert float(lk.min()) >= float(torch.tensor(1e-9))
+    # empty-ish / single element
+    y1, p1 = torch.tensor([[[[0.3]]]]), torch.tensor([[[[0.1]], [[-5.0]]]])
+    with torch.no_grad():
+        a = ours(y1.to(DEV), p1.to(DEV), is_train=False)
+        b = ref(y1, p1, is_train=False)
+    assert torch.equal(a[0].cpu(), b[0]) and rel_err(a[1], b[1]) < REL
+
+
+def test_gaussian_dual_matches_two_calls():
+    y, params = entropy_inputs(3, B=2, C=32, H=32, W=48)
+    nz = noise_like(y, 204)
+    ref = O.SteGaussianMeanScaleConditional(scale_bound=0.11)
+    with torch.no_grad():
+        yh_r, lk_r = ref(y, params, is_train=True, noise=nz)
+        _, lq_r = ref(y, params, is_train=False)
+    yh, lk, lq, bits, bits_q = D.gaussian_rate_dual(y.to(DEV), params.to(DEV), nz.to(DEV))
+    assert torch.equal(yh.cpu(), yh_r)
+    assert rel_err(lk, lk_r) < REL and rel_err(lq, lq_r) < REL
+    assert rel_err(bits, O.batch_bits(lk_r)) < REL and rel_err(bits_q, O.batch_bits(lq_r)) < REL
+
+
+def test_build_indexes_and_tables():
+    table = O.get_scale_table()
+    ref = O.GaussianMeanScaleConditional(scale_bound=0.11)
+    ref.update_scale_table(table)
+    ours = D.GaussianMeanScaleConditional(scale_bound=0.11).to(DEV)
+    assert ours.update_scale_table(D.get_scale_table()) is True
+    assert torch.equal(ours.scale_table.cpu(), ref.scale_table)
+    assert torch.equal(ours._offset.cpu(), ref._offset) and torch.equal(ours._cdf_length.cpu(), ref._cdf_length)
+    diff = (ours._quantized_cdf.cpu() - ref._quantized_cdf).abs()
+    assert int(diff.max()) <= 1 and float((diff > 0).float().mean()) < 1e-3   # erfc ulp-level differences only
+    _, params = entropy_inputs(4, B=2, C=16, H=8, W=8)
+    sg = params.chunk(2, 1)[1].contiguous()
+    sg.view(-1)[:64] = table            # exact table hits exercise the '<=' edge
+    assert torch.equal(ours.build_indexes(sg.to(DEV)).cpu(), ref.build_indexes(sg))
+
+
+@pytest.mark.parametrize("train", [False, True])
+def test_entropy_bottleneck_forward(train):
+    torch.manual_seed(3)
+    ref = O.SteEntropyBottleneck(channels=192)
+    with torch.no_grad():           # perturb away from the symmetric init
+        for n, p in ref.named_parameters():
+            if n != "quantiles":
+                p.add_(0.1 * torch.randn_like(p))
+        ref.quantiles[:, 0, 1] += 0.3 * torch.randn(192)
+    ours = D.SteEntropyBottleneck(channels=192)
+    ours.load_state_dict(ref.state_dict())
+    ours.to(DEV)
+    x = 3 * torch.randn(4, 192, 8, 8)
+    nz = noise_like(x, 205)
+    with torch.no_grad():
+        xh_r, lk_r = ref(x, is_train=train, noise=nz if train else None)
+        xh, lk = ours(x.to(DEV), is_train=train, noise=nz.to(DEV) if train else None)
+    assert torch.equal(xh.cpu(), xh_r)
+    assert rel_err(lk, lk_r) < REL
+    assert rel_err(D.batch_bits(lk), O.batch_bits(lk_r)) < REL
+    # plain (non-STE) wrapper
+    ours2 = D.DcvicEntropyBottleneck(channels=192)
+    ours2.load_state_dict(ref.state_dict())
+    ours2.to(DEV)
+    ref2 = O.DcvicEntropyBottleneck(channels=192)
+    ref2.load_state_dict(ref.state_dict())
+    with torch.no_grad():
+        a = ours2(x.to(DEV), train, noise=nz.to(DEV) if train else None)
+        b = ref2(x, train, noise=nz if train else None)
+    assert torch.equal(a[0].cpu(), b[0]) and rel_err(a[1], b[1]) < REL
+
+
+def test_entropy_bottleneck_backward_and_aux_loss():
+    torch.manual_seed(5)
+    ref = O.SteEntropyBottleneck(channels=6)
+    with torch.no_grad():
+        for n, p in ref.named_parameters():
+            if n != "quantiles":
+                p.add_(0.2 * torch.randn_like(p))
+    ours = D.SteEntropyBottleneck(channels=6)
+    ours.load_state_dict(ref.state_dict())
+    ours.to(DEV)
+    x = 2 * torch.randn(3, 6, 5, 7)
+    nz = noise_like(x, 206)
+    xr = x.clone().requires_grad_(True)
+    xo = x.to(DEV).requires_grad_(True)
+    xh_r, lk_r = ref(xr, is_train=True, noise=nz)
+    xh, lk = ours(xo, is_train=True, noise=nz.to(DEV))
+    w = torch.randn(x.shape, generator=torch.Generator().manual_seed(8))
+    (O.likelihood_to_bit(lk_r, 10)[0] + (xh_r * w).sum()).backward()
+    (D.likelihood_to_bit(lk, 10)[0] + (xh * w.to(DEV)).sum()).backward()
+    assert float((xo.grad.cpu() - xr.grad).abs().max()) <= 2e-4 * float(xr.grad.abs().max())
+    for (n, p), (_, pr) in zip(ours.named_parameters(), ref.named_parameters()):
+        if n == "quantiles":
+            assert p.grad is None and pr.grad is None
+            continue
+        assert float((p.grad.cpu() - pr.grad).abs().max()) <= 5e-4 * float(pr.grad.abs().max()) + 1e-6, n
+    assert abs(float(ours.loss()) - float(ref.loss())) <= 1e-5 * float(ref.loss())
+    ours.loss().backward()
+    assert ours.quantiles.grad is not None
+    assert ours.update() and ref.update()
+    assert torch.equal(ours._offset.cpu(), ref._offset) and torch.equal(ours._cdf_length.cpu(), ref._cdf_length)
+    assert int((ours._quantized_cdf.cpu() - ref._quantized_cdf).abs().max()) <= 1
+
+
+def test_rate_and_ste_round():
+    lik = torch.rand(5, 1000, generator=torch.Generator().manual_seed(2)).clamp_min(1e-9)
+    lo = lik.to(DEV).requires_grad_(True)
+    lr = lik.clone().requires_grad_(True)
+    b, bpp = D.likelihood_to_bit(lo, 77)
+    br, bppr = O.likelihood_to_bit(lr, 77)
+    assert abs(float(b) - float(br)) <= 1e-5 * float(br) and abs(float(bpp) - float(bppr)) <= 1e-5 * float(bppr)
+    assert rel_err(D.batch_bits(lo), O.batch_bits(lr)) < 1e-5
+    bpp.backward()
+    bppr.backward()
+    assert rel_err(lo.grad, lr.grad) < 1e-5
+    x = torch.tensor([0.5, 1.5, 2.5, -0.5, -1.5, 0.49999997, 1e6 + 0.5, -3.7], requires_grad=True)
+    xo = x.detach().to(DEV).requires_grad_(True)
+    out = D.ste_round(xo)
+    assert torch.equal(out.detach().cpu(), O.ste_round(x).detach())
+    out.sum().backward()
+    assert torch.equal(xo.grad.cpu(), torch.ones(8))
+
+
+@pytest.mark.parametrize("q", [0, 4])
+def test_full_size_c3_properties(q):
+    """BASELINE config 3 (64x320x32x32): full-size, checked through size-independent properties
+    plus the oracle on a bounded sample of the batch."""
+    y, params = entropy_inputs(q)
+    m = D.SteGaussianMeanScaleConditional(scale_bound=0.11).to(DEV)
+    yc, pc = y.to(DEV), params.to(DEV)
+    with torch.no_grad():
+        yh, lk = m(yc, pc, is_train=False)
+        mu = pc[:, :320]
+        assert torch.equal(yh, torch.round(yc - mu) + mu)
+        assert float(lk.min()) >= float(torch.tensor(1e-9)) and float(lk.max()) <= 1.0
+        yh2, lk2 = m(yh, pc, is_train=False)                     # quantization is idempotent
+        assert torch.equal(yh2, yh) and torch.equal(lk2, lk)
+        bits = D.batch_bits(lk)
+        total, _ = D.likelihood_to_bit(lk, 1)
+        assert abs(float(bits.double().sum()) - float(total)) <= 1e-5 * float(total)   # sum of per-sample sums
+        ref = O.SteGaussianMeanScaleConditional(scale_bound=0.11)
+        yh_r, lk_r = ref(y[:2], params[:2], is_train=False)
+    assert torch.equal(yh[:2].cpu(), yh_r) and rel_err(lk[:2], lk_r) < REL
+    assert rel_err(bits[:2], O.batch_bits(lk_r)) < REL
