@@ -61,21 +61,26 @@ extern "C" int dcvic_vq_forward(const float* z_nchw, const float* codebook, int 
   if (path == 0) {
     rc = vq_narrow_forward(z_nchw, codebook, B, D, HW, K, beta, legacy, zq_nchw, idx, loss, partials, counters, s);
   } else {
-    if (!(flags & DCVIC_VQ_REUSE_PREP)) {
+    if (!(flags & (DCVIC_VQ_REUSE_PREP | DCVIC_VQ_STAGE_FINISH_ONLY))) {
       rc = vq_prepare_codebook(codebook, K, D, ee, emax, path == 2 ? cb16 : nullptr, w.dpad16, s);
       if (rc) return rc;
     }
+    const bool do_search = !(flags & DCVIC_VQ_STAGE_FINISH_ONLY);
+    const bool do_finish = !(flags & DCVIC_VQ_STAGE_SEARCH_ONLY);
     if (path == 2) {
-      rc = vq_tensor_search(z_nchw, cb16, w.dpad16, emax, B, D, HW, K, cand, count, counters, s);
+      if (do_search) rc = vq_tensor_search(z_nchw, cb16, w.dpad16, emax, B, D, HW, K, cand, count, counters, s);
       if (rc) return rc;
-      rc = vq_finish(z_nchw, codebook, ee, cand, kCandCap, count, B, D, HW, K, beta, legacy, zq_nchw, idx, loss,
-                     partials, counters, s);
+      if (do_finish)
+        rc = vq_finish(z_nchw, codebook, ee, cand, kCandCap, count, B, D, HW, K, beta, legacy, zq_nchw, idx, loss,
+                       partials, counters, s);
     } else {
-      rc = vq_exact_search(z_nchw, codebook, ee, B, D, HW, K, cand, s);
+      if (do_search) rc = vq_exact_search(z_nchw, codebook, ee, B, D, HW, K, cand, s);
       if (rc) return rc;
-      rc = vq_finish(z_nchw, codebook, ee, cand, 1, nullptr, B, D, HW, K, beta, legacy, zq_nchw, idx, loss, partials,
-                     counters, s);
+      if (do_finish)
+        rc = vq_finish(z_nchw, codebook, ee, cand, 1, nullptr, B, D, HW, K, beta, legacy, zq_nchw, idx, loss,
+                       partials, counters, s);
     }
+    if (!do_finish) return rc;
   }
   if (rc) return rc;
   if (onehot || perplexity) rc = vq_v1_extras(idx, N, K, onehot, perplexity, hist, counters, s);

@@ -44,7 +44,11 @@ enum {
 enum {
   DCVIC_VQ_REUSE_PREP = 1,  /* workspace already holds the prepared codebook of this `codebook` */
   DCVIC_VQ_FORCE_EXACT = 2, /* skip the tcgen05 candidate search, use the FP32 SIMT scan */
-  DCVIC_VQ_FORCE_TENSOR = 4 /* fail with DCVIC_ERR_UNSUPPORTED instead of falling back to SIMT */
+  DCVIC_VQ_FORCE_TENSOR = 4, /* fail with DCVIC_ERR_UNSUPPORTED instead of falling back to SIMT */
+  /* measurement aids (bench.py / ncu): run only one stage of the two-stage paths; outputs of the
+   * skipped stage are left as the previous call on the same workspace produced them */
+  DCVIC_VQ_STAGE_SEARCH_ONLY = 8,  /* codebook prep + candidate search, no finish */
+  DCVIC_VQ_STAGE_FINISH_ONLY = 16  /* finish (re-rank + gather + STE + loss) from the workspace's candidates */
 };
 
 const char* dcvic_version(void);
