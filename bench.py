@@ -1,0 +1,341 @@
+#!/usr/bin/env python
+"""Benchmark of the DC-VIC hot path on B200 (contract: see the task statement / DESIGN.md section 5).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" = one pass of the hot path over one batch of synthetic input:
+  headline workload (BASELINE.json configs[1]): VectorQuantizer2 forward, codebook 1024x256,
+  z = 64x256x32x32 FP32 (65,536 tokens) per GPU -> metric vq_tokens_per_sec.
+  secondary block "entropy" (configs[2]): SteGaussianMeanScaleConditional eval forward +
+  per-sample rate on 64x320x32x32 latents -> latents/s.
+N > 1: launched by torchrun, one rank per GPU, every rank runs the same per-GPU workload on its
+own batch shard (weak scaling, no data-path collective); time = max over ranks.
+`--impl reference` times the reference's own CPU implementation of the path (the torch-CPU
+oracle port of taming's quantizer; the reference is pure PyTorch so this IS its CPU path).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import torch  # noqa: E402
+
+VQ_SHAPE = (64, 256, 32, 32, 1024)          # B, D, H, W, K  -> N = 65,536 tokens
+GC_SHAPE = (64, 320, 32, 32)
+VQ_WORKLOAD = "VQ codebook 1024x256 nearest-codeword search (VectorQuantizer2.forward) on synthetic 64x256x32x32 latents (65,536 tokens) per GPU"
+GC_WORKLOAD = "SteGaussianMeanScaleConditional eval forward + per-sample rate on synthetic ELIC latents 64x320x32x32 (q=2) per GPU"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], bf16=d["bf16_tflops"], bf16_sustained=d.get("bf16_tflops_sustained"),
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, bf16=1590.0, bf16_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------- CPU reference arm
+def cpu_vq_reference(steps: int, warmup: int):
+    """The reference's own CPU implementation of the path: its quantizer is plain PyTorch, so the
+    torch-CPU oracle port (oracle/vq_oracle.py, pinned to the vendored file by goldens) run with all
+    host threads is that path.  Bounded sample: the full 65,536-token batch per step."""
+    from oracle import vq_oracle as VO
+    from synth import vq_inputs
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    B, D, H, W, K = VQ_SHAPE
+    z, E = vq_inputs(0, "D0", B, D, H, W, K)
+    with torch.no_grad():
+        for _ in range(max(1, min(warmup, 2))):
+            VO.vq2_forward(z, E)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            VO.vq2_forward(z, E)
+        dt = (time.perf_counter() - t0) / steps
+    return (B * H * W) / dt, dt, cores
+
+
+def cpu_gc_reference(steps: int):
+    from oracle import entropy_oracle as EO
+    from synth import entropy_inputs
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    y, params = entropy_inputs(2, B=8)          # bounded sample: 8 of the 64 images
+    m = EO.SteGaussianMeanScaleConditional(scale_bound=0.11)
+    with torch.no_grad():
+        m(y, params, is_train=False)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            _, lk = m(y, params, is_train=False)
+            EO.batch_bits(lk)
+        dt = (time.perf_counter() - t0) / steps
+    return y.numel() / dt, cores
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 10))
+    val, dt, cores = cpu_vq_reference(steps, args.warmup)
+    line = {"impl": "reference", "metric": "vq_tokens_per_sec", "value": val, "unit": "tokens/s", "n_gpus": args.gpus,
+            "steps": steps, "warmup": min(args.warmup, 2), "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+            "config": {"workload": VQ_WORKLOAD, "where": "host CPU, torch FP32, all threads"},
+            "cpu_baseline": {"value": val, "unit": "tokens/s", "cores": cores, "kind": "port",
+                             "sample": f"full 65,536-token batch x {steps} steps (oracle port of taming VectorQuantizer2)"},
+            "e2e": {"value": val, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------- our arm
+def timed(fn, steps, warmup, barrier):
+    """W warm-ups, then exactly K steps between CUDA events on the current stream."""
+    for i in range(warmup):
+        fn(i)
+    torch.cuda.synchronize()
+    barrier()
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    start.record()
+    for i in range(steps):
+        fn(warmup + i)
+    end.record()
+    torch.cuda.synchronize()
+    barrier()
+    return start.elapsed_time(end) * 1e-3   # seconds
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    import dc_vic_b200 as D
+    from dc_vic_b200 import _lib
+    from synth import vq_inputs, entropy_inputs
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t)
+
+    lib = _lib.load()
+    pk = peaks()
+    K_steps, W_steps = args.steps, max(args.warmup, 3)
+    B, Dm, H, W, K = VQ_SHAPE
+    N = B * H * W
+
+    # ---------------- VQ: device-resident throughput through the C ABI -------------------------
+    ROT = 4   # rotate over 4 input/output sets: 4 x (67 + 67) MB > 126 MB L2, so no step re-reads a warm L2
+    z0, E = vq_inputs(rank, "D0", B, Dm, H, W, K)   # each rank quantizes its own shard of images
+    Ec = E.to(dev)
+    zs = [z0.to(dev)] + [torch.randn(B, Dm, H, W, device=dev) for _ in range(ROT - 1)]
+    zqs = [torch.empty_like(zs[0]) for _ in range(ROT)]
+    idxs = [torch.empty(N, dtype=torch.int64, device=dev) for _ in range(ROT)]
+    loss = torch.empty((), device=dev)
+    ws = torch.zeros(lib.dcvic_vq_workspace_bytes(B, Dm, H, W, K), dtype=torch.uint8, device=dev)
+    path = {0: "narrow-simt", 1: "exact-simt", 2: "tcgen05"}[lib.dcvic_vq_path(Dm, K, 0)]
+    stream = torch.cuda.current_stream()
+
+    def vq_step(i, flags=0):
+        j = i % ROT
+        rc = lib.dcvic_vq_forward(_lib.ptr(zs[j]), _lib.ptr(Ec), B, Dm, H, W, K, 0.25, 1, _lib.ptr(zqs[j]),
+                                  _lib.ptr(idxs[j]), _lib.ptr(loss), None, None, flags, _lib.ptr(ws), ws.numel(),
+                                  C.c_void_p(stream.cuda_stream))
+        _lib.check(rc, "dcvic_vq_forward")
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    t_full = max_over_ranks(timed(vq_step, K_steps, W_steps, barrier))
+    # dominant kernel alone (same launches, search stage only) for the roofline
+    t_search = timed(lambda i: vq_step(i, _lib.VQ_STAGE_SEARCH_ONLY | _lib.VQ_REUSE_PREP), K_steps, W_steps, barrier)
+    t_finish = timed(lambda i: vq_step(i, _lib.VQ_STAGE_FINISH_ONLY), K_steps, W_steps, barrier)
+    clocks = sampler.stop()
+
+    value = world * N * K_steps / t_full
+    flops = 2.0 * N * K * Dm
+    search_s = t_search / K_steps
+    finish_s = t_finish / K_steps
+    finish_bytes = N * (4 * Dm + 4 * Dm + 8)
+    if path == "tcgen05" or search_s >= finish_s:
+        roof = {"kernel": "vq_tensor_search" if path == "tcgen05" else "vq_exact_kernel", "bound": "tensor",
+                "achieved": flops / search_s / 1e12, "peak": pk["bf16"], "unit": "TFLOP/s",
+                "frac": flops / search_s / 1e12 / pk["bf16"], "traffic": None, "us_per_launch": search_s * 1e6,
+                "algorithmic": f"2*N*K*D = {flops:.4g} flop per launch", "peak_source": pk["source"] + ", bf16 burst"}
+    else:
+        roof = {"kernel": "vq_finish_kernel", "bound": "hbm", "achieved": finish_bytes / finish_s / 1e9,
+                "peak": pk["hbm"], "unit": "GB/s", "frac": finish_bytes / finish_s / 1e9 / pk["hbm"], "traffic": None,
+                "us_per_launch": finish_s * 1e6, "algorithmic": f"N*(8D+8) = {finish_bytes} B per launch",
+                "peak_source": pk["source"]}
+    stage = {"search_us": search_s * 1e6, "finish_us": finish_s * 1e6,
+             "finish_hbm_gbs": finish_bytes / finish_s / 1e9, "finish_hbm_frac": finish_bytes / finish_s / 1e9 / pk["hbm"],
+             "search_tflops": flops / search_s / 1e12}
+
+    # ---------------- VQ end to end: module API, pinned host buffers in and out -----------------
+    vq = D.VectorQuantizer2(K, Dm, 0.25, sane_index_shape=True).to(dev)
+    vq.embedding.weight.data.copy_(Ec)
+    vq.freeze_codebook()          # DC-VIC always freezes the VQGAN codebook
+    z_host = z0.pin_memory()
+    zq_host = torch.empty_like(z_host).pin_memory()
+    idx_host = torch.empty(B, H, W, dtype=torch.int64).pin_memory()
+    loss_host = torch.empty(()).pin_memory()
+    z_dev = torch.empty(B, Dm, H, W, device=dev)
+
+    def vq_e2e(i):
+        z_dev.copy_(z_host, non_blocking=True)
+        with torch.no_grad():
+            z_q, l, (_, _, idx) = vq(z_dev)
+        zq_host.copy_(z_q, non_blocking=True)
+        idx_host.copy_(idx, non_blocking=True)
+        loss_host.copy_(l, non_blocking=True)
+
+    e2e_steps = max(3, min(K_steps, 20))
+    t_e2e = max_over_ranks(timed(vq_e2e, e2e_steps, 3, barrier))
+    e2e = {"value": world * N * e2e_steps / t_e2e, "unit": "tokens/s", "h2d_bytes_per_step": z_host.numel() * 4,
+           "d2h_bytes_per_step": zq_host.numel() * 4 + idx_host.numel() * 8 + 4, "ms_per_step": t_e2e / e2e_steps * 1e3,
+           "api": "dc_vic_b200.VectorQuantizer2.forward on pinned host tensors (H2D z, D2H z_q + indices + loss)"}
+
+    # ---------------- entropy model (secondary block) -------------------------------------------
+    yb, pb = entropy_inputs(2)
+    yc, pc = yb.to(dev), pb.to(dev)
+    n_lat = yc.numel()
+    gb, gn = GC_SHAPE[0], n_lat // GC_SHAPE[0]
+    y_hat, lik = torch.empty_like(yc), torch.empty_like(yc)
+    bits = torch.empty(gb, device=dev)
+    gws = torch.zeros(lib.dcvic_gc_workspace_bytes(gb, gn), dtype=torch.uint8, device=dev)
+
+    def gc_step(i):
+        rc = lib.dcvic_gc_forward(_lib.ptr(yc), _lib.ptr(pc), C.c_void_p(pc.data_ptr() + gn * 4), None, gb, gn, gn,
+                                  2 * gn, 2 * gn, 0.11, 1e-9, 1, _lib.ptr(y_hat), _lib.ptr(lik), _lib.ptr(bits),
+                                  _lib.ptr(gws), gws.numel(), C.c_void_p(stream.cuda_stream))
+        _lib.check(rc, "dcvic_gc_forward")
+
+    t_gc = max_over_ranks(timed(gc_step, K_steps, W_steps, barrier))
+    gc_s = t_gc / K_steps
+    gc_bytes = 20.0 * n_lat
+    gcm = D.SteGaussianMeanScaleConditional(scale_bound=0.11).to(dev)
+    y_host, p_host = yb.pin_memory(), pb.pin_memory()
+    yh_host, lk_host = torch.empty_like(y_host).pin_memory(), torch.empty_like(y_host).pin_memory()
+    yd, pd = torch.empty_like(yc), torch.empty_like(pc)
+
+    def gc_e2e(i):
+        yd.copy_(y_host, non_blocking=True)
+        pd.copy_(p_host, non_blocking=True)
+        with torch.no_grad():
+            a, b = gcm(yd, pd, is_train=False)
+            _ = D.batch_bits(b)
+        yh_host.copy_(a, non_blocking=True)
+        lk_host.copy_(b, non_blocking=True)
+
+    t_gce = max_over_ranks(timed(gc_e2e, 5, 2, barrier))
+    entropy = {"metric": "bpp_estimate_latents_per_sec", "value": world * n_lat / gc_s, "unit": "latents/s",
+               "ms_per_step": gc_s * 1e3, "config": {"workload": GC_WORKLOAD},
+               "roofline": {"kernel": "gc_forward_kernel", "bound": "hbm", "achieved": gc_bytes / gc_s / 1e9,
+                            "peak": pk["hbm"], "unit": "GB/s", "frac": gc_bytes / gc_s / 1e9 / pk["hbm"],
+                            "traffic": None, "algorithmic": "20 B/latent (read y, mu, sigma; write y_hat, likelihood)",
+                            "peak_source": pk["source"]},
+               "e2e": {"value": world * n_lat * 5 / t_gce, "unit": "latents/s",
+                       "h2d_bytes_per_step": (y_host.numel() + p_host.numel()) * 4,
+                       "d2h_bytes_per_step": 2 * y_host.numel() * 4}}
+
+    if rank == 0:
+        cpu_val, _, cores = cpu_vq_reference(3, 1)
+        gc_cpu, _ = cpu_gc_reference(2)
+        entropy["cpu_baseline"] = {"value": gc_cpu, "unit": "latents/s", "cores": cores, "kind": "port",
+                                   "sample": "8 of 64 images (2.6M latents) x 2, CompressAI-1.2.4 restatement, torch CPU"}
+        launches_per_step = 3 if path != "narrow-simt" else 1
+        line = {"metric": "vq_tokens_per_sec", "value": value, "unit": "tokens/s", "n_gpus": world, "steps": K_steps,
+                "warmup": W_steps, "ms_per_step": t_full / K_steps * 1e3, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+                "config": {"workload": VQ_WORKLOAD, "search_path": path,
+                           "arithmetic": "bf16 tcgen05 candidate search + fp32 re-rank" if path == "tcgen05" else "fp32 SIMT",
+                           "l2": f"inputs/outputs rotated over {ROT} buffer sets (536 MB > 126 MB L2)",
+                           "codebook_prep": "inside every timed step", "sharding": "batch (images) per rank, no collective"},
+                "roofline": roof, "stages": stage,
+                "cpu_baseline": {"value": cpu_val, "unit": "tokens/s", "cores": cores, "kind": "port",
+                                 "sample": "full 65,536-token batch x 3 (oracle port of taming VectorQuantizer2, torch CPU)"},
+                "e2e": e2e, "gpu_launches": launches_per_step * K_steps, "clocks": clocks, "entropy": entropy}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()
