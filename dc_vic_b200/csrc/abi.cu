@@ -68,7 +68,7 @@ extern "C" int dcvic_vq_forward(const float* z_nchw, const float* codebook, int 
     const bool do_search = !(flags & DCVIC_VQ_STAGE_FINISH_ONLY);
     const bool do_finish = !(flags & DCVIC_VQ_STAGE_SEARCH_ONLY);
     if (path == 2) {
-      if (do_search) rc = vq_tensor_search(z_nchw, cb16, w.dpad16, emax, B, D, HW, K, cand, count, counters, s);
+      if (do_search) rc = vq_tensor_search(z_nchw, cb16, w.dpad16, ee, emax, B, D, HW, K, cand, count, counters, s);
       if (rc) return rc;
       if (do_finish)
         rc = vq_finish(z_nchw, codebook, ee, cand, kCandCap, count, B, D, HW, K, beta, legacy, zq_nchw, idx, loss,

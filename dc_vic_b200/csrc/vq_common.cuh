@@ -51,7 +51,7 @@ int vq_v1_extras(const int64_t* idx, int N, int K, float* onehot, float* perplex
 
 // vq_tcgen05.cu
 bool vq_tensor_supported(int D, int K);
-int vq_tensor_search(const float* z, const __nv_bfloat16* cb16, int dpad16, const float* emax, int B, int D, int HW,
-                     int K, int* cand, int* count, unsigned* counters, cudaStream_t s);
+int vq_tensor_search(const float* z, const __nv_bfloat16* cb16, int dpad16, const float* ee, const float* emax, int B,
+                     int D, int HW, int K, int* cand, int* count, unsigned* counters, cudaStream_t s);
 
 }  // namespace dcvic

@@ -1,7 +1,434 @@
-// placeholder until the tcgen05 search lands
+// Wide-codebook nearest-codeword CANDIDATE search on the 5th-gen tensor cores (sm_100a).
+//
+// Computes, for every token row z_t (FP32, read straight from NCHW) and every codeword e_k,
+//     s[t,k] = bf16(z_t) . bf16(e_k) - |e_k|^2 / 2        ( = (|z|^2 - d[t,k]) / 2 up to BF16 rounding )
+// with tcgen05.mma (BF16 x BF16 -> FP32 in TMEM), and keeps per row every k whose score is within a
+// PROVEN error margin of the row maximum.  The distance matrix never leaves the SM.  The FP32
+// re-rank of those few candidates (reference op order, lowest-index tie-break) happens in
+// vq_finish_kernel, which also streams z once more for the gather / STE / loss.
+//
+//   margin:  |s - s_exact| <= |z||e_k| (2^-7 + 2^-15)  (two RN-to-bf16 roundings per product, Cauchy-
+//            Schwarz over channels) so the true argmax is within 2*that of the computed maximum.
+//
+// Structure (one CTA per 128-token tile, persistent over tiles):
+//   warp 0      TMA producer: BF16 codebook tiles [256 codes x 64 ch] (SWIZZLE_128B) -> 4-stage ring
+//   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (M=128, N=256, K=16 per instruction)
+//   warps 2-5   A producers: read z (FP32, coalesced along tokens), convert to BF16, write the K-major
+//               SWIZZLE_128B operand tile, accumulate |z|^2 per token
+//   warps 6-9   epilogue: tcgen05.ld the 128x256 FP32 accumulator (double-buffered in TMEM, 2x256
+//               columns), running max + candidate list per row, then re-initialise the buffer with
+//               -|e|^2/2 for the N-tile after next (so the MMA accumulates onto it: no per-element add)
+// Reference semantics: taming/modules/vqvae/quantize.py:280-284 (distance + argmin).
 #include "vq_common.cuh"
+#include <cuda.h>
+
 namespace dcvic {
-bool vq_tensor_supported(int, int) { return false; }
-int vq_tensor_search(const float*, const __nv_bfloat16*, int, const float*, int, int, int, int, int*, int*, unsigned*,
-                     cudaStream_t) { return DCVIC_ERR_UNSUPPORTED; }
+
+namespace tc {
+
+constexpr int BM = 128;          // tokens per tile (UMMA M)
+constexpr int BN = 256;          // codes per N-tile (UMMA N)
+constexpr int BK = 64;           // channels per smem chunk: 64 bf16 = 128 B = one SWIZZLE_128B row
+constexpr int UK = 16;           // UMMA K for 16-bit inputs
+constexpr int MAX_KC = 4;        // e_dim <= 256
+constexpr int NSTAGE = 4;        // codebook ring depth
+constexpr int A_CHUNK_BYTES = BM * BK * 2;   // 16 KB
+constexpr int B_STAGE_BYTES = BN * BK * 2;   // 32 KB
+constexpr int MAX_K = 4096;
+constexpr int NTHREADS = 320;
+
+// dynamic shared memory map (base aligned to 1024 B)
+constexpr int OFF_A = 0;
+constexpr int OFF_B = OFF_A + MAX_KC * A_CHUNK_BYTES;                 // 65536
+constexpr int OFF_LIST = OFF_B + NSTAGE * B_STAGE_BYTES;              // 196608
+constexpr int OFF_EE = OFF_LIST + BM * kCandCap * 8;                  // +16384
+constexpr int OFF_ZZ = OFF_EE + MAX_K * 4;                            // +16384
+constexpr int OFF_BAR = OFF_ZZ + 2 * BM * 4;                          // +1024
+constexpr int SMEM_BYTES = OFF_BAR + 256;
+static_assert(SMEM_BYTES + 1024 <= 232448, "shared memory budget");
+
+// barrier slots (8 bytes each) inside OFF_BAR
+constexpr int BAR_B_FULL = 0;                  // [NSTAGE]
+constexpr int BAR_B_EMPTY = BAR_B_FULL + NSTAGE;
+constexpr int BAR_A_FULL = BAR_B_EMPTY + NSTAGE;   // [MAX_KC]
+constexpr int BAR_A_EMPTY = BAR_A_FULL + MAX_KC;   // [1]
+constexpr int BAR_T_FULL = BAR_A_EMPTY + 1;        // [2]
+constexpr int BAR_T_EMPTY = BAR_T_FULL + 2;        // [2]
+constexpr int BAR_COUNT = BAR_T_EMPTY + 2;
+constexpr int OFF_TMEM_PTR = OFF_BAR + BAR_COUNT * 8;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap* map, int x, int y, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+          smem_dst),
+      "l"(map), "r"(x), "r"(y), "r"(bar)
+      : "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 "version 1"):
+// rows are 128 B, 8-row groups 1024 B apart (SBO), LBO unused for swizzled K-major (canonical 1).
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
+         (2ull << 61);
+}
+// kind::f16 instruction descriptor: D=F32, A=B=BF16, both K-major, N=256, M=128
+constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(kIdesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+#define TMEM_LD32(r, taddr)                                                                                        \
+  asm volatile(                                                                                                    \
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18," \
+      "%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"                                               \
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),  \
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),       \
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),      \
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])                    \
+      : "r"(taddr)                                                                                                 \
+      : "memory")
+
+#define TMEM_ST32(taddr, r)                                                                                        \
+  asm volatile(                                                                                                    \
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,"   \
+      "%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};" ::"r"(taddr),                                 \
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), \
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),   \
+      "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),   \
+      "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])                                                               \
+      : "memory")
+
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+
+// write -|e|^2/2 of codes [k0, k0+256) into one TMEM accumulator buffer (this warp's 32 lanes)
+__device__ __forceinline__ void tmem_init_buffer(uint32_t taddr_buf, const float* s_neg_half_ee, int k0) {
+#pragma unroll 1
+  for (int cc = 0; cc < BN / 32; ++cc) {
+    uint32_t r[32];
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      const float4 v = *reinterpret_cast<const float4*>(s_neg_half_ee + k0 + cc * 32 + j);
+      r[j] = __float_as_uint(v.x); r[j + 1] = __float_as_uint(v.y);
+      r[j + 2] = __float_as_uint(v.z); r[j + 3] = __float_as_uint(v.w);
+    }
+    TMEM_ST32(taddr_buf + cc * 32, r);
+  }
+  tmem_wait_st();
+}
+
+}  // namespace tc
+
+using namespace tc;
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+vq_tensor_search_kernel(const __grid_constant__ CUtensorMap tmap_cb, const float* __restrict__ z,
+                        const float* __restrict__ ee, const float* __restrict__ emax_ptr, int N, int D, int HW, int K,
+                        int num_tiles, int* __restrict__ cand, int* __restrict__ count) {
+  extern __shared__ uint8_t smem_raw[];
+  // SWIZZLE_128B operands need 1024-byte alignment
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t bar0 = sbase + OFF_BAR;
+  auto bar = [&](int slot) { return bar0 + slot * 8; };
+  float* s_nhee = reinterpret_cast<float*>(smem + OFF_EE);     // -|e|^2/2
+  float* s_zz = reinterpret_cast<float*>(smem + OFF_ZZ);       // [2][BM]
+  volatile uint32_t* s_tmem = reinterpret_cast<volatile uint32_t*>(smem + OFF_TMEM_PTR);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int KC = D / BK;               // channel chunks
+  const int NT = K / BN;               // N-tiles per token tile
+  const int my_tiles = (num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NSTAGE; ++s) { mbar_init(bar(BAR_B_FULL + s), 1); mbar_init(bar(BAR_B_EMPTY + s), 1); }
+    for (int c = 0; c < MAX_KC; ++c) mbar_init(bar(BAR_A_FULL + c), 128);
+    mbar_init(bar(BAR_A_EMPTY), 1);
+    for (int b = 0; b < 2; ++b) { mbar_init(bar(BAR_T_FULL + b), 1); mbar_init(bar(BAR_T_EMPTY + b), 128); }
+    fence_barrier_init();
+  }
+  for (int k = threadIdx.x; k < K; k += NTHREADS) s_nhee[k] = -0.5f * ee[k];
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + OFF_TMEM_PTR),
+                 "r"(512u));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *s_tmem;
+
+  if (warp == 0) {
+    // ===================== TMA producer: codebook ring =====================
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_cb) : "memory");
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = 0; it < my_tiles; ++it)
+        for (int nt = 0; nt < NT; ++nt)
+          for (int kc = 0; kc < KC; ++kc) {
+            mbar_wait(bar(BAR_B_EMPTY + stage), phase ^ 1);
+            mbar_arrive_expect_tx(bar(BAR_B_FULL + stage), B_STAGE_BYTES);
+            tma_load_2d(sbase + OFF_B + stage * B_STAGE_BYTES, &tmap_cb, kc * BK, nt * BN, bar(BAR_B_FULL + stage));
+            if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+          }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t g = 0;   // running N-tile counter -> TMEM buffer g & 1
+      for (int it = 0; it < my_tiles; ++it) {
+        for (int nt = 0; nt < NT; ++nt, ++g) {
+          const uint32_t buf = g & 1;
+          mbar_wait(bar(BAR_T_EMPTY + buf), (g >> 1) & 1);      // epilogue drained + re-initialised this buffer
+          tc_fence_after();
+          const uint32_t tmem_d = tmem_base + buf * BN;
+          for (int kc = 0; kc < KC; ++kc) {
+            if (nt == 0) { mbar_wait(bar(BAR_A_FULL + kc), it & 1); }
+            mbar_wait(bar(BAR_B_FULL + stage), phase);
+            tc_fence_after();
+            const uint32_t a_addr = sbase + OFF_A + kc * A_CHUNK_BYTES;
+            const uint32_t b_addr = sbase + OFF_B + stage * B_STAGE_BYTES;
+#pragma unroll
+            for (int ks = 0; ks < BK / UK; ++ks)
+              umma_bf16(tmem_d, umma_desc_sw128(a_addr + ks * UK * 2), umma_desc_sw128(b_addr + ks * UK * 2), 1u);
+            umma_commit(bar(BAR_B_EMPTY + stage));     // frees the codebook stage when these MMAs retire
+            if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+          }
+          umma_commit(bar(BAR_T_FULL + buf));          // accumulator ready for the epilogue
+        }
+        umma_commit(bar(BAR_A_EMPTY));                 // token tile's operand may be overwritten
+      }
+    }
+  } else if (warp < 6) {
+    // ===================== A producers: FP32 NCHW -> BF16 K-major SWIZZLE_128B =====================
+    const int row = (warp - 2) * 32 + lane;
+    for (int it = 0; it < my_tiles; ++it) {
+      const int tile = blockIdx.x + it * gridDim.x;
+      const int t = tile * BM + row;
+      const bool valid = t < N;
+      const float* zp = z + (valid ? ((size_t)(t / HW) * D * HW + (size_t)(t % HW)) : 0);
+      mbar_wait(bar(BAR_A_EMPTY), (it & 1) ^ 1);
+      float zz = 0.f;
+      for (int kc = 0; kc < KC; ++kc) {
+        float v[BK];
+#pragma unroll
+        for (int j = 0; j < BK; ++j) v[j] = valid ? __ldg(zp + (size_t)(kc * BK + j) * HW) : 0.f;
+        uint8_t* arow = smem + OFF_A + kc * A_CHUNK_BYTES + row * 128;
+#pragma unroll
+        for (int c16 = 0; c16 < 8; ++c16) {
+          uint4 pk;
+          pk.x = pack_bf16x2(v[c16 * 8 + 0], v[c16 * 8 + 1]);
+          pk.y = pack_bf16x2(v[c16 * 8 + 2], v[c16 * 8 + 3]);
+          pk.z = pack_bf16x2(v[c16 * 8 + 4], v[c16 * 8 + 5]);
+          pk.w = pack_bf16x2(v[c16 * 8 + 6], v[c16 * 8 + 7]);
+          *reinterpret_cast<uint4*>(arow + ((c16 ^ (row & 7)) << 4)) = pk;
+        }
+#pragma unroll
+        for (int j = 0; j < BK; ++j) zz = fmaf(v[j], v[j], zz);
+        if (kc == KC - 1) s_zz[(it & 1) * BM + row] = zz;
+        fence_proxy_async();
+        mbar_arrive(bar(BAR_A_FULL + kc));
+      }
+    }
+  } else {
+    // ===================== epilogue: running max + candidate list per row =====================
+    const int part = warp & 3;                    // TMEM lane partition of this warp
+    const int row = part * 32 + lane;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(part * 32) << 16);
+    const float emax = *emax_ptr;
+    const uint32_t list_addr = sbase + OFF_LIST + row * kCandCap * 8;
+    const int total_nt = my_tiles * NT;
+    // first use of both accumulator buffers
+    for (int b = 0; b < 2 && b < total_nt; ++b) {
+      tmem_init_buffer(lane_addr + b * BN, s_nhee, (b % NT) * BN);
+      tc_fence_before();
+      mbar_arrive(bar(BAR_T_EMPTY + b));
+    }
+    uint32_t g = 0;
+    for (int it = 0; it < my_tiles; ++it) {
+      const int tile = blockIdx.x + it * gridDim.x;
+      const int t = tile * BM + row;
+      mbar_wait(bar(BAR_A_FULL + KC - 1), it & 1);   // |z|^2 of this tile is published
+      const float zz = s_zz[(it & 1) * BM + row];
+      // 2 * (2^-7 + 2^-15) |z| max|e|, 2 % slack, plus a few FP32 ulps of the distance itself
+      const float margin = 1.02f * 0.015686f * sqrtf(zz) * emax + 1.9e-6f * (zz + emax * emax);
+      float m = -INFINITY, thr = -INFINITY;
+      int cnt = 0;
+      bool overflow = false;
+      for (int nt = 0; nt < NT; ++nt, ++g) {
+        const uint32_t buf = g & 1;
+        mbar_wait(bar(BAR_T_FULL + buf), (g >> 1) & 1);
+        tc_fence_after();
+        const uint32_t taddr = lane_addr + buf * BN;
+#pragma unroll 1
+        for (int cc = 0; cc < BN / 32; ++cc) {
+          uint32_t r[32];
+          TMEM_LD32(r, taddr + cc * 32);
+          tmem_wait_ld();
+          const int col0 = nt * BN + cc * 32;
+#pragma unroll
+          for (int g8 = 0; g8 < 32; g8 += 8) {
+            const float m8 = fmaxf(fmaxf(fmaxf(__uint_as_float(r[g8]), __uint_as_float(r[g8 + 1])),
+                                         fmaxf(__uint_as_float(r[g8 + 2]), __uint_as_float(r[g8 + 3]))),
+                                   fmaxf(fmaxf(__uint_as_float(r[g8 + 4]), __uint_as_float(r[g8 + 5])),
+                                         fmaxf(__uint_as_float(r[g8 + 6]), __uint_as_float(r[g8 + 7]))));
+            if (__builtin_expect(m8 > thr, 0)) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float v = __uint_as_float(r[g8 + j]);
+                if (v > thr) {
+                  if (cnt == kCandCap) {
+                    // list full: drop entries that fell below the current threshold
+                    int w = 0;
+#pragma unroll 1
+                    for (int i = 0; i < kCandCap; ++i) {
+                      uint32_t ex, ey;
+                      asm volatile("ld.shared.v2.b32 {%0,%1}, [%2];" : "=r"(ex), "=r"(ey) : "r"(list_addr + i * 8));
+                      if (__uint_as_float(ex) >= thr) {
+                        asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(list_addr + w * 8), "r"(ex), "r"(ey));
+                        ++w;
+                      }
+                    }
+                    if (w == kCandCap) { overflow = true; w = kCandCap - 1; }
+                    cnt = w;
+                  }
+                  asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(list_addr + cnt * 8), "r"(r[g8 + j]),
+                               "r"((uint32_t)(col0 + g8 + j)));
+                  ++cnt;
+                  if (v > m) { m = v; thr = m - margin; }
+                }
+              }
+            }
+          }
+        }
+        // hand the buffer back, already holding -|e|^2/2 of the N-tile it will accumulate next
+        if ((int)g + 2 < total_nt) tmem_init_buffer(taddr, s_nhee, ((g + 2) % NT) * BN);
+        tc_fence_before();
+        mbar_arrive(bar(BAR_T_EMPTY + buf));
+      }
+      if (t < N) {
+        int out = 0;
+        if (overflow) {
+          out = -1;   // >= 16 codes inside the margin: the finish kernel scans the whole codebook for this token
+        } else {
+          for (int i = 0; i < cnt; ++i) {
+            uint32_t ex, ey;
+            asm volatile("ld.shared.v2.b32 {%0,%1}, [%2];" : "=r"(ex), "=r"(ey) : "r"(list_addr + i * 8));
+            if (__uint_as_float(ex) >= thr) cand[(size_t)t * kCandCap + out++] = (int)ey;
+          }
+        }
+        count[t] = out;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
+  }
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn() {
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess ||
+      q != cudaDriverEntryPointSuccess)
+    return nullptr;
+  return reinterpret_cast<EncodeTiledFn>(fn);
+}
+
+static bool device_is_sm100() {
+  int dev = 0, major = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return false; }
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return major == 10;
+}
+
+bool vq_tensor_supported(int D, int K) {
+  if (D % BK != 0 || D < BK || D > MAX_KC * BK) return false;
+  if (K % BN != 0 || K < BN || K > MAX_K) return false;
+  return device_is_sm100();
+}
+
+int vq_tensor_search(const float* z, const __nv_bfloat16* cb16, int dpad16, const float* ee, const float* emax, int B,
+                     int D, int HW, int K, int* cand, int* count, unsigned* counters, cudaStream_t s) {
+  (void)counters;
+  if (!vq_tensor_supported(D, K)) return DCVIC_ERR_UNSUPPORTED;
+  EncodeTiledFn encode = encode_tiled_fn();
+  if (!encode) return DCVIC_ERR_DEVICE;
+  CUtensorMap tmap;
+  const cuuint64_t gdim[2] = {(cuuint64_t)D, (cuuint64_t)K};
+  const cuuint64_t gstride[1] = {(cuuint64_t)dpad16 * sizeof(__nv_bfloat16)};
+  const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BN};
+  const cuuint32_t estr[2] = {1, 1};
+  if (encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(cb16), gdim, gstride, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    return DCVIC_ERR_CUDA;
+  const int N = B * HW;
+  const int num_tiles = (N + BM - 1) / BM;
+  const int grid = num_tiles < kNumSMs ? num_tiles : kNumSMs;
+  const int smem = SMEM_BYTES + 1024;
+  if (cudaFuncSetAttribute(vq_tensor_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+    return DCVIC_ERR_CUDA;
+  vq_tensor_search_kernel<<<grid, NTHREADS, smem, s>>>(tmap, z, ee, emax, N, D, HW, K, num_tiles, cand, count);
+  return dcvic_launch_status();
+}
+
+}  // namespace dcvic

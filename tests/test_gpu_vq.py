@@ -218,3 +218,30 @@ def test_from_reference_swap_keeps_codebook():
     assert isinstance(holder.quantize, D.VectorQuantizer2) and holder.quantize.sane_index_shape
     assert torch.equal(holder.quantize.embedding.weight.data, w)
     assert list(holder.state_dict()) == ["quantize.embedding.weight"]
+
+
+def test_tensor_core_path_is_selected_and_agrees_with_exact_scan():
+    """On sm_100 the benchmark codebook must run the tcgen05 search (no silent SIMT fallback) and
+    produce the same indices as the FP32 scan wherever the scan itself is not at a near-tie."""
+    assert torch.cuda.get_device_capability(0)[0] == 10
+    for kind in ("D0", "D1b"):
+        z, E = vq_inputs(3, kind, 4, 256, 32, 32, 1024)
+        m = make(D.VectorQuantizer2, E)
+        m.search = "tensor"                      # errors out instead of falling back
+        assert m.search_path() == "tcgen05"
+        with torch.no_grad():
+            zq_t, l_t, (_, _, i_t) = m(z.to(DEV))
+            m.search = "exact"
+            assert m.search_path() == "exact-simt"
+            zq_e, l_e, (_, _, i_e) = m(z.to(DEV))
+        n_mis, n_out, n_tie = O.allowed_index_mismatch(z, E, i_t.cpu())
+        assert n_out == 0
+        diff = int((i_t != i_e).sum())
+        assert diff <= n_tie, (diff, n_tie)
+        if kind == "D1b":
+            assert diff == 0 and torch.equal(zq_t, zq_e)
+    narrow = make(D.VectorQuantizer2, torch.randn(256, 4))
+    assert narrow.search_path() == "narrow-simt"
+    narrow.search = "tensor"
+    with pytest.raises(RuntimeError, match="not supported"):
+        narrow(torch.randn(1, 4, 8, 8, device=DEV))
