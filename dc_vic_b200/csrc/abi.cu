@@ -49,11 +49,13 @@ extern "C" int dcvic_vq_forward(const float* z_nchw, const float* codebook, int 
   char* ws = reinterpret_cast<char*>(workspace);
   unsigned* counters = reinterpret_cast<unsigned*>(ws + w.off_counters);
   float* ee = reinterpret_cast<float*>(ws + w.off_ee);
+  float* nhee = reinterpret_cast<float*>(ws + w.off_nhee);
   float* emax = reinterpret_cast<float*>(ws + w.off_emax);
   double* partials = reinterpret_cast<double*>(ws + w.off_partials);
   unsigned* hist = reinterpret_cast<unsigned*>(ws + w.off_hist);
   int* cand = reinterpret_cast<int*>(ws + w.off_cand);
-  int* count = reinterpret_cast<int*>(ws + w.off_count);
+  int* meta = reinterpret_cast<int*>(ws + w.off_meta);
+  uint2* list = reinterpret_cast<uint2*>(ws + w.off_list);
   __nv_bfloat16* cb16 = reinterpret_cast<__nv_bfloat16*>(ws + w.off_cb16);
   cudaStream_t s = (cudaStream_t)stream;
   int rc = DCVIC_OK;
@@ -62,23 +64,23 @@ extern "C" int dcvic_vq_forward(const float* z_nchw, const float* codebook, int 
     rc = vq_narrow_forward(z_nchw, codebook, B, D, HW, K, beta, legacy, zq_nchw, idx, loss, partials, counters, s);
   } else {
     if (!(flags & (DCVIC_VQ_REUSE_PREP | DCVIC_VQ_STAGE_FINISH_ONLY))) {
-      rc = vq_prepare_codebook(codebook, K, D, ee, emax, path == 2 ? cb16 : nullptr, w.dpad16, s);
+      rc = vq_prepare_codebook(codebook, K, D, ee, nhee, emax, path == 2 ? cb16 : nullptr, s);
       if (rc) return rc;
     }
     const bool do_search = !(flags & DCVIC_VQ_STAGE_FINISH_ONLY);
     const bool do_finish = !(flags & DCVIC_VQ_STAGE_SEARCH_ONLY);
     if (path == 2) {
-      if (do_search) rc = vq_tensor_search(z_nchw, cb16, w.dpad16, ee, emax, B, D, HW, K, cand, count, counters, s);
+      if (do_search) rc = vq_tensor_search(z_nchw, cb16, nhee, emax, B, D, HW, K, meta, list, s);
       if (rc) return rc;
       if (do_finish)
-        rc = vq_finish(z_nchw, codebook, ee, cand, kCandCap, count, B, D, HW, K, beta, legacy, zq_nchw, idx, loss,
+        rc = vq_finish(z_nchw, codebook, ee, emax, nullptr, meta, list, B, D, HW, K, beta, legacy, zq_nchw, idx, loss,
                        partials, counters, s);
     } else {
       if (do_search) rc = vq_exact_search(z_nchw, codebook, ee, B, D, HW, K, cand, s);
       if (rc) return rc;
       if (do_finish)
-        rc = vq_finish(z_nchw, codebook, ee, cand, 1, nullptr, B, D, HW, K, beta, legacy, zq_nchw, idx, loss,
-                       partials, counters, s);
+        rc = vq_finish(z_nchw, codebook, ee, emax, cand, nullptr, nullptr, B, D, HW, K, beta, legacy, zq_nchw, idx,
+                       loss, partials, counters, s);
     }
     if (!do_finish) return rc;
   }

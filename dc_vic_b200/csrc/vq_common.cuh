@@ -5,13 +5,22 @@
 
 namespace dcvic {
 
-constexpr int kCandCap = 16;          // candidate slots per token handed from the tensor search to the FP32 re-rank
 constexpr int kFinishTokens = 32;     // tokens per CTA in the finish (re-rank + gather + STE + loss) kernel
-constexpr int kTcK16Pad = 16;         // extra K columns of the BF16 codebook that fold -|e|^2/2 into the MMA
+constexpr int kListCap = 16;          // (chunk key, flag mask) entries per token and accumulator buffer
+constexpr int kChunk = 32;            // codes per flag mask (one tcgen05.ld.32x32b.x32 per row)
+constexpr int kCandMax = 24;          // FP32 re-rank candidates per token before falling back to a full scan
 
+// What the tensor search hands to the finish kernel, per token t:
+//   meta[4t + q]     float  running maximum of the BF16 score over the N-tiles that went through
+//                           accumulator buffer q (q = 0, 1)
+//   meta[4t + 2 + q] int    number of list entries of buffer q, or -1 if its list overflowed
+//   list[(2t + q) * kListCap + i] = { key, mask }:  key = (bits(chunk max) & ~0x7F) | chunk id,
+//                           mask bit j set <=> score of code (chunk id * 32 + j) was within the
+//                           margin of the running maximum when that chunk went by
 struct VqWorkspace {
-  size_t off_counters, off_ee, off_emax, off_partials, off_hist, off_cand, off_count, off_cb16, total;
-  int n_tokens, dpad16;
+  size_t off_counters, off_ee, off_nhee, off_emax, off_partials, off_hist, off_cand, off_meta, off_list, off_cb16,
+      total;
+  int n_tokens;
 };
 
 inline VqWorkspace vq_workspace_layout(int B, int D, int HW, int K) {
@@ -21,13 +30,14 @@ inline VqWorkspace vq_workspace_layout(int B, int D, int HW, int K) {
   auto take = [&](size_t bytes) { size_t at = o; o = align_up(o + bytes, 256); return at; };
   w.off_counters = take(64 * sizeof(unsigned));
   w.off_ee = take((size_t)K * sizeof(float));
+  w.off_nhee = take((size_t)K * sizeof(float));
   w.off_emax = take(4 * sizeof(float));
   w.off_partials = take((N / kFinishTokens + 2) * sizeof(double));
   w.off_hist = take((size_t)K * sizeof(unsigned));
-  w.off_cand = take(N * kCandCap * sizeof(int));
-  w.off_count = take(N * sizeof(int));
-  w.dpad16 = D + kTcK16Pad;
-  w.off_cb16 = take((size_t)K * w.dpad16 * sizeof(__nv_bfloat16));
+  w.off_cand = take(N * sizeof(int));
+  w.off_meta = take(N * 4 * sizeof(int));
+  w.off_list = take(N * 2 * kListCap * sizeof(uint2));
+  w.off_cb16 = take((size_t)K * D * sizeof(__nv_bfloat16));
   w.total = o;
   w.n_tokens = (int)N;
   return w;
@@ -36,22 +46,32 @@ inline VqWorkspace vq_workspace_layout(int B, int D, int HW, int K) {
 // counters[] slots
 enum { kCtrLoss = 0, kCtrOverflow = 1, kCtrPerp = 2, kCtrRerank = 3, kCtrTotalCand = 4 };
 
+// The proven bound on |bf16 score - exact score| differences that the search and the finish must
+// agree on: two round-to-nearest BF16 roundings per product (2^-7 + 2^-15 relative, Cauchy-Schwarz
+// over channels), doubled because it applies to the maximum and to the candidate, 2 % slack for the
+// tensor core's FP32 accumulation and the 7 mantissa bits dropped from the stored chunk maximum,
+// plus a few FP32 ulps of the reference distance itself (ties created by its rounding).
+__host__ __device__ __forceinline__ float vq_margin(float zz, float emax) {
+  return 1.02f * 0.015686f * sqrtf(zz) * emax + 1.9e-6f * (zz + emax * emax);
+}
+
 // vq_simt.cu
-int vq_prepare_codebook(const float* codebook, int K, int D, float* ee, float* emax, __nv_bfloat16* cb16, int dpad16,
-                        cudaStream_t s);
+int vq_prepare_codebook(const float* codebook, int K, int D, float* ee, float* nhee, float* emax,
+                        __nv_bfloat16* cb16, cudaStream_t s);
 int vq_narrow_forward(const float* z, const float* E, int B, int D, int HW, int K, float beta, int legacy, float* zq,
                       int64_t* idx, float* loss, double* partials, unsigned* counters, cudaStream_t s);
 int vq_exact_search(const float* z, const float* E, const float* ee, int B, int D, int HW, int K, int* cand,
                     cudaStream_t s);
-int vq_finish(const float* z, const float* E, const float* ee, const int* cand, int cap, const int* count, int B, int D,
-              int HW, int K, float beta, int legacy, float* zq, int64_t* idx, float* loss, double* partials,
-              unsigned* counters, cudaStream_t s);
+// cand != nullptr: one decided index per token (exact search).  Otherwise meta/list from the tensor search.
+int vq_finish(const float* z, const float* E, const float* ee, const float* emax, const int* cand, const int* meta,
+              const uint2* list, int B, int D, int HW, int K, float beta, int legacy, float* zq, int64_t* idx,
+              float* loss, double* partials, unsigned* counters, cudaStream_t s);
 int vq_v1_extras(const int64_t* idx, int N, int K, float* onehot, float* perplexity, unsigned* hist, unsigned* counters,
                  cudaStream_t s);
 
 // vq_tcgen05.cu
 bool vq_tensor_supported(int D, int K);
-int vq_tensor_search(const float* z, const __nv_bfloat16* cb16, int dpad16, const float* ee, const float* emax, int B,
-                     int D, int HW, int K, int* cand, int* count, unsigned* counters, cudaStream_t s);
+int vq_tensor_search(const float* z, const __nv_bfloat16* cb16, const float* nhee, const float* emax, int B, int D,
+                     int HW, int K, int* meta, uint2* list, cudaStream_t s);
 
 }  // namespace dcvic

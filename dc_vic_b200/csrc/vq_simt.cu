@@ -14,12 +14,13 @@
 namespace dcvic {
 
 // ------------------------------------------------------------------ codebook prepare
-// One warp per code.  ee[k] = sum_c fl(e^2) (lane-strided partials + xor tree), emax = max_k |e_k|
-// (atomicMax on the non-negative float's bit pattern), cb16[k][0..D) = bf16(e), cb16[k][D..D+3) =
-// three-way bf16 split of -ee/2, rest zero.
+// One warp per code.  ee[k] = sum_c fl(e^2) (lane-strided partials + xor tree), nhee[k] = -ee[k]/2
+// (what the tensor search pre-loads into its accumulators), emax = max_k |e_k| (atomicMax on the
+// non-negative float's bit pattern), cb16[k][0..D) = bf16(e).
 __global__ void __launch_bounds__(256) vq_prepare_kernel(const float* __restrict__ E, int K, int D,
-                                                          float* __restrict__ ee, float* __restrict__ emax,
-                                                          __nv_bfloat16* __restrict__ cb16, int dpad16) {
+                                                          float* __restrict__ ee, float* __restrict__ nhee,
+                                                          float* __restrict__ emax,
+                                                          __nv_bfloat16* __restrict__ cb16) {
   const int lane = threadIdx.x & 31;
   const int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (k >= K) return;
@@ -28,32 +29,20 @@ __global__ void __launch_bounds__(256) vq_prepare_kernel(const float* __restrict
   for (int c = lane; c < D; c += 32) {
     const float v = row[c];
     acc = __fadd_rn(acc, __fmul_rn(v, v));
-    if (cb16) cb16[(size_t)k * dpad16 + c] = __float2bfloat16_rn(v);
+    if (cb16) cb16[(size_t)k * D + c] = __float2bfloat16_rn(v);
   }
   acc = warp_sum(acc);
   if (lane == 0) {
     ee[k] = acc;
+    nhee[k] = -0.5f * acc;
     atomicMax(reinterpret_cast<unsigned*>(emax), __float_as_uint(sqrtf(acc) * 1.0000002f));
-  }
-  if (cb16 && lane < kTcK16Pad) {
-    const float v = -0.5f * acc;
-    const __nv_bfloat16 h = __float2bfloat16_rn(v);
-    const float r1 = v - __bfloat162float(h);
-    const __nv_bfloat16 m = __float2bfloat16_rn(r1);
-    const float r2 = r1 - __bfloat162float(m);
-    const __nv_bfloat16 l = __float2bfloat16_rn(r2);
-    __nv_bfloat16 out = __float2bfloat16_rn(0.f);
-    if (lane == 0) out = h;
-    if (lane == 1) out = m;
-    if (lane == 2) out = l;
-    cb16[(size_t)k * dpad16 + D + lane] = out;
   }
 }
 
-int vq_prepare_codebook(const float* codebook, int K, int D, float* ee, float* emax, __nv_bfloat16* cb16, int dpad16,
-                        cudaStream_t s) {
+int vq_prepare_codebook(const float* codebook, int K, int D, float* ee, float* nhee, float* emax,
+                        __nv_bfloat16* cb16, cudaStream_t s) {
   if (cudaMemsetAsync(emax, 0, sizeof(float), s) != cudaSuccess) return DCVIC_ERR_CUDA;
-  vq_prepare_kernel<<<ceil_div_i(K, 8), 256, 0, s>>>(codebook, K, D, ee, emax, cb16, dpad16);
+  vq_prepare_kernel<<<ceil_div_i(K, 8), 256, 0, s>>>(codebook, K, D, ee, nhee, emax, cb16);
   return dcvic_launch_status();
 }
 
@@ -285,64 +274,176 @@ int vq_exact_search(const float* z, const float* E, const float* ee, int B, int 
 // ------------------------------------------------------------------ finish
 // 32 tokens x e_dim per CTA staged (transposed, padded) in shared memory so that both the NCHW
 // side (lanes = tokens) and the codebook side (lanes = channels) are coalesced.
-//   count == nullptr : one candidate per token at cand[t*cap]
-//   count[t] in [1,cap] : FP32 re-rank of cand[t*cap .. +count)
-//   count[t] <= 0 or > cap : candidate list overflowed -> full FP32 scan of the codebook for that token
+//   cand != nullptr : the search already decided (exact FP32 scan): idx = cand[t]
+//   else            : meta/list from the tensor search (vq_common.cuh).  Per token: threshold =
+//                     max(m0, m1) - margin; every flagged code of every chunk whose maximum reaches the
+//                     threshold is re-ranked with the reference-order FP32 distance
+//                     (sum z^2 + sum e^2) - 2 z.e, ties to the lowest index.  Tokens whose list
+//                     overflowed (or that flag more than kCandMax codes) are scanned against the whole
+//                     codebook by the full CTA.
+// Phases: (0) stage z, |z|^2 per token  (1) one thread per token expands its lists into (token, code)
+// pairs  (2) warps take pairs round-robin: one FP32 dot each  (3) one thread per token picks the
+// minimum  (3b) full scans  (4) gather, straight-through value, loss partial, coalesced stores.
+constexpr int kPairCap = kFinishTokens * kCandMax;
+
 __global__ void __launch_bounds__(256) vq_finish_kernel(const float* __restrict__ z, const float* __restrict__ E,
-                                                         const float* __restrict__ ee, const int* __restrict__ cand,
-                                                         int cap, const int* __restrict__ count, int N, int D, int HW,
-                                                         int K, float beta, int legacy, float* __restrict__ zq,
+                                                         const float* __restrict__ ee,
+                                                         const float* __restrict__ emax_ptr,
+                                                         const int* __restrict__ cand, const int* __restrict__ meta,
+                                                         const uint2* __restrict__ list, int N, int D, int HW, int K,
+                                                         float beta, int legacy, float* __restrict__ zq,
                                                          int64_t* __restrict__ idx, float* __restrict__ loss,
                                                          double* __restrict__ partials,
                                                          unsigned* __restrict__ counters) {
   extern __shared__ __align__(16) float buf[];  // [D][33]
   __shared__ double scratch[32];
+  __shared__ float s_zz[kFinishTokens];
+  __shared__ int s_best[kFinishTokens];        // decided code, or -1 while undecided
+  __shared__ int s_first[kFinishTokens + 1];   // pair range of each token
+  __shared__ unsigned short s_pair_tok[kPairCap];
+  __shared__ unsigned short s_pair_k[kPairCap];
+  __shared__ float s_pair_d[kPairCap];
+  __shared__ float s_wd[8];
+  __shared__ int s_wk[8];
+  __shared__ int s_nc[kFinishTokens];
+  __shared__ unsigned short s_ck[kFinishTokens * kCandMax];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int t0 = blockIdx.x * kFinishTokens;
+  if (threadIdx.x < kFinishTokens) s_nc[threadIdx.x] = 0;
   const int tl = t0 + lane;
   const bool valid = tl < N;
   const size_t base = valid ? ((size_t)(tl / HW) * D * HW + (size_t)(tl % HW)) : 0;
 
+  // (0) stage the token tile
   for (int c = wid; c < D; c += 8) buf[c * 33 + lane] = valid ? z[base + (size_t)c * HW] : 0.f;
   __syncthreads();
 
-  float sq = 0.f;
-  for (int tok = wid; tok < kFinishTokens; tok += 8) {
-    const int t = t0 + tok;
-    if (t >= N) break;
-    int n = count ? count[t] : 1;
-    int best_k;
-    if (n == 1) {
-      best_k = cand[(size_t)t * cap];
-    } else {
+  if (cand) {
+    if (wid == 0) s_best[lane] = valid ? min(max(cand[tl], 0), K - 1) : 0;
+    __syncthreads();
+  } else {
+    for (int tok = wid; tok < kFinishTokens; tok += 8) {
       float zzp = 0.f;
       for (int c = lane; c < D; c += 32) {
         const float v = buf[c * 33 + tok];
         zzp = __fadd_rn(zzp, __fmul_rn(v, v));
       }
-      const float zz = warp_sum(zzp);
-      float best_d = FLT_MAX;
-      best_k = 0x7fffffff;
-      const bool full = (n <= 0 || n > cap);
-      const int iters = full ? K : n;
-      for (int i = 0; i < iters; ++i) {
-        const int k = full ? i : cand[(size_t)t * cap + i];
+      zzp = warp_sum(zzp);
+      if (lane == 0) s_zz[tok] = zzp;
+    }
+    __syncthreads();
+    // (1) expand lists -> candidate codes: 8 threads per token, 4 list entries each (all loads in flight
+    // at once); order within a token does not matter, the minimum is taken over (distance, index)
+    {
+      const int tok = threadIdx.x >> 3, sub = threadIdx.x & 7;
+      const int t = t0 + tok;
+      if (t < N) {
+        const int4 mt = *reinterpret_cast<const int4*>(meta + (size_t)t * 4);
+        const float thr = fmaxf(__int_as_float(mt.x), __int_as_float(mt.y)) - vq_margin(s_zz[tok], *emax_ptr);
+        const int q = sub >> 2, i0 = (sub & 3) * 4;
+        const int n = q == 0 ? mt.z : mt.w;
+        if (n < 0 && (sub & 3) == 0) atomicAdd(&s_nc[tok], 2 * kCandMax);   // overflowed list -> full scan
+        if (i0 < n) {
+          const uint4* lp = reinterpret_cast<const uint4*>(list + ((size_t)t * 2 + q) * kListCap + i0);
+          const uint4 e01 = lp[0], e23 = lp[1];
+          const unsigned key[4] = {e01.x, e01.z, e23.x, e23.z};
+          const unsigned msk[4] = {e01.y, e01.w, e23.y, e23.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            if (i0 + i >= n) break;
+            if (__uint_as_float(key[i] | 0x7Fu) < thr) continue;      // chunk maximum (rounded up) below threshold
+            unsigned mask = msk[i];
+            const int c0 = (int)(key[i] & 0x7Fu) * kChunk;
+            const int pos = atomicAdd(&s_nc[tok], __popc(mask));
+            int w = pos;
+            while (mask && w < kCandMax) {
+              const int j = __ffs(mask) - 1;
+              mask &= mask - 1;
+              s_ck[tok * kCandMax + w++] = (unsigned short)(c0 + j);
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();
+    // pair ranges (warp 0: lane = token); tokens with one candidate are decided here
+    if (wid == 0) {
+      const int nc = valid ? s_nc[lane] : 1;
+      const int ncand = nc > kCandMax ? -1 : nc;        // nc == 0 cannot happen (the maximum is always flagged)
+      const int npairs = ncand > 1 ? ncand : 0;
+      int off = npairs;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, off, o);
+        if (lane >= o) off += v;
+      }
+      s_first[lane + 1] = off;
+      if (lane == 0) s_first[0] = 0;
+      off -= npairs;
+      for (int i = 0; i < npairs; ++i) {
+        s_pair_tok[off + i] = (unsigned short)lane;
+        s_pair_k[off + i] = s_ck[lane * kCandMax + i];
+      }
+      int sb = 0;                                       // rows past the end: any valid code
+      if (valid) sb = ncand == 1 ? (int)s_ck[lane * kCandMax] : (ncand <= 0 ? -2 : -1);
+      s_best[lane] = sb;
+      if (valid && ncand != 1) atomicAdd(counters + (ncand < 0 ? kCtrOverflow : kCtrRerank), 1u);
+    }
+    __syncthreads();
+    // (2) one FP32 dot per (token, code) pair
+    const int total = s_first[kFinishTokens];
+    for (int p = wid; p < total; p += 8) {
+      const int tok = s_pair_tok[p], k = s_pair_k[p];
+      const float* er = E + (size_t)k * D;
+      float dp = 0.f;
+      for (int c = lane; c < D; c += 32) dp = fmaf(buf[c * 33 + tok], er[c], dp);
+      const float dot = warp_sum(dp);
+      if (lane == 0) s_pair_d[p] = fmaf(-2.f, dot, __fadd_rn(s_zz[tok], ee[k]));
+    }
+    __syncthreads();
+    // (3) minimum per token, ties to the lowest index
+    if (wid == 0 && s_best[lane] == -1) {
+      float bd = FLT_MAX;
+      int bk = 0x7fffffff;
+      for (int p = s_first[lane]; p < s_first[lane + 1]; ++p) {
+        const float d = s_pair_d[p];
+        const int k = s_pair_k[p];
+        if (d < bd || (d == bd && k < bk)) { bd = d; bk = k; }
+      }
+      s_best[lane] = bk;
+    }
+    __syncthreads();
+    // (3b) full scans: the whole CTA on one token at a time (rare)
+    for (int tok = 0; tok < kFinishTokens; ++tok) {
+      if (s_best[tok] != -2) continue;             // uniform: read from shared memory by all threads
+      const float zz = s_zz[tok];
+      float bd = FLT_MAX;
+      int bk = 0x7fffffff;
+      for (int k = wid; k < K; k += 8) {
         const float* er = E + (size_t)k * D;
         float dp = 0.f;
         for (int c = lane; c < D; c += 32) dp = fmaf(buf[c * 33 + tok], er[c], dp);
         const float dot = warp_sum(dp);
         const float d = fmaf(-2.f, dot, __fadd_rn(zz, ee[k]));
-        if (d < best_d || (d == best_d && k < best_k)) {
-          best_d = d;
-          best_k = k;
-        }
+        if (d < bd || (d == bd && k < bk)) { bd = d; bk = k; }
       }
-      if (lane == 0) {
-        if (full) atomicAdd(counters + kCtrOverflow, 1u);
-        else atomicAdd(counters + kCtrRerank, 1u);
+      if (lane == 0) { s_wd[wid] = bd; s_wk[wid] = bk; }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w)
+          if (s_wd[w] < bd || (s_wd[w] == bd && s_wk[w] < bk)) { bd = s_wd[w]; bk = s_wk[w]; }
+        s_best[tok] = bk;
       }
+      __syncthreads();
     }
-    best_k = min(max(best_k, 0), K - 1);
+  }
+
+  // (4) gather + straight-through value + loss partial
+  float sq = 0.f;
+  for (int tok = wid; tok < kFinishTokens; tok += 8) {
+    const int t = t0 + tok;
+    if (t >= N) break;
+    const int best_k = min(max(s_best[tok], 0), K - 1);
     const float* er = E + (size_t)best_k * D;
     for (int c = lane; c < D; c += 32) {
       const float zv = buf[c * 33 + tok];
@@ -363,16 +464,17 @@ __global__ void __launch_bounds__(256) vq_finish_kernel(const float* __restrict_
   }
 }
 
-int vq_finish(const float* z, const float* E, const float* ee, const int* cand, int cap, const int* count, int B, int D,
-              int HW, int K, float beta, int legacy, float* zq, int64_t* idx, float* loss, double* partials,
-              unsigned* counters, cudaStream_t s) {
+int vq_finish(const float* z, const float* E, const float* ee, const float* emax, const int* cand, const int* meta,
+              const uint2* list, int B, int D, int HW, int K, float beta, int legacy, float* zq, int64_t* idx,
+              float* loss, double* partials, unsigned* counters, cudaStream_t s) {
   const int N = B * HW;
   const size_t smem = (size_t)D * 33 * sizeof(float);
   if (smem > 200 * 1024) return DCVIC_ERR_UNSUPPORTED;
+  if (K > 65535 && !cand) return DCVIC_ERR_UNSUPPORTED;
   if (smem > 48 * 1024)
     cudaFuncSetAttribute(vq_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  vq_finish_kernel<<<ceil_div_i(N, kFinishTokens), 256, smem, s>>>(z, E, ee, cand, cap, count, N, D, HW, K, beta,
-                                                                    legacy, zq, idx, loss, partials, counters);
+  vq_finish_kernel<<<ceil_div_i(N, kFinishTokens), 256, smem, s>>>(z, E, ee, emax, cand, meta, list, N, D, HW, K,
+                                                                    beta, legacy, zq, idx, loss, partials, counters);
   return dcvic_launch_status();
 }
 

@@ -2,22 +2,25 @@
 //
 // Computes, for every token row z_t (FP32, read straight from NCHW) and every codeword e_k,
 //     s[t,k] = bf16(z_t) . bf16(e_k) - |e_k|^2 / 2        ( = (|z|^2 - d[t,k]) / 2 up to BF16 rounding )
-// with tcgen05.mma (BF16 x BF16 -> FP32 in TMEM), and keeps per row every k whose score is within a
-// PROVEN error margin of the row maximum.  The distance matrix never leaves the SM.  The FP32
-// re-rank of those few candidates (reference op order, lowest-index tie-break) happens in
-// vq_finish_kernel, which also streams z once more for the gather / STE / loss.
+// with tcgen05.mma (BF16 x BF16 -> FP32 in TMEM) and flags, per row, every k whose score is within a
+// PROVEN error margin (vq_margin) of the row's running maximum.  The distance matrix never leaves
+// the SM.  The FP32 re-rank of the few flagged codes (reference op order, lowest-index tie-break)
+// happens in vq_finish_kernel, which streams z once more for the gather / STE / loss.
 //
-//   margin:  |s - s_exact| <= |z||e_k| (2^-7 + 2^-15)  (two RN-to-bf16 roundings per product, Cauchy-
-//            Schwarz over channels) so the true argmax is within 2*that of the computed maximum.
-//
-// Structure (one CTA per 128-token tile, persistent over tiles):
-//   warp 0      TMA producer: BF16 codebook tiles [256 codes x 64 ch] (SWIZZLE_128B) -> 4-stage ring
-//   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (M=128, N=256, K=16 per instruction)
-//   warps 2-5   A producers: read z (FP32, coalesced along tokens), convert to BF16, write the K-major
-//               SWIZZLE_128B operand tile, accumulate |z|^2 per token
-//   warps 6-9   epilogue: tcgen05.ld the 128x256 FP32 accumulator (double-buffered in TMEM, 2x256
-//               columns), running max + candidate list per row, then re-initialise the buffer with
-//               -|e|^2/2 for the N-tile after next (so the MMA accumulates onto it: no per-element add)
+// Structure: persistent CTA pairs (cta_group::2, UMMA 256x256x16), each CTA owning 128 tokens of a
+// 256-token pair tile and half of every codebook tile (CG = 1 is the same code on single CTAs).
+//   warps 0-3   A producers: read z (FP32, coalesced along tokens), convert to BF16, write the K-major
+//               SWIZZLE_128B operand tile (double-buffered: tile i+1 loads while tile i multiplies),
+//               publish |z|^2 per token
+//   warps 4-7   epilogue of accumulator buffer 0 (N-tiles 0, 2, ..), warps 8-11 of buffer 1:
+//               tcgen05.ld 32 scores per row at a time (software pipelined), running max, one flag
+//               mask per 32 codes (FADD on the FMA pipe + funnel shift, branch-free), append
+//               {chunk max | chunk id, mask} to the token's list in global memory when non-empty, then
+//               re-initialise the buffer with -|e|^2/2 of the N-tile it accumulates next
+//   warp 12     TMA producer: this CTA's half of the BF16 codebook tile [256/CG codes x 64 ch]
+//               (SWIZZLE_128B) into a 4-stage ring; completion is signalled on the LEADER's barrier
+//   warp 13     TMEM allocator; in the leader CTA one thread issues every tcgen05.mma of the pair and
+//               multicasts the commits (stage free, accumulator full, operand tile free) to both CTAs
 // Reference semantics: taming/modules/vqvae/quantize.py:280-284 (distance + argmin).
 #include "vq_common.cuh"
 #include <cuda.h>
@@ -26,44 +29,67 @@ namespace dcvic {
 
 namespace tc {
 
-constexpr int BM = 128;          // tokens per tile (UMMA M)
+constexpr int BM = 128;          // tokens per CTA tile (UMMA M = 128 * CG)
 constexpr int BN = 256;          // codes per N-tile (UMMA N)
 constexpr int BK = 64;           // channels per smem chunk: 64 bf16 = 128 B = one SWIZZLE_128B row
 constexpr int UK = 16;           // UMMA K for 16-bit inputs
 constexpr int MAX_KC = 4;        // e_dim <= 256
-constexpr int NSTAGE = 4;        // codebook ring depth
-constexpr int A_CHUNK_BYTES = BM * BK * 2;   // 16 KB
-constexpr int B_STAGE_BYTES = BN * BK * 2;   // 32 KB
+constexpr int A_CHUNK_BYTES = BM * BK * 2;            // 16 KB
+constexpr int A_BUF_BYTES = MAX_KC * A_CHUNK_BYTES;   // 64 KB
 constexpr int MAX_K = 4096;
-constexpr int NTHREADS = 320;
+constexpr int NTHREADS = 448;
+constexpr int WARP_TMA = 12, WARP_MMA = 13;
+constexpr int ZZ_SLOTS = 4;
 
-// dynamic shared memory map (base aligned to 1024 B)
-constexpr int OFF_A = 0;
-constexpr int OFF_B = OFF_A + MAX_KC * A_CHUNK_BYTES;                 // 65536
-constexpr int OFF_LIST = OFF_B + NSTAGE * B_STAGE_BYTES;              // 196608
-constexpr int OFF_EE = OFF_LIST + BM * kCandCap * 8;                  // +16384
-constexpr int OFF_ZZ = OFF_EE + MAX_K * 4;                            // +16384
-constexpr int OFF_BAR = OFF_ZZ + 2 * BM * 4;                          // +1024
-constexpr int SMEM_BYTES = OFF_BAR + 256;
-static_assert(SMEM_BYTES + 1024 <= 232448, "shared memory budget");
-
-// barrier slots (8 bytes each) inside OFF_BAR
-constexpr int BAR_B_FULL = 0;                  // [NSTAGE]
-constexpr int BAR_B_EMPTY = BAR_B_FULL + NSTAGE;
-constexpr int BAR_A_FULL = BAR_B_EMPTY + NSTAGE;   // [MAX_KC]
-constexpr int BAR_A_EMPTY = BAR_A_FULL + MAX_KC;   // [1]
-constexpr int BAR_T_FULL = BAR_A_EMPTY + 1;        // [2]
-constexpr int BAR_T_EMPTY = BAR_T_FULL + 2;        // [2]
-constexpr int BAR_COUNT = BAR_T_EMPTY + 2;
-constexpr int OFF_TMEM_PTR = OFF_BAR + BAR_COUNT * 8;
+template <int CG>
+struct Cfg {
+  static constexpr int B_STAGE_BYTES = (BN / CG) * BK * 2;       // 32 KB (CG=1) / 16 KB (CG=2)
+  static constexpr int NSTAGE = CG == 2 ? 4 : 2;
+  // dynamic shared memory map (base aligned to 1024 B)
+  static constexpr int OFF_A = 0;                                  // [2][MAX_KC][BM x 128 B]
+  static constexpr int OFF_B = OFF_A + 2 * A_BUF_BYTES;            // [NSTAGE][BN/CG x 128 B]
+  static constexpr int OFF_ZZ = OFF_B + NSTAGE * B_STAGE_BYTES;    // [ZZ_SLOTS][BM] float
+  static constexpr int OFF_BAR = OFF_ZZ + ZZ_SLOTS * BM * 4;
+  // barrier slots (8 bytes each)
+  static constexpr int BAR_B_FULL = 0;                       // [NSTAGE]   leader only
+  static constexpr int BAR_B_EMPTY = BAR_B_FULL + NSTAGE;    // [NSTAGE]
+  static constexpr int BAR_A_FULL = BAR_B_EMPTY + NSTAGE;    // [2][MAX_KC] leader only
+  static constexpr int BAR_A_EMPTY = BAR_A_FULL + 2 * MAX_KC;  // [2]
+  static constexpr int BAR_T_FULL = BAR_A_EMPTY + 2;         // [2]
+  static constexpr int BAR_T_EMPTY = BAR_T_FULL + 2;         // [2]        leader only
+  static constexpr int BAR_ZZ = BAR_T_EMPTY + 2;             // [ZZ_SLOTS]
+  static constexpr int BAR_COUNT = BAR_ZZ + ZZ_SLOTS;
+  static constexpr int OFF_TMEM_PTR = OFF_BAR + BAR_COUNT * 8;
+  static constexpr int SMEM_BYTES = OFF_TMEM_PTR + 16;
+  static_assert(SMEM_BYTES + 1024 <= 232448, "shared memory budget");
+};
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+// shared::cluster address of `addr` (a shared::cta address of this CTA) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// arrive on a barrier given by its shared::cluster address (possibly in the peer CTA)
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
@@ -84,12 +110,22 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
+template <int CG>
 __device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap* map, int x, int y, uint32_t bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
-          smem_dst),
-      "l"(map), "r"(x), "r"(y), "r"(bar)
-      : "memory");
+  if constexpr (CG == 2) {
+    // `bar` is a shared::cluster address (the leader CTA's barrier)
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, "
+        "%3}], [%4];" ::"r"(smem_dst),
+        "l"(map), "r"(x), "r"(y), "r"(bar)
+        : "memory");
+  } else {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+            smem_dst),
+        "l"(map), "r"(x), "r"(y), "r"(bar)
+        : "memory");
+  }
 }
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 "version 1"):
@@ -98,20 +134,45 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
   return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
          (2ull << 61);
 }
-// kind::f16 instruction descriptor: D=F32, A=B=BF16, both K-major, N=256, M=128
-constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+// kind::f16 instruction descriptor: D=F32, A=B=BF16, both K-major, N=256, M=128*CG
+template <int CG>
+struct Idesc {
+  static constexpr uint32_t value =
+      (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((BM * CG) >> 4) << 24);
+};
 
+template <int CG>
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(kIdesc), "r"(accumulate)
-      : "memory");
+  if constexpr (CG == 2) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(Idesc<2>::value), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(Idesc<1>::value), "r"(accumulate)
+        : "memory");
+  }
 }
+// arrive on the barrier at shared::cta offset `bar` (in BOTH CTAs of the pair when CG == 2) once every
+// tcgen05.mma issued so far by this thread has retired
+template <int CG>
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+  if constexpr (CG == 2) {
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+        "h"((uint16_t)3)
+        : "memory");
+  } else {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+  }
 }
 
 #define TMEM_LD32(r, taddr)                                                                                        \
@@ -125,6 +186,18 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
       : "r"(taddr)                                                                                                 \
       : "memory")
 
+// tcgen05.wait::ld that also "touches" the 32 destination registers so that no use of them can be
+// scheduled above the wait
+#define TMEM_WAIT_LD32(r)                                                                                          \
+  asm volatile("tcgen05.wait::ld.sync.aligned;"                                                                    \
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),   \
+                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]),          \
+                 "+r"(r[15]), "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]),        \
+                 "+r"(r[22]), "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]),        \
+                 "+r"(r[29]), "+r"(r[30]), "+r"(r[31])                                                             \
+               :                                                                                                   \
+               : "memory")
+
 #define TMEM_ST32(taddr, r)                                                                                        \
   asm volatile(                                                                                                    \
       "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,"   \
@@ -135,7 +208,6 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
       "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])                                                               \
       : "memory")
 
-__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
@@ -144,122 +216,122 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   return r;
 }
 
-// write -|e|^2/2 of codes [k0, k0+256) into one TMEM accumulator buffer (this warp's 32 lanes)
-__device__ __forceinline__ void tmem_init_buffer(uint32_t taddr_buf, const float* s_neg_half_ee, int k0) {
+// write -|e|^2/2 of codes [k0, k0+256) into one TMEM accumulator buffer (this warp's 32 lanes);
+// every lane reads the same addresses (L1 broadcast)
+__device__ __forceinline__ void tmem_init_buffer(uint32_t taddr_buf, const float* __restrict__ nhee, int k0) {
 #pragma unroll 1
   for (int cc = 0; cc < BN / 32; ++cc) {
     uint32_t r[32];
+    const float4* src = reinterpret_cast<const float4*>(nhee + k0 + cc * 32);
 #pragma unroll
-    for (int j = 0; j < 32; j += 4) {
-      const float4 v = *reinterpret_cast<const float4*>(s_neg_half_ee + k0 + cc * 32 + j);
-      r[j] = __float_as_uint(v.x); r[j + 1] = __float_as_uint(v.y);
-      r[j + 2] = __float_as_uint(v.z); r[j + 3] = __float_as_uint(v.w);
+    for (int j = 0; j < 8; ++j) {
+      const float4 v = __ldg(src + j);
+      r[4 * j] = __float_as_uint(v.x); r[4 * j + 1] = __float_as_uint(v.y);
+      r[4 * j + 2] = __float_as_uint(v.z); r[4 * j + 3] = __float_as_uint(v.w);
     }
     TMEM_ST32(taddr_buf + cc * 32, r);
   }
   tmem_wait_st();
 }
 
+// One 32-code chunk of one row: chunk maximum, running maximum, flag mask of the scores within
+// `margin` of the running maximum.  Flags: d = s - thr on the FMA pipe, sign bits collected with
+// funnel shifts (bit j of the result <=> s[j] >= thr).
+__device__ __forceinline__ uint32_t chunk_flags(const uint32_t (&r)[32], float margin, float& m, float& cm_out) {
+  float a[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    a[j] = fmaxf(fmaxf(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1])),
+                 fmaxf(__uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])));
+  const float cm = fmaxf(fmaxf(fmaxf(a[0], a[1]), fmaxf(a[2], a[3])), fmaxf(fmaxf(a[4], a[5]), fmaxf(a[6], a[7])));
+  m = fmaxf(m, cm);
+  cm_out = cm;
+  const float thr = m - margin;
+  uint32_t neg[4] = {0u, 0u, 0u, 0u};   // four independent chains of 8 sign bits
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+#pragma unroll
+    for (int j = 7; j >= 0; --j) {
+      const float d = __fsub_rn(__uint_as_float(r[c * 8 + j]), thr);
+      neg[c] = __funnelshift_l(__float_as_uint(d), neg[c], 1);   // (neg << 1) | sign(d)
+    }
+  const uint32_t below = neg[0] | (neg[1] << 8) | (neg[2] << 16) | (neg[3] << 24);
+  return ~below;
+}
+
 }  // namespace tc
 
 using namespace tc;
 
+template <int CG>
 __global__ void __launch_bounds__(NTHREADS, 1)
 vq_tensor_search_kernel(const __grid_constant__ CUtensorMap tmap_cb, const float* __restrict__ z,
-                        const float* __restrict__ ee, const float* __restrict__ emax_ptr, int N, int D, int HW, int K,
-                        int num_tiles, int* __restrict__ cand, int* __restrict__ count) {
+                        const float* __restrict__ nhee, const float* __restrict__ emax_ptr, int N, int D, int HW,
+                        int K, int num_ptiles, int* __restrict__ meta, uint2* __restrict__ list) {
+  using C = Cfg<CG>;
   extern __shared__ uint8_t smem_raw[];
-  // SWIZZLE_128B operands need 1024-byte alignment
+  // SWIZZLE_128B operands need 1024-byte alignment (same adjustment in both CTAs of a pair)
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const uint32_t sbase = smem_u32(smem);
-  const uint32_t bar0 = sbase + OFF_BAR;
+  const uint32_t bar0 = sbase + C::OFF_BAR;
   auto bar = [&](int slot) { return bar0 + slot * 8; };
-  float* s_nhee = reinterpret_cast<float*>(smem + OFF_EE);     // -|e|^2/2
-  float* s_zz = reinterpret_cast<float*>(smem + OFF_ZZ);       // [2][BM]
-  volatile uint32_t* s_tmem = reinterpret_cast<volatile uint32_t*>(smem + OFF_TMEM_PTR);
+  float* s_zz = reinterpret_cast<float*>(smem + C::OFF_ZZ);       // [ZZ_SLOTS][BM]
+  volatile uint32_t* s_tmem = reinterpret_cast<volatile uint32_t*>(smem + C::OFF_TMEM_PTR);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
+  const bool leader = rank == 0;
+  const int pair = blockIdx.x / CG, npairs = gridDim.x / CG;
   const int KC = D / BK;               // channel chunks
-  const int NT = K / BN;               // N-tiles per token tile
-  const int my_tiles = (num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int NT = K / BN;               // N-tiles per token tile (even)
+  const int my_tiles = (num_ptiles - pair + npairs - 1) / npairs;
+  // barriers that live in the leader CTA, as shared::cluster addresses
+  auto leader_bar = [&](int slot) { return CG == 2 ? map_to_cta(bar(slot), 0) : bar(slot); };
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < NSTAGE; ++s) { mbar_init(bar(BAR_B_FULL + s), 1); mbar_init(bar(BAR_B_EMPTY + s), 1); }
-    for (int c = 0; c < MAX_KC; ++c) mbar_init(bar(BAR_A_FULL + c), 128);
-    mbar_init(bar(BAR_A_EMPTY), 1);
-    for (int b = 0; b < 2; ++b) { mbar_init(bar(BAR_T_FULL + b), 1); mbar_init(bar(BAR_T_EMPTY + b), 128); }
+    for (int s = 0; s < C::NSTAGE; ++s) { mbar_init(bar(C::BAR_B_FULL + s), 1); mbar_init(bar(C::BAR_B_EMPTY + s), 1); }
+    for (int c = 0; c < 2 * MAX_KC; ++c) mbar_init(bar(C::BAR_A_FULL + c), 4 * CG);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(bar(C::BAR_A_EMPTY + b), 1);
+      mbar_init(bar(C::BAR_T_FULL + b), 1);
+      mbar_init(bar(C::BAR_T_EMPTY + b), 4 * CG);
+    }
+    for (int s = 0; s < ZZ_SLOTS; ++s) mbar_init(bar(C::BAR_ZZ + s), 4);
     fence_barrier_init();
   }
-  for (int k = threadIdx.x; k < K; k += NTHREADS) s_nhee[k] = -0.5f * ee[k];
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + OFF_TMEM_PTR),
-                 "r"(512u));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  if (warp == WARP_MMA) {
+    if constexpr (CG == 2) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + C::OFF_TMEM_PTR),
+                   "r"(512u));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::);
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + C::OFF_TMEM_PTR),
+                   "r"(512u));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (CG == 2) cluster_sync();     // peer's barriers are initialised before anyone arrives remotely
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
 
-  if (warp == 0) {
-    // ===================== TMA producer: codebook ring =====================
-    if (lane == 0) {
-      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_cb) : "memory");
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int it = 0; it < my_tiles; ++it)
-        for (int nt = 0; nt < NT; ++nt)
-          for (int kc = 0; kc < KC; ++kc) {
-            mbar_wait(bar(BAR_B_EMPTY + stage), phase ^ 1);
-            mbar_arrive_expect_tx(bar(BAR_B_FULL + stage), B_STAGE_BYTES);
-            tma_load_2d(sbase + OFF_B + stage * B_STAGE_BYTES, &tmap_cb, kc * BK, nt * BN, bar(BAR_B_FULL + stage));
-            if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
-          }
-    }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      uint32_t g = 0;   // running N-tile counter -> TMEM buffer g & 1
-      for (int it = 0; it < my_tiles; ++it) {
-        for (int nt = 0; nt < NT; ++nt, ++g) {
-          const uint32_t buf = g & 1;
-          mbar_wait(bar(BAR_T_EMPTY + buf), (g >> 1) & 1);      // epilogue drained + re-initialised this buffer
-          tc_fence_after();
-          const uint32_t tmem_d = tmem_base + buf * BN;
-          for (int kc = 0; kc < KC; ++kc) {
-            if (nt == 0) { mbar_wait(bar(BAR_A_FULL + kc), it & 1); }
-            mbar_wait(bar(BAR_B_FULL + stage), phase);
-            tc_fence_after();
-            const uint32_t a_addr = sbase + OFF_A + kc * A_CHUNK_BYTES;
-            const uint32_t b_addr = sbase + OFF_B + stage * B_STAGE_BYTES;
-#pragma unroll
-            for (int ks = 0; ks < BK / UK; ++ks)
-              umma_bf16(tmem_d, umma_desc_sw128(a_addr + ks * UK * 2), umma_desc_sw128(b_addr + ks * UK * 2), 1u);
-            umma_commit(bar(BAR_B_EMPTY + stage));     // frees the codebook stage when these MMAs retire
-            if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
-          }
-          umma_commit(bar(BAR_T_FULL + buf));          // accumulator ready for the epilogue
-        }
-        umma_commit(bar(BAR_A_EMPTY));                 // token tile's operand may be overwritten
-      }
-    }
-  } else if (warp < 6) {
+  if (warp < 4) {
     // ===================== A producers: FP32 NCHW -> BF16 K-major SWIZZLE_128B =====================
-    const int row = (warp - 2) * 32 + lane;
+    const int row = warp * 32 + lane;
     for (int it = 0; it < my_tiles; ++it) {
-      const int tile = blockIdx.x + it * gridDim.x;
-      const int t = tile * BM + row;
+      const int ptile = pair + it * npairs;
+      const long long t = ((long long)ptile * CG + rank) * BM + row;
       const bool valid = t < N;
       const float* zp = z + (valid ? ((size_t)(t / HW) * D * HW + (size_t)(t % HW)) : 0);
-      mbar_wait(bar(BAR_A_EMPTY), (it & 1) ^ 1);
+      const int abuf = it & 1;
+      mbar_wait(bar(C::BAR_A_EMPTY + abuf), ((it >> 1) & 1) ^ 1);
       float zz = 0.f;
       for (int kc = 0; kc < KC; ++kc) {
         float v[BK];
 #pragma unroll
         for (int j = 0; j < BK; ++j) v[j] = valid ? __ldg(zp + (size_t)(kc * BK + j) * HW) : 0.f;
-        uint8_t* arow = smem + OFF_A + kc * A_CHUNK_BYTES + row * 128;
+        uint8_t* arow = smem + C::OFF_A + abuf * A_BUF_BYTES + kc * A_CHUNK_BYTES + row * 128;
 #pragma unroll
         for (int c16 = 0; c16 < 8; ++c16) {
           uint4 pk;
@@ -271,108 +343,146 @@ vq_tensor_search_kernel(const __grid_constant__ CUtensorMap tmap_cb, const float
         }
 #pragma unroll
         for (int j = 0; j < BK; ++j) zz = fmaf(v[j], v[j], zz);
-        if (kc == KC - 1) s_zz[(it & 1) * BM + row] = zz;
         fence_proxy_async();
-        mbar_arrive(bar(BAR_A_FULL + kc));
+        __syncwarp();
+        if (lane == 0) {
+          const uint32_t a_full = leader_bar(C::BAR_A_FULL + abuf * MAX_KC + kc);
+          if constexpr (CG == 2) mbar_arrive_cluster(a_full); else mbar_arrive(a_full);
+        }
       }
+      s_zz[(it & (ZZ_SLOTS - 1)) * BM + row] = zz;
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(C::BAR_ZZ + (it & (ZZ_SLOTS - 1))));
     }
-  } else {
-    // ===================== epilogue: running max + candidate list per row =====================
-    const int part = warp & 3;                    // TMEM lane partition of this warp
+  } else if (warp < 12) {
+    // ===================== epilogue: flag masks per 32 codes, running max per row =====================
+    const int q = (warp - 4) >> 2;                // accumulator buffer this warp quad drains
+    const int part = warp & 3;                    // TMEM lane quarter this warp may access
     const int row = part * 32 + lane;
-    const uint32_t lane_addr = tmem_base + ((uint32_t)(part * 32) << 16);
+    const uint32_t taddr = tmem_base + ((uint32_t)(part * 32) << 16) + q * BN;
+    const uint32_t t_empty = leader_bar(C::BAR_T_EMPTY + q);
     const float emax = *emax_ptr;
-    const uint32_t list_addr = sbase + OFF_LIST + row * kCandCap * 8;
-    const int total_nt = my_tiles * NT;
-    // first use of both accumulator buffers
-    for (int b = 0; b < 2 && b < total_nt; ++b) {
-      tmem_init_buffer(lane_addr + b * BN, s_nhee, (b % NT) * BN);
+    const int per_tile = NT / 2;                  // N-tiles of one token tile that go through this buffer
+    if (my_tiles > 0) {
+      tmem_init_buffer(taddr, nhee, q * BN);
       tc_fence_before();
-      mbar_arrive(bar(BAR_T_EMPTY + b));
+      __syncwarp();
+      if (lane == 0) { if constexpr (CG == 2) mbar_arrive_cluster(t_empty); else mbar_arrive(t_empty); }
     }
-    uint32_t g = 0;
+    uint32_t u = 0;                               // N-tiles drained by this quad so far
     for (int it = 0; it < my_tiles; ++it) {
-      const int tile = blockIdx.x + it * gridDim.x;
-      const int t = tile * BM + row;
-      mbar_wait(bar(BAR_A_FULL + KC - 1), it & 1);   // |z|^2 of this tile is published
-      const float zz = s_zz[(it & 1) * BM + row];
-      // 2 * (2^-7 + 2^-15) |z| max|e|, 2 % slack, plus a few FP32 ulps of the distance itself
-      const float margin = 1.02f * 0.015686f * sqrtf(zz) * emax + 1.9e-6f * (zz + emax * emax);
-      float m = -INFINITY, thr = -INFINITY;
-      int cnt = 0;
-      bool overflow = false;
-      for (int nt = 0; nt < NT; ++nt, ++g) {
-        const uint32_t buf = g & 1;
-        mbar_wait(bar(BAR_T_FULL + buf), (g >> 1) & 1);
+      const int ptile = pair + it * npairs;
+      const long long t = ((long long)ptile * CG + rank) * BM + row;
+      const bool valid = t < N;
+      mbar_wait(bar(C::BAR_ZZ + (it & (ZZ_SLOTS - 1))), (it / ZZ_SLOTS) & 1);
+      const float zz = s_zz[(it & (ZZ_SLOTS - 1)) * BM + row];
+      const float margin = vq_margin(zz, emax);
+      float m = -INFINITY;
+      int n = 0;                                  // list entries written
+      uint2* my_list = list + ((size_t)(valid ? t : 0) * 2 + q) * kListCap;
+      for (int i = 0; i < per_tile; ++i, ++u) {
+        const int nt = 2 * i + q;
+        mbar_wait(bar(C::BAR_T_FULL + q), u & 1);
         tc_fence_after();
-        const uint32_t taddr = lane_addr + buf * BN;
+        uint32_t ra[32], rb[32];
+        TMEM_LD32(ra, taddr);
 #pragma unroll 1
-        for (int cc = 0; cc < BN / 32; ++cc) {
-          uint32_t r[32];
-          TMEM_LD32(r, taddr + cc * 32);
-          tmem_wait_ld();
-          const int col0 = nt * BN + cc * 32;
-#pragma unroll
-          for (int g8 = 0; g8 < 32; g8 += 8) {
-            const float m8 = fmaxf(fmaxf(fmaxf(__uint_as_float(r[g8]), __uint_as_float(r[g8 + 1])),
-                                         fmaxf(__uint_as_float(r[g8 + 2]), __uint_as_float(r[g8 + 3]))),
-                                   fmaxf(fmaxf(__uint_as_float(r[g8 + 4]), __uint_as_float(r[g8 + 5])),
-                                         fmaxf(__uint_as_float(r[g8 + 6]), __uint_as_float(r[g8 + 7]))));
-            if (__builtin_expect(m8 > thr, 0)) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float v = __uint_as_float(r[g8 + j]);
-                if (v > thr) {
-                  if (cnt == kCandCap) {
-                    // list full: drop entries that fell below the current threshold
-                    int w = 0;
-#pragma unroll 1
-                    for (int i = 0; i < kCandCap; ++i) {
-                      uint32_t ex, ey;
-                      asm volatile("ld.shared.v2.b32 {%0,%1}, [%2];" : "=r"(ex), "=r"(ey) : "r"(list_addr + i * 8));
-                      if (__uint_as_float(ex) >= thr) {
-                        asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(list_addr + w * 8), "r"(ex), "r"(ey));
-                        ++w;
-                      }
-                    }
-                    if (w == kCandCap) { overflow = true; w = kCandCap - 1; }
-                    cnt = w;
-                  }
-                  asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(list_addr + cnt * 8), "r"(r[g8 + j]),
-                               "r"((uint32_t)(col0 + g8 + j)));
-                  ++cnt;
-                  if (v > m) { m = v; thr = m - margin; }
-                }
-              }
+        for (int cc = 0; cc < BN / 32; cc += 2) {
+          TMEM_WAIT_LD32(ra);
+          TMEM_LD32(rb, taddr + (cc + 1) * 32);
+          {
+            float cm;
+            const uint32_t mask = chunk_flags(ra, margin, m, cm);
+            if (mask != 0u && valid) {
+              const uint32_t chunk = (uint32_t)(nt * (BN / 32) + cc);
+              my_list[min(n, kListCap - 1)] = make_uint2((__float_as_uint(cm) & 0xFFFFFF80u) | chunk, mask);
+              ++n;
+            }
+          }
+          TMEM_WAIT_LD32(rb);
+          if (cc + 2 < BN / 32) TMEM_LD32(ra, taddr + (cc + 2) * 32);
+          {
+            float cm;
+            const uint32_t mask = chunk_flags(rb, margin, m, cm);
+            if (mask != 0u && valid) {
+              const uint32_t chunk = (uint32_t)(nt * (BN / 32) + cc + 1);
+              my_list[min(n, kListCap - 1)] = make_uint2((__float_as_uint(cm) & 0xFFFFFF80u) | chunk, mask);
+              ++n;
             }
           }
         }
         // hand the buffer back, already holding -|e|^2/2 of the N-tile it will accumulate next
-        if ((int)g + 2 < total_nt) tmem_init_buffer(taddr, s_nhee, ((g + 2) % NT) * BN);
-        tc_fence_before();
-        mbar_arrive(bar(BAR_T_EMPTY + buf));
-      }
-      if (t < N) {
-        int out = 0;
-        if (overflow) {
-          out = -1;   // >= 16 codes inside the margin: the finish kernel scans the whole codebook for this token
-        } else {
-          for (int i = 0; i < cnt; ++i) {
-            uint32_t ex, ey;
-            asm volatile("ld.shared.v2.b32 {%0,%1}, [%2];" : "=r"(ex), "=r"(ey) : "r"(list_addr + i * 8));
-            if (__uint_as_float(ex) >= thr) cand[(size_t)t * kCandCap + out++] = (int)ey;
-          }
+        const bool more = (i + 1 < per_tile) || (it + 1 < my_tiles);
+        if (more) {
+          const int nt_next = (i + 1 < per_tile) ? nt + 2 : q;
+          tmem_init_buffer(taddr, nhee, nt_next * BN);
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) { if constexpr (CG == 2) mbar_arrive_cluster(t_empty); else mbar_arrive(t_empty); }
         }
-        count[t] = out;
+      }
+      if (valid) {
+        meta[(size_t)t * 4 + q] = __float_as_int(m);
+        meta[(size_t)t * 4 + 2 + q] = n > kListCap ? -1 : n;
+      }
+    }
+  } else if (warp == WARP_TMA) {
+    // ===================== TMA producer: this CTA's half of every codebook tile =====================
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_cb) : "memory");
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = 0; it < my_tiles; ++it)
+        for (int nt = 0; nt < NT; ++nt)
+          for (int kc = 0; kc < KC; ++kc) {
+            mbar_wait(bar(C::BAR_B_EMPTY + stage), phase ^ 1);
+            if (leader) mbar_arrive_expect_tx(bar(C::BAR_B_FULL + stage), CG * C::B_STAGE_BYTES);
+            tma_load_2d<CG>(sbase + C::OFF_B + stage * C::B_STAGE_BYTES, &tmap_cb, kc * BK,
+                            nt * BN + (int)rank * (BN / CG), leader_bar(C::BAR_B_FULL + stage));
+            if (++stage == C::NSTAGE) { stage = 0; phase ^= 1; }
+          }
+    }
+  } else if (leader) {
+    // ===================== MMA issuer (leader CTA, one thread) =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t g = 0;   // running N-tile counter -> TMEM buffer g & 1 (NT is even, so g & 1 == nt & 1)
+      for (int it = 0; it < my_tiles; ++it) {
+        const int abuf = it & 1;
+        for (int nt = 0; nt < NT; ++nt, ++g) {
+          const uint32_t buf = g & 1;
+          mbar_wait(bar(C::BAR_T_EMPTY + buf), (g >> 1) & 1);   // both CTAs drained + re-initialised this buffer
+          tc_fence_after();
+          const uint32_t tmem_d = tmem_base + buf * BN;
+          for (int kc = 0; kc < KC; ++kc) {
+            if (nt == 0) mbar_wait(bar(C::BAR_A_FULL + abuf * MAX_KC + kc), (it >> 1) & 1);
+            mbar_wait(bar(C::BAR_B_FULL + stage), phase);
+            tc_fence_after();
+            const uint32_t a_addr = sbase + C::OFF_A + abuf * A_BUF_BYTES + kc * A_CHUNK_BYTES;
+            const uint32_t b_addr = sbase + C::OFF_B + stage * C::B_STAGE_BYTES;
+#pragma unroll
+            for (int ks = 0; ks < BK / UK; ++ks)
+              umma_bf16<CG>(tmem_d, umma_desc_sw128(a_addr + ks * UK * 2), umma_desc_sw128(b_addr + ks * UK * 2), 1u);
+            umma_commit<CG>(bar(C::BAR_B_EMPTY + stage));     // frees the codebook stage when these MMAs retire
+            if (++stage == C::NSTAGE) { stage = 0; phase ^= 1; }
+          }
+          umma_commit<CG>(bar(C::BAR_T_FULL + buf));          // accumulator ready for the epilogue quads
+        }
+        umma_commit<CG>(bar(C::BAR_A_EMPTY + abuf));          // operand tile may be overwritten
       }
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if constexpr (CG == 2) cluster_sync();     // no CTA leaves while its peer may still touch its smem / barriers
+  if (warp == WARP_MMA) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
+    if constexpr (CG == 2)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
   }
 }
 
@@ -402,33 +512,60 @@ static bool device_is_sm100() {
 
 bool vq_tensor_supported(int D, int K) {
   if (D % BK != 0 || D < BK || D > MAX_KC * BK) return false;
-  if (K % BN != 0 || K < BN || K > MAX_K) return false;
+  if (K % (2 * BN) != 0 || K < 2 * BN || K > MAX_K) return false;   // two accumulator buffers alternate per N-tile
   return device_is_sm100();
 }
 
-int vq_tensor_search(const float* z, const __nv_bfloat16* cb16, int dpad16, const float* ee, const float* emax, int B,
-                     int D, int HW, int K, int* cand, int* count, unsigned* counters, cudaStream_t s) {
-  (void)counters;
+template <int CG>
+static int launch_search(const CUtensorMap& tmap, const float* z, const float* nhee, const float* emax, int N, int D,
+                         int HW, int K, int* meta, uint2* list, cudaStream_t s) {
+  using C = Cfg<CG>;
+  const int num_ptiles = (N + BM * CG - 1) / (BM * CG);
+  const int max_pairs = kNumSMs / CG;
+  const int grid = CG * (num_ptiles < max_pairs ? num_ptiles : max_pairs);
+  const int smem = C::SMEM_BYTES + 1024;
+  if (cudaFuncSetAttribute(vq_tensor_search_kernel<CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) !=
+      cudaSuccess)
+    return DCVIC_ERR_CUDA;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(NTHREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (cudaLaunchKernelEx(&cfg, vq_tensor_search_kernel<CG>, tmap, z, nhee, emax, N, D, HW, K, num_ptiles, meta,
+                         list) != cudaSuccess)
+    return DCVIC_ERR_CUDA;
+  return dcvic_launch_status();
+}
+
+int vq_tensor_search(const float* z, const __nv_bfloat16* cb16, const float* nhee, const float* emax, int B, int D,
+                     int HW, int K, int* meta, uint2* list, cudaStream_t s) {
   if (!vq_tensor_supported(D, K)) return DCVIC_ERR_UNSUPPORTED;
+  static const int cta_group = [] {
+    const char* e = getenv("DCVIC_VQ_CTA_GROUP");
+    return (e && e[0] == '1') ? 1 : 2;
+  }();
   EncodeTiledFn encode = encode_tiled_fn();
   if (!encode) return DCVIC_ERR_DEVICE;
   CUtensorMap tmap;
   const cuuint64_t gdim[2] = {(cuuint64_t)D, (cuuint64_t)K};
-  const cuuint64_t gstride[1] = {(cuuint64_t)dpad16 * sizeof(__nv_bfloat16)};
-  const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BN};
+  const cuuint64_t gstride[1] = {(cuuint64_t)D * sizeof(__nv_bfloat16)};
+  const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)(BN / cta_group)};
   const cuuint32_t estr[2] = {1, 1};
   if (encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(cb16), gdim, gstride, box, estr,
              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
     return DCVIC_ERR_CUDA;
   const int N = B * HW;
-  const int num_tiles = (N + BM - 1) / BM;
-  const int grid = num_tiles < kNumSMs ? num_tiles : kNumSMs;
-  const int smem = SMEM_BYTES + 1024;
-  if (cudaFuncSetAttribute(vq_tensor_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
-    return DCVIC_ERR_CUDA;
-  vq_tensor_search_kernel<<<grid, NTHREADS, smem, s>>>(tmap, z, ee, emax, N, D, HW, K, num_tiles, cand, count);
-  return dcvic_launch_status();
+  return cta_group == 2 ? launch_search<2>(tmap, z, nhee, emax, N, D, HW, K, meta, list, s)
+                        : launch_search<1>(tmap, z, nhee, emax, N, D, HW, K, meta, list, s);
 }
 
 }  // namespace dcvic
