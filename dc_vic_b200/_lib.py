@@ -48,11 +48,13 @@ SIGNATURES = {
 
 
 def load(path: str = LIB_PATH):
-    """Load the library (once).  Raises RuntimeError when it has not been built."""
+    """Load the library (once).  Raises RuntimeError when it has not been built.
+    DCVIC_B200_LIB overrides the path (used by tools/trace_run.py to load the -DDCVIC_TRACE build)."""
     global _lib
     with _lock:
         if _lib is not None:
             return _lib
+        path = os.environ.get("DCVIC_B200_LIB", path)
         if not os.path.exists(path):
             raise RuntimeError(
                 f"{path} not found: the CUDA extension is not built (run `python -m dc_vic_b200.build`). "

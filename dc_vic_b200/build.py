@@ -34,21 +34,24 @@ def is_stale() -> bool:
     return any(os.path.exists(d) and os.path.getmtime(d) > built for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not is_stale():
+def build(force: bool = False, verbose: bool = False, trace: bool = False) -> str:
+    """trace=True builds lib/libdcvic_b200_trace.so with -DDCVIC_TRACE (role timing in the tcgen05 kernel;
+    a measurement aid for tools/trace_run.py, never loaded by the package itself)."""
+    out = LIB_PATH.replace(".so", "_trace.so") if trace else LIB_PATH
+    if not trace and not force and not is_stale():
         return LIB_PATH
     os.makedirs(LIB_DIR, exist_ok=True)
     srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
-    flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")]
-    cmd = [_nvcc()] + flags + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + srcs
+    flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")] + (["-DDCVIC_TRACE"] if trace else [])
+    cmd = [_nvcc()] + flags + (["-Xptxas", "-v"] if verbose else []) + ["-o", out] + srcs
     proc = subprocess.run(cmd, capture_output=True, text=True)
     if proc.returncode != 0:
         sys.stderr.write(proc.stdout + proc.stderr)
         raise RuntimeError("nvcc failed building libdcvic_b200.so")
     if verbose:
         sys.stderr.write(proc.stderr)
-    return LIB_PATH
+    return out
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, trace="--trace" in sys.argv))

@@ -21,7 +21,7 @@ static inline bool vq_narrow_ok(int D) { return D == 4 || D == 8; }
 
 extern "C" int dcvic_vq_path(int D, int K, int flags) {
   if (D <= 0 || K <= 0) return DCVIC_ERR_BAD_ARG;
-  if (!(flags & DCVIC_VQ_FORCE_EXACT) && vq_tensor_supported(D, K)) return 2;
+  if (!(flags & (DCVIC_VQ_FORCE_EXACT | DCVIC_VQ_RAGGED_HW)) && vq_tensor_supported(D, K)) return 2;
   if (flags & DCVIC_VQ_FORCE_TENSOR) return DCVIC_ERR_UNSUPPORTED;
   if (vq_narrow_ok(D) && !(flags & DCVIC_VQ_FORCE_EXACT)) return 0;
   return D <= 1024 ? 1 : DCVIC_ERR_UNSUPPORTED;
@@ -40,9 +40,11 @@ extern "C" int dcvic_vq_forward(const float* z_nchw, const float* codebook, int 
   DCVIC_CHECK_ARG(z_nchw && codebook && zq_nchw && idx && loss && workspace);
   DCVIC_CHECK_ARG(B > 0 && D > 0 && H > 0 && W > 0 && K > 0);
   if ((long long)B * H * W > 0x7fffffffLL || (long long)K * D > 0x7fffffffLL) return DCVIC_ERR_UNSUPPORTED;
-  const int path = dcvic_vq_path(D, K, flags);
-  if (path < 0) return path;
   const int HW = H * W, N = B * HW;
+  // the tensor search reads 4 tokens per 16-byte load: needs H*W % 4 == 0 and a 16-byte aligned z
+  const bool ragged = (HW & 3) != 0 || (reinterpret_cast<uintptr_t>(z_nchw) & 15) != 0;
+  const int path = dcvic_vq_path(D, K, flags | (ragged ? DCVIC_VQ_RAGGED_HW : 0));
+  if (path < 0) return path;
   const VqWorkspace w = vq_workspace_layout(B, D, HW, K);
   if (ws_bytes < w.total) return DCVIC_ERR_WORKSPACE;
   if (reinterpret_cast<uintptr_t>(workspace) & 255) return DCVIC_ERR_BAD_ARG;
@@ -70,7 +72,7 @@ extern "C" int dcvic_vq_forward(const float* z_nchw, const float* codebook, int 
     const bool do_search = !(flags & DCVIC_VQ_STAGE_FINISH_ONLY);
     const bool do_finish = !(flags & DCVIC_VQ_STAGE_SEARCH_ONLY);
     if (path == 2) {
-      if (do_search) rc = vq_tensor_search(z_nchw, cb16, nhee, emax, B, D, HW, K, meta, list, s);
+      if (do_search) rc = vq_tensor_search(z_nchw, cb16, emax, B, D, HW, K, meta, list, s);
       if (rc) return rc;
       if (do_finish)
         rc = vq_finish(z_nchw, codebook, ee, emax, nullptr, meta, list, B, D, HW, K, beta, legacy, zq_nchw, idx, loss,

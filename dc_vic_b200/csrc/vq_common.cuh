@@ -8,6 +8,7 @@ namespace dcvic {
 constexpr int kFinishTokens = 32;     // tokens per CTA in the finish (re-rank + gather + STE + loss) kernel
 constexpr int kListCap = 16;          // (chunk key, flag mask) entries per token and accumulator buffer
 constexpr int kChunk = 32;            // codes per flag mask (one tcgen05.ld.32x32b.x32 per row)
+constexpr int kCb16Pad = 64;          // extra BF16 codebook columns: a 3-way split of -|e|^2/2 in the first three
 constexpr int kCandMax = 24;          // FP32 re-rank candidates per token before falling back to a full scan
 
 // What the tensor search hands to the finish kernel, per token t:
@@ -37,7 +38,7 @@ inline VqWorkspace vq_workspace_layout(int B, int D, int HW, int K) {
   w.off_cand = take(N * sizeof(int));
   w.off_meta = take(N * 4 * sizeof(int));
   w.off_list = take(N * 2 * kListCap * sizeof(uint2));
-  w.off_cb16 = take((size_t)K * D * sizeof(__nv_bfloat16));
+  w.off_cb16 = take((size_t)K * (D + kCb16Pad) * sizeof(__nv_bfloat16));
   w.total = o;
   w.n_tokens = (int)N;
   return w;
@@ -71,7 +72,7 @@ int vq_v1_extras(const int64_t* idx, int N, int K, float* onehot, float* perplex
 
 // vq_tcgen05.cu
 bool vq_tensor_supported(int D, int K);
-int vq_tensor_search(const float* z, const __nv_bfloat16* cb16, const float* nhee, const float* emax, int B, int D,
-                     int HW, int K, int* meta, uint2* list, cudaStream_t s);
+int vq_tensor_search(const float* z, const __nv_bfloat16* cb16, const float* emax, int B, int D, int HW, int K,
+                     int* meta, uint2* list, cudaStream_t s);
 
 }  // namespace dcvic

@@ -14,9 +14,9 @@
 namespace dcvic {
 
 // ------------------------------------------------------------------ codebook prepare
-// One warp per code.  ee[k] = sum_c fl(e^2) (lane-strided partials + xor tree), nhee[k] = -ee[k]/2
-// (what the tensor search pre-loads into its accumulators), emax = max_k |e_k| (atomicMax on the
-// non-negative float's bit pattern), cb16[k][0..D) = bf16(e).
+// One warp per code.  ee[k] = sum_c fl(e^2) (lane-strided partials + xor tree), nhee[k] = -ee[k]/2,
+// emax = max_k |e_k| (atomicMax on the non-negative float's bit pattern), cb16[k][0..D) = bf16(e),
+// cb16[k][D..D+3) = three-way BF16 split of -ee[k]/2 (exact: 3 x 8 significant bits), rest of the pad zero.
 __global__ void __launch_bounds__(256) vq_prepare_kernel(const float* __restrict__ E, int K, int D,
                                                           float* __restrict__ ee, float* __restrict__ nhee,
                                                           float* __restrict__ emax,
@@ -25,17 +25,28 @@ __global__ void __launch_bounds__(256) vq_prepare_kernel(const float* __restrict
   const int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (k >= K) return;
   const float* row = E + (size_t)k * D;
+  const size_t ld = (size_t)(D + kCb16Pad);
   float acc = 0.f;
   for (int c = lane; c < D; c += 32) {
     const float v = row[c];
     acc = __fadd_rn(acc, __fmul_rn(v, v));
-    if (cb16) cb16[(size_t)k * D + c] = __float2bfloat16_rn(v);
+    if (cb16) cb16[(size_t)k * ld + c] = __float2bfloat16_rn(v);
   }
   acc = warp_sum(acc);
   if (lane == 0) {
     ee[k] = acc;
     nhee[k] = -0.5f * acc;
     atomicMax(reinterpret_cast<unsigned*>(emax), __float_as_uint(sqrtf(acc) * 1.0000002f));
+  }
+  if (cb16) {
+    const float v = -0.5f * acc;
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    const float r1 = v - __bfloat162float(h);
+    const __nv_bfloat16 m = __float2bfloat16_rn(r1);
+    const float r2 = r1 - __bfloat162float(m);
+    const __nv_bfloat16 l = __float2bfloat16_rn(r2);
+    for (int c = lane; c < kCb16Pad; c += 32)
+      cb16[(size_t)k * ld + D + c] = c == 0 ? h : (c == 1 ? m : (c == 2 ? l : __float2bfloat16_rn(0.f)));
   }
 }
 

@@ -9,18 +9,22 @@
 //
 // Structure: persistent CTA pairs (cta_group::2, UMMA 256x256x16), each CTA owning 128 tokens of a
 // 256-token pair tile and half of every codebook tile (CG = 1 is the same code on single CTAs).
-//   warps 0-3   A producers: read z (FP32, coalesced along tokens), convert to BF16, write the K-major
-//               SWIZZLE_128B operand tile (double-buffered: tile i+1 loads while tile i multiplies),
-//               publish |z|^2 per token
-//   warps 4-7   epilogue of accumulator buffer 0 (N-tiles 0, 2, ..), warps 8-11 of buffer 1:
-//               tcgen05.ld 32 scores per row at a time (software pipelined), running max, one flag
-//               mask per 32 codes (FADD on the FMA pipe + funnel shift, branch-free), append
-//               {chunk max | chunk id, mask} to the token's list in global memory when non-empty, then
-//               re-initialise the buffer with -|e|^2/2 of the N-tile it accumulates next
-//   warp 12     TMA producer: this CTA's half of the BF16 codebook tile [256/CG codes x 64 ch]
+//   warps 0-7   A producers: read z (FP32, 16-byte loads of 4 consecutive tokens, two 8-load sets in
+//               flight per thread, next-next tile prefetched into L2 with cp.async.bulk.prefetch),
+//               convert to BF16, write the K-major SWIZZLE_128B operand tile (double-buffered: tile i+1
+//               loads while tile i multiplies), publish |z|^2 per token
+//   warps 8-15  epilogue: warps 8-11 take columns 0-127 of every accumulator, warps 12-15 columns
+//               128-255.  tcgen05.ld 32 scores per row at a time (software pipelined), running max, one
+//               flag mask per 32 codes (FADD on the FMA pipe + funnel shift, branch-free), append
+//               {chunk max | chunk id, mask} to the token's list in global memory when non-empty.  The
+//               accumulator goes back to the MMA as soon as its last scores are in registers.
+//   warp 16     TMA producer: this CTA's half of the BF16 codebook tile [256/CG codes x 64 ch]
 //               (SWIZZLE_128B) into a 4-stage ring; completion is signalled on the LEADER's barrier
-//   warp 13     TMEM allocator; in the leader CTA one thread issues every tcgen05.mma of the pair and
+//   warp 17     TMEM allocator; in the leader CTA one thread issues every tcgen05.mma of the pair and
 //               multicasts the commits (stage free, accumulator full, operand tile free) to both CTAs
+// -|e|^2/2 enters through the contraction itself: the BF16 codebook carries one extra 64-column chunk
+// whose first three columns are a 3-way BF16 split of -|e_k|^2/2, multiplied (one K=16 step, which
+// also zero-initialises the accumulator) with a constant operand chunk of ones.
 // Reference semantics: taming/modules/vqvae/quantize.py:280-284 (distance + argmin).
 #include "vq_common.cuh"
 #include <cuda.h>
@@ -37,8 +41,9 @@ constexpr int MAX_KC = 4;        // e_dim <= 256
 constexpr int A_CHUNK_BYTES = BM * BK * 2;            // 16 KB
 constexpr int A_BUF_BYTES = MAX_KC * A_CHUNK_BYTES;   // 64 KB
 constexpr int MAX_K = 4096;
-constexpr int NTHREADS = 448;
-constexpr int WARP_TMA = 12, WARP_MMA = 13;
+constexpr int NTHREADS = 576;
+constexpr int NPROD = 8;                       // A-producer warps (warps 0-7); epilogue warps 8-15
+constexpr int WARP_TMA = 16, WARP_MMA = 17;
 constexpr int ZZ_SLOTS = 4;
 
 template <int CG>
@@ -47,9 +52,10 @@ struct Cfg {
   static constexpr int NSTAGE = CG == 2 ? 4 : 2;
   // dynamic shared memory map (base aligned to 1024 B)
   static constexpr int OFF_A = 0;                                  // [2][MAX_KC][BM x 128 B]
-  static constexpr int OFF_B = OFF_A + 2 * A_BUF_BYTES;            // [NSTAGE][BN/CG x 128 B]
-  static constexpr int OFF_ZZ = OFF_B + NSTAGE * B_STAGE_BYTES;    // [ZZ_SLOTS][BM] float
-  static constexpr int OFF_BAR = OFF_ZZ + ZZ_SLOTS * BM * 4;
+  static constexpr int OFF_APAD = OFF_A + 2 * A_BUF_BYTES;         // [BM x 128 B] constant: ones in columns 0-2
+  static constexpr int OFF_B = OFF_APAD + A_CHUNK_BYTES;           // [NSTAGE][BN/CG x 128 B]
+  static constexpr int OFF_ZZ = OFF_B + NSTAGE * B_STAGE_BYTES;    // [ZZ_SLOTS][2 channel halves][BM] float
+  static constexpr int OFF_BAR = OFF_ZZ + 2 * ZZ_SLOTS * BM * 4;
   // barrier slots (8 bytes each)
   static constexpr int BAR_B_FULL = 0;                       // [NSTAGE]   leader only
   static constexpr int BAR_B_EMPTY = BAR_B_FULL + NSTAGE;    // [NSTAGE]
@@ -89,7 +95,7 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 }
 // arrive on a barrier given by its shared::cluster address (possibly in the peer CTA)
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
@@ -198,17 +204,6 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
                :                                                                                                   \
                : "memory")
 
-#define TMEM_ST32(taddr, r)                                                                                        \
-  asm volatile(                                                                                                    \
-      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,"   \
-      "%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};" ::"r"(taddr),                                 \
-      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), \
-      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),   \
-      "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),   \
-      "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])                                                               \
-      : "memory")
-
-__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   uint32_t r;
@@ -216,27 +211,9 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   return r;
 }
 
-// write -|e|^2/2 of codes [k0, k0+256) into one TMEM accumulator buffer (this warp's 32 lanes);
-// every lane reads the same addresses (L1 broadcast)
-__device__ __forceinline__ void tmem_init_buffer(uint32_t taddr_buf, const float* __restrict__ nhee, int k0) {
-#pragma unroll 1
-  for (int cc = 0; cc < BN / 32; ++cc) {
-    uint32_t r[32];
-    const float4* src = reinterpret_cast<const float4*>(nhee + k0 + cc * 32);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float4 v = __ldg(src + j);
-      r[4 * j] = __float_as_uint(v.x); r[4 * j + 1] = __float_as_uint(v.y);
-      r[4 * j + 2] = __float_as_uint(v.z); r[4 * j + 3] = __float_as_uint(v.w);
-    }
-    TMEM_ST32(taddr_buf + cc * 32, r);
-  }
-  tmem_wait_st();
-}
-
 // One 32-code chunk of one row: chunk maximum, running maximum, flag mask of the scores within
-// `margin` of the running maximum.  Flags: d = s - thr on the FMA pipe, sign bits collected with
-// funnel shifts (bit j of the result <=> s[j] >= thr).
+// `margin` of the running maximum (which already includes this chunk).  Flags: d = s - thr on the FMA
+// pipe, sign bits collected with funnel shifts (bit j of the result <=> s[j] >= thr).
 __device__ __forceinline__ uint32_t chunk_flags(const uint32_t (&r)[32], float margin, float& m, float& cm_out) {
   float a[8];
 #pragma unroll
@@ -249,9 +226,9 @@ __device__ __forceinline__ uint32_t chunk_flags(const uint32_t (&r)[32], float m
   const float thr = m - margin;
   uint32_t neg[4] = {0u, 0u, 0u, 0u};   // four independent chains of 8 sign bits
 #pragma unroll
-  for (int c = 0; c < 4; ++c)
+  for (int j = 7; j >= 0; --j)
 #pragma unroll
-    for (int j = 7; j >= 0; --j) {
+    for (int c = 0; c < 4; ++c) {
       const float d = __fsub_rn(__uint_as_float(r[c * 8 + j]), thr);
       neg[c] = __funnelshift_l(__float_as_uint(d), neg[c], 1);   // (neg << 1) | sign(d)
     }
@@ -263,11 +240,24 @@ __device__ __forceinline__ uint32_t chunk_flags(const uint32_t (&r)[32], float m
 
 using namespace tc;
 
+// Optional role timing (build with -DDCVIC_TRACE; tools/trace_run.py): cycles each warp role spends
+// waiting / working, summed over the launch, per CTA.
+#ifdef DCVIC_TRACE
+__device__ unsigned long long g_trace[kNumSMs * 2][16];
+#define TR_NOW() clock64()
+#define TR_ADD(acc, t0) acc += clock64() - (t0)
+#define TR_PUT(slot, v) g_trace[blockIdx.x][slot] = (v)
+#else
+#define TR_NOW() 0ull
+#define TR_ADD(acc, t0) (void)(t0)
+#define TR_PUT(slot, v)
+#endif
+
 template <int CG>
 __global__ void __launch_bounds__(NTHREADS, 1)
 vq_tensor_search_kernel(const __grid_constant__ CUtensorMap tmap_cb, const float* __restrict__ z,
-                        const float* __restrict__ nhee, const float* __restrict__ emax_ptr, int N, int D, int HW,
-                        int K, int num_ptiles, int* __restrict__ meta, uint2* __restrict__ list) {
+                        const float* __restrict__ emax_ptr, int N, int D, int HW, int K, int num_ptiles,
+                        int* __restrict__ meta, uint2* __restrict__ list) {
   using C = Cfg<CG>;
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B operands need 1024-byte alignment (same adjustment in both CTAs of a pair)
@@ -275,7 +265,7 @@ vq_tensor_search_kernel(const __grid_constant__ CUtensorMap tmap_cb, const float
   const uint32_t sbase = smem_u32(smem);
   const uint32_t bar0 = sbase + C::OFF_BAR;
   auto bar = [&](int slot) { return bar0 + slot * 8; };
-  float* s_zz = reinterpret_cast<float*>(smem + C::OFF_ZZ);       // [ZZ_SLOTS][BM]
+  float* s_zz = reinterpret_cast<float*>(smem + C::OFF_ZZ);
   volatile uint32_t* s_tmem = reinterpret_cast<volatile uint32_t*>(smem + C::OFF_TMEM_PTR);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -283,22 +273,32 @@ vq_tensor_search_kernel(const __grid_constant__ CUtensorMap tmap_cb, const float
   const bool leader = rank == 0;
   const int pair = blockIdx.x / CG, npairs = gridDim.x / CG;
   const int KC = D / BK;               // channel chunks
-  const int NT = K / BN;               // N-tiles per token tile (even)
+  const int NT = K / BN;               // N-tiles per token tile
   const int my_tiles = (num_ptiles - pair + npairs - 1) / npairs;
   // barriers that live in the leader CTA, as shared::cluster addresses
   auto leader_bar = [&](int slot) { return CG == 2 ? map_to_cta(bar(slot), 0) : bar(slot); };
+  auto arrive_leader = [&](uint32_t b) { if constexpr (CG == 2) mbar_arrive_cluster(b); else mbar_arrive(b); };
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < C::NSTAGE; ++s) { mbar_init(bar(C::BAR_B_FULL + s), 1); mbar_init(bar(C::BAR_B_EMPTY + s), 1); }
-    for (int c = 0; c < 2 * MAX_KC; ++c) mbar_init(bar(C::BAR_A_FULL + c), 4 * CG);
+    for (int c = 0; c < 2 * MAX_KC; ++c) mbar_init(bar(C::BAR_A_FULL + c), NPROD * CG);
     for (int b = 0; b < 2; ++b) {
       mbar_init(bar(C::BAR_A_EMPTY + b), 1);
       mbar_init(bar(C::BAR_T_FULL + b), 1);
-      mbar_init(bar(C::BAR_T_EMPTY + b), 4 * CG);
+      mbar_init(bar(C::BAR_T_EMPTY + b), 8 * CG);
     }
-    for (int s = 0; s < ZZ_SLOTS; ++s) mbar_init(bar(C::BAR_ZZ + s), 4);
+    for (int s = 0; s < ZZ_SLOTS; ++s) mbar_init(bar(C::BAR_ZZ + s), NPROD);
     fence_barrier_init();
   }
+  // constant operand chunk for the -|e|^2/2 step: bf16 1.0 in columns 0-2 of every row.  Columns 0-7 sit in
+  // 16-byte piece (0 ^ (row & 7)) of the row (SWIZZLE_128B), all other pieces are zero.
+  for (int i = threadIdx.x; i < BM * 8; i += NTHREADS) {
+    const int row = i >> 3, piece = i & 7;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (piece == (row & 7)) { v.x = 0x3F803F80u; v.y = 0x00003F80u; }
+    *reinterpret_cast<uint4*>(smem + C::OFF_APAD + row * 128 + piece * 16) = v;
+  }
+  fence_proxy_async();
   if (warp == WARP_MMA) {
     if constexpr (CG == 2) {
       asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + C::OFF_TMEM_PTR),
@@ -312,120 +312,169 @@ vq_tensor_search_kernel(const __grid_constant__ CUtensorMap tmap_cb, const float
   }
   tc_fence_before();
   __syncthreads();
-  if constexpr (CG == 2) cluster_sync();     // peer's barriers are initialised before anyone arrives remotely
+  if constexpr (CG == 2) cluster_sync();     // peer's barriers / constant chunk are in place before anyone uses them
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
 
-  if (warp < 4) {
+  if (warp < NPROD) {
     // ===================== A producers: FP32 NCHW -> BF16 K-major SWIZZLE_128B =====================
-    const int row = warp * 32 + lane;
+    // Warp w owns tokens [32(w&3), +32) of the tile and channel half ch = w>>2 of every 64-channel chunk.
+    // lane = cg*8 + tq: token quad tq (4 consecutive tokens, one 16-byte load per channel) and channel
+    // group cg.  One step = 8 channels x 4 tokens per thread (8 LDG.128, 512 contiguous bytes per
+    // channel and warp); two steps are in flight per thread.  The smem store of one (token, 8 channels)
+    // 16-byte piece hits 8 distinct swizzled bank groups across the warp (4 wavefronts, the minimum
+    // for 512 bytes).
+    const int tq = lane & 7, cg = lane >> 3, ch = warp >> 2;
+    const int row0 = (warp & 3) * 32 + tq * 4;
+    const int g = cg + 4 * ch;                  // 8-channel group inside a 64-channel chunk
+    const size_t sHW = (size_t)HW;
+    // L2 prefetch of one whole tile: thread c asks for channel row c (up to 512 contiguous bytes)
+    auto prefetch_tile = [&](int it) {
+      if (it >= my_tiles) return;
+      const long long tn = ((long long)(pair + it * npairs) * CG + rank) * BM;
+      if (tn >= N) return;
+      const long long hw0 = tn % HW;
+      long long run = HW - hw0;                  // tokens of this tile before the image ends
+      if (run > BM) run = BM;
+      if (run > N - tn) run = N - tn;
+      const float* zb = z + (size_t)(tn / HW) * D * HW + (size_t)hw0;
+      for (int c = threadIdx.x; c < D; c += NPROD * 32) {
+        const float* pp = zb + (size_t)c * sHW;
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(pp), "r"((uint32_t)run * 4u) : "memory");
+      }
+    };
+    prefetch_tile(0);
+    prefetch_tile(1);
+    [[maybe_unused]] unsigned long long tr_wait = 0, tr_work = 0;
     for (int it = 0; it < my_tiles; ++it) {
       const int ptile = pair + it * npairs;
-      const long long t = ((long long)ptile * CG + rank) * BM + row;
-      const bool valid = t < N;
-      const float* zp = z + (valid ? ((size_t)(t / HW) * D * HW + (size_t)(t % HW)) : 0);
+      const long long t = ((long long)ptile * CG + rank) * BM + row0;
+      const bool valid = t < N;                 // N and HW are multiples of 4: a quad is valid as a whole
+      const float* zc = z + (valid ? ((size_t)(t / HW) * D * HW + (size_t)(t % HW) + (size_t)(g * 8) * sHW) : 0);
       const int abuf = it & 1;
+      unsigned long long tr0 = TR_NOW();
       mbar_wait(bar(C::BAR_A_EMPTY + abuf), ((it >> 1) & 1) ^ 1);
-      float zz = 0.f;
-      for (int kc = 0; kc < KC; ++kc) {
-        float v[BK];
+      TR_ADD(tr_wait, tr0);
+      tr0 = TR_NOW();
+      float zz4[4] = {0.f, 0.f, 0.f, 0.f};
+      uint8_t* abase = smem + C::OFF_A + abuf * A_BUF_BYTES + row0 * 128;
+      auto load_step = [&](float4 (&v)[8], int kc) {
+        const float* p = zc + (size_t)(BK * kc) * sHW;
 #pragma unroll
-        for (int j = 0; j < BK; ++j) v[j] = valid ? __ldg(zp + (size_t)(kc * BK + j) * HW) : 0.f;
-        uint8_t* arow = smem + C::OFF_A + abuf * A_BUF_BYTES + kc * A_CHUNK_BYTES + row * 128;
+        for (int k = 0; k < 8; ++k)
+          v[k] = valid ? ldg_stream(reinterpret_cast<const float4*>(p + (size_t)k * sHW)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      };
+      auto store_step = [&](const float4 (&v)[8], int kc) {
+        uint8_t* a = abase + kc * A_CHUNK_BYTES;
+        const float* f = reinterpret_cast<const float*>(v);     // f[4k + i] = channel k, token i
 #pragma unroll
-        for (int c16 = 0; c16 < 8; ++c16) {
+        for (int i = 0; i < 4; ++i) {
           uint4 pk;
-          pk.x = pack_bf16x2(v[c16 * 8 + 0], v[c16 * 8 + 1]);
-          pk.y = pack_bf16x2(v[c16 * 8 + 2], v[c16 * 8 + 3]);
-          pk.z = pack_bf16x2(v[c16 * 8 + 4], v[c16 * 8 + 5]);
-          pk.w = pack_bf16x2(v[c16 * 8 + 6], v[c16 * 8 + 7]);
-          *reinterpret_cast<uint4*>(arow + ((c16 ^ (row & 7)) << 4)) = pk;
-        }
+          pk.x = pack_bf16x2(f[0 + i], f[4 + i]);
+          pk.y = pack_bf16x2(f[8 + i], f[12 + i]);
+          pk.z = pack_bf16x2(f[16 + i], f[20 + i]);
+          pk.w = pack_bf16x2(f[24 + i], f[28 + i]);
+          const int r7 = (row0 + i) & 7;
+          *reinterpret_cast<uint4*>(a + i * 128 + ((g ^ r7) << 4)) = pk;
 #pragma unroll
-        for (int j = 0; j < BK; ++j) zz = fmaf(v[j], v[j], zz);
+          for (int k = 0; k < 8; ++k) zz4[i] = fmaf(f[4 * k + i], f[4 * k + i], zz4[i]);
+        }
         fence_proxy_async();
         __syncwarp();
-        if (lane == 0) {
-          const uint32_t a_full = leader_bar(C::BAR_A_FULL + abuf * MAX_KC + kc);
-          if constexpr (CG == 2) mbar_arrive_cluster(a_full); else mbar_arrive(a_full);
-        }
+        if (lane == 0) arrive_leader(leader_bar(C::BAR_A_FULL + abuf * MAX_KC + kc));
+      };
+      float4 va[8], vb[8];
+      load_step(va, 0);
+      if (KC > 1) load_step(vb, 1);
+      prefetch_tile(it + 2);                    // behind this tile's own loads in the memory queues
+#pragma unroll 1
+      for (int kc = 0; kc < KC; kc += 2) {
+        store_step(va, kc);
+        if (kc + 2 < KC) load_step(va, kc + 2);
+        if (kc + 1 < KC) store_step(vb, kc + 1);
+        if (kc + 3 < KC) load_step(vb, kc + 3);
       }
-      s_zz[(it & (ZZ_SLOTS - 1)) * BM + row] = zz;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        zz4[i] += __shfl_xor_sync(0xffffffffu, zz4[i], 8);
+        zz4[i] += __shfl_xor_sync(0xffffffffu, zz4[i], 16);
+      }
+      if (cg == 0)
+        *reinterpret_cast<float4*>(s_zz + ((it & (ZZ_SLOTS - 1)) * 2 + ch) * BM + row0) =
+            make_float4(zz4[0], zz4[1], zz4[2], zz4[3]);
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(C::BAR_ZZ + (it & (ZZ_SLOTS - 1))));
+      TR_ADD(tr_work, tr0);
     }
-  } else if (warp < 12) {
+    if (threadIdx.x == 0) { TR_PUT(0, tr_wait); TR_PUT(1, tr_work); }
+  } else if (warp < NPROD + 8) {
     // ===================== epilogue: flag masks per 32 codes, running max per row =====================
-    const int q = (warp - 4) >> 2;                // accumulator buffer this warp quad drains
+    const int q = (warp - NPROD) >> 2;            // column half of every accumulator this warp quad drains
     const int part = warp & 3;                    // TMEM lane quarter this warp may access
     const int row = part * 32 + lane;
-    const uint32_t taddr = tmem_base + ((uint32_t)(part * 32) << 16) + q * BN;
-    const uint32_t t_empty = leader_bar(C::BAR_T_EMPTY + q);
+    const uint32_t tlane = tmem_base + ((uint32_t)(part * 32) << 16) + q * (BN / 2);
     const float emax = *emax_ptr;
-    const int per_tile = NT / 2;                  // N-tiles of one token tile that go through this buffer
-    if (my_tiles > 0) {
-      tmem_init_buffer(taddr, nhee, q * BN);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) { if constexpr (CG == 2) mbar_arrive_cluster(t_empty); else mbar_arrive(t_empty); }
-    }
-    uint32_t u = 0;                               // N-tiles drained by this quad so far
+    uint32_t g = 0;                               // running N-tile counter (same sequence as the MMA issuer)
+    [[maybe_unused]] unsigned long long tr_zz = 0, tr_full = 0, tr_proc = 0;
     for (int it = 0; it < my_tiles; ++it) {
       const int ptile = pair + it * npairs;
       const long long t = ((long long)ptile * CG + rank) * BM + row;
       const bool valid = t < N;
+      unsigned long long tr0 = TR_NOW();
       mbar_wait(bar(C::BAR_ZZ + (it & (ZZ_SLOTS - 1))), (it / ZZ_SLOTS) & 1);
-      const float zz = s_zz[(it & (ZZ_SLOTS - 1)) * BM + row];
+      TR_ADD(tr_zz, tr0);
+      const float zz = s_zz[(it & (ZZ_SLOTS - 1)) * 2 * BM + row] + s_zz[((it & (ZZ_SLOTS - 1)) * 2 + 1) * BM + row];
       const float margin = vq_margin(zz, emax);
       float m = -INFINITY;
       int n = 0;                                  // list entries written
       uint2* my_list = list + ((size_t)(valid ? t : 0) * 2 + q) * kListCap;
-      for (int i = 0; i < per_tile; ++i, ++u) {
-        const int nt = 2 * i + q;
-        mbar_wait(bar(C::BAR_T_FULL + q), u & 1);
+      for (int nt = 0; nt < NT; ++nt, ++g) {
+        const uint32_t buf = g & 1;
+        tr0 = TR_NOW();
+        mbar_wait(bar(C::BAR_T_FULL + buf), (g >> 1) & 1);
+        TR_ADD(tr_full, tr0);
+        tr0 = TR_NOW();
         tc_fence_after();
-        uint32_t ra[32], rb[32];
-        TMEM_LD32(ra, taddr);
-#pragma unroll 1
-        for (int cc = 0; cc < BN / 32; cc += 2) {
-          TMEM_WAIT_LD32(ra);
-          TMEM_LD32(rb, taddr + (cc + 1) * 32);
-          {
-            float cm;
-            const uint32_t mask = chunk_flags(ra, margin, m, cm);
-            if (mask != 0u && valid) {
-              const uint32_t chunk = (uint32_t)(nt * (BN / 32) + cc);
-              my_list[min(n, kListCap - 1)] = make_uint2((__float_as_uint(cm) & 0xFFFFFF80u) | chunk, mask);
-              ++n;
-            }
+        const uint32_t taddr = tlane + buf * BN;
+        const uint32_t chunk0 = (uint32_t)(nt * (BN / 32) + q * (BN / 64));
+        auto emit = [&](uint32_t mask, float cm, uint32_t chunk) {
+          if (mask != 0u && valid) {
+            my_list[min(n, kListCap - 1)] = make_uint2((__float_as_uint(cm) & 0xFFFFFF80u) | chunk, mask);
+            ++n;
           }
-          TMEM_WAIT_LD32(rb);
-          if (cc + 2 < BN / 32) TMEM_LD32(ra, taddr + (cc + 2) * 32);
-          {
-            float cm;
-            const uint32_t mask = chunk_flags(rb, margin, m, cm);
-            if (mask != 0u && valid) {
-              const uint32_t chunk = (uint32_t)(nt * (BN / 32) + cc + 1);
-              my_list[min(n, kListCap - 1)] = make_uint2((__float_as_uint(cm) & 0xFFFFFF80u) | chunk, mask);
-              ++n;
-            }
-          }
-        }
-        // hand the buffer back, already holding -|e|^2/2 of the N-tile it will accumulate next
-        const bool more = (i + 1 < per_tile) || (it + 1 < my_tiles);
-        if (more) {
-          const int nt_next = (i + 1 < per_tile) ? nt + 2 : q;
-          tmem_init_buffer(taddr, nhee, nt_next * BN);
-          tc_fence_before();
           __syncwarp();
-          if (lane == 0) { if constexpr (CG == 2) mbar_arrive_cluster(t_empty); else mbar_arrive(t_empty); }
-        }
+        };
+        uint32_t ra[32], rb[32];
+        float cm;
+        uint32_t mask;
+        TMEM_LD32(ra, taddr);
+        TMEM_WAIT_LD32(ra);
+        TMEM_LD32(rb, taddr + 32);
+        mask = chunk_flags(ra, margin, m, cm);
+        emit(mask, cm, chunk0);
+        TMEM_WAIT_LD32(rb);
+        TMEM_LD32(ra, taddr + 64);
+        mask = chunk_flags(rb, margin, m, cm);
+        emit(mask, cm, chunk0 + 1);
+        TMEM_WAIT_LD32(ra);
+        TMEM_LD32(rb, taddr + 96);
+        mask = chunk_flags(ra, margin, m, cm);
+        emit(mask, cm, chunk0 + 2);
+        TMEM_WAIT_LD32(rb);
+        // every score of this warp's slice is in registers: the accumulator can be overwritten
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) arrive_leader(leader_bar(C::BAR_T_EMPTY + buf));
+        mask = chunk_flags(rb, margin, m, cm);
+        emit(mask, cm, chunk0 + 3);
+        TR_ADD(tr_proc, tr0);
       }
       if (valid) {
         meta[(size_t)t * 4 + q] = __float_as_int(m);
         meta[(size_t)t * 4 + 2 + q] = n > kListCap ? -1 : n;
       }
     }
+    if (part == 0 && lane == 0) { TR_PUT(2 + 4 * q, tr_zz); TR_PUT(3 + 4 * q, tr_full); TR_PUT(4 + 4 * q, tr_proc); }
   } else if (warp == WARP_TMA) {
     // ===================== TMA producer: this CTA's half of every codebook tile =====================
     if (lane == 0) {
@@ -434,10 +483,10 @@ vq_tensor_search_kernel(const __grid_constant__ CUtensorMap tmap_cb, const float
       uint32_t phase = 0;
       for (int it = 0; it < my_tiles; ++it)
         for (int nt = 0; nt < NT; ++nt)
-          for (int kc = 0; kc < KC; ++kc) {
+          for (int kc = -1; kc < KC; ++kc) {      // kc == -1: the -|e|^2/2 chunk (columns D .. D+63)
             mbar_wait(bar(C::BAR_B_EMPTY + stage), phase ^ 1);
             if (leader) mbar_arrive_expect_tx(bar(C::BAR_B_FULL + stage), CG * C::B_STAGE_BYTES);
-            tma_load_2d<CG>(sbase + C::OFF_B + stage * C::B_STAGE_BYTES, &tmap_cb, kc * BK,
+            tma_load_2d<CG>(sbase + C::OFF_B + stage * C::B_STAGE_BYTES, &tmap_cb, kc < 0 ? D : kc * BK,
                             nt * BN + (int)rank * (BN / CG), leader_bar(C::BAR_B_FULL + stage));
             if (++stage == C::NSTAGE) { stage = 0; phase ^= 1; }
           }
@@ -447,30 +496,47 @@ vq_tensor_search_kernel(const __grid_constant__ CUtensorMap tmap_cb, const float
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      uint32_t g = 0;   // running N-tile counter -> TMEM buffer g & 1 (NT is even, so g & 1 == nt & 1)
+      uint32_t g = 0;   // running N-tile counter -> TMEM buffer g & 1
+      const uint32_t rt_one = my_tiles > 0 ? 1u : 0u;   // 1, but not a compile-time constant
+      [[maybe_unused]] unsigned long long tr_te = 0, tr_af = 0, tr_bf = 0, tr0;
+      [[maybe_unused]] const unsigned long long tr_start = TR_NOW();
       for (int it = 0; it < my_tiles; ++it) {
         const int abuf = it & 1;
         for (int nt = 0; nt < NT; ++nt, ++g) {
           const uint32_t buf = g & 1;
-          mbar_wait(bar(C::BAR_T_EMPTY + buf), (g >> 1) & 1);   // both CTAs drained + re-initialised this buffer
+          tr0 = TR_NOW();
+          if (g >= 2) mbar_wait(bar(C::BAR_T_EMPTY + buf), ((g >> 1) - 1) & 1);   // both CTAs drained this buffer
+          TR_ADD(tr_te, tr0);
           tc_fence_after();
           const uint32_t tmem_d = tmem_base + buf * BN;
-          for (int kc = 0; kc < KC; ++kc) {
-            if (nt == 0) mbar_wait(bar(C::BAR_A_FULL + abuf * MAX_KC + kc), (it >> 1) & 1);
+          for (int kc = -1; kc < KC; ++kc) {      // kc == -1: the -|e|^2/2 step, which also overwrites the buffer
+            tr0 = TR_NOW();
+            if (nt == 0 && kc >= 0) mbar_wait(bar(C::BAR_A_FULL + abuf * MAX_KC + kc), (it >> 1) & 1);
+            TR_ADD(tr_af, tr0);
+            tr0 = TR_NOW();
             mbar_wait(bar(C::BAR_B_FULL + stage), phase);
+            TR_ADD(tr_bf, tr0);
             tc_fence_after();
-            const uint32_t a_addr = sbase + C::OFF_A + abuf * A_BUF_BYTES + kc * A_CHUNK_BYTES;
+            // Descriptors advance by 32 bytes (2 in the >>4 address field) per K=16 step.  The accumulate flags
+            // are run-time values on purpose: with a literal 0 ptxas 12.9 emitted a predicated UTCHMMA whose
+            // result was wrong in cta_group::2 (caught by the D1 / D1b parity tests).
             const uint32_t b_addr = sbase + C::OFF_B + stage * C::B_STAGE_BYTES;
-#pragma unroll
-            for (int ks = 0; ks < BK / UK; ++ks)
-              umma_bf16<CG>(tmem_d, umma_desc_sw128(a_addr + ks * UK * 2), umma_desc_sw128(b_addr + ks * UK * 2), 1u);
+            const uint32_t a_addr = sbase + (kc < 0 ? C::OFF_APAD : C::OFF_A + abuf * A_BUF_BYTES + kc * A_CHUNK_BYTES);
+            const uint64_t ad = umma_desc_sw128(a_addr), bd = umma_desc_sw128(b_addr);
+            umma_bf16<CG>(tmem_d, ad, bd, kc < 0 ? 0u : rt_one);
+            if (kc >= 0) {
+              umma_bf16<CG>(tmem_d, ad + 2, bd + 2, rt_one);
+              umma_bf16<CG>(tmem_d, ad + 4, bd + 4, rt_one);
+              umma_bf16<CG>(tmem_d, ad + 6, bd + 6, rt_one);
+            }
             umma_commit<CG>(bar(C::BAR_B_EMPTY + stage));     // frees the codebook stage when these MMAs retire
             if (++stage == C::NSTAGE) { stage = 0; phase ^= 1; }
           }
-          umma_commit<CG>(bar(C::BAR_T_FULL + buf));          // accumulator ready for the epilogue quads
+          umma_commit<CG>(bar(C::BAR_T_FULL + buf));          // accumulator ready for the epilogue warps
         }
         umma_commit<CG>(bar(C::BAR_A_EMPTY + abuf));          // operand tile may be overwritten
       }
+      TR_PUT(10, tr_te); TR_PUT(11, tr_af); TR_PUT(12, tr_bf); TR_PUT(13, TR_NOW() - tr_start);
     }
   }
 
@@ -510,15 +576,16 @@ static bool device_is_sm100() {
   return major == 10;
 }
 
+// (callers additionally require H*W % 4 == 0: the operand producer reads 4 tokens per 16-byte load)
 bool vq_tensor_supported(int D, int K) {
   if (D % BK != 0 || D < BK || D > MAX_KC * BK) return false;
-  if (K % (2 * BN) != 0 || K < 2 * BN || K > MAX_K) return false;   // two accumulator buffers alternate per N-tile
+  if (K % BN != 0 || K < BN || K > MAX_K) return false;
   return device_is_sm100();
 }
 
 template <int CG>
-static int launch_search(const CUtensorMap& tmap, const float* z, const float* nhee, const float* emax, int N, int D,
-                         int HW, int K, int* meta, uint2* list, cudaStream_t s) {
+static int launch_search(const CUtensorMap& tmap, const float* z, const float* emax, int N, int D, int HW, int K,
+                         int* meta, uint2* list, cudaStream_t s) {
   using C = Cfg<CG>;
   const int num_ptiles = (N + BM * CG - 1) / (BM * CG);
   const int max_pairs = kNumSMs / CG;
@@ -539,14 +606,21 @@ static int launch_search(const CUtensorMap& tmap, const float* z, const float* n
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  if (cudaLaunchKernelEx(&cfg, vq_tensor_search_kernel<CG>, tmap, z, nhee, emax, N, D, HW, K, num_ptiles, meta,
-                         list) != cudaSuccess)
+  if (cudaLaunchKernelEx(&cfg, vq_tensor_search_kernel<CG>, tmap, z, emax, N, D, HW, K, num_ptiles, meta, list) != cudaSuccess)
     return DCVIC_ERR_CUDA;
   return dcvic_launch_status();
 }
 
-int vq_tensor_search(const float* z, const __nv_bfloat16* cb16, const float* nhee, const float* emax, int B, int D,
-                     int HW, int K, int* meta, uint2* list, cudaStream_t s) {
+#ifdef DCVIC_TRACE
+}  // namespace dcvic
+extern "C" int dcvic_debug_read_trace(unsigned long long* host_out /* [296][16] */) {
+  return cudaMemcpyFromSymbol(host_out, dcvic::g_trace, sizeof(dcvic::g_trace)) == cudaSuccess ? 0 : -4;
+}
+namespace dcvic {
+#endif
+
+int vq_tensor_search(const float* z, const __nv_bfloat16* cb16, const float* emax, int B, int D, int HW, int K,
+                     int* meta, uint2* list, cudaStream_t s) {
   if (!vq_tensor_supported(D, K)) return DCVIC_ERR_UNSUPPORTED;
   static const int cta_group = [] {
     const char* e = getenv("DCVIC_VQ_CTA_GROUP");
@@ -555,8 +629,8 @@ int vq_tensor_search(const float* z, const __nv_bfloat16* cb16, const float* nhe
   EncodeTiledFn encode = encode_tiled_fn();
   if (!encode) return DCVIC_ERR_DEVICE;
   CUtensorMap tmap;
-  const cuuint64_t gdim[2] = {(cuuint64_t)D, (cuuint64_t)K};
-  const cuuint64_t gstride[1] = {(cuuint64_t)D * sizeof(__nv_bfloat16)};
+  const cuuint64_t gdim[2] = {(cuuint64_t)(D + kCb16Pad), (cuuint64_t)K};
+  const cuuint64_t gstride[1] = {(cuuint64_t)(D + kCb16Pad) * sizeof(__nv_bfloat16)};
   const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)(BN / cta_group)};
   const cuuint32_t estr[2] = {1, 1};
   if (encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(cb16), gdim, gstride, box, estr,
@@ -564,8 +638,8 @@ int vq_tensor_search(const float* z, const __nv_bfloat16* cb16, const float* nhe
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
     return DCVIC_ERR_CUDA;
   const int N = B * HW;
-  return cta_group == 2 ? launch_search<2>(tmap, z, nhee, emax, N, D, HW, K, meta, list, s)
-                        : launch_search<1>(tmap, z, nhee, emax, N, D, HW, K, meta, list, s);
+  return cta_group == 2 ? launch_search<2>(tmap, z, emax, N, D, HW, K, meta, list, s)
+                        : launch_search<1>(tmap, z, emax, N, D, HW, K, meta, list, s);
 }
 
 }  // namespace dcvic

@@ -48,7 +48,9 @@ enum {
   /* measurement aids (bench.py / ncu): run only one stage of the two-stage paths; outputs of the
    * skipped stage are left as the previous call on the same workspace produced them */
   DCVIC_VQ_STAGE_SEARCH_ONLY = 8,  /* codebook prep + candidate search, no finish */
-  DCVIC_VQ_STAGE_FINISH_ONLY = 16  /* finish (re-rank + gather + STE + loss) from the workspace's candidates */
+  DCVIC_VQ_STAGE_FINISH_ONLY = 16, /* finish (re-rank + gather + STE + loss) from the workspace's candidates */
+  DCVIC_VQ_RAGGED_HW = 32   /* dcvic_vq_path only: H*W is not a multiple of 4 (or z is not 16-byte aligned), which
+                               the tcgen05 search does not take; dcvic_vq_forward sets it by itself */
 };
 
 const char* dcvic_version(void);
