@@ -10,7 +10,7 @@
 // Structure: persistent CTA pairs (cta_group::2, UMMA 256x256x16), each CTA owning 128 tokens of a
 // 256-token pair tile and half of every codebook tile (CG = 1 is the same code on single CTAs).
 //   warps 0-7   A producers: read z (FP32, 16-byte loads of 4 consecutive tokens, two 8-load sets in
-//               flight per thread, next-next tile prefetched into L2 with cp.async.bulk.prefetch),
+//               flight per thread, running ahead into the next tile),
 //               convert to BF16, write the K-major SWIZZLE_128B operand tile (double-buffered: tile i+1
 //               loads while tile i multiplies), publish |z|^2 per token
 //   warps 8-15  epilogue: warps 8-11 take columns 0-127 of every accumulator, warps 12-15 columns
@@ -319,38 +319,33 @@ vq_tensor_search_kernel(const __grid_constant__ CUtensorMap tmap_cb, const float
   if (warp < NPROD) {
     // ===================== A producers: FP32 NCHW -> BF16 K-major SWIZZLE_128B =====================
     // Warp w owns tokens [32(w&3), +32) of the tile and channel half ch = w>>2 of every 64-channel chunk.
-    // lane = cg*8 + tq: token quad tq (4 consecutive tokens, one 16-byte load per channel) and channel
-    // group cg.  One step = 8 channels x 4 tokens per thread (8 LDG.128, 512 contiguous bytes per
+    // lane = tq*4 + cg: token quad tq (4 consecutive tokens, one 16-byte load per channel) and channel
+    // group cg (every quarter warp then covers all 8 swizzled bank groups in its 16-byte stores).  One step = 8 channels x 4 tokens per thread (8 LDG.128, 512 contiguous bytes per
     // channel and warp); two steps are in flight per thread.  The smem store of one (token, 8 channels)
     // 16-byte piece hits 8 distinct swizzled bank groups across the warp (4 wavefronts, the minimum
     // for 512 bytes).
-    const int tq = lane & 7, cg = lane >> 3, ch = warp >> 2;
+    const int cg = lane & 3, tq = lane >> 2, ch = warp >> 2;
     const int row0 = (warp & 3) * 32 + tq * 4;
     const int g = cg + 4 * ch;                  // 8-channel group inside a 64-channel chunk
     const size_t sHW = (size_t)HW;
-    // L2 prefetch of one whole tile: thread c asks for channel row c (up to 512 contiguous bytes)
-    auto prefetch_tile = [&](int it) {
-      if (it >= my_tiles) return;
-      const long long tn = ((long long)(pair + it * npairs) * CG + rank) * BM;
-      if (tn >= N) return;
-      const long long hw0 = tn % HW;
-      long long run = HW - hw0;                  // tokens of this tile before the image ends
-      if (run > BM) run = BM;
-      if (run > N - tn) run = N - tn;
-      const float* zb = z + (size_t)(tn / HW) * D * HW + (size_t)hw0;
-      for (int c = threadIdx.x; c < D; c += NPROD * 32) {
-        const float* pp = zb + (size_t)c * sHW;
-        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(pp), "r"((uint32_t)run * 4u) : "memory");
-      }
-    };
-    prefetch_tile(0);
-    prefetch_tile(1);
     [[maybe_unused]] unsigned long long tr_wait = 0, tr_work = 0;
+    float4 va[8], vb[8];
+    auto tile_ptr = [&](int it, bool& valid) {
+      const long long t = ((long long)(pair + it * npairs) * CG + rank) * BM + row0;
+      valid = it < my_tiles && t < N;           // N and HW are multiples of 4: a quad is valid as a whole
+      return z + (valid ? ((size_t)(t / HW) * D * HW + (size_t)(t % HW) + (size_t)(g * 8) * sHW) : 0);
+    };
+    auto load_step = [&](float4 (&v)[8], const float* zc, bool valid, int kc) {
+      const float* p = zc + (size_t)(BK * kc) * sHW;
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        v[k] = valid ? ldg_stream(reinterpret_cast<const float4*>(p + (size_t)k * sHW)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+    bool valid;
+    const float* zc = tile_ptr(0, valid);
+    load_step(va, zc, valid, 0);
+    if (KC > 1) load_step(vb, zc, valid, 1);
     for (int it = 0; it < my_tiles; ++it) {
-      const int ptile = pair + it * npairs;
-      const long long t = ((long long)ptile * CG + rank) * BM + row0;
-      const bool valid = t < N;                 // N and HW are multiples of 4: a quad is valid as a whole
-      const float* zc = z + (valid ? ((size_t)(t / HW) * D * HW + (size_t)(t % HW) + (size_t)(g * 8) * sHW) : 0);
       const int abuf = it & 1;
       unsigned long long tr0 = TR_NOW();
       mbar_wait(bar(C::BAR_A_EMPTY + abuf), ((it >> 1) & 1) ^ 1);
@@ -358,12 +353,6 @@ vq_tensor_search_kernel(const __grid_constant__ CUtensorMap tmap_cb, const float
       tr0 = TR_NOW();
       float zz4[4] = {0.f, 0.f, 0.f, 0.f};
       uint8_t* abase = smem + C::OFF_A + abuf * A_BUF_BYTES + row0 * 128;
-      auto load_step = [&](float4 (&v)[8], int kc) {
-        const float* p = zc + (size_t)(BK * kc) * sHW;
-#pragma unroll
-        for (int k = 0; k < 8; ++k)
-          v[k] = valid ? ldg_stream(reinterpret_cast<const float4*>(p + (size_t)k * sHW)) : make_float4(0.f, 0.f, 0.f, 0.f);
-      };
       auto store_step = [&](const float4 (&v)[8], int kc) {
         uint8_t* a = abase + kc * A_CHUNK_BYTES;
         const float* f = reinterpret_cast<const float*>(v);     // f[4k + i] = channel k, token i
@@ -383,21 +372,23 @@ vq_tensor_search_kernel(const __grid_constant__ CUtensorMap tmap_cb, const float
         __syncwarp();
         if (lane == 0) arrive_leader(leader_bar(C::BAR_A_FULL + abuf * MAX_KC + kc));
       };
-      float4 va[8], vb[8];
-      load_step(va, 0);
-      if (KC > 1) load_step(vb, 1);
-      prefetch_tile(it + 2);                    // behind this tile's own loads in the memory queues
+      // the next tile's first two steps are requested before this tile's last two are stored, so the
+      // memory pipe never drains between tiles (registers, not the smem buffer, are the landing zone)
+      bool nvalid;
+      const float* nzc = tile_ptr(it + 1, nvalid);
 #pragma unroll 1
       for (int kc = 0; kc < KC; kc += 2) {
         store_step(va, kc);
-        if (kc + 2 < KC) load_step(va, kc + 2);
+        if (kc + 2 < KC) load_step(va, zc, valid, kc + 2); else load_step(va, nzc, nvalid, 0);
         if (kc + 1 < KC) store_step(vb, kc + 1);
-        if (kc + 3 < KC) load_step(vb, kc + 3);
+        if (kc + 3 < KC) load_step(vb, zc, valid, kc + 3); else if (KC > 1) load_step(vb, nzc, nvalid, 1);
       }
+      zc = nzc;
+      valid = nvalid;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        zz4[i] += __shfl_xor_sync(0xffffffffu, zz4[i], 8);
-        zz4[i] += __shfl_xor_sync(0xffffffffu, zz4[i], 16);
+        zz4[i] += __shfl_xor_sync(0xffffffffu, zz4[i], 1);
+        zz4[i] += __shfl_xor_sync(0xffffffffu, zz4[i], 2);
       }
       if (cg == 0)
         *reinterpret_cast<float4*>(s_zz + ((it & (ZZ_SLOTS - 1)) * 2 + ch) * BM + row0) =

@@ -47,6 +47,66 @@ __global__ void __launch_bounds__(NW * 32) tile_read(const float* __restrict__ z
   }
   if (acc == 123.456f) *out = acc;
 }
+// tile pattern + L2 prefetch of the tile `dist` iterations ahead (MODE 1: cp.async.bulk.prefetch.L2 512 B per
+// channel row, MODE 2: prefetch.global.L2 per 128 B line)
+template <int NW, int MODE>
+__global__ void __launch_bounds__(NW * 32) tile_read_pf(const float* __restrict__ z, int N, int D, int HW, int dist, float* out) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cg = lane & 3, tq = lane >> 2;
+  const int tokgrp = warp & 3, part = warp >> 2;
+  constexpr int PARTS = NW / 4;
+  const int ntiles = N / 128;
+  float acc = 0.f;
+  auto pf = [&](int tile) {
+    if (tile >= ntiles) return;
+    const long long t0 = (long long)tile * 128;
+    const float* zb = z + (size_t)(t0 / HW) * D * HW + (t0 % HW);
+    for (int c = threadIdx.x; c < D; c += NW * 32) {
+      const float* pp = zb + (size_t)c * HW;
+      if (MODE == 1) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(pp), "r"(512u) : "memory");
+      else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) asm volatile("prefetch.global.L2 [%0];" ::"l"(pp + 32 * j) : "memory");
+      }
+    }
+  };
+  for (int d = 0; d < dist; ++d) pf(blockIdx.x + d * gridDim.x);
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    pf(tile + dist * gridDim.x);
+    const long long t = (long long)tile * 128 + tokgrp * 32 + tq * 4;
+    const float* zc = z + (size_t)(t / HW) * D * HW + (t % HW);
+    float4 v[2][8];
+    const int nsteps = D / (32 * PARTS);
+#pragma unroll 1
+    for (int s0 = 0; s0 < nsteps; s0 += 2) {
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int g = cg + 4 * part + 4 * PARTS * (s0 + u);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[u][k] = ldg_stream(reinterpret_cast<const float4*>(zc + (size_t)(g * 8 + k) * HW));
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc += v[u][k].x + v[u][k].w;
+    }
+  }
+  if (acc == 123.456f) *out = acc;
+}
+// linear, U float4 loads in flight per thread, then consume (same issue structure as tile_read)
+template <int U>
+__global__ void linear_read_u(const float4* __restrict__ p, size_t n4, float* out) {
+  float acc = 0.f;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i + (U - 1) * stride < n4; i += U * stride) {
+    float4 v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) v[u] = ldg_stream(p + i + u * stride);
+#pragma unroll
+    for (int u = 0; u < U; ++u) acc += v[u].x + v[u].w;
+  }
+  if (acc == 123.456f) *out = acc;
+}
 template <class F> float timeit(F f, int iters = 20) {
   cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
   for (int i = 0; i < 3; ++i) f();
@@ -74,6 +134,33 @@ int main() {
   printf("tile 16 warps, 4 sets(256KB): %.1f GB/s\n", gb / ms * 1e3);
   ms = timeit([&] { tile_read<8, 2><<<296, 256>>>(z, N, D, HW, out); });
   printf("tile 8 warps, 2 sets, 2 CTA/SM: %.1f GB/s\n", gb / ms * 1e3);
+  ms = timeit([&] { linear_read_u<16><<<148, 128>>>((const float4*)z, n / 4, out); });
+  printf("linear 148x128 thr, 16 in flight (32KB/SM): %.1f GB/s\n", gb / ms * 1e3);
+  ms = timeit([&] { linear_read_u<16><<<148, 256>>>((const float4*)z, n / 4, out); });
+  printf("linear 148x256 thr, 16 in flight (64KB/SM): %.1f GB/s\n", gb / ms * 1e3);
+  ms = timeit([&] { linear_read_u<16><<<148, 512>>>((const float4*)z, n / 4, out); });
+  printf("linear 148x512 thr, 16 in flight (128KB/SM): %.1f GB/s\n", gb / ms * 1e3);
+  {  // L2-resident footprint (32 MB): same kernels
+    const int Ns = 32 * HW; const size_t ns = (size_t)Ns * D; const double gbs = ns * 4 / 1e9;
+    ms = timeit([&] { linear_read_u<16><<<148, 128>>>((const float4*)z, ns / 4, out); }, 50);
+    printf("L2-resident linear 128 thr 16 in flight: %.1f GB/s\n", gbs / ms * 1e3);
+    ms = timeit([&] { linear_read_u<16><<<148, 256>>>((const float4*)z, ns / 4, out); }, 50);
+    printf("L2-resident linear 256 thr 16 in flight: %.1f GB/s\n", gbs / ms * 1e3);
+    ms = timeit([&] { tile_read<4, 2><<<148, 128>>>(z, Ns, D, HW, out); }, 50);
+    printf("L2-resident tile 4 warps 2 sets: %.1f GB/s\n", gbs / ms * 1e3);
+    ms = timeit([&] { tile_read<8, 2><<<148, 256>>>(z, Ns, D, HW, out); }, 50);
+    printf("L2-resident tile 8 warps 2 sets: %.1f GB/s\n", gbs / ms * 1e3);
+  }
+  for (int dist = 1; dist <= 1; ++dist) {
+    ms = timeit([&] { tile_read_pf<4, 1><<<148, 128>>>(z, N, D, HW, dist, out); });
+    printf("tile 4 warps 2 sets + bulk prefetch dist %d : %.1f GB/s\n", dist, gb / ms * 1e3);
+    ms = timeit([&] { tile_read_pf<4, 2><<<148, 128>>>(z, N, D, HW, dist, out); });
+    printf("tile 4 warps 2 sets + line prefetch dist %d : %.1f GB/s\n", dist, gb / ms * 1e3);
+    ms = timeit([&] { tile_read_pf<8, 1><<<148, 256>>>(z, N, D, HW, dist, out); });
+    printf("tile 8 warps 2 sets + bulk prefetch dist %d : %.1f GB/s\n", dist, gb / ms * 1e3);
+    ms = timeit([&] { tile_read_pf<8, 2><<<148, 256>>>(z, N, D, HW, dist, out); });
+    printf("tile 8 warps 2 sets + line prefetch dist %d : %.1f GB/s\n", dist, gb / ms * 1e3);
+  }
   cudaError_t e = cudaDeviceSynchronize(); printf("status %s\n", cudaGetErrorString(e));
   return 0;
 }
