@@ -58,7 +58,7 @@ extern "C" int dcvic_vq_forward(const float* z_nchw, const float* codebook, int 
   int* cand = reinterpret_cast<int*>(ws + w.off_cand);
   int* meta = reinterpret_cast<int*>(ws + w.off_meta);
   uint2* list = reinterpret_cast<uint2*>(ws + w.off_list);
-  __nv_bfloat16* cb16 = reinterpret_cast<__nv_bfloat16*>(ws + w.off_cb16);
+  __half* cb16 = reinterpret_cast<__half*>(ws + w.off_cb16);
   cudaStream_t s = (cudaStream_t)stream;
   int rc = DCVIC_OK;
 

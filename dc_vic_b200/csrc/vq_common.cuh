@@ -1,19 +1,19 @@
 // Internal interfaces between the VQ translation units.
 #pragma once
 #include "common.cuh"
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 namespace dcvic {
 
 constexpr int kFinishTokens = 32;     // tokens per CTA in the finish (re-rank + gather + STE + loss) kernel
 constexpr int kListCap = 16;          // (chunk key, flag mask) entries per token and accumulator buffer
 constexpr int kChunk = 32;            // codes per flag mask (one tcgen05.ld.32x32b.x32 per row)
-constexpr int kCb16Pad = 64;          // extra BF16 codebook columns: a 3-way split of -|e|^2/2 in the first three
+constexpr int kCb16Pad = 64;          // extra FP16 codebook columns: a 3-way split of -|e|^2/2 in the first three
 constexpr int kCandMax = 24;          // FP32 re-rank candidates per token before falling back to a full scan
 
 // What the tensor search hands to the finish kernel, per token t:
-//   meta[4t + q]     float  running maximum of the BF16 score over the N-tiles that went through
-//                           accumulator buffer q (q = 0, 1)
+//   meta[4t + q]     float  running maximum of the FP16 score over the columns of every accumulator that went to
+//                           epilogue warp quad q (q = 0: columns 0-127, 1: columns 128-255)
 //   meta[4t + 2 + q] int    number of list entries of buffer q, or -1 if its list overflowed
 //   list[(2t + q) * kListCap + i] = { key, mask }:  key = (bits(chunk max) & ~0x7F) | chunk id,
 //                           mask bit j set <=> score of code (chunk id * 32 + j) was within the
@@ -33,12 +33,12 @@ inline VqWorkspace vq_workspace_layout(int B, int D, int HW, int K) {
   w.off_ee = take((size_t)K * sizeof(float));
   w.off_nhee = take((size_t)K * sizeof(float));
   w.off_emax = take(4 * sizeof(float));
-  w.off_partials = take((N / kFinishTokens + 2) * sizeof(double));
+  w.off_partials = take((N / 8 + 2) * sizeof(double));   // one per finish CTA (8 tokens in the smallest variant)
   w.off_hist = take((size_t)K * sizeof(unsigned));
   w.off_cand = take(N * sizeof(int));
   w.off_meta = take(N * 4 * sizeof(int));
   w.off_list = take(N * 2 * kListCap * sizeof(uint2));
-  w.off_cb16 = take((size_t)K * (D + kCb16Pad) * sizeof(__nv_bfloat16));
+  w.off_cb16 = take((size_t)K * (D + kCb16Pad) * sizeof(__half));
   w.total = o;
   w.n_tokens = (int)N;
   return w;
@@ -47,18 +47,23 @@ inline VqWorkspace vq_workspace_layout(int B, int D, int HW, int K) {
 // counters[] slots
 enum { kCtrLoss = 0, kCtrOverflow = 1, kCtrPerp = 2, kCtrRerank = 3, kCtrTotalCand = 4 };
 
-// The proven bound on |bf16 score - exact score| differences that the search and the finish must
-// agree on: two round-to-nearest BF16 roundings per product (2^-7 + 2^-15 relative, Cauchy-Schwarz
-// over channels), doubled because it applies to the maximum and to the candidate, 2 % slack for the
-// tensor core's FP32 accumulation and the 7 mantissa bits dropped from the stored chunk maximum,
-// plus a few FP32 ulps of the reference distance itself (ties created by its rounding).
+// The proven bound on |fp16 score - exact score| differences that the search and the finish must agree on.
+// Both operands are rounded to nearest FP16 (relative 2^-11 each, so 2^-10 + 2^-22 per product, summed with
+// Cauchy-Schwarz over channels) and the bound applies to the maximum and to the candidate (x2); 2 % slack for
+// the tensor core's FP32 accumulation and the 7 mantissa bits dropped from the stored chunk maximum; an
+// absolute term for operands in FP16's subnormal range (2^-25 each, e_dim <= 256); plus a few FP32 ulps of
+// the reference distance itself (ties created by its rounding).
+// Tokens with |z|^2 >= kVqFp16Zz2Max (an element could exceed FP16's range) and codebooks flagged by the
+// prepare kernel (emax[1] != 0) are not searched on the tensor cores at all: they take the full FP32 scan.
+constexpr float kVqFp16Zz2Max = 3.6e9f;       // (6e4)^2
 __host__ __device__ __forceinline__ float vq_margin(float zz, float emax) {
-  return 1.02f * 0.015686f * sqrtf(zz) * emax + 1.9e-6f * (zz + emax * emax);
+  const float nz = sqrtf(zz);
+  return 1.02f * 0.0019536f * nz * emax + 9.6e-7f * (nz + emax) + 1.9e-6f * (zz + emax * emax);
 }
 
 // vq_simt.cu
 int vq_prepare_codebook(const float* codebook, int K, int D, float* ee, float* nhee, float* emax,
-                        __nv_bfloat16* cb16, cudaStream_t s);
+                        __half* cb16, cudaStream_t s);
 int vq_narrow_forward(const float* z, const float* E, int B, int D, int HW, int K, float beta, int legacy, float* zq,
                       int64_t* idx, float* loss, double* partials, unsigned* counters, cudaStream_t s);
 int vq_exact_search(const float* z, const float* E, const float* ee, int B, int D, int HW, int K, int* cand,
@@ -72,7 +77,7 @@ int vq_v1_extras(const int64_t* idx, int N, int K, float* onehot, float* perplex
 
 // vq_tcgen05.cu
 bool vq_tensor_supported(int D, int K);
-int vq_tensor_search(const float* z, const __nv_bfloat16* cb16, const float* emax, int B, int D, int HW, int K,
+int vq_tensor_search(const float* z, const __half* cb16, const float* emax, int B, int D, int HW, int K,
                      int* meta, uint2* list, cudaStream_t s);
 
 }  // namespace dcvic

@@ -1,5 +1,5 @@
 // FP32 SIMT kernels of the VQ quantizer path (sm_100a):
-//   * codebook preparation (|e|^2, max|e|, BF16 copy with the -|e|^2/2 fold for the tensor search)
+//   * codebook preparation (|e|^2, max|e|, FP16 copy with the -|e|^2/2 fold for the tensor search)
 //   * narrow fused forward   (e_dim 4 / 8: the codebooks DC-VIC itself uses, K=256..16384)
 //   * exact FP32 search      (any e_dim <= 1024, any K): register-tiled distance scan + argmin
 //   * finish                 (FP32 re-rank of candidates + gather + straight-through value + loss)
@@ -15,44 +15,48 @@ namespace dcvic {
 
 // ------------------------------------------------------------------ codebook prepare
 // One warp per code.  ee[k] = sum_c fl(e^2) (lane-strided partials + xor tree), nhee[k] = -ee[k]/2,
-// emax = max_k |e_k| (atomicMax on the non-negative float's bit pattern), cb16[k][0..D) = bf16(e),
-// cb16[k][D..D+3) = three-way BF16 split of -ee[k]/2 (exact: 3 x 8 significant bits), rest of the pad zero.
+// emax[0] = max_k |e_k| (atomicMax on the non-negative float's bit pattern), emax[1] != 0 if the codebook does
+// not fit FP16's range, cb16[k][0..D) = fp16(e), cb16[k][D..D+3) = three-way FP16 split of -ee[k]/2 (exact:
+// 3 x 11 significant bits), rest of the pad zero.
 __global__ void __launch_bounds__(256) vq_prepare_kernel(const float* __restrict__ E, int K, int D,
                                                           float* __restrict__ ee, float* __restrict__ nhee,
-                                                          float* __restrict__ emax,
-                                                          __nv_bfloat16* __restrict__ cb16) {
+                                                          float* __restrict__ emax, __half* __restrict__ cb16) {
   const int lane = threadIdx.x & 31;
   const int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (k >= K) return;
   const float* row = E + (size_t)k * D;
   const size_t ld = (size_t)(D + kCb16Pad);
   float acc = 0.f;
+  bool unsafe = false;
   for (int c = lane; c < D; c += 32) {
     const float v = row[c];
     acc = __fadd_rn(acc, __fmul_rn(v, v));
-    if (cb16) cb16[(size_t)k * ld + c] = __float2bfloat16_rn(v);
+    unsafe |= !(fabsf(v) < 6.0e4f);
+    if (cb16) cb16[(size_t)k * ld + c] = __float2half_rn(v);
   }
   acc = warp_sum(acc);
+  unsafe |= !(acc < 1.2e5f);                    // -ee/2 must be representable as well
   if (lane == 0) {
     ee[k] = acc;
     nhee[k] = -0.5f * acc;
     atomicMax(reinterpret_cast<unsigned*>(emax), __float_as_uint(sqrtf(acc) * 1.0000002f));
   }
+  if (__any_sync(0xffffffffu, unsafe) && lane == 0) atomicMax(reinterpret_cast<unsigned*>(emax + 1), 1u);
   if (cb16) {
-    const float v = -0.5f * acc;
-    const __nv_bfloat16 h = __float2bfloat16_rn(v);
-    const float r1 = v - __bfloat162float(h);
-    const __nv_bfloat16 m = __float2bfloat16_rn(r1);
-    const float r2 = r1 - __bfloat162float(m);
-    const __nv_bfloat16 l = __float2bfloat16_rn(r2);
+    const float v = unsafe ? 0.f : -0.5f * acc;
+    const __half h = __float2half_rn(v);
+    const float r1 = v - __half2float(h);
+    const __half m = __float2half_rn(r1);
+    const float r2 = r1 - __half2float(m);
+    const __half l = __float2half_rn(r2);
     for (int c = lane; c < kCb16Pad; c += 32)
-      cb16[(size_t)k * ld + D + c] = c == 0 ? h : (c == 1 ? m : (c == 2 ? l : __float2bfloat16_rn(0.f)));
+      cb16[(size_t)k * ld + D + c] = c == 0 ? h : (c == 1 ? m : (c == 2 ? l : __float2half_rn(0.f)));
   }
 }
 
-int vq_prepare_codebook(const float* codebook, int K, int D, float* ee, float* nhee, float* emax,
-                        __nv_bfloat16* cb16, cudaStream_t s) {
-  if (cudaMemsetAsync(emax, 0, sizeof(float), s) != cudaSuccess) return DCVIC_ERR_CUDA;
+int vq_prepare_codebook(const float* codebook, int K, int D, float* ee, float* nhee, float* emax, __half* cb16,
+                        cudaStream_t s) {
+  if (cudaMemsetAsync(emax, 0, 2 * sizeof(float), s) != cudaSuccess) return DCVIC_ERR_CUDA;
   vq_prepare_kernel<<<ceil_div_i(K, 8), 256, 0, s>>>(codebook, K, D, ee, nhee, emax, cb16);
   return dcvic_launch_status();
 }
@@ -398,7 +402,12 @@ __global__ void __launch_bounds__(256) vq_finish_kernel(const float* __restrict_
       int sb = 0;                                       // rows past the end: any valid code
       if (valid) sb = ncand == 1 ? (int)s_ck[lane * kCandMax] : (ncand <= 0 ? -2 : -1);
       s_best[lane] = sb;
-      if (valid && ncand != 1) atomicAdd(counters + (ncand < 0 ? kCtrOverflow : kCtrRerank), 1u);
+      {   // statistics: one atomic per CTA and counter (same-address atomics from every token serialise in L2)
+        const unsigned nr = __popc(__ballot_sync(0xffffffffu, valid && ncand > 1));
+        const unsigned nf = __popc(__ballot_sync(0xffffffffu, valid && ncand < 1));
+        if (lane == 0 && nr) atomicAdd(counters + kCtrRerank, nr);
+        if (lane == 0 && nf) atomicAdd(counters + kCtrOverflow, nf);
+      }
     }
     __syncthreads();
     // (2) one FP32 dot per (token, code) pair
@@ -475,19 +484,592 @@ __global__ void __launch_bounds__(256) vq_finish_kernel(const float* __restrict_
   }
 }
 
+// ------------------------------------------------------------------ finish, 128-bit version
+// Same phases and arithmetic as vq_finish_kernel, for e_dim % 4 == 0 and H*W % 4 == 0 (16-byte aligned
+// tensors): the token tile lives in shared memory token-major ([32][D+4] floats), so that
+//   * NCHW loads / stores move 4 consecutive tokens per thread (LDG.128 / STG.128, 128 contiguous bytes per
+//     8 lanes) and are transposed 4x4 in registers on the way in and out,
+//   * codebook rows and token rows are both read as float4 along channels (lane = 4 channels of each
+//     128-channel block), so one (token, code) dot costs 2 LDS.128 + 2 LDG.128 + 8 FFMA + the warp sum.
+// Row stride D+4 floats keeps every quarter-warp's 16-byte accesses on 8 distinct bank groups.
+constexpr int kFT = kFinishTokens;
+#ifdef DCVIC_TRACE
+__device__ unsigned long long g_trace_fin[4096][12];
+#define FT_MARK(i)                                         \
+  do {                                                     \
+    if (threadIdx.x == 0) {                                \
+      const unsigned long long now = clock64();            \
+      ft_acc[i] += now - ft_t;                             \
+      ft_t = now;                                          \
+    }                                                      \
+  } while (0)
+#else
+#define FT_MARK(i)
+#endif
+
+template <int DT>   // DT = e_dim when it is one of the specialised sizes (64, 128, 256), else 0 (run-time e_dim)
+__global__ void __launch_bounds__(256, 3) vq_finish_v4_kernel(const float* __restrict__ z, const float* __restrict__ E,
+                                                            const float* __restrict__ ee,
+                                                            const float* __restrict__ emax_ptr,
+                                                            const int* __restrict__ cand,
+                                                            const int* __restrict__ meta,
+                                                            const uint2* __restrict__ list, int N, int Drt, int HW, int K,
+                                                            float beta, int legacy, float* __restrict__ zq,
+                                                            int64_t* __restrict__ idx, float* __restrict__ loss,
+                                                            double* __restrict__ partials,
+                                                            unsigned* __restrict__ counters) {
+  extern __shared__ __align__(16) float zt[];  // [kFT][D + 4]
+  __shared__ double scratch[32];
+  __shared__ float s_zz[kFT];
+  __shared__ int s_best[kFT];                  // decided code, -1 while undecided, -2 = scan the whole codebook
+  __shared__ int s_first[kFT + 1];             // pair range of each token
+  __shared__ unsigned short s_pair_tok[kPairCap];
+  __shared__ unsigned short s_pair_k[kPairCap];
+  __shared__ float s_pair_d[kPairCap];
+  __shared__ float s_wd[8];
+  __shared__ int s_wk[8];
+  __shared__ int s_nc[kFT];
+  __shared__ unsigned short s_ck[kFT * kCandMax];
+  __shared__ int s_nfull;
+  const int D = DT ? DT : Drt;
+  constexpr int NV = DT ? (DT + 127) / 128 : 8;      // float4 per lane and row (run-time e_dim: up to 1024)
+  constexpr int NP = DT ? (DT + 127) / 128 : 0;      // staging passes of the NEXT tile held in registers (0: none)
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int ld = D + 4;
+  const int num_tiles = (N + kFT - 1) / kFT;
+  // staging map: lane = tq*4 + cq, token quad tq (tokens 4tq..4tq+3), channel quad cq; warp w takes channels
+  // [16w, 16w+16) of every 128-channel pass
+  const int tq = lane >> 2, cq = lane & 3;
+  auto quad_base = [&](int tile, bool& ok) {
+    const int tokq = tile * kFT + 4 * tq;                // N % 4 == 0: quads are valid as a whole
+    ok = tile < num_tiles && tokq < N;
+    return ok ? ((size_t)(tokq / HW) * D * HW + (size_t)(tokq % HW)) : (size_t)0;
+  };
+  float4 pv[NP ? NP : 1][4];
+  auto load_tile_regs = [&](int tile) {
+    bool ok;
+    const size_t qb = quad_base(tile, ok);
+#pragma unroll
+    for (int h = 0; h < NP; ++h) {
+      const int c = h * 128 + wid * 16 + cq * 4;
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        pv[h][k] = (ok && c < D) ? ldg_stream(reinterpret_cast<const float4*>(z + qb + (size_t)(c + k) * HW))
+                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+  auto store_quad = [&](const float4 (&v)[4], int c) {   // 4x4 transpose: 4 tokens x 4 channels
+    float* dst = zt + (4 * tq) * ld + c;
+    *reinterpret_cast<float4*>(dst) = make_float4(v[0].x, v[1].x, v[2].x, v[3].x);
+    *reinterpret_cast<float4*>(dst + ld) = make_float4(v[0].y, v[1].y, v[2].y, v[3].y);
+    *reinterpret_cast<float4*>(dst + 2 * ld) = make_float4(v[0].z, v[1].z, v[2].z, v[3].z);
+    *reinterpret_cast<float4*>(dst + 3 * ld) = make_float4(v[0].w, v[1].w, v[2].w, v[3].w);
+  };
+  if (NP) load_tile_regs(blockIdx.x);
+  float sq = 0.f;
+#ifdef DCVIC_TRACE
+  unsigned long long ft_acc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, ft_t = clock64();
+#endif
+
+  for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+  const int t0 = tile * kFT;
+  bool qvalid;
+  const size_t qbase = quad_base(tile, qvalid);
+  if (threadIdx.x < kFT) s_nc[threadIdx.x] = 0;
+  if (threadIdx.x == 0) s_nfull = 0;
+  // (0) stage the token tile; the next tile of this CTA is requested right away and stays in flight (in
+  // registers) while this one is processed
+  if (NP) {
+#pragma unroll
+    for (int h = 0; h < NP; ++h) {
+      const int c = h * 128 + wid * 16 + cq * 4;
+      if (c < D) store_quad(pv[h], c);
+    }
+    load_tile_regs(tile + gridDim.x);
+  } else {
+    for (int c0 = wid * 16; c0 < D; c0 += 128) {
+      const int c = c0 + cq * 4;
+      if (c < D) {
+        float4 v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          v[k] = qvalid ? ldg_stream(reinterpret_cast<const float4*>(z + qbase + (size_t)(c + k) * HW))
+                        : make_float4(0.f, 0.f, 0.f, 0.f);
+        store_quad(v, c);
+      }
+    }
+  }
+  __syncthreads();
+  FT_MARK(0);
+
+  // FP32 dot of token row `tok` with codebook row k: lane takes channels 4*lane + 128*h, sequential FMAs
+  // inside the lane, xor tree across lanes.  load_e / dot_e are split so that several rows can be in flight.
+  auto load_e = [&](float4 (&b)[NV], const float* er) {
+#pragma unroll
+    for (int h = 0; h < NV; ++h) {
+      const int c = lane * 4 + 128 * h;
+      b[h] = c < D ? __ldg(reinterpret_cast<const float4*>(er + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+  auto dot_e = [&](int tok, const float4 (&b)[NV]) {
+    float dp = 0.f;
+#pragma unroll
+    for (int h = 0; h < NV; ++h) {
+      const int c = lane * 4 + 128 * h;
+      if (c < D) {
+        const float4 a = *reinterpret_cast<const float4*>(zt + tok * ld + c);
+        dp = fmaf(a.x, b[h].x, dp); dp = fmaf(a.y, b[h].y, dp); dp = fmaf(a.z, b[h].z, dp); dp = fmaf(a.w, b[h].w, dp);
+      }
+    }
+    return warp_sum(dp);
+  };
+
+  if (cand) {
+    if (wid == 0) s_best[lane] = (t0 + lane < N) ? min(max(cand[t0 + lane], 0), K - 1) : 0;
+    __syncthreads();
+  } else {
+    for (int tok = wid; tok < kFT; tok += 8) {
+      float zzp = 0.f;
+#pragma unroll
+      for (int h = 0; h < NV; ++h) {
+        const int c = lane * 4 + 128 * h;
+        if (c < D) {
+          const float4 a = *reinterpret_cast<const float4*>(zt + tok * ld + c);
+          zzp = __fadd_rn(zzp, __fmul_rn(a.x, a.x)); zzp = __fadd_rn(zzp, __fmul_rn(a.y, a.y));
+          zzp = __fadd_rn(zzp, __fmul_rn(a.z, a.z)); zzp = __fadd_rn(zzp, __fmul_rn(a.w, a.w));
+        }
+      }
+      zzp = warp_sum(zzp);
+      if (lane == 0) s_zz[tok] = zzp;
+    }
+    __syncthreads();
+    FT_MARK(1);
+    // (1) expand lists -> candidate codes: 8 threads per token, 4 list entries each (all loads in flight
+    // at once); order within a token does not matter, the minimum is taken over (distance, index)
+    {
+      const int tok = threadIdx.x >> 3, sub = threadIdx.x & 7;
+      const int t = t0 + tok;
+      if (t < N) {
+        const int4 mt = *reinterpret_cast<const int4*>(meta + (size_t)t * 4);
+        const float thr = fmaxf(__int_as_float(mt.x), __int_as_float(mt.y)) - vq_margin(s_zz[tok], *emax_ptr);
+        const int q = sub >> 2, i0 = (sub & 3) * 4;
+        const int n = q == 0 ? mt.z : mt.w;
+        if (n < 0 && (sub & 3) == 0) atomicAdd(&s_nc[tok], 2 * kCandMax);   // overflowed list -> full scan
+        if (i0 < n) {
+          const uint4* lp = reinterpret_cast<const uint4*>(list + ((size_t)t * 2 + q) * kListCap + i0);
+          const uint4 e01 = lp[0], e23 = lp[1];
+          const unsigned key[4] = {e01.x, e01.z, e23.x, e23.z};
+          const unsigned msk[4] = {e01.y, e01.w, e23.y, e23.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            if (i0 + i >= n) break;
+            if (__uint_as_float(key[i] | 0x7Fu) < thr) continue;      // chunk maximum (rounded up) below threshold
+            unsigned mask = msk[i];
+            const int c0 = (int)(key[i] & 0x7Fu) * kChunk;
+            const int pos = atomicAdd(&s_nc[tok], __popc(mask));
+            int w = pos;
+            while (mask && w < kCandMax) {
+              const int j = __ffs(mask) - 1;
+              mask &= mask - 1;
+              s_ck[tok * kCandMax + w++] = (unsigned short)(c0 + j);
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();
+    FT_MARK(2);
+    // pair ranges (warp 0: lane = token); tokens with one candidate are decided here
+    if (wid == 0) {
+      const bool valid = t0 + lane < N;
+      const int nc = valid ? s_nc[lane] : 1;
+      const int ncand = nc > kCandMax ? -1 : nc;        // nc == 0 cannot happen (the maximum is always flagged)
+      const int npairs = ncand > 1 ? ncand : 0;
+      int off = npairs;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, off, o);
+        if (lane >= o) off += v;
+      }
+      s_first[lane + 1] = off;
+      if (lane == 0) s_first[0] = 0;
+      off -= npairs;
+      for (int i = 0; i < npairs; ++i) {
+        s_pair_tok[off + i] = (unsigned short)lane;
+        s_pair_k[off + i] = s_ck[lane * kCandMax + i];
+      }
+      int sb = 0;                                       // rows past the end: any valid code
+      if (valid) sb = ncand == 1 ? (int)s_ck[lane * kCandMax] : (ncand <= 0 ? -2 : -1);
+      s_best[lane] = sb;
+      {   // statistics: one atomic per CTA and counter (same-address atomics from every token serialise in L2)
+        const unsigned nr = __popc(__ballot_sync(0xffffffffu, valid && ncand > 1));
+        const unsigned nf = __popc(__ballot_sync(0xffffffffu, valid && ncand < 1));
+        if (lane == 0 && nr) atomicAdd(counters + kCtrRerank, nr);
+        if (lane == 0 && nf) atomicAdd(counters + kCtrOverflow, nf);
+      }
+      if (sb == -2) atomicAdd(&s_nfull, 1);
+    }
+    __syncthreads();
+    FT_MARK(3);
+    // (2) one FP32 dot per (token, code) pair
+    const int total = s_first[kFT];
+    for (int p = wid; p < total; p += 16) {              // two pairs in flight per warp
+      const int p2 = p + 8;
+      const bool two = p2 < total;
+      const int tok1 = s_pair_tok[p], k1 = s_pair_k[p];
+      const int tok2 = two ? s_pair_tok[p2] : tok1, k2 = two ? s_pair_k[p2] : k1;
+      float4 b1[NV], b2[NV];
+      load_e(b1, E + (size_t)k1 * D);
+      load_e(b2, E + (size_t)k2 * D);
+      const float ee1 = __ldg(ee + k1), ee2 = __ldg(ee + k2);
+      const float dot1 = dot_e(tok1, b1), dot2 = dot_e(tok2, b2);
+      if (lane == 0) {
+        s_pair_d[p] = fmaf(-2.f, dot1, __fadd_rn(s_zz[tok1], ee1));
+        if (two) s_pair_d[p2] = fmaf(-2.f, dot2, __fadd_rn(s_zz[tok2], ee2));
+      }
+    }
+    __syncthreads();
+    FT_MARK(4);
+    // (3) minimum per token, ties to the lowest index
+    if (wid == 0 && s_best[lane] == -1) {
+      float bd = FLT_MAX;
+      int bk = 0x7fffffff;
+      for (int p = s_first[lane]; p < s_first[lane + 1]; ++p) {
+        const float d = s_pair_d[p];
+        const int k = s_pair_k[p];
+        if (d < bd || (d == bd && k < bk)) { bd = d; bk = k; }
+      }
+      s_best[lane] = bk;
+    }
+    __syncthreads();
+    FT_MARK(5);
+    // (3b) full scans: the whole CTA on one token at a time (rare)
+    for (int tok = 0; tok < kFT && s_nfull > 0; ++tok) {
+      if (s_best[tok] != -2) continue;             // uniform: read from shared memory by all threads
+      const float zz = s_zz[tok];
+      float bd = FLT_MAX;
+      int bk = 0x7fffffff;
+      for (int k = wid; k < K; k += 8) {
+        float4 b[NV];
+        load_e(b, E + (size_t)k * D);
+        const float dot = dot_e(tok, b);
+        const float d = fmaf(-2.f, dot, __fadd_rn(zz, ee[k]));
+        if (d < bd || (d == bd && k < bk)) { bd = d; bk = k; }
+      }
+      if (lane == 0) { s_wd[wid] = bd; s_wk[wid] = bk; }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w)
+          if (s_wd[w] < bd || (s_wd[w] == bd && s_wk[w] < bk)) { bd = s_wd[w]; bk = s_wk[w]; }
+        s_best[tok] = bk;
+      }
+      __syncthreads();
+    }
+  }
+
+  FT_MARK(6);
+  // (4) gather + straight-through value + loss partial (warp per token, lane = 4 channels per 128)
+  for (int tok = wid; tok < kFT; tok += 8) {
+    const int t = t0 + tok;
+    if (t >= N) break;
+    const int best_k = min(max(s_best[tok], 0), K - 1);
+    float4 eb[NV];
+    load_e(eb, E + (size_t)best_k * D);
+#pragma unroll
+    for (int h = 0; h < NV; ++h) {
+      const int c = lane * 4 + 128 * h;
+      if (c < D) {
+        float4* zp = reinterpret_cast<float4*>(zt + tok * ld + c);
+        const float4 a = *zp, e = eb[h];
+        const float dx = __fsub_rn(e.x, a.x), dy = __fsub_rn(e.y, a.y), dz = __fsub_rn(e.z, a.z), dw = __fsub_rn(e.w, a.w);
+        *zp = make_float4(__fadd_rn(a.x, dx), __fadd_rn(a.y, dy), __fadd_rn(a.z, dz), __fadd_rn(a.w, dw));
+        sq = fmaf(dx, dx, sq); sq = fmaf(dy, dy, sq); sq = fmaf(dz, dz, sq); sq = fmaf(dw, dw, sq);
+      }
+    }
+    if (lane == 0) idx[t] = (int64_t)best_k;
+  }
+  __syncthreads();
+  FT_MARK(7);
+  // (5) write z_q back NCHW: the transpose of (0)
+  if (qvalid)
+    for (int c0 = wid * 16; c0 < D; c0 += 128) {
+      const int c = c0 + cq * 4;
+      if (c < D) {
+        const float* src = zt + (4 * tq) * ld + c;
+        const float4 r0 = *reinterpret_cast<const float4*>(src), r1 = *reinterpret_cast<const float4*>(src + ld),
+                     r2 = *reinterpret_cast<const float4*>(src + 2 * ld), r3 = *reinterpret_cast<const float4*>(src + 3 * ld);
+        float* o = zq + qbase + (size_t)c * HW;
+        stg_stream(reinterpret_cast<float4*>(o), make_float4(r0.x, r1.x, r2.x, r3.x));
+        stg_stream(reinterpret_cast<float4*>(o + (size_t)HW), make_float4(r0.y, r1.y, r2.y, r3.y));
+        stg_stream(reinterpret_cast<float4*>(o + 2 * (size_t)HW), make_float4(r0.z, r1.z, r2.z, r3.z));
+        stg_stream(reinterpret_cast<float4*>(o + 3 * (size_t)HW), make_float4(r0.w, r1.w, r2.w, r3.w));
+      }
+    }
+  __syncthreads();                             // the tile buffer and the per-tile arrays are reused
+  FT_MARK(8);
+  }  // tile loop
+#ifdef DCVIC_TRACE
+  if (threadIdx.x == 0 && blockIdx.x < 4096)
+    for (int i = 0; i < 12; ++i) g_trace_fin[blockIdx.x][i] = ft_acc[i];
+#endif
+
+  const double bsum = block_sum((double)sq, scratch);
+  double total;
+  if (publish_and_elect_last(bsum, partials, counters + kCtrLoss, gridDim.x, blockIdx.x, scratch, &total)) {
+    if (threadIdx.x == 0) write_loss(total, (long long)N * D, beta, legacy, loss);
+  }
+}
+
+// ------------------------------------------------------------------ finish, warp-autonomous version
+// One warp owns 4 consecutive tokens (one 16-byte token quad per channel) from the first load to the last
+// store; nothing is shared between warps but the loss partial, so there is no block barrier in the token
+// path and a stalled warp never holds others back.  The token quad lives in registers: lane l keeps channels
+// l, l+32, ... (DT/32 float4, 4 tokens each); codebook rows are read with the same lane-strided pattern
+// (128 contiguous bytes per warp load), a (token, code) dot is DT/32 FFMAs + the xor-tree warp sum, and z_q
+// goes back as one STG.128 per channel.  The two halves of every 32-byte sector of z belong to two
+// neighbouring warps of the same CTA, so the loads allocate in L1.
+// Arithmetic, candidate filtering and tie-breaking are those of vq_finish_kernel.
+constexpr int kQW = 8;   // warps per CTA of the warp-autonomous finish (small CTAs: a slow warp holds back one neighbour)
+
+template <int DT>
+__global__ void __launch_bounds__(kQW * 32, 4) vq_finish_quad_kernel(const float* __restrict__ z, const float* __restrict__ E,
+                                                              const float* __restrict__ ee,
+                                                              const float* __restrict__ emax_ptr,
+                                                              const int* __restrict__ cand,
+                                                              const int* __restrict__ meta,
+                                                              const uint2* __restrict__ list, int N, int HW, int K,
+                                                              float beta, int legacy, float* __restrict__ zq,
+                                                              int64_t* __restrict__ idx, float* __restrict__ loss,
+                                                              double* __restrict__ partials,
+                                                              unsigned* __restrict__ counters) {
+  constexpr int NJ = DT / 32;                  // channels per lane
+  __shared__ double s_part[kQW];
+  __shared__ int s_done;
+  __shared__ int s_nc[kQW][4];
+  __shared__ unsigned short s_ck[kQW][4][kCandMax];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int t0 = (blockIdx.x * kQW + wid) * 4;   // first token of this warp's quad (N % 4 == 0)
+  float sq = 0.f;
+  if (threadIdx.x == 0) s_done = 0;
+  __syncthreads();                             // the only block barrier: warps meet again only at the election below
+  if (t0 < N) {
+    const size_t qbase = (size_t)(t0 / HW) * DT * HW + (size_t)(t0 % HW);
+    float4 zr[NJ];
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) zr[j] = __ldg(reinterpret_cast<const float4*>(z + qbase + (size_t)(lane + 32 * j) * HW));
+    int best[4];
+    unsigned n_rerank = 0, n_full = 0;         // statistics, one atomic per warp (same-address atomics serialise in L2)
+    if (cand) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) best[i] = min(max(cand[t0 + i], 0), K - 1);
+    } else {
+      // lists of the 4 tokens: lane = token*8 + sub, 4 entries per lane, requested before anything depends on z
+      const int tok = lane >> 3, sub = lane & 7;
+      const int q = sub >> 2, i0 = (sub & 3) * 4;
+      const int4 mt = *reinterpret_cast<const int4*>(meta + (size_t)(t0 + tok) * 4);
+      const uint4* lp = reinterpret_cast<const uint4*>(list + ((size_t)(t0 + tok) * 2 + q) * kListCap + i0);
+      const uint4 e01 = lp[0], e23 = lp[1];
+      if (lane < 4) s_nc[wid][lane] = 0;
+      // |z|^2 per token: lane-strided partials, xor tree
+      float zz[4];
+      {
+        float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+          p0 = __fadd_rn(p0, __fmul_rn(zr[j].x, zr[j].x)); p1 = __fadd_rn(p1, __fmul_rn(zr[j].y, zr[j].y));
+          p2 = __fadd_rn(p2, __fmul_rn(zr[j].z, zr[j].z)); p3 = __fadd_rn(p3, __fmul_rn(zr[j].w, zr[j].w));
+        }
+        zz[0] = warp_sum(p0); zz[1] = warp_sum(p1); zz[2] = warp_sum(p2); zz[3] = warp_sum(p3);
+      }
+      __syncwarp();
+      {
+        const float zzt = tok == 0 ? zz[0] : (tok == 1 ? zz[1] : (tok == 2 ? zz[2] : zz[3]));
+        const float thr = fmaxf(__int_as_float(mt.x), __int_as_float(mt.y)) - vq_margin(zzt, *emax_ptr);
+        const int n = q == 0 ? mt.z : mt.w;
+        if (n < 0 && (sub & 3) == 0) atomicAdd(&s_nc[wid][tok], 2 * kCandMax);   // overflowed list -> full scan
+        const unsigned key[4] = {e01.x, e01.z, e23.x, e23.z};
+        const unsigned msk[4] = {e01.y, e01.w, e23.y, e23.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if (i0 + i >= n) break;
+          if (__uint_as_float(key[i] | 0x7Fu) < thr) continue;      // chunk maximum (rounded up) below threshold
+          unsigned mask = msk[i];
+          const int c0 = (int)(key[i] & 0x7Fu) * kChunk;
+          int w = atomicAdd(&s_nc[wid][tok], __popc(mask));
+          while (mask && w < kCandMax) {
+            const int jb = __ffs(mask) - 1;
+            mask &= mask - 1;
+            s_ck[wid][tok][w++] = (unsigned short)(c0 + jb);
+          }
+        }
+      }
+      __syncwarp();
+      // re-rank: FP32 distance of every candidate, ties to the lowest index
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int nc = s_nc[wid][i];
+        const float zzi = zz[i];
+        float bd = FLT_MAX;
+        int bk = 0x7fffffff;
+        auto consider = [&](int k, const float (&e)[NJ], float eek) {
+          float dp = 0.f;
+#pragma unroll
+          for (int j = 0; j < NJ; ++j) {
+            const float zv = i == 0 ? zr[j].x : (i == 1 ? zr[j].y : (i == 2 ? zr[j].z : zr[j].w));
+            dp = fmaf(zv, e[j], dp);
+          }
+          const float d = fmaf(-2.f, warp_sum(dp), __fadd_rn(zzi, eek));
+          if (d < bd || (d == bd && k < bk)) { bd = d; bk = k; }
+        };
+        auto load_row = [&](float (&e)[NJ], int k) {
+          const float* er = E + (size_t)k * DT + lane;
+#pragma unroll
+          for (int j = 0; j < NJ; ++j) e[j] = __ldg(er + 32 * j);
+        };
+        if (nc == 1) {
+          bk = s_ck[wid][i][0];
+        } else if (nc > kCandMax || nc <= 0) {
+          ++n_full;
+          for (int k = 0; k < K; k += 2) {                       // whole codebook, two rows in flight
+            float e0[NJ], e1[NJ];
+            load_row(e0, k);
+            load_row(e1, min(k + 1, K - 1));
+            consider(k, e0, __ldg(ee + k));
+            if (k + 1 < K) consider(k + 1, e1, __ldg(ee + k + 1));
+          }
+        } else {
+          ++n_rerank;
+          for (int c = 0; c < nc; c += 2) {                      // two candidate rows in flight
+            const int k0 = s_ck[wid][i][c], k1 = s_ck[wid][i][min(c + 1, nc - 1)];
+            float e0[NJ], e1[NJ];
+            load_row(e0, k0);
+            load_row(e1, k1);
+            const float ee0 = __ldg(ee + k0), ee1 = __ldg(ee + k1);
+            consider(k0, e0, ee0);
+            if (c + 1 < nc) consider(k1, e1, ee1);
+          }
+        }
+        best[i] = min(max(bk, 0), K - 1);
+      }
+    }
+    if (lane == 0 && n_rerank) atomicAdd(counters + kCtrRerank, n_rerank);
+    if (lane == 0 && n_full) atomicAdd(counters + kCtrOverflow, n_full);
+    // gather + straight-through value (in place) + loss partial, two rows in flight
+#pragma unroll
+    for (int i = 0; i < 4; i += 2) {
+      float e0[NJ], e1[NJ];
+      const float* r0 = E + (size_t)best[i] * DT + lane;
+      const float* r1 = E + (size_t)best[i + 1] * DT + lane;
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) { e0[j] = __ldg(r0 + 32 * j); e1[j] = __ldg(r1 + 32 * j); }
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        float& za = i == 0 ? zr[j].x : zr[j].z;
+        float& zb = i == 0 ? zr[j].y : zr[j].w;
+        const float da = __fsub_rn(e0[j], za), db = __fsub_rn(e1[j], zb);
+        sq = fmaf(da, da, sq); sq = fmaf(db, db, sq);
+        za = __fadd_rn(za, da); zb = __fadd_rn(zb, db);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < NJ; ++j)
+      stg_stream(reinterpret_cast<float4*>(zq + qbase + (size_t)(lane + 32 * j) * HW), zr[j]);
+    if (lane < 4) idx[t0 + lane] = (int64_t)(lane == 0 ? best[0] : (lane == 1 ? best[1] : (lane == 2 ? best[2] : best[3])));
+  }
+  // loss: warp partial -> the CTA's last warp sums the CTA's partials in warp order -> the grid's last CTA sums
+  // the CTA partials in CTA order (deterministic; no barrier, so a slow warp never parks its neighbours)
+  const double wsum = warp_sum((double)sq);
+  int last = 0;
+  if (lane == 0) {
+    s_part[wid] = wsum;
+    __threadfence_block();
+    last = (atomicAdd(&s_done, 1) == kQW - 1);
+  }
+  last = __shfl_sync(0xffffffffu, last, 0);
+  if (!last) return;
+  __threadfence_block();
+  int glast = 0;
+  if (lane == 0) {
+    double b = 0.0;
+    for (int w = 0; w < kQW; ++w) b += s_part[w];
+    partials[blockIdx.x] = b;
+    __threadfence();
+    glast = (atomicAdd(counters + kCtrLoss, 1u) == gridDim.x - 1);
+  }
+  glast = __shfl_sync(0xffffffffu, glast, 0);
+  if (!glast) return;
+  __threadfence();
+  double tot = 0.0;
+  for (unsigned i = lane; i < gridDim.x; i += 32) tot += __ldcg(partials + i);
+  tot = warp_sum(tot);
+  if (lane == 0) {
+    write_loss(tot, (long long)N * DT, beta, legacy, loss);
+    counters[kCtrLoss] = 0u;
+  }
+}
+
 int vq_finish(const float* z, const float* E, const float* ee, const float* emax, const int* cand, const int* meta,
               const uint2* list, int B, int D, int HW, int K, float beta, int legacy, float* zq, int64_t* idx,
               float* loss, double* partials, unsigned* counters, cudaStream_t s) {
   const int N = B * HW;
+  if (K > 65535 && !cand) return DCVIC_ERR_UNSUPPORTED;
+  const bool vec = (D % 4 == 0) && (HW % 4 == 0) && ((reinterpret_cast<uintptr_t>(z) & 15) == 0) &&
+                   ((reinterpret_cast<uintptr_t>(zq) & 15) == 0) && ((reinterpret_cast<uintptr_t>(E) & 15) == 0);
+  // measurement switch: DCVIC_FINISH=quad selects the warp-autonomous variant (slower on B200 as measured:
+  // its 16-byte-per-lane z loads waste DRAM bursts); default is the token-tile variant below
+  static const bool use_quad = getenv("DCVIC_FINISH") && getenv("DCVIC_FINISH")[0] == 'q';
+  if (vec && use_quad && (D == 256 || D == 128 || D == 64)) {
+    const int grid = ceil_div_i(N, 4 * kQW);
+    if (D == 256)
+      vq_finish_quad_kernel<256><<<grid, kQW * 32, 0, s>>>(z, E, ee, emax, cand, meta, list, N, HW, K, beta, legacy, zq, idx,
+                                                      loss, partials, counters);
+    else if (D == 128)
+      vq_finish_quad_kernel<128><<<grid, kQW * 32, 0, s>>>(z, E, ee, emax, cand, meta, list, N, HW, K, beta, legacy, zq, idx,
+                                                      loss, partials, counters);
+    else
+      vq_finish_quad_kernel<64><<<grid, kQW * 32, 0, s>>>(z, E, ee, emax, cand, meta, list, N, HW, K, beta, legacy, zq, idx,
+                                                     loss, partials, counters);
+    return dcvic_launch_status();
+  }
+  if (vec) {
+    const size_t smem = (size_t)kFT * (D + 4) * sizeof(float);
+    if (smem > 200 * 1024) return DCVIC_ERR_UNSUPPORTED;
+#define DCVIC_LAUNCH_FINISH(DT)                                                                                     \
+  do {                                                                                                             \
+    if (smem > 40 * 1024)                                                                                          \
+      cudaFuncSetAttribute(vq_finish_v4_kernel<DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);       \
+    static int per_sm_##DT = 0;                                                                                    \
+    if (per_sm_##DT == 0 && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_##DT, vq_finish_v4_kernel<DT>, 256, \
+                                                                         smem) != cudaSuccess)                    \
+      per_sm_##DT = 1;                                                                                             \
+    const int tiles = ceil_div_i(N, kFT);                                                                          \
+    const int grid = DT ? min(tiles, kNumSMs * max(per_sm_##DT, 1)) : tiles;                                       \
+    vq_finish_v4_kernel<DT><<<grid, 256, smem, s>>>(z, E, ee, emax, cand, meta, list, N, D, HW, K, beta, legacy,    \
+                                                    zq, idx, loss, partials, counters);                            \
+  } while (0)
+    if (D == 256) DCVIC_LAUNCH_FINISH(256);
+    else if (D == 128) DCVIC_LAUNCH_FINISH(128);
+    else if (D == 64) DCVIC_LAUNCH_FINISH(64);
+    else DCVIC_LAUNCH_FINISH(0);
+#undef DCVIC_LAUNCH_FINISH
+    return dcvic_launch_status();
+  }
   const size_t smem = (size_t)D * 33 * sizeof(float);
   if (smem > 200 * 1024) return DCVIC_ERR_UNSUPPORTED;
-  if (K > 65535 && !cand) return DCVIC_ERR_UNSUPPORTED;
-  if (smem > 48 * 1024)
+  if (smem > 40 * 1024)
     cudaFuncSetAttribute(vq_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   vq_finish_kernel<<<ceil_div_i(N, kFinishTokens), 256, smem, s>>>(z, E, ee, emax, cand, meta, list, N, D, HW, K,
                                                                     beta, legacy, zq, idx, loss, partials, counters);
   return dcvic_launch_status();
 }
+
+#ifdef DCVIC_TRACE
+}  // namespace dcvic
+extern "C" int dcvic_debug_read_finish_trace(unsigned long long* host_out /* [4096][12] */) {
+  return cudaMemcpyFromSymbol(host_out, dcvic::g_trace_fin, sizeof(dcvic::g_trace_fin)) == cudaSuccess ? 0 : -4;
+}
+namespace dcvic {
+#endif
 
 // ------------------------------------------------------------------ V1 extras
 __global__ void __launch_bounds__(256) vq_onehot_rows_kernel(const int64_t* __restrict__ idx, int N, int K,

@@ -1,8 +1,9 @@
 // Wide-codebook nearest-codeword CANDIDATE search on the 5th-gen tensor cores (sm_100a).
 //
 // Computes, for every token row z_t (FP32, read straight from NCHW) and every codeword e_k,
-//     s[t,k] = bf16(z_t) . bf16(e_k) - |e_k|^2 / 2        ( = (|z|^2 - d[t,k]) / 2 up to BF16 rounding )
-// with tcgen05.mma (BF16 x BF16 -> FP32 in TMEM) and flags, per row, every k whose score is within a
+//     s[t,k] = fp16(z_t) . fp16(e_k) - |e_k|^2 / 2        ( = (|z|^2 - d[t,k]) / 2 up to FP16 rounding )
+// with tcgen05.mma (FP16 x FP16 -> FP32 in TMEM; FP16 rather than BF16 because its 11-bit significand keeps
+// the proven margin 8x tighter, i.e. ~1.2 instead of ~2.7 FP32 re-rank candidates per token) and flags, per row, every k whose score is within a
 // PROVEN error margin (vq_margin) of the row's running maximum.  The distance matrix never leaves
 // the SM.  The FP32 re-rank of the few flagged codes (reference op order, lowest-index tie-break)
 // happens in vq_finish_kernel, which streams z once more for the gather / STE / loss.
@@ -11,19 +12,19 @@
 // 256-token pair tile and half of every codebook tile (CG = 1 is the same code on single CTAs).
 //   warps 0-7   A producers: read z (FP32, 16-byte loads of 4 consecutive tokens, two 8-load sets in
 //               flight per thread, running ahead into the next tile),
-//               convert to BF16, write the K-major SWIZZLE_128B operand tile (double-buffered: tile i+1
+//               convert to FP16, write the K-major SWIZZLE_128B operand tile (double-buffered: tile i+1
 //               loads while tile i multiplies), publish |z|^2 per token
 //   warps 8-15  epilogue: warps 8-11 take columns 0-127 of every accumulator, warps 12-15 columns
 //               128-255.  tcgen05.ld 32 scores per row at a time (software pipelined), running max, one
 //               flag mask per 32 codes (FADD on the FMA pipe + funnel shift, branch-free), append
 //               {chunk max | chunk id, mask} to the token's list in global memory when non-empty.  The
 //               accumulator goes back to the MMA as soon as its last scores are in registers.
-//   warp 16     TMA producer: this CTA's half of the BF16 codebook tile [256/CG codes x 64 ch]
+//   warp 16     TMA producer: this CTA's half of the FP16 codebook tile [256/CG codes x 64 ch]
 //               (SWIZZLE_128B) into a 4-stage ring; completion is signalled on the LEADER's barrier
 //   warp 17     TMEM allocator; in the leader CTA one thread issues every tcgen05.mma of the pair and
 //               multicasts the commits (stage free, accumulator full, operand tile free) to both CTAs
-// -|e|^2/2 enters through the contraction itself: the BF16 codebook carries one extra 64-column chunk
-// whose first three columns are a 3-way BF16 split of -|e_k|^2/2, multiplied (one K=16 step, which
+// -|e|^2/2 enters through the contraction itself: the FP16 codebook carries one extra 64-column chunk
+// whose first three columns are a 3-way FP16 split of -|e_k|^2/2, multiplied (one K=16 step, which
 // also zero-initialises the accumulator) with a constant operand chunk of ones.
 // Reference semantics: taming/modules/vqvae/quantize.py:280-284 (distance + argmin).
 #include "vq_common.cuh"
@@ -35,7 +36,7 @@ namespace tc {
 
 constexpr int BM = 128;          // tokens per CTA tile (UMMA M = 128 * CG)
 constexpr int BN = 256;          // codes per N-tile (UMMA N)
-constexpr int BK = 64;           // channels per smem chunk: 64 bf16 = 128 B = one SWIZZLE_128B row
+constexpr int BK = 64;           // channels per smem chunk: 64 fp16 = 128 B = one SWIZZLE_128B row
 constexpr int UK = 16;           // UMMA K for 16-bit inputs
 constexpr int MAX_KC = 4;        // e_dim <= 256
 constexpr int A_CHUNK_BYTES = BM * BK * 2;            // 16 KB
@@ -140,15 +141,15 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
   return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
          (2ull << 61);
 }
-// kind::f16 instruction descriptor: D=F32, A=B=BF16, both K-major, N=256, M=128*CG
+// kind::f16 instruction descriptor: D=F32 (bit 4), A=B=F16 (format 0), both K-major, N=256, M=128*CG
 template <int CG>
 struct Idesc {
   static constexpr uint32_t value =
-      (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((BM * CG) >> 4) << 24);
+      (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((BM * CG) >> 4) << 24);
 };
 
 template <int CG>
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
   if constexpr (CG == 2) {
     asm volatile(
         "{\n\t"
@@ -205,9 +206,9 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
                : "memory")
 
 
-__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
   uint32_t r;
-  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
   return r;
 }
 
@@ -290,12 +291,12 @@ vq_tensor_search_kernel(const __grid_constant__ CUtensorMap tmap_cb, const float
     for (int s = 0; s < ZZ_SLOTS; ++s) mbar_init(bar(C::BAR_ZZ + s), NPROD);
     fence_barrier_init();
   }
-  // constant operand chunk for the -|e|^2/2 step: bf16 1.0 in columns 0-2 of every row.  Columns 0-7 sit in
+  // constant operand chunk for the -|e|^2/2 step: fp16 1.0 in columns 0-2 of every row.  Columns 0-7 sit in
   // 16-byte piece (0 ^ (row & 7)) of the row (SWIZZLE_128B), all other pieces are zero.
   for (int i = threadIdx.x; i < BM * 8; i += NTHREADS) {
     const int row = i >> 3, piece = i & 7;
     uint4 v = make_uint4(0u, 0u, 0u, 0u);
-    if (piece == (row & 7)) { v.x = 0x3F803F80u; v.y = 0x00003F80u; }
+    if (piece == (row & 7)) { v.x = 0x3C003C00u; v.y = 0x00003C00u; }
     *reinterpret_cast<uint4*>(smem + C::OFF_APAD + row * 128 + piece * 16) = v;
   }
   fence_proxy_async();
@@ -317,7 +318,7 @@ vq_tensor_search_kernel(const __grid_constant__ CUtensorMap tmap_cb, const float
   const uint32_t tmem_base = *s_tmem;
 
   if (warp < NPROD) {
-    // ===================== A producers: FP32 NCHW -> BF16 K-major SWIZZLE_128B =====================
+    // ===================== A producers: FP32 NCHW -> FP16 K-major SWIZZLE_128B =====================
     // Warp w owns tokens [32(w&3), +32) of the tile and channel half ch = w>>2 of every 64-channel chunk.
     // lane = tq*4 + cg: token quad tq (4 consecutive tokens, one 16-byte load per channel) and channel
     // group cg (every quarter warp then covers all 8 swizzled bank groups in its 16-byte stores).  One step = 8 channels x 4 tokens per thread (8 LDG.128, 512 contiguous bytes per
@@ -359,10 +360,10 @@ vq_tensor_search_kernel(const __grid_constant__ CUtensorMap tmap_cb, const float
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           uint4 pk;
-          pk.x = pack_bf16x2(f[0 + i], f[4 + i]);
-          pk.y = pack_bf16x2(f[8 + i], f[12 + i]);
-          pk.z = pack_bf16x2(f[16 + i], f[20 + i]);
-          pk.w = pack_bf16x2(f[24 + i], f[28 + i]);
+          pk.x = pack_f16x2(f[0 + i], f[4 + i]);
+          pk.y = pack_f16x2(f[8 + i], f[12 + i]);
+          pk.z = pack_f16x2(f[16 + i], f[20 + i]);
+          pk.w = pack_f16x2(f[24 + i], f[28 + i]);
           const int r7 = (row0 + i) & 7;
           *reinterpret_cast<uint4*>(a + i * 128 + ((g ^ r7) << 4)) = pk;
 #pragma unroll
@@ -404,7 +405,8 @@ vq_tensor_search_kernel(const __grid_constant__ CUtensorMap tmap_cb, const float
     const int part = warp & 3;                    // TMEM lane quarter this warp may access
     const int row = part * 32 + lane;
     const uint32_t tlane = tmem_base + ((uint32_t)(part * 32) << 16) + q * (BN / 2);
-    const float emax = *emax_ptr;
+    const float emax = emax_ptr[0];
+    const bool cb_unsafe = __float_as_uint(emax_ptr[1]) != 0u;   // codebook outside FP16's range: FP32 scan for all
     uint32_t g = 0;                               // running N-tile counter (same sequence as the MMA issuer)
     [[maybe_unused]] unsigned long long tr_zz = 0, tr_full = 0, tr_proc = 0;
     for (int it = 0; it < my_tiles; ++it) {
@@ -462,7 +464,7 @@ vq_tensor_search_kernel(const __grid_constant__ CUtensorMap tmap_cb, const float
       }
       if (valid) {
         meta[(size_t)t * 4 + q] = __float_as_int(m);
-        meta[(size_t)t * 4 + 2 + q] = n > kListCap ? -1 : n;
+        meta[(size_t)t * 4 + 2 + q] = (n > kListCap || cb_unsafe || !(zz < kVqFp16Zz2Max)) ? -1 : n;
       }
     }
     if (part == 0 && lane == 0) { TR_PUT(2 + 4 * q, tr_zz); TR_PUT(3 + 4 * q, tr_full); TR_PUT(4 + 4 * q, tr_proc); }
@@ -514,11 +516,11 @@ vq_tensor_search_kernel(const __grid_constant__ CUtensorMap tmap_cb, const float
             const uint32_t b_addr = sbase + C::OFF_B + stage * C::B_STAGE_BYTES;
             const uint32_t a_addr = sbase + (kc < 0 ? C::OFF_APAD : C::OFF_A + abuf * A_BUF_BYTES + kc * A_CHUNK_BYTES);
             const uint64_t ad = umma_desc_sw128(a_addr), bd = umma_desc_sw128(b_addr);
-            umma_bf16<CG>(tmem_d, ad, bd, kc < 0 ? 0u : rt_one);
+            umma_f16<CG>(tmem_d, ad, bd, kc < 0 ? 0u : rt_one);
             if (kc >= 0) {
-              umma_bf16<CG>(tmem_d, ad + 2, bd + 2, rt_one);
-              umma_bf16<CG>(tmem_d, ad + 4, bd + 4, rt_one);
-              umma_bf16<CG>(tmem_d, ad + 6, bd + 6, rt_one);
+              umma_f16<CG>(tmem_d, ad + 2, bd + 2, rt_one);
+              umma_f16<CG>(tmem_d, ad + 4, bd + 4, rt_one);
+              umma_f16<CG>(tmem_d, ad + 6, bd + 6, rt_one);
             }
             umma_commit<CG>(bar(C::BAR_B_EMPTY + stage));     // frees the codebook stage when these MMAs retire
             if (++stage == C::NSTAGE) { stage = 0; phase ^= 1; }
@@ -610,7 +612,7 @@ extern "C" int dcvic_debug_read_trace(unsigned long long* host_out /* [296][16] 
 namespace dcvic {
 #endif
 
-int vq_tensor_search(const float* z, const __nv_bfloat16* cb16, const float* emax, int B, int D, int HW, int K,
+int vq_tensor_search(const float* z, const __half* cb16, const float* emax, int B, int D, int HW, int K,
                      int* meta, uint2* list, cudaStream_t s) {
   if (!vq_tensor_supported(D, K)) return DCVIC_ERR_UNSUPPORTED;
   static const int cta_group = [] {
@@ -621,10 +623,10 @@ int vq_tensor_search(const float* z, const __nv_bfloat16* cb16, const float* ema
   if (!encode) return DCVIC_ERR_DEVICE;
   CUtensorMap tmap;
   const cuuint64_t gdim[2] = {(cuuint64_t)(D + kCb16Pad), (cuuint64_t)K};
-  const cuuint64_t gstride[1] = {(cuuint64_t)(D + kCb16Pad) * sizeof(__nv_bfloat16)};
+  const cuuint64_t gstride[1] = {(cuuint64_t)(D + kCb16Pad) * sizeof(__half)};
   const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)(BN / cta_group)};
   const cuuint32_t estr[2] = {1, 1};
-  if (encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(cb16), gdim, gstride, box, estr,
+  if (encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(cb16), gdim, gstride, box, estr,
              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
     return DCVIC_ERR_CUDA;

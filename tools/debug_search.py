@@ -50,11 +50,11 @@ off_partials = take((N // 32 + 2) * 8); off_hist = take(K * 4); off_cand = take(
 off_list = take(N * 2 * 16 * 8); off_cb16 = take(K * (D + 64) * 2)
 meta = ws[off_meta:off_meta + N * 16].view(torch.int32).view(N, 4).cpu()
 m_gpu = meta[:, :2].contiguous().view(torch.float32)
-cb16 = ws[off_cb16:off_cb16 + K * (D + 64) * 2].view(torch.bfloat16).view(K, D + 64).float().cpu()
+cb16 = ws[off_cb16:off_cb16 + K * (D + 64) * 2].view(torch.float16).view(K, D + 64).float().cpu()
 ee = ws[off_ee:off_ee + K * 4].view(torch.float32).cpu()
 print("pad cols vs -ee/2 max abs err:", float((cb16[:, D:D + 3].sum(1) + 0.5 * ee).abs().max()), " pad rest max:", float(cb16[:, D + 3:].abs().max()))
 rows = z.permute(0, 2, 3, 1).reshape(N, D)
-s = rows.bfloat16().float() @ E.bfloat16().float().t() - 0.5 * ee[None, :]
+s = rows.half().float() @ E.half().float().t() - 0.5 * ee[None, :]
 s4 = s.view(N, K // 256, 2, 128)          # [token][nt][column half][128]
 m_ref = s4.amax(dim=(1, 3))               # per column half
 err = (m_gpu - m_ref).abs()
