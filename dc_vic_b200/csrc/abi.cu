@@ -56,7 +56,7 @@ extern "C" int dcvic_vq_forward(const float* z_nchw, const float* codebook, int 
   double* partials = reinterpret_cast<double*>(ws + w.off_partials);
   unsigned* hist = reinterpret_cast<unsigned*>(ws + w.off_hist);
   int* cand = reinterpret_cast<int*>(ws + w.off_cand);
-  int* meta = reinterpret_cast<int*>(ws + w.off_meta);
+  VqMeta* meta = reinterpret_cast<VqMeta*>(ws + w.off_meta);
   uint2* list = reinterpret_cast<uint2*>(ws + w.off_list);
   __half* cb16 = reinterpret_cast<__half*>(ws + w.off_cb16);
   cudaStream_t s = (cudaStream_t)stream;

@@ -11,7 +11,13 @@ constexpr int kChunk = 32;            // codes per flag mask (one tcgen05.ld.32x
 constexpr int kCb16Pad = 64;          // extra FP16 codebook columns: a 3-way split of -|e|^2/2 in the first three
 constexpr int kCandMax = 24;          // FP32 re-rank candidates per token before falling back to a full scan
 
-// What the tensor search hands to the finish kernel, per token t:
+// What the tensor search hands to the finish kernel, per token t: one VqMeta record and two lists.
+struct __align__(16) VqMeta {
+  float m0, m1;     // running maximum of the FP16 score over columns 0-127 / 128-255 of every accumulator
+  short n0, n1;     // list entries of epilogue warp quad 0 / 1, or -1: scan the whole codebook for this token
+  float zz;         // |z|^2 as the search computed it (its margin and the finish's threshold use the same value)
+};
+// (older description of the same data:)
 //   meta[4t + q]     float  running maximum of the FP16 score over the columns of every accumulator that went to
 //                           epilogue warp quad q (q = 0: columns 0-127, 1: columns 128-255)
 //   meta[4t + 2 + q] int    number of list entries of buffer q, or -1 if its list overflowed
@@ -33,10 +39,10 @@ inline VqWorkspace vq_workspace_layout(int B, int D, int HW, int K) {
   w.off_ee = take((size_t)K * sizeof(float));
   w.off_nhee = take((size_t)K * sizeof(float));
   w.off_emax = take(4 * sizeof(float));
-  w.off_partials = take((N / 8 + 2) * sizeof(double));   // one per finish CTA (8 tokens in the smallest variant)
+  w.off_partials = take((N / 8 + 2) * sizeof(double));   // one per finish CTA (>= 16 tokens each)
   w.off_hist = take((size_t)K * sizeof(unsigned));
   w.off_cand = take(N * sizeof(int));
-  w.off_meta = take(N * 4 * sizeof(int));
+  w.off_meta = take(N * sizeof(VqMeta));
   w.off_list = take(N * 2 * kListCap * sizeof(uint2));
   w.off_cb16 = take((size_t)K * (D + kCb16Pad) * sizeof(__half));
   w.total = o;
@@ -69,7 +75,7 @@ int vq_narrow_forward(const float* z, const float* E, int B, int D, int HW, int 
 int vq_exact_search(const float* z, const float* E, const float* ee, int B, int D, int HW, int K, int* cand,
                     cudaStream_t s);
 // cand != nullptr: one decided index per token (exact search).  Otherwise meta/list from the tensor search.
-int vq_finish(const float* z, const float* E, const float* ee, const float* emax, const int* cand, const int* meta,
+int vq_finish(const float* z, const float* E, const float* ee, const float* emax, const int* cand, const VqMeta* meta,
               const uint2* list, int B, int D, int HW, int K, float beta, int legacy, float* zq, int64_t* idx,
               float* loss, double* partials, unsigned* counters, cudaStream_t s);
 int vq_v1_extras(const int64_t* idx, int N, int K, float* onehot, float* perplexity, unsigned* hist, unsigned* counters,
@@ -78,6 +84,6 @@ int vq_v1_extras(const int64_t* idx, int N, int K, float* onehot, float* perplex
 // vq_tcgen05.cu
 bool vq_tensor_supported(int D, int K);
 int vq_tensor_search(const float* z, const __half* cb16, const float* emax, int B, int D, int HW, int K,
-                     int* meta, uint2* list, cudaStream_t s);
+                     VqMeta* meta, uint2* list, cudaStream_t s);
 
 }  // namespace dcvic

@@ -304,7 +304,8 @@ constexpr int kPairCap = kFinishTokens * kCandMax;
 __global__ void __launch_bounds__(256) vq_finish_kernel(const float* __restrict__ z, const float* __restrict__ E,
                                                          const float* __restrict__ ee,
                                                          const float* __restrict__ emax_ptr,
-                                                         const int* __restrict__ cand, const int* __restrict__ meta,
+                                                         const int* __restrict__ cand,
+                                                         const VqMeta* __restrict__ meta,
                                                          const uint2* __restrict__ list, int N, int D, int HW, int K,
                                                          float beta, int legacy, float* __restrict__ zq,
                                                          int64_t* __restrict__ idx, float* __restrict__ loss,
@@ -353,10 +354,10 @@ __global__ void __launch_bounds__(256) vq_finish_kernel(const float* __restrict_
       const int tok = threadIdx.x >> 3, sub = threadIdx.x & 7;
       const int t = t0 + tok;
       if (t < N) {
-        const int4 mt = *reinterpret_cast<const int4*>(meta + (size_t)t * 4);
-        const float thr = fmaxf(__int_as_float(mt.x), __int_as_float(mt.y)) - vq_margin(s_zz[tok], *emax_ptr);
+        const VqMeta mt = meta[t];
+        const float thr = fmaxf(mt.m0, mt.m1) - vq_margin(mt.zz, *emax_ptr);
         const int q = sub >> 2, i0 = (sub & 3) * 4;
-        const int n = q == 0 ? mt.z : mt.w;
+        const int n = q == 0 ? mt.n0 : mt.n1;
         if (n < 0 && (sub & 3) == 0) atomicAdd(&s_nc[tok], 2 * kCandMax);   // overflowed list -> full scan
         if (i0 < n) {
           const uint4* lp = reinterpret_cast<const uint4*>(list + ((size_t)t * 2 + q) * kListCap + i0);
@@ -485,13 +486,18 @@ __global__ void __launch_bounds__(256) vq_finish_kernel(const float* __restrict_
 }
 
 // ------------------------------------------------------------------ finish, 128-bit version
-// Same phases and arithmetic as vq_finish_kernel, for e_dim % 4 == 0 and H*W % 4 == 0 (16-byte aligned
-// tensors): the token tile lives in shared memory token-major ([32][D+4] floats), so that
+// Same arithmetic as vq_finish_kernel, for e_dim % 4 == 0 and H*W % 4 == 0 (16-byte aligned tensors).  The
+// 32-token tile lives in shared memory token-major ([32][D+4] floats), so that
 //   * NCHW loads / stores move 4 consecutive tokens per thread (LDG.128 / STG.128, 128 contiguous bytes per
 //     8 lanes) and are transposed 4x4 in registers on the way in and out,
 //   * codebook rows and token rows are both read as float4 along channels (lane = 4 channels of each
-//     128-channel block), so one (token, code) dot costs 2 LDS.128 + 2 LDG.128 + 8 FFMA + the warp sum.
+//     128-channel block): one (token, code) dot costs 2 LDS.128 + 2 LDG.128 + 8 FFMA + the warp sum at e_dim 256.
 // Row stride D+4 floats keeps every quarter-warp's 16-byte accesses on 8 distinct bank groups.
+// Three block barriers per tile: (A) tile staged, meta + list entries (requested first, they do not depend on
+// z) expanded into per-token candidate codes with the search's own |z|^2; (B) every warp takes 4 tokens from
+// candidates to z_q: re-rank where more than one code was flagged (two codebook rows in flight), then the 4
+// winning rows are fetched together for the gather / straight-through value / loss partial; (C) coalesced
+// stores.  Tokens that need the whole codebook (overflowed list, FP16-unsafe) are scanned by the full CTA.
 constexpr int kFT = kFinishTokens;
 #ifdef DCVIC_TRACE
 __device__ unsigned long long g_trace_fin[4096][12];
@@ -507,103 +513,102 @@ __device__ unsigned long long g_trace_fin[4096][12];
 #define FT_MARK(i)
 #endif
 
-template <int DT>   // DT = e_dim when it is one of the specialised sizes (64, 128, 256), else 0 (run-time e_dim)
-__global__ void __launch_bounds__(256, 3) vq_finish_v4_kernel(const float* __restrict__ z, const float* __restrict__ E,
+// DT = e_dim when it is one of the specialised sizes (64, 128, 256), else 0 (run-time e_dim); T = tokens per CTA
+// (16 or 32; T/4 warps, each owning 4 tokens in phase B)
+template <int DT, int T>
+__global__ void __launch_bounds__(T * 8) vq_finish_v5_kernel(const float* __restrict__ z, const float* __restrict__ E,
                                                             const float* __restrict__ ee,
                                                             const float* __restrict__ emax_ptr,
                                                             const int* __restrict__ cand,
-                                                            const int* __restrict__ meta,
+                                                            const VqMeta* __restrict__ meta,
                                                             const uint2* __restrict__ list, int N, int Drt, int HW, int K,
                                                             float beta, int legacy, float* __restrict__ zq,
                                                             int64_t* __restrict__ idx, float* __restrict__ loss,
                                                             double* __restrict__ partials,
                                                             unsigned* __restrict__ counters) {
-  extern __shared__ __align__(16) float zt[];  // [kFT][D + 4]
+  extern __shared__ __align__(16) float zt[];  // [T][D + 4]
   __shared__ double scratch[32];
-  __shared__ float s_zz[kFT];
-  __shared__ int s_best[kFT];                  // decided code, -1 while undecided, -2 = scan the whole codebook
-  __shared__ int s_first[kFT + 1];             // pair range of each token
-  __shared__ unsigned short s_pair_tok[kPairCap];
-  __shared__ unsigned short s_pair_k[kPairCap];
-  __shared__ float s_pair_d[kPairCap];
-  __shared__ float s_wd[8];
-  __shared__ int s_wk[8];
-  __shared__ int s_nc[kFT];
-  __shared__ unsigned short s_ck[kFT * kCandMax];
-  __shared__ int s_nfull;
+  __shared__ int s_best[T];                  // decided code
+  __shared__ float s_wd[T / 4];
+  __shared__ int s_wk[T / 4];
+  __shared__ int s_nc[T];                    // flagged codes per token (> kCandMax: scan the whole codebook)
+  __shared__ unsigned short s_ck[T * kCandMax];
+  __shared__ int s_nfull, s_nrerank;
   const int D = DT ? DT : Drt;
   constexpr int NV = DT ? (DT + 127) / 128 : 8;      // float4 per lane and row (run-time e_dim: up to 1024)
-  constexpr int NP = DT ? (DT + 127) / 128 : 0;      // staging passes of the NEXT tile held in registers (0: none)
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int ld = D + 4;
-  const int num_tiles = (N + kFT - 1) / kFT;
-  // staging map: lane = tq*4 + cq, token quad tq (tokens 4tq..4tq+3), channel quad cq; warp w takes channels
-  // [16w, 16w+16) of every 128-channel pass
-  const int tq = lane >> 2, cq = lane & 3;
-  auto quad_base = [&](int tile, bool& ok) {
-    const int tokq = tile * kFT + 4 * tq;                // N % 4 == 0: quads are valid as a whole
-    ok = tile < num_tiles && tokq < N;
-    return ok ? ((size_t)(tokq / HW) * D * HW + (size_t)(tokq % HW)) : (size_t)0;
-  };
-  float4 pv[NP ? NP : 1][4];
-  auto load_tile_regs = [&](int tile) {
-    bool ok;
-    const size_t qb = quad_base(tile, ok);
-#pragma unroll
-    for (int h = 0; h < NP; ++h) {
-      const int c = h * 128 + wid * 16 + cq * 4;
-#pragma unroll
-      for (int k = 0; k < 4; ++k)
-        pv[h][k] = (ok && c < D) ? ldg_stream(reinterpret_cast<const float4*>(z + qb + (size_t)(c + k) * HW))
-                                 : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-  };
-  auto store_quad = [&](const float4 (&v)[4], int c) {   // 4x4 transpose: 4 tokens x 4 channels
-    float* dst = zt + (4 * tq) * ld + c;
-    *reinterpret_cast<float4*>(dst) = make_float4(v[0].x, v[1].x, v[2].x, v[3].x);
-    *reinterpret_cast<float4*>(dst + ld) = make_float4(v[0].y, v[1].y, v[2].y, v[3].y);
-    *reinterpret_cast<float4*>(dst + 2 * ld) = make_float4(v[0].z, v[1].z, v[2].z, v[3].z);
-    *reinterpret_cast<float4*>(dst + 3 * ld) = make_float4(v[0].w, v[1].w, v[2].w, v[3].w);
-  };
-  if (NP) load_tile_regs(blockIdx.x);
-  float sq = 0.f;
+  constexpr int W = T / 4;                    // warps
+  constexpr int TQ = T / 4, CQ = 32 / TQ;     // token quads per tile, channel quads per warp-iteration
+  const int t0 = blockIdx.x * T;
 #ifdef DCVIC_TRACE
   unsigned long long ft_acc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, ft_t = clock64();
 #endif
+  if (threadIdx.x < T) s_nc[threadIdx.x] = 0;
+  if (threadIdx.x == 0) { s_nfull = 0; s_nrerank = 0; }
 
-  for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-  const int t0 = tile * kFT;
-  bool qvalid;
-  const size_t qbase = quad_base(tile, qvalid);
-  if (threadIdx.x < kFT) s_nc[threadIdx.x] = 0;
-  if (threadIdx.x == 0) s_nfull = 0;
-  // (0) stage the token tile; the next tile of this CTA is requested right away and stays in flight (in
-  // registers) while this one is processed
-  if (NP) {
+  // requests that do not depend on z go first: meta + this thread's 4 list entries (8 threads per token)
+  const int ltok = threadIdx.x >> 3, sub = threadIdx.x & 7;
+  const int lq = sub >> 2, li0 = (sub & 3) * 4;
+  const bool lvalid = !cand && (t0 + ltok) < N;
+  VqMeta mt = {};
+  uint4 e01 = make_uint4(0u, 0u, 0u, 0u), e23 = e01;
+  if (lvalid) {
+    mt = meta[t0 + ltok];
+    const uint4* lp = reinterpret_cast<const uint4*>(list + ((size_t)(t0 + ltok) * 2 + lq) * kListCap + li0);
+    e01 = __ldg(lp);
+    e23 = __ldg(lp + 1);
+  }
+
+  // (A) stage the token tile: lane = tq*CQ + cq, token quad tq (tokens 4tq..4tq+3), channel quad cq; warp w takes
+  // channels [4*CQ*w, 4*CQ*(w+1)) of every 128-channel pass (a quarter warp = 8 channel quads or 2 token quads x 4
+  // channel quads: 8 distinct bank groups for its 16-byte stores either way)
+  const int tq = lane / CQ, cq = lane % CQ;
+  const int tokq = t0 + 4 * tq;                          // first token of this thread's quad
+  const bool qvalid = tokq < N;                          // N % 4 == 0: quads are valid as a whole
+  const size_t qbase = qvalid ? ((size_t)(tokq / HW) * D * HW + (size_t)(tokq % HW)) : 0;
+  for (int c0 = wid * (4 * CQ); c0 < D; c0 += 128) {
+    const int c = c0 + cq * 4;
+    if (c < D) {
+      float4 v[4];
 #pragma unroll
-    for (int h = 0; h < NP; ++h) {
-      const int c = h * 128 + wid * 16 + cq * 4;
-      if (c < D) store_quad(pv[h], c);
+      for (int k = 0; k < 4; ++k)
+        v[k] = qvalid ? ldg_stream(reinterpret_cast<const float4*>(z + qbase + (size_t)(c + k) * HW))
+                      : make_float4(0.f, 0.f, 0.f, 0.f);
+      float* dst = zt + (4 * tq) * ld + c;                // 4x4 transpose: 4 tokens x 4 channels
+      *reinterpret_cast<float4*>(dst) = make_float4(v[0].x, v[1].x, v[2].x, v[3].x);
+      *reinterpret_cast<float4*>(dst + ld) = make_float4(v[0].y, v[1].y, v[2].y, v[3].y);
+      *reinterpret_cast<float4*>(dst + 2 * ld) = make_float4(v[0].z, v[1].z, v[2].z, v[3].z);
+      *reinterpret_cast<float4*>(dst + 3 * ld) = make_float4(v[0].w, v[1].w, v[2].w, v[3].w);
     }
-    load_tile_regs(tile + gridDim.x);
-  } else {
-    for (int c0 = wid * 16; c0 < D; c0 += 128) {
-      const int c = c0 + cq * 4;
-      if (c < D) {
-        float4 v[4];
+  }
+  // expand list entries -> candidate codes (order within a token does not matter: the minimum is over
+  // (distance, index)).  The threshold uses the |z|^2 the search itself used for its margin.
+  if (lvalid) {
+    const float thr = fmaxf(mt.m0, mt.m1) - vq_margin(mt.zz, *emax_ptr);
+    const int n = lq == 0 ? mt.n0 : mt.n1;
+    if (n < 0 && (sub & 3) == 0) atomicAdd(&s_nc[ltok], 2 * kCandMax);   // overflowed / unsafe -> full scan
+    const unsigned key[4] = {e01.x, e01.z, e23.x, e23.z};
+    const unsigned msk[4] = {e01.y, e01.w, e23.y, e23.w};
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          v[k] = qvalid ? ldg_stream(reinterpret_cast<const float4*>(z + qbase + (size_t)(c + k) * HW))
-                        : make_float4(0.f, 0.f, 0.f, 0.f);
-        store_quad(v, c);
+    for (int i = 0; i < 4; ++i) {
+      if (li0 + i >= n) break;
+      if (__uint_as_float(key[i] | 0x7Fu) < thr) continue;      // chunk maximum (rounded up) below threshold
+      unsigned mask = msk[i];
+      const int c0 = (int)(key[i] & 0x7Fu) * kChunk;
+      int w = atomicAdd(&s_nc[ltok], __popc(mask));
+      while (mask && w < kCandMax) {
+        const int j = __ffs(mask) - 1;
+        mask &= mask - 1;
+        s_ck[ltok * kCandMax + w++] = (unsigned short)(c0 + j);
       }
     }
   }
   __syncthreads();
   FT_MARK(0);
 
-  // FP32 dot of token row `tok` with codebook row k: lane takes channels 4*lane + 128*h, sequential FMAs
-  // inside the lane, xor tree across lanes.  load_e / dot_e are split so that several rows can be in flight.
+  // FP32 dot of token row `tok` with a codebook row: lane takes channels 4*lane + 128*h, sequential FMAs inside
+  // the lane, xor tree across lanes.  load_e / dot_e are split so that several rows can be in flight.
   auto load_e = [&](float4 (&b)[NV], const float* er) {
 #pragma unroll
     for (int h = 0; h < NV; ++h) {
@@ -623,176 +628,131 @@ __global__ void __launch_bounds__(256, 3) vq_finish_v4_kernel(const float* __res
     }
     return warp_sum(dp);
   };
-
-  if (cand) {
-    if (wid == 0) s_best[lane] = (t0 + lane < N) ? min(max(cand[t0 + lane], 0), K - 1) : 0;
-    __syncthreads();
-  } else {
-    for (int tok = wid; tok < kFT; tok += 8) {
-      float zzp = 0.f;
+  auto zz_row = [&](int tok) {
+    float zzp = 0.f;
 #pragma unroll
-      for (int h = 0; h < NV; ++h) {
-        const int c = lane * 4 + 128 * h;
-        if (c < D) {
-          const float4 a = *reinterpret_cast<const float4*>(zt + tok * ld + c);
-          zzp = __fadd_rn(zzp, __fmul_rn(a.x, a.x)); zzp = __fadd_rn(zzp, __fmul_rn(a.y, a.y));
-          zzp = __fadd_rn(zzp, __fmul_rn(a.z, a.z)); zzp = __fadd_rn(zzp, __fmul_rn(a.w, a.w));
-        }
+    for (int h = 0; h < NV; ++h) {
+      const int c = lane * 4 + 128 * h;
+      if (c < D) {
+        const float4 a = *reinterpret_cast<const float4*>(zt + tok * ld + c);
+        zzp = __fadd_rn(zzp, __fmul_rn(a.x, a.x)); zzp = __fadd_rn(zzp, __fmul_rn(a.y, a.y));
+        zzp = __fadd_rn(zzp, __fmul_rn(a.z, a.z)); zzp = __fadd_rn(zzp, __fmul_rn(a.w, a.w));
       }
-      zzp = warp_sum(zzp);
-      if (lane == 0) s_zz[tok] = zzp;
     }
-    __syncthreads();
-    FT_MARK(1);
-    // (1) expand lists -> candidate codes: 8 threads per token, 4 list entries each (all loads in flight
-    // at once); order within a token does not matter, the minimum is taken over (distance, index)
-    {
-      const int tok = threadIdx.x >> 3, sub = threadIdx.x & 7;
-      const int t = t0 + tok;
-      if (t < N) {
-        const int4 mt = *reinterpret_cast<const int4*>(meta + (size_t)t * 4);
-        const float thr = fmaxf(__int_as_float(mt.x), __int_as_float(mt.y)) - vq_margin(s_zz[tok], *emax_ptr);
-        const int q = sub >> 2, i0 = (sub & 3) * 4;
-        const int n = q == 0 ? mt.z : mt.w;
-        if (n < 0 && (sub & 3) == 0) atomicAdd(&s_nc[tok], 2 * kCandMax);   // overflowed list -> full scan
-        if (i0 < n) {
-          const uint4* lp = reinterpret_cast<const uint4*>(list + ((size_t)t * 2 + q) * kListCap + i0);
-          const uint4 e01 = lp[0], e23 = lp[1];
-          const unsigned key[4] = {e01.x, e01.z, e23.x, e23.z};
-          const unsigned msk[4] = {e01.y, e01.w, e23.y, e23.w};
+    return warp_sum(zzp);
+  };
+
+  // (B) warp w owns tokens w, w+8, w+16, w+24 from candidates to z_q
+  int best[4];
+  unsigned n_rerank = 0, n_full = 0;
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            if (i0 + i >= n) break;
-            if (__uint_as_float(key[i] | 0x7Fu) < thr) continue;      // chunk maximum (rounded up) below threshold
-            unsigned mask = msk[i];
-            const int c0 = (int)(key[i] & 0x7Fu) * kChunk;
-            const int pos = atomicAdd(&s_nc[tok], __popc(mask));
-            int w = pos;
-            while (mask && w < kCandMax) {
-              const int j = __ffs(mask) - 1;
-              mask &= mask - 1;
-              s_ck[tok * kCandMax + w++] = (unsigned short)(c0 + j);
+  for (int i = 0; i < 4; ++i) {
+    const int tok = wid + W * i;
+    const int t = t0 + tok;
+    int bk = 0;
+    if (t < N) {
+      if (cand) {
+        bk = min(max(cand[t], 0), K - 1);
+      } else {
+        const int nc = s_nc[tok];
+        if (nc == 1) {
+          bk = s_ck[tok * kCandMax];
+        } else if (nc > kCandMax || nc <= 0) {
+          bk = -2;                                        // whole codebook, below
+          ++n_full;
+        } else {
+          ++n_rerank;
+          const float zz = zz_row(tok);
+          float bd = FLT_MAX;
+          bk = 0x7fffffff;
+          for (int c = 0; c < nc; c += 2) {               // two candidate rows in flight
+            const int k0 = s_ck[tok * kCandMax + c], k1 = s_ck[tok * kCandMax + min(c + 1, nc - 1)];
+            float4 b0[NV], b1[NV];
+            load_e(b0, E + (size_t)k0 * D);
+            load_e(b1, E + (size_t)k1 * D);
+            const float ee0 = __ldg(ee + k0), ee1 = __ldg(ee + k1);
+            const float d0 = fmaf(-2.f, dot_e(tok, b0), __fadd_rn(zz, ee0));
+            if (d0 < bd || (d0 == bd && k0 < bk)) { bd = d0; bk = k0; }
+            if (c + 1 < nc) {
+              const float d1 = fmaf(-2.f, dot_e(tok, b1), __fadd_rn(zz, ee1));
+              if (d1 < bd || (d1 == bd && k1 < bk)) { bd = d1; bk = k1; }
             }
           }
         }
       }
     }
-    __syncthreads();
-    FT_MARK(2);
-    // pair ranges (warp 0: lane = token); tokens with one candidate are decided here
-    if (wid == 0) {
-      const bool valid = t0 + lane < N;
-      const int nc = valid ? s_nc[lane] : 1;
-      const int ncand = nc > kCandMax ? -1 : nc;        // nc == 0 cannot happen (the maximum is always flagged)
-      const int npairs = ncand > 1 ? ncand : 0;
-      int off = npairs;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int v = __shfl_up_sync(0xffffffffu, off, o);
-        if (lane >= o) off += v;
-      }
-      s_first[lane + 1] = off;
-      if (lane == 0) s_first[0] = 0;
-      off -= npairs;
-      for (int i = 0; i < npairs; ++i) {
-        s_pair_tok[off + i] = (unsigned short)lane;
-        s_pair_k[off + i] = s_ck[lane * kCandMax + i];
-      }
-      int sb = 0;                                       // rows past the end: any valid code
-      if (valid) sb = ncand == 1 ? (int)s_ck[lane * kCandMax] : (ncand <= 0 ? -2 : -1);
-      s_best[lane] = sb;
-      {   // statistics: one atomic per CTA and counter (same-address atomics from every token serialise in L2)
-        const unsigned nr = __popc(__ballot_sync(0xffffffffu, valid && ncand > 1));
-        const unsigned nf = __popc(__ballot_sync(0xffffffffu, valid && ncand < 1));
-        if (lane == 0 && nr) atomicAdd(counters + kCtrRerank, nr);
-        if (lane == 0 && nf) atomicAdd(counters + kCtrOverflow, nf);
-      }
-      if (sb == -2) atomicAdd(&s_nfull, 1);
-    }
-    __syncthreads();
-    FT_MARK(3);
-    // (2) one FP32 dot per (token, code) pair
-    const int total = s_first[kFT];
-    for (int p = wid; p < total; p += 16) {              // two pairs in flight per warp
-      const int p2 = p + 8;
-      const bool two = p2 < total;
-      const int tok1 = s_pair_tok[p], k1 = s_pair_k[p];
-      const int tok2 = two ? s_pair_tok[p2] : tok1, k2 = two ? s_pair_k[p2] : k1;
-      float4 b1[NV], b2[NV];
-      load_e(b1, E + (size_t)k1 * D);
-      load_e(b2, E + (size_t)k2 * D);
-      const float ee1 = __ldg(ee + k1), ee2 = __ldg(ee + k2);
-      const float dot1 = dot_e(tok1, b1), dot2 = dot_e(tok2, b2);
-      if (lane == 0) {
-        s_pair_d[p] = fmaf(-2.f, dot1, __fadd_rn(s_zz[tok1], ee1));
-        if (two) s_pair_d[p2] = fmaf(-2.f, dot2, __fadd_rn(s_zz[tok2], ee2));
-      }
-    }
-    __syncthreads();
-    FT_MARK(4);
-    // (3) minimum per token, ties to the lowest index
-    if (wid == 0 && s_best[lane] == -1) {
-      float bd = FLT_MAX;
-      int bk = 0x7fffffff;
-      for (int p = s_first[lane]; p < s_first[lane + 1]; ++p) {
-        const float d = s_pair_d[p];
-        const int k = s_pair_k[p];
-        if (d < bd || (d == bd && k < bk)) { bd = d; bk = k; }
-      }
-      s_best[lane] = bk;
-    }
-    __syncthreads();
-    FT_MARK(5);
-    // (3b) full scans: the whole CTA on one token at a time (rare)
-    for (int tok = 0; tok < kFT && s_nfull > 0; ++tok) {
+    best[i] = bk;
+    if (lane == 0) s_best[tok] = bk;
+  }
+  if (lane == 0 && n_full) atomicAdd(&s_nfull, (int)n_full);
+  if (lane == 0 && n_rerank) atomicAdd(&s_nrerank, (int)n_rerank);
+  __syncthreads();
+  FT_MARK(1);
+  // full scans: the whole CTA on one token at a time (rare)
+  if (s_nfull > 0) {
+    for (int tok = 0; tok < T; ++tok) {
       if (s_best[tok] != -2) continue;             // uniform: read from shared memory by all threads
-      const float zz = s_zz[tok];
+      const float zz = zz_row(tok);
       float bd = FLT_MAX;
       int bk = 0x7fffffff;
-      for (int k = wid; k < K; k += 8) {
+      for (int k = wid; k < K; k += W) {
         float4 b[NV];
         load_e(b, E + (size_t)k * D);
-        const float dot = dot_e(tok, b);
-        const float d = fmaf(-2.f, dot, __fadd_rn(zz, ee[k]));
+        const float d = fmaf(-2.f, dot_e(tok, b), __fadd_rn(zz, ee[k]));
         if (d < bd || (d == bd && k < bk)) { bd = d; bk = k; }
       }
       if (lane == 0) { s_wd[wid] = bd; s_wk[wid] = bk; }
       __syncthreads();
       if (threadIdx.x == 0) {
-        for (int w = 1; w < 8; ++w)
+        for (int w = 1; w < W; ++w)
           if (s_wd[w] < bd || (s_wd[w] == bd && s_wk[w] < bk)) { bd = s_wd[w]; bk = s_wk[w]; }
         s_best[tok] = bk;
       }
       __syncthreads();
     }
-  }
-
-  FT_MARK(6);
-  // (4) gather + straight-through value + loss partial (warp per token, lane = 4 channels per 128)
-  for (int tok = wid; tok < kFT; tok += 8) {
-    const int t = t0 + tok;
-    if (t >= N) break;
-    const int best_k = min(max(s_best[tok], 0), K - 1);
-    float4 eb[NV];
-    load_e(eb, E + (size_t)best_k * D);
 #pragma unroll
-    for (int h = 0; h < NV; ++h) {
-      const int c = lane * 4 + 128 * h;
-      if (c < D) {
-        float4* zp = reinterpret_cast<float4*>(zt + tok * ld + c);
-        const float4 a = *zp, e = eb[h];
-        const float dx = __fsub_rn(e.x, a.x), dy = __fsub_rn(e.y, a.y), dz = __fsub_rn(e.z, a.z), dw = __fsub_rn(e.w, a.w);
-        *zp = make_float4(__fadd_rn(a.x, dx), __fadd_rn(a.y, dy), __fadd_rn(a.z, dz), __fadd_rn(a.w, dw));
-        sq = fmaf(dx, dx, sq); sq = fmaf(dy, dy, sq); sq = fmaf(dz, dz, sq); sq = fmaf(dw, dw, sq);
+    for (int i = 0; i < 4; ++i) best[i] = s_best[wid + W * i];
+  }
+  if (threadIdx.x == 0) {   // statistics: one atomic per CTA and counter (same-address atomics serialise in L2)
+    if (s_nrerank) atomicAdd(counters + kCtrRerank, (unsigned)s_nrerank);
+    if (s_nfull) atomicAdd(counters + kCtrOverflow, (unsigned)s_nfull);
+  }
+  // gather + straight-through value + loss partial: the 4 winning rows of this warp are requested together
+  float sq = 0.f;
+  {
+    constexpr int G = DT ? 4 : 1;               // rows fetched together (run-time e_dim: one, to bound registers)
+#pragma unroll
+    for (int i0 = 0; i0 < 4; i0 += G) {
+      float4 eb[G][NV];
+#pragma unroll
+      for (int g = 0; g < G; ++g) load_e(eb[g], E + (size_t)min(max(best[i0 + g], 0), K - 1) * D);
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        const int i = i0 + g;
+        const int tok = wid + W * i;
+        const int t = t0 + tok;
+        if (t < N) {
+#pragma unroll
+          for (int h = 0; h < NV; ++h) {
+            const int c = lane * 4 + 128 * h;
+            if (c < D) {
+              float4* zp = reinterpret_cast<float4*>(zt + tok * ld + c);
+              const float4 a = *zp, e = eb[g][h];
+              const float dx = __fsub_rn(e.x, a.x), dy = __fsub_rn(e.y, a.y), dz = __fsub_rn(e.z, a.z), dw = __fsub_rn(e.w, a.w);
+              *zp = make_float4(__fadd_rn(a.x, dx), __fadd_rn(a.y, dy), __fadd_rn(a.z, dz), __fadd_rn(a.w, dw));
+              sq = fmaf(dx, dx, sq); sq = fmaf(dy, dy, sq); sq = fmaf(dz, dz, sq); sq = fmaf(dw, dw, sq);
+            }
+          }
+          if (lane == 0) idx[t] = (int64_t)min(max(best[i], 0), K - 1);
+        }
       }
     }
-    if (lane == 0) idx[t] = (int64_t)best_k;
   }
   __syncthreads();
-  FT_MARK(7);
-  // (5) write z_q back NCHW: the transpose of (0)
+  FT_MARK(2);
+  // (C) write z_q back NCHW: the transpose of (A)
   if (qvalid)
-    for (int c0 = wid * 16; c0 < D; c0 += 128) {
+    for (int c0 = wid * (4 * CQ); c0 < D; c0 += 128) {
       const int c = c0 + cq * 4;
       if (c < D) {
         const float* src = zt + (4 * tq) * ld + c;
@@ -805,9 +765,7 @@ __global__ void __launch_bounds__(256, 3) vq_finish_v4_kernel(const float* __res
         stg_stream(reinterpret_cast<float4*>(o + 3 * (size_t)HW), make_float4(r0.w, r1.w, r2.w, r3.w));
       }
     }
-  __syncthreads();                             // the tile buffer and the per-tile arrays are reused
-  FT_MARK(8);
-  }  // tile loop
+  FT_MARK(3);
 #ifdef DCVIC_TRACE
   if (threadIdx.x == 0 && blockIdx.x < 4096)
     for (int i = 0; i < 12; ++i) g_trace_fin[blockIdx.x][i] = ft_acc[i];
@@ -820,237 +778,36 @@ __global__ void __launch_bounds__(256, 3) vq_finish_v4_kernel(const float* __res
   }
 }
 
-// ------------------------------------------------------------------ finish, warp-autonomous version
-// One warp owns 4 consecutive tokens (one 16-byte token quad per channel) from the first load to the last
-// store; nothing is shared between warps but the loss partial, so there is no block barrier in the token
-// path and a stalled warp never holds others back.  The token quad lives in registers: lane l keeps channels
-// l, l+32, ... (DT/32 float4, 4 tokens each); codebook rows are read with the same lane-strided pattern
-// (128 contiguous bytes per warp load), a (token, code) dot is DT/32 FFMAs + the xor-tree warp sum, and z_q
-// goes back as one STG.128 per channel.  The two halves of every 32-byte sector of z belong to two
-// neighbouring warps of the same CTA, so the loads allocate in L1.
-// Arithmetic, candidate filtering and tie-breaking are those of vq_finish_kernel.
-constexpr int kQW = 8;   // warps per CTA of the warp-autonomous finish (small CTAs: a slow warp holds back one neighbour)
-
-template <int DT>
-__global__ void __launch_bounds__(kQW * 32, 4) vq_finish_quad_kernel(const float* __restrict__ z, const float* __restrict__ E,
-                                                              const float* __restrict__ ee,
-                                                              const float* __restrict__ emax_ptr,
-                                                              const int* __restrict__ cand,
-                                                              const int* __restrict__ meta,
-                                                              const uint2* __restrict__ list, int N, int HW, int K,
-                                                              float beta, int legacy, float* __restrict__ zq,
-                                                              int64_t* __restrict__ idx, float* __restrict__ loss,
-                                                              double* __restrict__ partials,
-                                                              unsigned* __restrict__ counters) {
-  constexpr int NJ = DT / 32;                  // channels per lane
-  __shared__ double s_part[kQW];
-  __shared__ int s_done;
-  __shared__ int s_nc[kQW][4];
-  __shared__ unsigned short s_ck[kQW][4][kCandMax];
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int t0 = (blockIdx.x * kQW + wid) * 4;   // first token of this warp's quad (N % 4 == 0)
-  float sq = 0.f;
-  if (threadIdx.x == 0) s_done = 0;
-  __syncthreads();                             // the only block barrier: warps meet again only at the election below
-  if (t0 < N) {
-    const size_t qbase = (size_t)(t0 / HW) * DT * HW + (size_t)(t0 % HW);
-    float4 zr[NJ];
-#pragma unroll
-    for (int j = 0; j < NJ; ++j) zr[j] = __ldg(reinterpret_cast<const float4*>(z + qbase + (size_t)(lane + 32 * j) * HW));
-    int best[4];
-    unsigned n_rerank = 0, n_full = 0;         // statistics, one atomic per warp (same-address atomics serialise in L2)
-    if (cand) {
-#pragma unroll
-      for (int i = 0; i < 4; ++i) best[i] = min(max(cand[t0 + i], 0), K - 1);
-    } else {
-      // lists of the 4 tokens: lane = token*8 + sub, 4 entries per lane, requested before anything depends on z
-      const int tok = lane >> 3, sub = lane & 7;
-      const int q = sub >> 2, i0 = (sub & 3) * 4;
-      const int4 mt = *reinterpret_cast<const int4*>(meta + (size_t)(t0 + tok) * 4);
-      const uint4* lp = reinterpret_cast<const uint4*>(list + ((size_t)(t0 + tok) * 2 + q) * kListCap + i0);
-      const uint4 e01 = lp[0], e23 = lp[1];
-      if (lane < 4) s_nc[wid][lane] = 0;
-      // |z|^2 per token: lane-strided partials, xor tree
-      float zz[4];
-      {
-        float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;
-#pragma unroll
-        for (int j = 0; j < NJ; ++j) {
-          p0 = __fadd_rn(p0, __fmul_rn(zr[j].x, zr[j].x)); p1 = __fadd_rn(p1, __fmul_rn(zr[j].y, zr[j].y));
-          p2 = __fadd_rn(p2, __fmul_rn(zr[j].z, zr[j].z)); p3 = __fadd_rn(p3, __fmul_rn(zr[j].w, zr[j].w));
-        }
-        zz[0] = warp_sum(p0); zz[1] = warp_sum(p1); zz[2] = warp_sum(p2); zz[3] = warp_sum(p3);
-      }
-      __syncwarp();
-      {
-        const float zzt = tok == 0 ? zz[0] : (tok == 1 ? zz[1] : (tok == 2 ? zz[2] : zz[3]));
-        const float thr = fmaxf(__int_as_float(mt.x), __int_as_float(mt.y)) - vq_margin(zzt, *emax_ptr);
-        const int n = q == 0 ? mt.z : mt.w;
-        if (n < 0 && (sub & 3) == 0) atomicAdd(&s_nc[wid][tok], 2 * kCandMax);   // overflowed list -> full scan
-        const unsigned key[4] = {e01.x, e01.z, e23.x, e23.z};
-        const unsigned msk[4] = {e01.y, e01.w, e23.y, e23.w};
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          if (i0 + i >= n) break;
-          if (__uint_as_float(key[i] | 0x7Fu) < thr) continue;      // chunk maximum (rounded up) below threshold
-          unsigned mask = msk[i];
-          const int c0 = (int)(key[i] & 0x7Fu) * kChunk;
-          int w = atomicAdd(&s_nc[wid][tok], __popc(mask));
-          while (mask && w < kCandMax) {
-            const int jb = __ffs(mask) - 1;
-            mask &= mask - 1;
-            s_ck[wid][tok][w++] = (unsigned short)(c0 + jb);
-          }
-        }
-      }
-      __syncwarp();
-      // re-rank: FP32 distance of every candidate, ties to the lowest index
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int nc = s_nc[wid][i];
-        const float zzi = zz[i];
-        float bd = FLT_MAX;
-        int bk = 0x7fffffff;
-        auto consider = [&](int k, const float (&e)[NJ], float eek) {
-          float dp = 0.f;
-#pragma unroll
-          for (int j = 0; j < NJ; ++j) {
-            const float zv = i == 0 ? zr[j].x : (i == 1 ? zr[j].y : (i == 2 ? zr[j].z : zr[j].w));
-            dp = fmaf(zv, e[j], dp);
-          }
-          const float d = fmaf(-2.f, warp_sum(dp), __fadd_rn(zzi, eek));
-          if (d < bd || (d == bd && k < bk)) { bd = d; bk = k; }
-        };
-        auto load_row = [&](float (&e)[NJ], int k) {
-          const float* er = E + (size_t)k * DT + lane;
-#pragma unroll
-          for (int j = 0; j < NJ; ++j) e[j] = __ldg(er + 32 * j);
-        };
-        if (nc == 1) {
-          bk = s_ck[wid][i][0];
-        } else if (nc > kCandMax || nc <= 0) {
-          ++n_full;
-          for (int k = 0; k < K; k += 2) {                       // whole codebook, two rows in flight
-            float e0[NJ], e1[NJ];
-            load_row(e0, k);
-            load_row(e1, min(k + 1, K - 1));
-            consider(k, e0, __ldg(ee + k));
-            if (k + 1 < K) consider(k + 1, e1, __ldg(ee + k + 1));
-          }
-        } else {
-          ++n_rerank;
-          for (int c = 0; c < nc; c += 2) {                      // two candidate rows in flight
-            const int k0 = s_ck[wid][i][c], k1 = s_ck[wid][i][min(c + 1, nc - 1)];
-            float e0[NJ], e1[NJ];
-            load_row(e0, k0);
-            load_row(e1, k1);
-            const float ee0 = __ldg(ee + k0), ee1 = __ldg(ee + k1);
-            consider(k0, e0, ee0);
-            if (c + 1 < nc) consider(k1, e1, ee1);
-          }
-        }
-        best[i] = min(max(bk, 0), K - 1);
-      }
-    }
-    if (lane == 0 && n_rerank) atomicAdd(counters + kCtrRerank, n_rerank);
-    if (lane == 0 && n_full) atomicAdd(counters + kCtrOverflow, n_full);
-    // gather + straight-through value (in place) + loss partial, two rows in flight
-#pragma unroll
-    for (int i = 0; i < 4; i += 2) {
-      float e0[NJ], e1[NJ];
-      const float* r0 = E + (size_t)best[i] * DT + lane;
-      const float* r1 = E + (size_t)best[i + 1] * DT + lane;
-#pragma unroll
-      for (int j = 0; j < NJ; ++j) { e0[j] = __ldg(r0 + 32 * j); e1[j] = __ldg(r1 + 32 * j); }
-#pragma unroll
-      for (int j = 0; j < NJ; ++j) {
-        float& za = i == 0 ? zr[j].x : zr[j].z;
-        float& zb = i == 0 ? zr[j].y : zr[j].w;
-        const float da = __fsub_rn(e0[j], za), db = __fsub_rn(e1[j], zb);
-        sq = fmaf(da, da, sq); sq = fmaf(db, db, sq);
-        za = __fadd_rn(za, da); zb = __fadd_rn(zb, db);
-      }
-    }
-#pragma unroll
-    for (int j = 0; j < NJ; ++j)
-      stg_stream(reinterpret_cast<float4*>(zq + qbase + (size_t)(lane + 32 * j) * HW), zr[j]);
-    if (lane < 4) idx[t0 + lane] = (int64_t)(lane == 0 ? best[0] : (lane == 1 ? best[1] : (lane == 2 ? best[2] : best[3])));
-  }
-  // loss: warp partial -> the CTA's last warp sums the CTA's partials in warp order -> the grid's last CTA sums
-  // the CTA partials in CTA order (deterministic; no barrier, so a slow warp never parks its neighbours)
-  const double wsum = warp_sum((double)sq);
-  int last = 0;
-  if (lane == 0) {
-    s_part[wid] = wsum;
-    __threadfence_block();
-    last = (atomicAdd(&s_done, 1) == kQW - 1);
-  }
-  last = __shfl_sync(0xffffffffu, last, 0);
-  if (!last) return;
-  __threadfence_block();
-  int glast = 0;
-  if (lane == 0) {
-    double b = 0.0;
-    for (int w = 0; w < kQW; ++w) b += s_part[w];
-    partials[blockIdx.x] = b;
-    __threadfence();
-    glast = (atomicAdd(counters + kCtrLoss, 1u) == gridDim.x - 1);
-  }
-  glast = __shfl_sync(0xffffffffu, glast, 0);
-  if (!glast) return;
-  __threadfence();
-  double tot = 0.0;
-  for (unsigned i = lane; i < gridDim.x; i += 32) tot += __ldcg(partials + i);
-  tot = warp_sum(tot);
-  if (lane == 0) {
-    write_loss(tot, (long long)N * DT, beta, legacy, loss);
-    counters[kCtrLoss] = 0u;
-  }
-}
-
-int vq_finish(const float* z, const float* E, const float* ee, const float* emax, const int* cand, const int* meta,
+int vq_finish(const float* z, const float* E, const float* ee, const float* emax, const int* cand, const VqMeta* meta,
               const uint2* list, int B, int D, int HW, int K, float beta, int legacy, float* zq, int64_t* idx,
               float* loss, double* partials, unsigned* counters, cudaStream_t s) {
   const int N = B * HW;
   if (K > 65535 && !cand) return DCVIC_ERR_UNSUPPORTED;
   const bool vec = (D % 4 == 0) && (HW % 4 == 0) && ((reinterpret_cast<uintptr_t>(z) & 15) == 0) &&
                    ((reinterpret_cast<uintptr_t>(zq) & 15) == 0) && ((reinterpret_cast<uintptr_t>(E) & 15) == 0);
-  // measurement switch: DCVIC_FINISH=quad selects the warp-autonomous variant (slower on B200 as measured:
-  // its 16-byte-per-lane z loads waste DRAM bursts); default is the token-tile variant below
-  static const bool use_quad = getenv("DCVIC_FINISH") && getenv("DCVIC_FINISH")[0] == 'q';
-  if (vec && use_quad && (D == 256 || D == 128 || D == 64)) {
-    const int grid = ceil_div_i(N, 4 * kQW);
-    if (D == 256)
-      vq_finish_quad_kernel<256><<<grid, kQW * 32, 0, s>>>(z, E, ee, emax, cand, meta, list, N, HW, K, beta, legacy, zq, idx,
-                                                      loss, partials, counters);
-    else if (D == 128)
-      vq_finish_quad_kernel<128><<<grid, kQW * 32, 0, s>>>(z, E, ee, emax, cand, meta, list, N, HW, K, beta, legacy, zq, idx,
-                                                      loss, partials, counters);
-    else
-      vq_finish_quad_kernel<64><<<grid, kQW * 32, 0, s>>>(z, E, ee, emax, cand, meta, list, N, HW, K, beta, legacy, zq, idx,
-                                                     loss, partials, counters);
-    return dcvic_launch_status();
-  }
   if (vec) {
-    const size_t smem = (size_t)kFT * (D + 4) * sizeof(float);
+    static const int tile_tokens = (getenv("DCVIC_FINISH_TILE") && atoi(getenv("DCVIC_FINISH_TILE")) == 16) ? 16 : 32;
+    const size_t smem = (size_t)tile_tokens * (D + 4) * sizeof(float);
     if (smem > 200 * 1024) return DCVIC_ERR_UNSUPPORTED;
-#define DCVIC_LAUNCH_FINISH(DT)                                                                                     \
+#define DCVIC_LAUNCH_FINISH(DT, T)                                                                                  \
   do {                                                                                                             \
     if (smem > 40 * 1024)                                                                                          \
-      cudaFuncSetAttribute(vq_finish_v4_kernel<DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);       \
-    static int per_sm_##DT = 0;                                                                                    \
-    if (per_sm_##DT == 0 && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_##DT, vq_finish_v4_kernel<DT>, 256, \
-                                                                         smem) != cudaSuccess)                    \
-      per_sm_##DT = 1;                                                                                             \
-    const int tiles = ceil_div_i(N, kFT);                                                                          \
-    const int grid = DT ? min(tiles, kNumSMs * max(per_sm_##DT, 1)) : tiles;                                       \
-    vq_finish_v4_kernel<DT><<<grid, 256, smem, s>>>(z, E, ee, emax, cand, meta, list, N, D, HW, K, beta, legacy,    \
-                                                    zq, idx, loss, partials, counters);                            \
+      cudaFuncSetAttribute(vq_finish_v5_kernel<DT, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
+    vq_finish_v5_kernel<DT, T><<<ceil_div_i(N, T), T * 8, smem, s>>>(z, E, ee, emax, cand, meta, list, N, D, HW, K, \
+                                                                     beta, legacy, zq, idx, loss, partials,        \
+                                                                     counters);                                    \
   } while (0)
-    if (D == 256) DCVIC_LAUNCH_FINISH(256);
-    else if (D == 128) DCVIC_LAUNCH_FINISH(128);
-    else if (D == 64) DCVIC_LAUNCH_FINISH(64);
-    else DCVIC_LAUNCH_FINISH(0);
+    if (tile_tokens == 32) {
+      if (D == 256) DCVIC_LAUNCH_FINISH(256, 32);
+      else if (D == 128) DCVIC_LAUNCH_FINISH(128, 32);
+      else if (D == 64) DCVIC_LAUNCH_FINISH(64, 32);
+      else DCVIC_LAUNCH_FINISH(0, 32);
+    } else {
+      if (D == 256) DCVIC_LAUNCH_FINISH(256, 16);
+      else if (D == 128) DCVIC_LAUNCH_FINISH(128, 16);
+      else if (D == 64) DCVIC_LAUNCH_FINISH(64, 16);
+      else DCVIC_LAUNCH_FINISH(0, 16);
+    }
 #undef DCVIC_LAUNCH_FINISH
     return dcvic_launch_status();
   }

@@ -258,7 +258,7 @@ template <int CG>
 __global__ void __launch_bounds__(NTHREADS, 1)
 vq_tensor_search_kernel(const __grid_constant__ CUtensorMap tmap_cb, const float* __restrict__ z,
                         const float* __restrict__ emax_ptr, int N, int D, int HW, int K, int num_ptiles,
-                        int* __restrict__ meta, uint2* __restrict__ list) {
+                        VqMeta* __restrict__ meta, uint2* __restrict__ list) {
   using C = Cfg<CG>;
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B operands need 1024-byte alignment (same adjustment in both CTAs of a pair)
@@ -463,8 +463,9 @@ vq_tensor_search_kernel(const __grid_constant__ CUtensorMap tmap_cb, const float
         TR_ADD(tr_proc, tr0);
       }
       if (valid) {
-        meta[(size_t)t * 4 + q] = __float_as_int(m);
-        meta[(size_t)t * 4 + 2 + q] = (n > kListCap || cb_unsafe || !(zz < kVqFp16Zz2Max)) ? -1 : n;
+        const short nn = (n > kListCap || cb_unsafe || !(zz < kVqFp16Zz2Max)) ? (short)-1 : (short)n;
+        if (q == 0) { meta[t].m0 = m; meta[t].n0 = nn; meta[t].zz = zz; }
+        else        { meta[t].m1 = m; meta[t].n1 = nn; }
       }
     }
     if (part == 0 && lane == 0) { TR_PUT(2 + 4 * q, tr_zz); TR_PUT(3 + 4 * q, tr_full); TR_PUT(4 + 4 * q, tr_proc); }
@@ -578,7 +579,7 @@ bool vq_tensor_supported(int D, int K) {
 
 template <int CG>
 static int launch_search(const CUtensorMap& tmap, const float* z, const float* emax, int N, int D, int HW, int K,
-                         int* meta, uint2* list, cudaStream_t s) {
+                         VqMeta* meta, uint2* list, cudaStream_t s) {
   using C = Cfg<CG>;
   const int num_ptiles = (N + BM * CG - 1) / (BM * CG);
   const int max_pairs = kNumSMs / CG;
@@ -613,7 +614,7 @@ namespace dcvic {
 #endif
 
 int vq_tensor_search(const float* z, const __half* cb16, const float* emax, int B, int D, int HW, int K,
-                     int* meta, uint2* list, cudaStream_t s) {
+                     VqMeta* meta, uint2* list, cudaStream_t s) {
   if (!vq_tensor_supported(D, K)) return DCVIC_ERR_UNSUPPORTED;
   static const int cta_group = [] {
     const char* e = getenv("DCVIC_VQ_CTA_GROUP");

@@ -48,8 +48,9 @@ def take(n):
 off_counters = take(64 * 4); off_ee = take(K * 4); off_nhee = take(K * 4); off_emax = take(16)
 off_partials = take((N // 32 + 2) * 8); off_hist = take(K * 4); off_cand = take(N * 4); off_meta = take(N * 16)
 off_list = take(N * 2 * 16 * 8); off_cb16 = take(K * (D + 64) * 2)
-meta = ws[off_meta:off_meta + N * 16].view(torch.int32).view(N, 4).cpu()
-m_gpu = meta[:, :2].contiguous().view(torch.float32)
+meta_raw = ws[off_meta:off_meta + N * 16].cpu()
+m_gpu = meta_raw.view(torch.float32).view(N, 4)[:, :2].contiguous()
+meta = meta_raw.view(torch.int16).view(N, 8)[:, 4:6].to(torch.int32)
 cb16 = ws[off_cb16:off_cb16 + K * (D + 64) * 2].view(torch.float16).view(K, D + 64).float().cpu()
 ee = ws[off_ee:off_ee + K * 4].view(torch.float32).cpu()
 print("pad cols vs -ee/2 max abs err:", float((cb16[:, D:D + 3].sum(1) + 0.5 * ee).abs().max()), " pad rest max:", float(cb16[:, D + 3:].abs().max()))
@@ -64,7 +65,7 @@ print("bad rows:", bad[:10].tolist(), "count", len(bad))
 for r in (0, 1, 2, 127, 128, 129, 255):
     if r < N:
         print("row", r, "m_gpu", m_gpu[r].tolist(), "m_ref", m_ref[r].tolist(), "max|z.e| half0", float((s4[r, :, 0] + 0.5 * ee.view(K // 256, 2, 128)[:, 0]).amax()))
-print("n entries min/max:", int(meta[:, 2:].min()), int(meta[:, 2:].max()))
+print("n entries min/max:", int(meta.min()), int(meta.max()))
 call(_lib.VQ_STAGE_FINISH_ONLY, "finish")
 ref = (rows.pow(2).sum(1, keepdim=True) + E.pow(2).sum(1)[None] - 2 * rows @ E.t()).argmin(1)
 print("idx mismatches vs torch fp32:", int((idx.cpu() != ref).sum()), "of", N)
