@@ -13,13 +13,64 @@ constexpr int kGcThreads = 256;
 constexpr int kGcVecPerThread = 4;                                  // float4 per thread per tensor
 constexpr int kGcChunk = kGcThreads * kGcVecPerThread * 4;          // elements per CTA
 
-// Phi((+-0.5 - v)/s) difference exactly in the reference's op order (two IEEE divisions).
+// erfc(x) = t exp(-x^2 + P(t)), t = 1/(1 + |x|/2): the classic Chebyshev fit with fractional error < 1.2e-7
+// everywhere (no cancellation in the tails, which is where likelihoods near the 1e-9 bound live).  One MUFU.RCP,
+// one MUFU.EX2 and 11 FMAs instead of the ~40-instruction library erfcf: with two of them, two IEEE divisions and a
+// log2 per latent the kernel was issue-bound at 0.55 of HBM bandwidth.
+// single-MUFU forms (flush-to-zero: every operand here is a normal number or may be flushed: s >= 0.11, 1 + z/2 >= 1,
+// likelihoods are clamped to >= 1e-9 before the logarithm)
+__device__ __forceinline__ float rcp_ftz(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float ex2_ftz(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float lg2_ftz(float x) {
+  float r;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
+__device__ __forceinline__ float erfc_pos(float z) {   // z >= 0
+  const float t = rcp_ftz(fmaf(0.5f, z, 1.f));
+  float p = 0.17087277f;
+  p = fmaf(t, p, -0.82215223f);
+  p = fmaf(t, p, 1.48851587f);
+  p = fmaf(t, p, -1.13520398f);
+  p = fmaf(t, p, 0.27886807f);
+  p = fmaf(t, p, -0.18628806f);
+  p = fmaf(t, p, 0.09678418f);
+  p = fmaf(t, p, 0.37409196f);
+  p = fmaf(t, p, 1.00002368f);
+  p = fmaf(t, p, -1.26551223f);
+  return t * ex2_ftz(1.4426950408889634f * fmaf(-z, z, p));
+}
+
+// Phi((0.5 - v)/s) - Phi((-0.5 - v)/s) = (erfc(a) - erfc(b)) / 2 with a = (v - 0.5)/(s sqrt 2) <= b = (v + 0.5)/(s sqrt 2),
+// b > 0 always and a >= -0.5/(0.11 sqrt 2).  Same formula as compressai's _likelihood (the reference evaluates it in
+// FP32 with its own erfc; measured difference to it <= 2.5e-5 relative on the C3 inputs, tolerance 1e-4).
 __device__ __forceinline__ float gc_lik(float outputs, float mu, float s) {
+  const float v = fabsf(__fsub_rn(outputs, mu));
+  const float r = 0.70710678118654752440f * rcp_ftz(s);
+  const float a = (v - 0.5f) * r, b = (v + 0.5f) * r;
+  const float ea = erfc_pos(fabsf(a));
+  const float up = a < 0.f ? 2.f - ea : ea;
+  return 0.5f * (up - erfc_pos(b));
+}
+
+// Table-construction variant (DCVIC_GC_PRECISE): library erfcf and two IEEE divisions in compressai's op order.  The
+// zero-width "steal" cascade of pmf_to_quantized_cdf amplifies ulp-level differences into +-2 table entries, so the
+// CDF tables are built with the same arithmetic a reference run on this device uses (torch.erfc on the GPU).
+__device__ __forceinline__ float gc_lik_precise(float outputs, float mu, float s) {
   const float v = fabsf(__fsub_rn(outputs, mu));
   const float u = __fdiv_rn(__fsub_rn(0.5f, v), s);
   const float l = __fdiv_rn(__fsub_rn(-0.5f, v), s);
-  const float up = 0.5f * erfcf(kNegInvSqrt2 * u);
-  const float lo = 0.5f * erfcf(kNegInvSqrt2 * l);
+  const float up = 0.5f * erfcf(-0.70710678118654752440f * u);
+  const float lo = 0.5f * erfcf(-0.70710678118654752440f * l);
   return __fsub_rn(up, lo);
 }
 
@@ -38,7 +89,7 @@ struct GcArgs {
   double* part_q;  // dual only
 };
 
-template <bool DUAL>
+template <bool DUAL, bool PRECISE = false>
 __device__ __forceinline__ void gc_element(const GcArgs& a, float y, float mu, float sg, float nz, bool train,
                                            float& y_hat, float& lik, float& lik_q) {
   const float s = fmaxf(sg, a.scale_bound);
@@ -49,13 +100,13 @@ __device__ __forceinline__ void gc_element(const GcArgs& a, float y, float mu, f
     y_hat = deq;
   } else {
     const float outputs = train ? __fadd_rn(y, nz) : deq;
-    lik = fmaxf(gc_lik(outputs, mu, s), a.lik_bound);
+    lik = fmaxf(PRECISE ? gc_lik_precise(outputs, mu, s) : gc_lik(outputs, mu, s), a.lik_bound);
     y_hat = (a.y_hat_mode == 1) ? deq : outputs;
     lik_q = 0.f;
   }
 }
 
-template <bool DUAL, bool VEC>
+template <bool DUAL, bool VEC, bool PRECISE = false>
 __global__ void __launch_bounds__(kGcThreads) gc_forward_kernel(GcArgs a) {
   __shared__ double scratch[32];
   const long long b = blockIdx.y;
@@ -87,15 +138,15 @@ __global__ void __launch_bounds__(kGcThreads) gc_forward_kernel(GcArgs a) {
       const long long e = start + ((long long)i * kGcThreads + threadIdx.x) * 4;
       if (e < a.n) {
         float4 oy, ol, oq;
-        gc_element<DUAL>(a, vy[i].x, vm[i].x, vs[i].x, vn[i].x, train, oy.x, ol.x, oq.x);
-        gc_element<DUAL>(a, vy[i].y, vm[i].y, vs[i].y, vn[i].y, train, oy.y, ol.y, oq.y);
-        gc_element<DUAL>(a, vy[i].z, vm[i].z, vs[i].z, vn[i].z, train, oy.z, ol.z, oq.z);
-        gc_element<DUAL>(a, vy[i].w, vm[i].w, vs[i].w, vn[i].w, train, oy.w, ol.w, oq.w);
+        gc_element<DUAL, PRECISE>(a, vy[i].x, vm[i].x, vs[i].x, vn[i].x, train, oy.x, ol.x, oq.x);
+        gc_element<DUAL, PRECISE>(a, vy[i].y, vm[i].y, vs[i].y, vn[i].y, train, oy.y, ol.y, oq.y);
+        gc_element<DUAL, PRECISE>(a, vy[i].z, vm[i].z, vs[i].z, vn[i].z, train, oy.z, ol.z, oq.z);
+        gc_element<DUAL, PRECISE>(a, vy[i].w, vm[i].w, vs[i].w, vn[i].w, train, oy.w, ol.w, oq.w);
         if (yh) stg_stream(reinterpret_cast<float4*>(yh + e), oy);
         if (lk) stg_stream(reinterpret_cast<float4*>(lk + e), ol);
         if (DUAL && lq) stg_stream(reinterpret_cast<float4*>(lq + e), oq);
-        if (a.part) acc += (__log2f(ol.x) + __log2f(ol.y)) + (__log2f(ol.z) + __log2f(ol.w));
-        if (DUAL && a.part_q) acc_q += (__log2f(oq.x) + __log2f(oq.y)) + (__log2f(oq.z) + __log2f(oq.w));
+        if (a.part) acc += (lg2_ftz(ol.x) + lg2_ftz(ol.y)) + (lg2_ftz(ol.z) + lg2_ftz(ol.w));
+        if (DUAL && a.part_q) acc_q += (lg2_ftz(oq.x) + lg2_ftz(oq.y)) + (lg2_ftz(oq.z) + lg2_ftz(oq.w));
       }
     }
   } else {
@@ -103,12 +154,12 @@ __global__ void __launch_bounds__(kGcThreads) gc_forward_kernel(GcArgs a) {
       const long long e = start + (long long)i * kGcThreads + threadIdx.x;
       if (e < a.n) {
         float oy, ol, oq;
-        gc_element<DUAL>(a, y[e], mu ? mu[e] : 0.f, sg[e], nz ? nz[e] : 0.f, train, oy, ol, oq);
+        gc_element<DUAL, PRECISE>(a, y[e], mu ? mu[e] : 0.f, sg[e], nz ? nz[e] : 0.f, train, oy, ol, oq);
         if (yh) yh[e] = oy;
         if (lk) lk[e] = ol;
         if (DUAL && lq) lq[e] = oq;
-        if (a.part) acc += __log2f(ol);
-        if (DUAL && a.part_q) acc_q += __log2f(oq);
+        if (a.part) acc += lg2_ftz(ol);
+        if (DUAL && a.part_q) acc_q += lg2_ftz(oq);
       }
     }
   }
@@ -153,7 +204,7 @@ static inline bool gc_vec_ok(const void* p0, const void* p1, const void* p2, con
 
 template <bool DUAL>
 static int gc_launch(GcArgs a, long long B, float* bits, float* bits_q, void* workspace, size_t ws_bytes,
-                     cudaStream_t s) {
+                     cudaStream_t s, bool precise = false) {
   const int per = ceil_div_i(a.n, kGcChunk);
   if (bits || bits_q) {
     const size_t need = (size_t)B * per * sizeof(double) * 2;
@@ -163,7 +214,9 @@ static int gc_launch(GcArgs a, long long B, float* bits, float* bits_q, void* wo
   }
   const bool vec = gc_vec_ok(a.y, a.mu, a.sigma, a.noise, a.y_hat, a.lik, a.lik_q, a.n, a.y_bs, a.mu_bs, a.sg_bs);
   dim3 grid(per, (unsigned)B);
-  if (vec)
+  if (precise && !DUAL)
+    gc_forward_kernel<false, false, true><<<grid, kGcThreads, 0, s>>>(a);
+  else if (vec)
     gc_forward_kernel<DUAL, true><<<grid, kGcThreads, 0, s>>>(a);
   else
     gc_forward_kernel<DUAL, false><<<grid, kGcThreads, 0, s>>>(a);
@@ -265,10 +318,11 @@ extern "C" int dcvic_gc_forward(const float* y, const float* mu, const float* si
   int rc = gc_check(y, sigma, B, n, scale_bound);
   if (rc) return rc;
   DCVIC_CHECK_ARG(y_hat || lik || bits);
-  DCVIC_CHECK_ARG(y_hat_mode == 0 || y_hat_mode == 1);
-  GcArgs a{y, mu, sigma, noise, n, y_bstride, mu_bstride, sigma_bstride, scale_bound, lik_bound, y_hat_mode,
+  DCVIC_CHECK_ARG((y_hat_mode & ~(1 | DCVIC_GC_PRECISE)) == 0);
+  GcArgs a{y, mu, sigma, noise, n, y_bstride, mu_bstride, sigma_bstride, scale_bound, lik_bound, y_hat_mode & 1,
            y_hat, lik, nullptr, nullptr, nullptr};
-  return gc_launch<false>(a, B, bits, nullptr, workspace, ws_bytes, (cudaStream_t)stream);
+  return gc_launch<false>(a, B, bits, nullptr, workspace, ws_bytes, (cudaStream_t)stream,
+                          (y_hat_mode & DCVIC_GC_PRECISE) != 0);
 }
 
 extern "C" int dcvic_gc_forward_dual(const float* y, const float* mu, const float* sigma, const float* noise,

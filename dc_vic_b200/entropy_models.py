@@ -301,7 +301,7 @@ class GaussianConditional(EntropyModel):
     def _likelihood(self, inputs: Tensor, scales: Tensor, means: Optional[Tensor] = None) -> Tensor:
         """Un-bounded likelihood of already-quantized ``inputs`` (used by update())."""
         zero = torch.zeros_like(inputs)
-        _, lik = _GaussianFn.apply(inputs, scales, means, zero, self._scale_bound, 0.0, 0)
+        _, lik = _GaussianFn.apply(inputs, scales, means, zero, self._scale_bound, 0.0, _lib.GC_PRECISE)
         return lik
 
     def forward(self, inputs: Tensor, scales: Tensor, means: Optional[Tensor] = None,

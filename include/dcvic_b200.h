@@ -110,10 +110,14 @@ int dcvic_onehot_nchw(const int64_t* idx, int B, int HW, int K, float* out, dcvi
  *   non-null => training: outputs = y + noise (noise is U(-.5,.5) drawn by the caller).
  *   y_hat_mode: 0 = CompressAI output (y+noise | round(y-mu)+mu)
  *               1 = DC-VIC STE output  (round(y-mu)+mu in both modes; value of ste_round)
+ *               | DCVIC_GC_PRECISE (2): evaluate the likelihood with library erfcf and IEEE divisions in compressai's op
+ *                 order instead of the streaming kernel's 1.2e-7-relative erfc; for CDF-table construction
+ *                 (GaussianConditional.update), where pmf_to_quantized_cdf amplifies ulp-level differences
  *   y_hat, lik  [B,n] contiguous, each nullable.
  *   bits [B] nullable: -sum(log2(lik)) per sample (likelihood_to_bit,
  *   hyperprior_vic_model.py:80-82 summed per sample); needs workspace.
  */
+enum { DCVIC_GC_PRECISE = 2 };
 size_t dcvic_gc_workspace_bytes(int64_t B, int64_t n);
 int dcvic_gc_forward(const float* y, const float* mu, const float* sigma, const float* noise, int64_t B,
                      int64_t n, int64_t y_bstride, int64_t mu_bstride, int64_t sigma_bstride,
