@@ -212,13 +212,8 @@ def run_ours(args):
     sampler.start()
     t_full = max_over_ranks(timed(vq_step, K_steps, W_steps, barrier))
     # dominant kernel alone (same launches, search stage only) for the roofline
-    # (stage flags: the tensor kernel alone re-uses the FP16 operand matrix left in the workspace; the finish stage is
-    #  timed as whole step minus the stages before it, because its input lists must belong to the same z)
-    t_search = timed(lambda i: vq_step(i, _lib.VQ_STAGE_SEARCH_ONLY | _lib.VQ_REUSE_PREP | _lib.VQ_SKIP_CONVERT),
-                     K_steps, W_steps, barrier)
-    t_conv_search = timed(lambda i: vq_step(i, _lib.VQ_STAGE_SEARCH_ONLY | _lib.VQ_REUSE_PREP), K_steps, W_steps, barrier)
-    t_prep_conv_search = timed(lambda i: vq_step(i, _lib.VQ_STAGE_SEARCH_ONLY), K_steps, W_steps, barrier)
-    t_finish = max(t_full - t_prep_conv_search, 0.0)
+    t_search = timed(lambda i: vq_step(i, _lib.VQ_STAGE_SEARCH_ONLY | _lib.VQ_REUSE_PREP), K_steps, W_steps, barrier)
+    t_finish = timed(lambda i: vq_step(i, _lib.VQ_STAGE_FINISH_ONLY), K_steps, W_steps, barrier)
     clocks = sampler.stop()
 
     value = world * N * K_steps / t_full
@@ -236,9 +231,7 @@ def run_ours(args):
                 "peak": pk["hbm"], "unit": "GB/s", "frac": finish_bytes / finish_s / 1e9 / pk["hbm"], "traffic": None,
                 "us_per_launch": finish_s * 1e6, "algorithmic": f"N*(8D+8) = {finish_bytes} B per launch",
                 "peak_source": pk["source"]}
-    stage = {"prepare_us": (t_prep_conv_search - t_conv_search) / K_steps * 1e6,
-             "convert_us": (t_conv_search - t_search) / K_steps * 1e6,
-             "search_us": search_s * 1e6, "finish_us": finish_s * 1e6,
+    stage = {"search_us": search_s * 1e6, "finish_us": finish_s * 1e6,
              "finish_hbm_gbs": finish_bytes / finish_s / 1e9, "finish_hbm_frac": finish_bytes / finish_s / 1e9 / pk["hbm"],
              "search_tflops": flops / search_s / 1e12}
 
@@ -314,12 +307,12 @@ def run_ours(args):
         gc_cpu, _ = cpu_gc_reference(2)
         entropy["cpu_baseline"] = {"value": gc_cpu, "unit": "latents/s", "cores": cores, "kind": "port",
                                    "sample": "8 of 64 images (2.6M latents) x 2, CompressAI-1.2.4 restatement, torch CPU"}
-        launches_per_step = {"tcgen05": 4, "exact-simt": 3, "narrow-simt": 1}[path]   # prepare, convert, search, finish
+        launches_per_step = 3 if path != "narrow-simt" else 1
         line = {"metric": "vq_tokens_per_sec", "value": value, "unit": "tokens/s", "n_gpus": world, "steps": K_steps,
                 "warmup": W_steps, "ms_per_step": t_full / K_steps * 1e3, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
                 "config": {"workload": VQ_WORKLOAD, "search_path": path,
-                           "arithmetic": "fp16 tcgen05 candidate search (fp32 accumulate) + fp32 re-rank" if path == "tcgen05" else "fp32 SIMT",
+                           "arithmetic": "bf16 tcgen05 candidate search + fp32 re-rank" if path == "tcgen05" else "fp32 SIMT",
                            "l2": f"inputs/outputs rotated over {ROT} buffer sets (536 MB > 126 MB L2)",
                            "codebook_prep": "inside every timed step", "sharding": "batch (images) per rank, no collective"},
                 "roofline": roof, "stages": stage,

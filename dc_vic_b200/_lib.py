@@ -15,7 +15,6 @@ OK = 0
 VQ_REUSE_PREP, VQ_FORCE_EXACT, VQ_FORCE_TENSOR = 1, 2, 4
 VQ_STAGE_SEARCH_ONLY, VQ_STAGE_FINISH_ONLY = 8, 16
 GC_PRECISE = 2
-VQ_SKIP_CONVERT = 64
 
 _lock = threading.Lock()
 _lib = None

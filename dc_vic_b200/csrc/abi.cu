@@ -59,8 +59,6 @@ extern "C" int dcvic_vq_forward(const float* z_nchw, const float* codebook, int 
   VqMeta* meta = reinterpret_cast<VqMeta*>(ws + w.off_meta);
   uint2* list = reinterpret_cast<uint2*>(ws + w.off_list);
   __half* cb16 = reinterpret_cast<__half*>(ws + w.off_cb16);
-  __half* a16 = reinterpret_cast<__half*>(ws + w.off_a16);
-  float* zz = reinterpret_cast<float*>(ws + w.off_zz);
   cudaStream_t s = (cudaStream_t)stream;
   int rc = DCVIC_OK;
 
@@ -74,9 +72,7 @@ extern "C" int dcvic_vq_forward(const float* z_nchw, const float* codebook, int 
     const bool do_search = !(flags & DCVIC_VQ_STAGE_FINISH_ONLY);
     const bool do_finish = !(flags & DCVIC_VQ_STAGE_SEARCH_ONLY);
     if (path == 2) {
-      if (do_search && !(flags & DCVIC_VQ_SKIP_CONVERT)) rc = vq_convert_fp16(z_nchw, B, D, HW, a16, zz, s);
-      if (rc) return rc;
-      if (do_search) rc = vq_tensor_search(a16, zz, cb16, emax, N, D, K, meta, list, s);
+      if (do_search) rc = vq_tensor_search(z_nchw, cb16, emax, B, D, HW, K, meta, list, s);
       if (rc) return rc;
       if (do_finish)
         rc = vq_finish(z_nchw, codebook, ee, emax, nullptr, meta, list, B, D, HW, K, beta, legacy, zq_nchw, idx, loss,

@@ -26,7 +26,7 @@ struct __align__(16) VqMeta {
 //                           margin of the running maximum when that chunk went by
 struct VqWorkspace {
   size_t off_counters, off_ee, off_nhee, off_emax, off_partials, off_hist, off_cand, off_meta, off_list, off_cb16,
-      off_zz, off_a16, total;
+      total;
   int n_tokens;
 };
 
@@ -45,8 +45,6 @@ inline VqWorkspace vq_workspace_layout(int B, int D, int HW, int K) {
   w.off_meta = take(N * sizeof(VqMeta));
   w.off_list = take(N * 2 * kListCap * sizeof(uint2));
   w.off_cb16 = take((size_t)K * (D + kCb16Pad) * sizeof(__half));
-  w.off_zz = take(N * sizeof(float));
-  w.off_a16 = take(N * (size_t)D * sizeof(__half));   // token-major FP16 operand matrix of the tensor search
   w.total = o;
   w.n_tokens = (int)N;
   return w;
@@ -72,8 +70,6 @@ __host__ __device__ __forceinline__ float vq_margin(float zz, float emax) {
 // vq_simt.cu
 int vq_prepare_codebook(const float* codebook, int K, int D, float* ee, float* nhee, float* emax,
                         __half* cb16, cudaStream_t s);
-// z [B,D,HW] FP32 NCHW -> a16 [B*HW][D] FP16 (round to nearest) + zz[t] = |z_t|^2; needs D % 4 == 0, HW % 4 == 0
-int vq_convert_fp16(const float* z, int B, int D, int HW, __half* a16, float* zz, cudaStream_t s);
 int vq_narrow_forward(const float* z, const float* E, int B, int D, int HW, int K, float beta, int legacy, float* zq,
                       int64_t* idx, float* loss, double* partials, unsigned* counters, cudaStream_t s);
 int vq_exact_search(const float* z, const float* E, const float* ee, int B, int D, int HW, int K, int* cand,
@@ -87,7 +83,7 @@ int vq_v1_extras(const int64_t* idx, int N, int K, float* onehot, float* perplex
 
 // vq_tcgen05.cu
 bool vq_tensor_supported(int D, int K);
-int vq_tensor_search(const __half* a16, const float* zz, const __half* cb16, const float* emax, int N, int D, int K,
+int vq_tensor_search(const float* z, const __half* cb16, const float* emax, int B, int D, int HW, int K,
                      VqMeta* meta, uint2* list, cudaStream_t s);
 
 }  // namespace dcvic

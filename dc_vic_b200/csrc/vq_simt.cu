@@ -61,78 +61,6 @@ int vq_prepare_codebook(const float* codebook, int K, int D, float* ee, float* n
   return dcvic_launch_status();
 }
 
-// ------------------------------------------------------------------ FP16 operand matrix for the tensor search
-// One CTA = 32 tokens x all channels.  Loads: lane = tq*4 + cq (token quad tq, channel quad cq), one LDG.128 of 4
-// consecutive tokens per channel (128 contiguous bytes per 8 lanes); the 32 x D FP16 tile is assembled in shared
-// memory token-major and leaves as one contiguous 32*D*2-byte block (16-byte stores).  |z|^2 per token: sequential
-// FMAs per thread, xor over the 4 channel-quad lanes, then the 8 warps' partials in warp order (deterministic).
-// HBM-bound streaming kernel: 4 B/element in, 2 B/element out.
-__global__ void __launch_bounds__(256) vq_convert_kernel(const float* __restrict__ z, int N, int D, int HW,
-                                                          __half* __restrict__ a16, float* __restrict__ zz) {
-  extern __shared__ __align__(16) unsigned char cv_smem[];
-  __half* tile = reinterpret_cast<__half*>(cv_smem);                       // [32][D + 8] (row pad: 16 B)
-  float* s_part = reinterpret_cast<float*>(cv_smem + (size_t)32 * (D + 8) * sizeof(__half));   // [8][32]
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int tq = lane >> 2, cq = lane & 3;
-  const int t0 = blockIdx.x * 32;
-  const int tokq = t0 + 4 * tq;
-  const bool qvalid = tokq < N;
-  const size_t qbase = qvalid ? ((size_t)(tokq / HW) * D * HW + (size_t)(tokq % HW)) : 0;
-  const int ldh = D + 8;
-  float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;
-  for (int c0 = wid * 16; c0 < D; c0 += 128) {
-    const int c = c0 + cq * 4;
-    if (c < D) {
-      float4 v[4];
-#pragma unroll
-      for (int k = 0; k < 4; ++k)
-        v[k] = qvalid ? ldg_stream(reinterpret_cast<const float4*>(z + qbase + (size_t)(c + k) * HW))
-                      : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        p0 = fmaf(v[k].x, v[k].x, p0); p1 = fmaf(v[k].y, v[k].y, p1);
-        p2 = fmaf(v[k].z, v[k].z, p2); p3 = fmaf(v[k].w, v[k].w, p3);
-      }
-      __half2* d0 = reinterpret_cast<__half2*>(tile + (4 * tq) * ldh + c);
-      d0[0] = __floats2half2_rn(v[0].x, v[1].x); d0[1] = __floats2half2_rn(v[2].x, v[3].x);
-      __half2* d1 = reinterpret_cast<__half2*>(tile + (4 * tq + 1) * ldh + c);
-      d1[0] = __floats2half2_rn(v[0].y, v[1].y); d1[1] = __floats2half2_rn(v[2].y, v[3].y);
-      __half2* d2 = reinterpret_cast<__half2*>(tile + (4 * tq + 2) * ldh + c);
-      d2[0] = __floats2half2_rn(v[0].z, v[1].z); d2[1] = __floats2half2_rn(v[2].z, v[3].z);
-      __half2* d3 = reinterpret_cast<__half2*>(tile + (4 * tq + 3) * ldh + c);
-      d3[0] = __floats2half2_rn(v[0].w, v[1].w); d3[1] = __floats2half2_rn(v[2].w, v[3].w);
-    }
-  }
-  // |z|^2: lanes cq = 0..3 of a token quad, then the warps
-  p0 += __shfl_xor_sync(0xffffffffu, p0, 1); p0 += __shfl_xor_sync(0xffffffffu, p0, 2);
-  p1 += __shfl_xor_sync(0xffffffffu, p1, 1); p1 += __shfl_xor_sync(0xffffffffu, p1, 2);
-  p2 += __shfl_xor_sync(0xffffffffu, p2, 1); p2 += __shfl_xor_sync(0xffffffffu, p2, 2);
-  p3 += __shfl_xor_sync(0xffffffffu, p3, 1); p3 += __shfl_xor_sync(0xffffffffu, p3, 2);
-  if (cq == 0) *reinterpret_cast<float4*>(s_part + wid * 32 + 4 * tq) = make_float4(p0, p1, p2, p3);
-  __syncthreads();
-  if (threadIdx.x < 32 && t0 + threadIdx.x < N) {
-    float acc = 0.f;
-#pragma unroll
-    for (int w = 0; w < 8; ++w) acc += s_part[w * 32 + threadIdx.x];
-    zz[t0 + threadIdx.x] = acc;
-  }
-  // contiguous output: rows t0 .. t0+31 of a16, D halves each, 16 bytes per thread and step
-  const int vec_per_row = D / 8;
-  for (int i = threadIdx.x; i < 32 * vec_per_row; i += 256) {
-    const int r = i / vec_per_row, cv = i - r * vec_per_row;
-    if (t0 + r < N)
-      *reinterpret_cast<uint4*>(a16 + (size_t)(t0 + r) * D + cv * 8) = *reinterpret_cast<const uint4*>(tile + r * ldh + cv * 8);
-  }
-}
-
-int vq_convert_fp16(const float* z, int B, int D, int HW, __half* a16, float* zz, cudaStream_t s) {
-  const int N = B * HW;
-  if ((D & 7) || (HW & 3)) return DCVIC_ERR_UNSUPPORTED;
-  const size_t smem = (size_t)32 * (D + 8) * sizeof(__half) + 8 * 32 * sizeof(float);
-  vq_convert_kernel<<<ceil_div_i(N, 32), 256, smem, s>>>(z, N, D, HW, a16, zz);
-  return dcvic_launch_status();
-}
-
 // Shared tail: turn sum((e-z)^2) into the reference's loss scalar.
 __device__ __forceinline__ void write_loss(double total, long long numel, float beta, int legacy, float* loss) {
   const float m = (float)(total / (double)numel);

@@ -1,6 +1,6 @@
 // Wide-codebook nearest-codeword CANDIDATE search on the 5th-gen tensor cores (sm_100a).
 //
-// Computes, for every token row z_t (converted to FP16 by vq_convert_kernel) and every codeword e_k,
+// Computes, for every token row z_t (FP32, read straight from NCHW) and every codeword e_k,
 //     s[t,k] = fp16(z_t) . fp16(e_k) - |e_k|^2 / 2        ( = (|z|^2 - d[t,k]) / 2 up to FP16 rounding )
 // with tcgen05.mma (FP16 x FP16 -> FP32 in TMEM; FP16 rather than BF16 because its 11-bit significand keeps
 // the proven margin 8x tighter, i.e. ~1.2 instead of ~2.7 FP32 re-rank candidates per token) and flags, per row, every k whose score is within a
@@ -9,21 +9,19 @@
 // happens in vq_finish_kernel, which streams z once more for the gather / STE / loss.
 //
 // Structure: persistent CTA pairs (cta_group::2, UMMA 256x256x16), each CTA owning 128 tokens of a
-// 256-token pair tile and half of every codebook tile (CG = 1 is the same code on single CTAs).  The FP16
-// operand matrix A16[N][D] (+ |z|^2 per token) is written by vq_convert_kernel right before: a streaming
-// kernel reaches HBM speed with 2048 threads per SM in flight, which a few producer warps inside this kernel
-// could not (registers as landing zone: 3.8 TB/s, tools/bw_probe.cu), and A16 (33 MB at C2) is still in L2
-// when it is read back here.
-//   warps 0-7   epilogue: warps 0-3 take columns 0-127 of every accumulator, warps 4-7 columns 128-255.
-//               tcgen05.ld 32 scores per row at a time (software pipelined), running max, one flag mask per
-//               32 codes (FADD on the FMA pipe + funnel shift, branch-free), append {chunk max | chunk id,
-//               mask} to the token's list in global memory when non-empty.  The accumulator goes back to the
-//               MMA as soon as its last scores are in registers.
-//   warp 8      TMA producer A: this CTA's [128 tokens x 64 ch] operand chunks (SWIZZLE_128B), double-buffered
-//               per token tile (tile i+1 lands while tile i multiplies)
-//   warp 9      TMA producer B: this CTA's half of the FP16 codebook tile [256/CG codes x 64 ch] into a 4-stage
-//               ring.  Both producers signal completion on the LEADER's barriers.
-//   warp 10     TMEM allocator; in the leader CTA one thread issues every tcgen05.mma of the pair and
+// 256-token pair tile and half of every codebook tile (CG = 1 is the same code on single CTAs).
+//   warps 0-7   A producers: read z (FP32, 16-byte loads of 4 consecutive tokens, two 8-load sets in
+//               flight per thread, running ahead into the next tile),
+//               convert to FP16, write the K-major SWIZZLE_128B operand tile (double-buffered: tile i+1
+//               loads while tile i multiplies), publish |z|^2 per token
+//   warps 8-15  epilogue: warps 8-11 take columns 0-127 of every accumulator, warps 12-15 columns
+//               128-255.  tcgen05.ld 32 scores per row at a time (software pipelined), running max, one
+//               flag mask per 32 codes (FADD on the FMA pipe + funnel shift, branch-free), append
+//               {chunk max | chunk id, mask} to the token's list in global memory when non-empty.  The
+//               accumulator goes back to the MMA as soon as its last scores are in registers.
+//   warp 16     TMA producer: this CTA's half of the FP16 codebook tile [256/CG codes x 64 ch]
+//               (SWIZZLE_128B) into a 4-stage ring; completion is signalled on the LEADER's barrier
+//   warp 17     TMEM allocator; in the leader CTA one thread issues every tcgen05.mma of the pair and
 //               multicasts the commits (stage free, accumulator full, operand tile free) to both CTAs
 // -|e|^2/2 enters through the contraction itself: the FP16 codebook carries one extra 64-column chunk
 // whose first three columns are a 3-way FP16 split of -|e_k|^2/2, multiplied (one K=16 step, which
@@ -44,8 +42,10 @@ constexpr int MAX_KC = 4;        // e_dim <= 256
 constexpr int A_CHUNK_BYTES = BM * BK * 2;            // 16 KB
 constexpr int A_BUF_BYTES = MAX_KC * A_CHUNK_BYTES;   // 64 KB
 constexpr int MAX_K = 4096;
-constexpr int NTHREADS = 352;                  // epilogue warps 0-7, then:
-constexpr int WARP_TMA_A = 8, WARP_TMA_B = 9, WARP_MMA = 10;
+constexpr int NTHREADS = 576;
+constexpr int NPROD = 8;                       // A-producer warps (warps 0-7); epilogue warps 8-15
+constexpr int WARP_TMA = 16, WARP_MMA = 17;
+constexpr int ZZ_SLOTS = 4;
 
 template <int CG>
 struct Cfg {
@@ -55,7 +55,8 @@ struct Cfg {
   static constexpr int OFF_A = 0;                                  // [2][MAX_KC][BM x 128 B]
   static constexpr int OFF_APAD = OFF_A + 2 * A_BUF_BYTES;         // [BM x 128 B] constant: ones in columns 0-2
   static constexpr int OFF_B = OFF_APAD + A_CHUNK_BYTES;           // [NSTAGE][BN/CG x 128 B]
-  static constexpr int OFF_BAR = OFF_B + NSTAGE * B_STAGE_BYTES;
+  static constexpr int OFF_ZZ = OFF_B + NSTAGE * B_STAGE_BYTES;    // [ZZ_SLOTS][2 channel halves][BM] float
+  static constexpr int OFF_BAR = OFF_ZZ + 2 * ZZ_SLOTS * BM * 4;
   // barrier slots (8 bytes each)
   static constexpr int BAR_B_FULL = 0;                       // [NSTAGE]   leader only
   static constexpr int BAR_B_EMPTY = BAR_B_FULL + NSTAGE;    // [NSTAGE]
@@ -63,7 +64,8 @@ struct Cfg {
   static constexpr int BAR_A_EMPTY = BAR_A_FULL + 2 * MAX_KC;  // [2]
   static constexpr int BAR_T_FULL = BAR_A_EMPTY + 2;         // [2]
   static constexpr int BAR_T_EMPTY = BAR_T_FULL + 2;         // [2]        leader only
-  static constexpr int BAR_COUNT = BAR_T_EMPTY + 2;
+  static constexpr int BAR_ZZ = BAR_T_EMPTY + 2;             // [ZZ_SLOTS]
+  static constexpr int BAR_COUNT = BAR_ZZ + ZZ_SLOTS;
   static constexpr int OFF_TMEM_PTR = OFF_BAR + BAR_COUNT * 8;
   static constexpr int SMEM_BYTES = OFF_TMEM_PTR + 16;
   static_assert(SMEM_BYTES + 1024 <= 232448, "shared memory budget");
@@ -254,9 +256,9 @@ __device__ unsigned long long g_trace[kNumSMs * 2][16];
 
 template <int CG>
 __global__ void __launch_bounds__(NTHREADS, 1)
-vq_tensor_search_kernel(const __grid_constant__ CUtensorMap tmap_cb, const __grid_constant__ CUtensorMap tmap_a,
-                        const float* __restrict__ zzg, const float* __restrict__ emax_ptr, int N, int D, int K,
-                        int num_ptiles, VqMeta* __restrict__ meta, uint2* __restrict__ list) {
+vq_tensor_search_kernel(const __grid_constant__ CUtensorMap tmap_cb, const float* __restrict__ z,
+                        const float* __restrict__ emax_ptr, int N, int D, int HW, int K, int num_ptiles,
+                        VqMeta* __restrict__ meta, uint2* __restrict__ list) {
   using C = Cfg<CG>;
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B operands need 1024-byte alignment (same adjustment in both CTAs of a pair)
@@ -264,6 +266,7 @@ vq_tensor_search_kernel(const __grid_constant__ CUtensorMap tmap_cb, const __gri
   const uint32_t sbase = smem_u32(smem);
   const uint32_t bar0 = sbase + C::OFF_BAR;
   auto bar = [&](int slot) { return bar0 + slot * 8; };
+  float* s_zz = reinterpret_cast<float*>(smem + C::OFF_ZZ);
   volatile uint32_t* s_tmem = reinterpret_cast<volatile uint32_t*>(smem + C::OFF_TMEM_PTR);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -279,12 +282,13 @@ vq_tensor_search_kernel(const __grid_constant__ CUtensorMap tmap_cb, const __gri
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < C::NSTAGE; ++s) { mbar_init(bar(C::BAR_B_FULL + s), 1); mbar_init(bar(C::BAR_B_EMPTY + s), 1); }
-    for (int c = 0; c < 2 * MAX_KC; ++c) mbar_init(bar(C::BAR_A_FULL + c), 1);
+    for (int c = 0; c < 2 * MAX_KC; ++c) mbar_init(bar(C::BAR_A_FULL + c), NPROD * CG);
     for (int b = 0; b < 2; ++b) {
       mbar_init(bar(C::BAR_A_EMPTY + b), 1);
       mbar_init(bar(C::BAR_T_FULL + b), 1);
       mbar_init(bar(C::BAR_T_EMPTY + b), 8 * CG);
     }
+    for (int s = 0; s < ZZ_SLOTS; ++s) mbar_init(bar(C::BAR_ZZ + s), NPROD);
     fence_barrier_init();
   }
   // constant operand chunk for the -|e|^2/2 step: fp16 1.0 in columns 0-2 of every row.  Columns 0-7 sit in
@@ -313,22 +317,106 @@ vq_tensor_search_kernel(const __grid_constant__ CUtensorMap tmap_cb, const __gri
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
 
-  if (warp < 8) {
+  if (warp < NPROD) {
+    // ===================== A producers: FP32 NCHW -> FP16 K-major SWIZZLE_128B =====================
+    // Warp w owns tokens [32(w&3), +32) of the tile and channel half ch = w>>2 of every 64-channel chunk.
+    // lane = tq*4 + cg: token quad tq (4 consecutive tokens, one 16-byte load per channel) and channel
+    // group cg (every quarter warp then covers all 8 swizzled bank groups in its 16-byte stores).  One step = 8 channels x 4 tokens per thread (8 LDG.128, 512 contiguous bytes per
+    // channel and warp); two steps are in flight per thread.  The smem store of one (token, 8 channels)
+    // 16-byte piece hits 8 distinct swizzled bank groups across the warp (4 wavefronts, the minimum
+    // for 512 bytes).
+    const int cg = lane & 3, tq = lane >> 2, ch = warp >> 2;
+    const int row0 = (warp & 3) * 32 + tq * 4;
+    const int g = cg + 4 * ch;                  // 8-channel group inside a 64-channel chunk
+    const size_t sHW = (size_t)HW;
+    [[maybe_unused]] unsigned long long tr_wait = 0, tr_work = 0;
+    float4 va[8], vb[8];
+    auto tile_ptr = [&](int it, bool& valid) {
+      const long long t = ((long long)(pair + it * npairs) * CG + rank) * BM + row0;
+      valid = it < my_tiles && t < N;           // N and HW are multiples of 4: a quad is valid as a whole
+      return z + (valid ? ((size_t)(t / HW) * D * HW + (size_t)(t % HW) + (size_t)(g * 8) * sHW) : 0);
+    };
+    auto load_step = [&](float4 (&v)[8], const float* zc, bool valid, int kc) {
+      const float* p = zc + (size_t)(BK * kc) * sHW;
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        v[k] = valid ? ldg_stream(reinterpret_cast<const float4*>(p + (size_t)k * sHW)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+    bool valid;
+    const float* zc = tile_ptr(0, valid);
+    load_step(va, zc, valid, 0);
+    if (KC > 1) load_step(vb, zc, valid, 1);
+    for (int it = 0; it < my_tiles; ++it) {
+      const int abuf = it & 1;
+      unsigned long long tr0 = TR_NOW();
+      mbar_wait(bar(C::BAR_A_EMPTY + abuf), ((it >> 1) & 1) ^ 1);
+      TR_ADD(tr_wait, tr0);
+      tr0 = TR_NOW();
+      float zz4[4] = {0.f, 0.f, 0.f, 0.f};
+      uint8_t* abase = smem + C::OFF_A + abuf * A_BUF_BYTES + row0 * 128;
+      auto store_step = [&](const float4 (&v)[8], int kc) {
+        uint8_t* a = abase + kc * A_CHUNK_BYTES;
+        const float* f = reinterpret_cast<const float*>(v);     // f[4k + i] = channel k, token i
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          uint4 pk;
+          pk.x = pack_f16x2(f[0 + i], f[4 + i]);
+          pk.y = pack_f16x2(f[8 + i], f[12 + i]);
+          pk.z = pack_f16x2(f[16 + i], f[20 + i]);
+          pk.w = pack_f16x2(f[24 + i], f[28 + i]);
+          const int r7 = (row0 + i) & 7;
+          *reinterpret_cast<uint4*>(a + i * 128 + ((g ^ r7) << 4)) = pk;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) zz4[i] = fmaf(f[4 * k + i], f[4 * k + i], zz4[i]);
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) arrive_leader(leader_bar(C::BAR_A_FULL + abuf * MAX_KC + kc));
+      };
+      // the next tile's first two steps are requested before this tile's last two are stored, so the
+      // memory pipe never drains between tiles (registers, not the smem buffer, are the landing zone)
+      bool nvalid;
+      const float* nzc = tile_ptr(it + 1, nvalid);
+#pragma unroll 1
+      for (int kc = 0; kc < KC; kc += 2) {
+        store_step(va, kc);
+        if (kc + 2 < KC) load_step(va, zc, valid, kc + 2); else load_step(va, nzc, nvalid, 0);
+        if (kc + 1 < KC) store_step(vb, kc + 1);
+        if (kc + 3 < KC) load_step(vb, zc, valid, kc + 3); else if (KC > 1) load_step(vb, nzc, nvalid, 1);
+      }
+      zc = nzc;
+      valid = nvalid;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        zz4[i] += __shfl_xor_sync(0xffffffffu, zz4[i], 1);
+        zz4[i] += __shfl_xor_sync(0xffffffffu, zz4[i], 2);
+      }
+      if (cg == 0)
+        *reinterpret_cast<float4*>(s_zz + ((it & (ZZ_SLOTS - 1)) * 2 + ch) * BM + row0) =
+            make_float4(zz4[0], zz4[1], zz4[2], zz4[3]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(C::BAR_ZZ + (it & (ZZ_SLOTS - 1))));
+      TR_ADD(tr_work, tr0);
+    }
+    if (threadIdx.x == 0) { TR_PUT(0, tr_wait); TR_PUT(1, tr_work); }
+  } else if (warp < NPROD + 8) {
     // ===================== epilogue: flag masks per 32 codes, running max per row =====================
-    const int q = warp >> 2;                      // column half of every accumulator this warp quad drains
+    const int q = (warp - NPROD) >> 2;            // column half of every accumulator this warp quad drains
     const int part = warp & 3;                    // TMEM lane quarter this warp may access
     const int row = part * 32 + lane;
     const uint32_t tlane = tmem_base + ((uint32_t)(part * 32) << 16) + q * (BN / 2);
     const float emax = emax_ptr[0];
     const bool cb_unsafe = __float_as_uint(emax_ptr[1]) != 0u;   // codebook outside FP16's range: FP32 scan for all
     uint32_t g = 0;                               // running N-tile counter (same sequence as the MMA issuer)
-    [[maybe_unused]] unsigned long long tr_full = 0, tr_proc = 0;
+    [[maybe_unused]] unsigned long long tr_zz = 0, tr_full = 0, tr_proc = 0;
     for (int it = 0; it < my_tiles; ++it) {
       const int ptile = pair + it * npairs;
       const long long t = ((long long)ptile * CG + rank) * BM + row;
       const bool valid = t < N;
-      unsigned long long tr0;
-      const float zz = valid ? __ldg(zzg + t) : 0.f;
+      unsigned long long tr0 = TR_NOW();
+      mbar_wait(bar(C::BAR_ZZ + (it & (ZZ_SLOTS - 1))), (it / ZZ_SLOTS) & 1);
+      TR_ADD(tr_zz, tr0);
+      const float zz = s_zz[(it & (ZZ_SLOTS - 1)) * 2 * BM + row] + s_zz[((it & (ZZ_SLOTS - 1)) * 2 + 1) * BM + row];
       const float margin = vq_margin(zz, emax);
       float m = -INFINITY;
       int n = 0;                                  // list entries written
@@ -380,28 +468,9 @@ vq_tensor_search_kernel(const __grid_constant__ CUtensorMap tmap_cb, const __gri
         else        { meta[t].m1 = m; meta[t].n1 = nn; }
       }
     }
-    if (part == 0 && lane == 0) { TR_PUT(3 + 4 * q, tr_full); TR_PUT(4 + 4 * q, tr_proc); }
-  } else if (warp == WARP_TMA_A) {
-    // ===================== TMA producer A: this CTA's 128-token operand tiles =====================
-    if (lane == 0) {
-      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
-      [[maybe_unused]] unsigned long long tr_wait = 0, tr0;
-      for (int it = 0; it < my_tiles; ++it) {
-        const int abuf = it & 1;
-        const int row0 = ((pair + it * npairs) * CG + (int)rank) * BM;    // rows past N are zero-filled by the TMA
-        tr0 = TR_NOW();
-        mbar_wait(bar(C::BAR_A_EMPTY + abuf), ((it >> 1) & 1) ^ 1);
-        TR_ADD(tr_wait, tr0);
-        for (int kc = 0; kc < KC; ++kc) {
-          if (leader) mbar_arrive_expect_tx(bar(C::BAR_A_FULL + abuf * MAX_KC + kc), CG * A_CHUNK_BYTES);
-          tma_load_2d<CG>(sbase + C::OFF_A + abuf * A_BUF_BYTES + kc * A_CHUNK_BYTES, &tmap_a, kc * BK, row0,
-                          leader_bar(C::BAR_A_FULL + abuf * MAX_KC + kc));
-        }
-      }
-      TR_PUT(0, tr_wait);
-    }
-  } else if (warp == WARP_TMA_B) {
-    // ===================== TMA producer B: this CTA's half of every codebook tile =====================
+    if (part == 0 && lane == 0) { TR_PUT(2 + 4 * q, tr_zz); TR_PUT(3 + 4 * q, tr_full); TR_PUT(4 + 4 * q, tr_proc); }
+  } else if (warp == WARP_TMA) {
+    // ===================== TMA producer: this CTA's half of every codebook tile =====================
     if (lane == 0) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_cb) : "memory");
       int stage = 0;
@@ -509,8 +578,8 @@ bool vq_tensor_supported(int D, int K) {
 }
 
 template <int CG>
-static int launch_search(const CUtensorMap& tmap, const CUtensorMap& tmap_a, const float* zz, const float* emax, int N,
-                         int D, int K, VqMeta* meta, uint2* list, cudaStream_t s) {
+static int launch_search(const CUtensorMap& tmap, const float* z, const float* emax, int N, int D, int HW, int K,
+                         VqMeta* meta, uint2* list, cudaStream_t s) {
   using C = Cfg<CG>;
   const int num_ptiles = (N + BM * CG - 1) / (BM * CG);
   const int max_pairs = kNumSMs / CG;
@@ -531,7 +600,7 @@ static int launch_search(const CUtensorMap& tmap, const CUtensorMap& tmap_a, con
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  if (cudaLaunchKernelEx(&cfg, vq_tensor_search_kernel<CG>, tmap, tmap_a, zz, emax, N, D, K, num_ptiles, meta, list) != cudaSuccess)
+  if (cudaLaunchKernelEx(&cfg, vq_tensor_search_kernel<CG>, tmap, z, emax, N, D, HW, K, num_ptiles, meta, list) != cudaSuccess)
     return DCVIC_ERR_CUDA;
   return dcvic_launch_status();
 }
@@ -544,7 +613,7 @@ extern "C" int dcvic_debug_read_trace(unsigned long long* host_out /* [296][16] 
 namespace dcvic {
 #endif
 
-int vq_tensor_search(const __half* a16, const float* zz, const __half* cb16, const float* emax, int N, int D, int K,
+int vq_tensor_search(const float* z, const __half* cb16, const float* emax, int B, int D, int HW, int K,
                      VqMeta* meta, uint2* list, cudaStream_t s) {
   if (!vq_tensor_supported(D, K)) return DCVIC_ERR_UNSUPPORTED;
   static const int cta_group = [] {
@@ -562,17 +631,9 @@ int vq_tensor_search(const __half* a16, const float* zz, const __half* cb16, con
              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
     return DCVIC_ERR_CUDA;
-  // operand matrix A16[N][D] (token-major FP16): one [64 ch x 128 tokens] box per chunk
-  CUtensorMap tmap_a;
-  const cuuint64_t adim[2] = {(cuuint64_t)D, (cuuint64_t)N};
-  const cuuint64_t astride[1] = {(cuuint64_t)D * sizeof(__half)};
-  const cuuint32_t abox[2] = {(cuuint32_t)BK, (cuuint32_t)BM};
-  if (encode(&tmap_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(a16), adim, astride, abox, estr,
-             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
-    return DCVIC_ERR_CUDA;
-  return cta_group == 2 ? launch_search<2>(tmap, tmap_a, zz, emax, N, D, K, meta, list, s)
-                        : launch_search<1>(tmap, tmap_a, zz, emax, N, D, K, meta, list, s);
+  const int N = B * HW;
+  return cta_group == 2 ? launch_search<2>(tmap, z, emax, N, D, HW, K, meta, list, s)
+                        : launch_search<1>(tmap, z, emax, N, D, HW, K, meta, list, s);
 }
 
 }  // namespace dcvic

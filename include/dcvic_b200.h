@@ -49,8 +49,6 @@ enum {
    * skipped stage are left as the previous call on the same workspace produced them */
   DCVIC_VQ_STAGE_SEARCH_ONLY = 8,  /* codebook prep + candidate search, no finish */
   DCVIC_VQ_STAGE_FINISH_ONLY = 16, /* finish (re-rank + gather + STE + loss) from the workspace's candidates */
-  DCVIC_VQ_SKIP_CONVERT = 64, /* measurement aid: the tcgen05 search reuses the FP16 operand matrix the previous call
-                                 left in the workspace (times the tensor kernel alone) */
   DCVIC_VQ_RAGGED_HW = 32   /* dcvic_vq_path only: H*W is not a multiple of 4 (or z is not 16-byte aligned), which
                                the tcgen05 search does not take; dcvic_vq_forward sets it by itself */
 };

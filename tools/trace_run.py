@@ -29,8 +29,8 @@ lib = _lib.load()
 buf = (C.c_ulonglong * (296 * 16))()
 lib.dcvic_debug_read_trace.restype = C.c_int
 assert lib.dcvic_debug_read_trace(buf) == 0
-names = ["TMA-A wait_empty", "-", "-", "E0 wait_full", "E0 process", "-", "-",
-         "E1 wait_full", "E1 process", "-", "MMA wait_t_empty", "MMA wait_a_full", "MMA wait_b_full", "MMA total"]
+names = ["A wait_empty", "A load+cvt", "E0 wait_zz", "E0 wait_full", "E0 process", "E0 reinit", "E1 wait_zz",
+         "E1 wait_full", "E1 process", "E1 reinit", "MMA wait_t_empty", "MMA wait_a_full", "MMA wait_b_full", "MMA total"]
 rows = [[buf[b * 16 + i] for i in range(16)] for b in range(148)]
 for i, n in enumerate(names):
     col = [r[i] for r in rows if (i < 10 or r[13] > 0)]
