@@ -213,7 +213,9 @@ def run_ours(args):
     t_full = max_over_ranks(timed(vq_step, K_steps, W_steps, barrier))
     # dominant kernel alone (same launches, search stage only) for the roofline
     t_search = timed(lambda i: vq_step(i, _lib.VQ_STAGE_SEARCH_ONLY | _lib.VQ_REUSE_PREP), K_steps, W_steps, barrier)
-    t_finish = timed(lambda i: vq_step(i, _lib.VQ_STAGE_FINISH_ONLY), K_steps, W_steps, barrier)
+    t_prep_search = timed(lambda i: vq_step(i, _lib.VQ_STAGE_SEARCH_ONLY), K_steps, W_steps, barrier)
+    # the finish stage needs lists that belong to the same z, so it is timed as whole step minus the stages before it
+    t_finish = max(t_full - t_prep_search, 0.0)
     clocks = sampler.stop()
 
     value = world * N * K_steps / t_full
@@ -231,7 +233,8 @@ def run_ours(args):
                 "peak": pk["hbm"], "unit": "GB/s", "frac": finish_bytes / finish_s / 1e9 / pk["hbm"], "traffic": None,
                 "us_per_launch": finish_s * 1e6, "algorithmic": f"N*(8D+8) = {finish_bytes} B per launch",
                 "peak_source": pk["source"]}
-    stage = {"search_us": search_s * 1e6, "finish_us": finish_s * 1e6,
+    stage = {"prepare_us": (t_prep_search - t_search) / K_steps * 1e6,
+             "search_us": search_s * 1e6, "finish_us": finish_s * 1e6,
              "finish_hbm_gbs": finish_bytes / finish_s / 1e9, "finish_hbm_frac": finish_bytes / finish_s / 1e9 / pk["hbm"],
              "search_tflops": flops / search_s / 1e12}
 
@@ -312,7 +315,7 @@ def run_ours(args):
                 "warmup": W_steps, "ms_per_step": t_full / K_steps * 1e3, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
                 "config": {"workload": VQ_WORKLOAD, "search_path": path,
-                           "arithmetic": "bf16 tcgen05 candidate search + fp32 re-rank" if path == "tcgen05" else "fp32 SIMT",
+                           "arithmetic": "fp16 tcgen05 candidate search (fp32 accumulate) + fp32 re-rank" if path == "tcgen05" else "fp32 SIMT",
                            "l2": f"inputs/outputs rotated over {ROT} buffer sets (536 MB > 126 MB L2)",
                            "codebook_prep": "inside every timed step", "sharding": "batch (images) per rank, no collective"},
                 "roofline": roof, "stages": stage,
