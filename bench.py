@@ -239,28 +239,58 @@ def run_ours(args):
              "search_tflops": flops / search_s / 1e12}
 
     # ---------------- VQ end to end: module API, pinned host buffers in and out -----------------
-    vq = D.VectorQuantizer2(K, Dm, 0.25, sane_index_shape=True).to(dev)
-    vq.embedding.weight.data.copy_(Ec)
-    vq.freeze_codebook()          # DC-VIC always freezes the VQGAN codebook
-    z_host = z0.pin_memory()
-    zq_host = torch.empty_like(z_host).pin_memory()
-    idx_host = torch.empty(B, H, W, dtype=torch.int64).pin_memory()
-    loss_host = torch.empty(()).pin_memory()
-    z_dev = torch.empty(B, Dm, H, W, device=dev)
+    # Every step copies its input from pinned host memory and its results (z_q, indices, loss) back, inside the timed
+    # region.  Steps alternate between two lanes (stream + buffers + module instance), so step i+1's upload overlaps
+    # step i's download on the full-duplex PCIe link -- what a serving loop around the module does.
+    class Lane:
+        def __init__(self):
+            self.stream = torch.cuda.Stream(device=dev)
+            self.vq = D.VectorQuantizer2(K, Dm, 0.25, sane_index_shape=True).to(dev)
+            self.vq.embedding.weight.data.copy_(Ec)
+            self.vq.freeze_codebook()          # DC-VIC always freezes the VQGAN codebook
+            self.z_host = z0.clone().pin_memory()
+            self.zq_host = torch.empty_like(self.z_host).pin_memory()
+            self.idx_host = torch.empty(B, H, W, dtype=torch.int64).pin_memory()
+            self.loss_host = torch.empty(()).pin_memory()
+            self.z_dev = torch.empty(B, Dm, H, W, device=dev)
 
-    def vq_e2e(i):
-        z_dev.copy_(z_host, non_blocking=True)
-        with torch.no_grad():
-            z_q, l, (_, _, idx) = vq(z_dev)
-        zq_host.copy_(z_q, non_blocking=True)
-        idx_host.copy_(idx, non_blocking=True)
-        loss_host.copy_(l, non_blocking=True)
+        def step(self):
+            with torch.cuda.stream(self.stream), torch.no_grad():
+                self.z_dev.copy_(self.z_host, non_blocking=True)
+                z_q, l, (_, _, idx) = self.vq(self.z_dev)
+                self.zq_host.copy_(z_q, non_blocking=True)
+                self.idx_host.copy_(idx, non_blocking=True)
+                self.loss_host.copy_(l, non_blocking=True)
 
-    e2e_steps = max(3, min(K_steps, 20))
-    t_e2e = max_over_ranks(timed(vq_e2e, e2e_steps, 3, barrier))
+    lanes = [Lane(), Lane()]
+
+    def e2e_run(steps):
+        cur = torch.cuda.current_stream()
+        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        start.record(cur)
+        for ln in lanes:
+            ln.stream.wait_event(start)
+        for i in range(steps):
+            lanes[i % 2].step()
+        for ln in lanes:
+            done = torch.cuda.Event()
+            done.record(ln.stream)
+            cur.wait_event(done)
+        end.record(cur)
+        torch.cuda.synchronize()
+        return start.elapsed_time(end) * 1e-3
+
+    e2e_steps = max(4, min(K_steps, 20))
+    e2e_run(4)                                   # warm-up (allocator, workspaces, codebook preparation)
+    torch.cuda.synchronize()
+    barrier()
+    t_e2e = max_over_ranks(e2e_run(e2e_steps))
+    barrier()
+    z_host, zq_host, idx_host = lanes[0].z_host, lanes[0].zq_host, lanes[0].idx_host
     e2e = {"value": world * N * e2e_steps / t_e2e, "unit": "tokens/s", "h2d_bytes_per_step": z_host.numel() * 4,
            "d2h_bytes_per_step": zq_host.numel() * 4 + idx_host.numel() * 8 + 4, "ms_per_step": t_e2e / e2e_steps * 1e3,
-           "api": "dc_vic_b200.VectorQuantizer2.forward on pinned host tensors (H2D z, D2H z_q + indices + loss)"}
+           "api": "dc_vic_b200.VectorQuantizer2.forward on pinned host tensors (H2D z, D2H z_q + indices + loss), "
+                  "steps alternating over two streams so upload and download overlap"}
 
     # ---------------- entropy model (secondary block) -------------------------------------------
     yb, pb = entropy_inputs(2)

@@ -516,7 +516,7 @@ __device__ unsigned long long g_trace_fin[4096][12];
 // DT = e_dim when it is one of the specialised sizes (64, 128, 256), else 0 (run-time e_dim); T = tokens per CTA
 // (16 or 32; T/4 warps, each owning 4 tokens in phase B)
 template <int DT, int T>
-__global__ void __launch_bounds__(T * 8) vq_finish_v5_kernel(const float* __restrict__ z, const float* __restrict__ E,
+__global__ void __launch_bounds__(T * 8, DT ? 1536 / (T * 8) : 1) vq_finish_v5_kernel(const float* __restrict__ z, const float* __restrict__ E,
                                                             const float* __restrict__ ee,
                                                             const float* __restrict__ emax_ptr,
                                                             const int* __restrict__ cand,
@@ -720,7 +720,7 @@ __global__ void __launch_bounds__(T * 8) vq_finish_v5_kernel(const float* __rest
   // gather + straight-through value + loss partial: the 4 winning rows of this warp are requested together
   float sq = 0.f;
   {
-    constexpr int G = DT ? 4 : 1;               // rows fetched together (run-time e_dim: one, to bound registers)
+    constexpr int G = DT ? 2 : 1;               // rows fetched together (bounded by the register budget of 6 CTAs/SM)
 #pragma unroll
     for (int i0 = 0; i0 < 4; i0 += G) {
       float4 eb[G][NV];

@@ -245,3 +245,34 @@ def test_tensor_core_path_is_selected_and_agrees_with_exact_scan():
     narrow.search = "tensor"
     with pytest.raises(RuntimeError, match="not supported"):
         narrow(torch.randn(1, 4, 8, 8, device=DEV))
+
+
+def test_tensor_path_outside_fp16_range_stays_exact():
+    """Tokens / codebooks whose values do not fit FP16 must come out exactly as the FP32 reference
+    (they are flagged by the search and scanned in FP32 by the finish kernel)."""
+    z, E = vq_inputs(3, "D1b", 1, 256, 8, 16, 1024)
+    z = z.clone()
+    z[0, :, 0, :4] *= 3.0e5            # 4 tokens with |z| far beyond 65504
+    z[0, 5, 1, 0] = 7.0e4              # one element just over the FP16 maximum
+    m = make(D.VectorQuantizer2, E, sane_index_shape=True)
+    assert m.search_path() == "tcgen05"
+    with torch.no_grad():
+        out = m(z.to(DEV))
+    check_against_oracle(z, E, out, out[2][2], allow_near_ties=True)
+    E2 = E.clone()
+    E2[7] *= 1.0e4                     # |e|^2 / 2 no longer representable: the whole codebook is flagged unsafe
+    m2 = make(D.VectorQuantizer2, E2, sane_index_shape=True)
+    z2 = vq_inputs(4, "D1b", 1, 256, 8, 16, 1024)[0]
+    with torch.no_grad():
+        out2 = m2(z2.to(DEV))
+    check_against_oracle(z2, E2, out2, out2[2][2], allow_near_ties=True)
+
+
+def test_tensor_path_larger_codebooks():
+    for K, Dm in ((2048, 128), (768, 64)):
+        z, E = vq_inputs(5, "D1b", 1, Dm, 16, 16, K)
+        m = make(D.VectorQuantizer2, E, sane_index_shape=True)
+        assert m.search_path() == "tcgen05"
+        with torch.no_grad():
+            out = m(z.to(DEV))
+        check_against_oracle(z, E, out, out[2][2], allow_near_ties=False)

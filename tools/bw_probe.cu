@@ -107,6 +107,36 @@ __global__ void linear_read_u(const float4* __restrict__ p, size_t n4, float* ou
   }
   if (acc == 123.456f) *out = acc;
 }
+// finish-kernel staging pattern: CTA of 256 threads reads (and optionally writes back) TT tokens x 256 channels,
+// i.e. 256 pieces of TT*4 bytes at 4 KB stride
+template <int TT, bool WRITE>
+__global__ void __launch_bounds__(256) fin_pattern(const float* __restrict__ z, float* __restrict__ o, int N, int D, int HW, float* out) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  constexpr int TQ = TT / 4, CQ = 32 / TQ;
+  const int tq = lane / CQ, cq = lane % CQ;
+  const long long t = (long long)blockIdx.x * TT + 4 * tq;
+  const size_t base = (size_t)(t / HW) * D * HW + (t % HW);
+  float acc = 0.f;
+  float4 v[2][4];
+#pragma unroll
+  for (int h = 0; h < 2; ++h)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int c = h * 128 + wid * (4 * CQ) + cq * 4 + k;
+      v[h][k] = ldg_stream(reinterpret_cast<const float4*>(z + base + (size_t)c * HW));
+    }
+#pragma unroll
+  for (int h = 0; h < 2; ++h)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int c = h * 128 + wid * (4 * CQ) + cq * 4 + k;
+      if (WRITE) {
+        float4 w = v[h][k]; w.x += 1.f;
+        asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(o + base + (size_t)c * HW), "f"(w.x), "f"(w.y), "f"(w.z), "f"(w.w) : "memory");
+      } else acc += v[h][k].x + v[h][k].w;
+    }
+  if (!WRITE && acc == 123.456f) *out = acc;
+}
 template <class F> float timeit(F f, int iters = 20) {
   cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
   for (int i = 0; i < 3; ++i) f();
@@ -151,7 +181,17 @@ int main() {
     ms = timeit([&] { tile_read<8, 2><<<148, 256>>>(z, Ns, D, HW, out); }, 50);
     printf("L2-resident tile 8 warps 2 sets: %.1f GB/s\n", gbs / ms * 1e3);
   }
-  for (int dist = 1; dist <= 1; ++dist) {
+  {
+    float* o; cudaMalloc(&o, n * 4);
+    ms = timeit([&] { fin_pattern<32, false><<<N / 32, 256>>>(z, o, N, D, HW, out); });
+    printf("finish pattern read  32-token tiles (128 B pieces): %.1f GB/s\n", gb / ms * 1e3);
+    ms = timeit([&] { fin_pattern<16, false><<<N / 16, 256>>>(z, o, N, D, HW, out); });
+    printf("finish pattern read  16-token tiles ( 64 B pieces): %.1f GB/s\n", gb / ms * 1e3);
+    ms = timeit([&] { fin_pattern<32, true><<<N / 32, 256>>>(z, o, N, D, HW, out); });
+    printf("finish pattern read+write 32-token tiles: %.1f GB/s (r+w bytes)\n", 2 * gb / ms * 1e3);
+    cudaFree(o);
+  }
+  for (int dist = 1; dist <= 0; ++dist) {
     ms = timeit([&] { tile_read_pf<4, 1><<<148, 128>>>(z, N, D, HW, dist, out); });
     printf("tile 4 warps 2 sets + bulk prefetch dist %d : %.1f GB/s\n", dist, gb / ms * 1e3);
     ms = timeit([&] { tile_read_pf<4, 2><<<148, 128>>>(z, N, D, HW, dist, out); });

@@ -39,7 +39,7 @@ for i, n in enumerate(names):
 fb = (C.c_ulonglong * (4096 * 12))()
 lib.dcvic_debug_read_finish_trace.restype = C.c_int
 if lib.dcvic_debug_read_finish_trace(fb) == 0:
-    fn = ["stage+lists", "rerank+gather", "sync", "store"]
+    fn = ["stage z + lists", "re-rank", "gather", "store"]
     rows = [[fb[b * 12 + i] for i in range(12)] for b in range(4096)]
     rows = [r for r in rows if sum(r) > 0]
     print("finish: CTAs traced", len(rows))
