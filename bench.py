@@ -37,6 +37,16 @@ VQ_WORKLOAD = "VQ codebook 1024x256 nearest-codeword search (VectorQuantizer2.fo
 GC_WORKLOAD = "SteGaussianMeanScaleConditional eval forward + per-sample rate on synthetic ELIC latents 64x320x32x32 (q=2) per GPU"
 
 
+def ncu_traffic(kernel):
+    """dram bytes per launch of `kernel` from the committed ncu capture (profiles/), or None."""
+    p = os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")
+    try:
+        d = json.load(open(p))[kernel]
+        return d["dram_bytes_read"] + d["dram_bytes_write"]
+    except Exception:
+        return None
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -226,7 +236,9 @@ def run_ours(args):
     if path == "tcgen05" or search_s >= finish_s:
         roof = {"kernel": "vq_tensor_search" if path == "tcgen05" else "vq_exact_kernel", "bound": "tensor",
                 "achieved": flops / search_s / 1e12, "peak": pk["bf16"], "unit": "TFLOP/s",
-                "frac": flops / search_s / 1e12 / pk["bf16"], "traffic": None, "us_per_launch": search_s * 1e6,
+                "frac": flops / search_s / 1e12 / pk["bf16"],
+                "traffic": ncu_traffic("vq_tensor_search_kernel") if path == "tcgen05" else None,
+                "us_per_launch": search_s * 1e6,
                 "algorithmic": f"2*N*K*D = {flops:.4g} flop per launch", "peak_source": pk["source"] + ", bf16 burst"}
     else:
         roof = {"kernel": "vq_finish_kernel", "bound": "hbm", "achieved": finish_bytes / finish_s / 1e9,
@@ -329,7 +341,7 @@ def run_ours(args):
                "ms_per_step": gc_s * 1e3, "config": {"workload": GC_WORKLOAD},
                "roofline": {"kernel": "gc_forward_kernel", "bound": "hbm", "achieved": gc_bytes / gc_s / 1e9,
                             "peak": pk["hbm"], "unit": "GB/s", "frac": gc_bytes / gc_s / 1e9 / pk["hbm"],
-                            "traffic": None, "algorithmic": "20 B/latent (read y, mu, sigma; write y_hat, likelihood)",
+                            "traffic": ncu_traffic("gc_forward_kernel"), "algorithmic": "20 B/latent (read y, mu, sigma; write y_hat, likelihood)",
                             "peak_source": pk["source"]},
                "e2e": {"value": world * n_lat * 5 / t_gce, "unit": "latents/s",
                        "h2d_bytes_per_step": (y_host.numel() + p_host.numel()) * 4,
@@ -352,7 +364,8 @@ def run_ours(args):
                 "cpu_baseline": {"value": cpu_val, "unit": "tokens/s", "cores": cores, "kind": "port",
                                  "sample": "full 65,536-token batch x 3 (oracle port of taming VectorQuantizer2, torch CPU)"},
                 "e2e": e2e, "gpu_launches": launches_per_step * K_steps, "clocks": clocks, "entropy": entropy}
-        print(json.dumps(line))
+        sys.stdout.flush()
+        print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
