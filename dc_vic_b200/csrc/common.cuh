@@ -75,6 +75,13 @@ __device__ __forceinline__ bool publish_and_elect_last(double block_partial, dou
   return true;
 }
 
+// Programmatic dependent launch (PDL): a kernel launched with the programmatic-stream-serialization attribute may
+// start while its predecessor in the stream is still running; pdl_wait() blocks until that predecessor has completed
+// and its writes are visible, pdl_launch_dependents() lets the successor start early.  Everything a kernel reads
+// from its predecessor's outputs must come after pdl_wait().
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ float4 ldg_stream(const float4* p) {
   float4 r;
   asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"

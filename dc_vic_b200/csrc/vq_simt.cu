@@ -21,6 +21,7 @@ namespace dcvic {
 __global__ void __launch_bounds__(256) vq_prepare_kernel(const float* __restrict__ E, int K, int D,
                                                           float* __restrict__ ee, float* __restrict__ nhee,
                                                           float* __restrict__ emax, __half* __restrict__ cb16) {
+  pdl_launch_dependents();      // the tensor search may start loading z while the codebook is being prepared
   const int lane = threadIdx.x & 31;
   const int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (k >= K) return;
@@ -547,19 +548,6 @@ __global__ void __launch_bounds__(T * 8, DT ? 1536 / (T * 8) : 1) vq_finish_v5_k
   if (threadIdx.x < T) s_nc[threadIdx.x] = 0;
   if (threadIdx.x == 0) { s_nfull = 0; s_nrerank = 0; }
 
-  // requests that do not depend on z go first: meta + this thread's 4 list entries (8 threads per token)
-  const int ltok = threadIdx.x >> 3, sub = threadIdx.x & 7;
-  const int lq = sub >> 2, li0 = (sub & 3) * 4;
-  const bool lvalid = !cand && (t0 + ltok) < N;
-  VqMeta mt = {};
-  uint4 e01 = make_uint4(0u, 0u, 0u, 0u), e23 = e01;
-  if (lvalid) {
-    mt = meta[t0 + ltok];
-    const uint4* lp = reinterpret_cast<const uint4*>(list + ((size_t)(t0 + ltok) * 2 + lq) * kListCap + li0);
-    e01 = __ldg(lp);
-    e23 = __ldg(lp + 1);
-  }
-
   // (A) stage the token tile: lane = tq*CQ + cq, token quad tq (tokens 4tq..4tq+3), channel quad cq; warp w takes
   // channels [4*CQ*w, 4*CQ*(w+1)) of every 128-channel pass (a quarter warp = 8 channel quads or 2 token quads x 4
   // channel quads: 8 distinct bank groups for its 16-byte stores either way)
@@ -581,6 +569,21 @@ __global__ void __launch_bounds__(T * 8, DT ? 1536 / (T * 8) : 1) vq_finish_v5_k
       *reinterpret_cast<float4*>(dst + 2 * ld) = make_float4(v[0].z, v[1].z, v[2].z, v[3].z);
       *reinterpret_cast<float4*>(dst + 3 * ld) = make_float4(v[0].w, v[1].w, v[2].w, v[3].w);
     }
+  }
+  // Everything above only read z (an input of the whole call), so with programmatic dependent launch it overlaps
+  // the tail of the search kernel; its outputs (meta, lists, cand) are read from here on.
+  pdl_wait();
+  // meta + this thread's 4 list entries (8 threads per token)
+  const int ltok = threadIdx.x >> 3, sub = threadIdx.x & 7;
+  const int lq = sub >> 2, li0 = (sub & 3) * 4;
+  const bool lvalid = !cand && (t0 + ltok) < N;
+  VqMeta mt = {};
+  uint4 e01 = make_uint4(0u, 0u, 0u, 0u), e23 = e01;
+  if (lvalid) {
+    mt = meta[t0 + ltok];
+    const uint4* lp = reinterpret_cast<const uint4*>(list + ((size_t)(t0 + ltok) * 2 + lq) * kListCap + li0);
+    e01 = __ldg(lp);
+    e23 = __ldg(lp + 1);
   }
   // expand list entries -> candidate codes (order within a token does not matter: the minimum is over
   // (distance, index)).  The threshold uses the |z|^2 the search itself used for its margin.
@@ -793,9 +796,19 @@ int vq_finish(const float* z, const float* E, const float* ee, const float* emax
   do {                                                                                                             \
     if (smem > 40 * 1024)                                                                                          \
       cudaFuncSetAttribute(vq_finish_v5_kernel<DT, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
-    vq_finish_v5_kernel<DT, T><<<ceil_div_i(N, T), T * 8, smem, s>>>(z, E, ee, emax, cand, meta, list, N, D, HW, K, \
-                                                                     beta, legacy, zq, idx, loss, partials,        \
-                                                                     counters);                                    \
+    cudaLaunchConfig_t cfg{};                                                                                      \
+    cfg.gridDim = dim3(ceil_div_i(N, T));                                                                          \
+    cfg.blockDim = dim3(T * 8);                                                                                    \
+    cfg.dynamicSmemBytes = smem;                                                                                   \
+    cfg.stream = s;                                                                                                \
+    cudaLaunchAttribute pdl[1];                                                                                    \
+    pdl[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                                                \
+    pdl[0].val.programmaticStreamSerializationAllowed = 1;                                                         \
+    cfg.attrs = pdl;                                                                                               \
+    cfg.numAttrs = 1;                                                                                              \
+    if (cudaLaunchKernelEx(&cfg, vq_finish_v5_kernel<DT, T>, z, E, ee, emax, cand, meta, list, N, D, HW, K, beta,   \
+                           legacy, zq, idx, loss, partials, counters) != cudaSuccess)                              \
+      return DCVIC_ERR_CUDA;                                                                                       \
   } while (0)
     if (tile_tokens == 32) {
       if (D == 256) DCVIC_LAUNCH_FINISH(256, 32);

@@ -269,6 +269,10 @@ vq_tensor_search_kernel(const __grid_constant__ CUtensorMap tmap_cb, const float
   float* s_zz = reinterpret_cast<float*>(smem + C::OFF_ZZ);
   volatile uint32_t* s_tmem = reinterpret_cast<volatile uint32_t*>(smem + C::OFF_TMEM_PTR);
 
+  // PDL: this kernel may have started before its predecessor (codebook prepare, or the previous call's finish) ended;
+  // the roles that read the predecessor's outputs wait for it below, the z loads do not.  Its own successor (finish)
+  // may start as soon as SMs free up: it only touches z until it waits for this grid.
+  pdl_launch_dependents();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
   const bool leader = rank == 0;
@@ -405,6 +409,7 @@ vq_tensor_search_kernel(const __grid_constant__ CUtensorMap tmap_cb, const float
     const int part = warp & 3;                    // TMEM lane quarter this warp may access
     const int row = part * 32 + lane;
     const uint32_t tlane = tmem_base + ((uint32_t)(part * 32) << 16) + q * (BN / 2);
+    pdl_wait();                                   // emax (prepare kernel); the previous call's finish is done with meta/list
     const float emax = emax_ptr[0];
     const bool cb_unsafe = __float_as_uint(emax_ptr[1]) != 0u;   // codebook outside FP16's range: FP32 scan for all
     uint32_t g = 0;                               // running N-tile counter (same sequence as the MMA issuer)
@@ -473,6 +478,7 @@ vq_tensor_search_kernel(const __grid_constant__ CUtensorMap tmap_cb, const float
     // ===================== TMA producer: this CTA's half of every codebook tile =====================
     if (lane == 0) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_cb) : "memory");
+      pdl_wait();                                 // the FP16 codebook is written by the prepare kernel
       int stage = 0;
       uint32_t phase = 0;
       for (int it = 0; it < my_tiles; ++it)
@@ -593,13 +599,15 @@ static int launch_search(const CUtensorMap& tmap, const float* z, const float* e
   cfg.blockDim = dim3(NTHREADS);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = s;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CG;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = 2;
   if (cudaLaunchKernelEx(&cfg, vq_tensor_search_kernel<CG>, tmap, z, emax, N, D, HW, K, num_ptiles, meta, list) != cudaSuccess)
     return DCVIC_ERR_CUDA;
   return dcvic_launch_status();
