@@ -39,7 +39,7 @@ inline VqWorkspace vq_workspace_layout(int B, int D, int HW, int K) {
   w.off_ee = take((size_t)K * sizeof(float));
   w.off_nhee = take((size_t)K * sizeof(float));
   w.off_emax = take(4 * sizeof(float));
-  w.off_partials = take((N / 8 + 2) * sizeof(double));   // one per finish CTA (>= 16 tokens each)
+  w.off_partials = take((N / 4 + 8) * sizeof(double));   // one per finish warp (4 tokens each)
   w.off_hist = take((size_t)K * sizeof(unsigned));
   w.off_cand = take(N * sizeof(int));
   w.off_meta = take(N * sizeof(VqMeta));

@@ -499,7 +499,6 @@ __global__ void __launch_bounds__(256) vq_finish_kernel(const float* __restrict_
 // candidates to z_q: re-rank where more than one code was flagged (two codebook rows in flight), then the 4
 // winning rows are fetched together for the gather / straight-through value / loss partial; (C) coalesced
 // stores.  Tokens that need the whole codebook (overflowed list, FP16-unsafe) are scanned by the full CTA.
-constexpr int kFT = kFinishTokens;
 #ifdef DCVIC_TRACE
 __device__ unsigned long long g_trace_fin[4096][12];
 #define FT_MARK(i)                                         \
@@ -517,7 +516,7 @@ __device__ unsigned long long g_trace_fin[4096][12];
 // DT = e_dim when it is one of the specialised sizes (64, 128, 256), else 0 (run-time e_dim); T = tokens per CTA
 // (16 or 32; T/4 warps, each owning 4 tokens in phase B)
 template <int DT, int T>
-__global__ void __launch_bounds__(T * 8, DT ? 1536 / (T * 8) : 1) vq_finish_v5_kernel(const float* __restrict__ z, const float* __restrict__ E,
+__global__ void __launch_bounds__(T * 8, DT ? 1024 / (T * 8) : 1) vq_finish_v5_kernel(const float* __restrict__ z, const float* __restrict__ E,
                                                             const float* __restrict__ ee,
                                                             const float* __restrict__ emax_ptr,
                                                             const int* __restrict__ cand,
@@ -528,7 +527,6 @@ __global__ void __launch_bounds__(T * 8, DT ? 1536 / (T * 8) : 1) vq_finish_v5_k
                                                             double* __restrict__ partials,
                                                             unsigned* __restrict__ counters) {
   extern __shared__ __align__(16) float zt[];  // [T][D + 4]
-  __shared__ double scratch[32];
   __shared__ int s_best[T];                  // decided code
   __shared__ float s_wd[T / 4];
   __shared__ int s_wk[T / 4];
@@ -555,19 +553,28 @@ __global__ void __launch_bounds__(T * 8, DT ? 1536 / (T * 8) : 1) vq_finish_v5_k
   const int tokq = t0 + 4 * tq;                          // first token of this thread's quad
   const bool qvalid = tokq < N;                          // N % 4 == 0: quads are valid as a whole
   const size_t qbase = qvalid ? ((size_t)(tokq / HW) * D * HW + (size_t)(tokq % HW)) : 0;
-  for (int c0 = wid * (4 * CQ); c0 < D; c0 += 128) {
-    const int c = c0 + cq * 4;
-    if (c < D) {
-      float4 v[4];
+  constexpr int NPASS = DT ? (DT + 127) / 128 : 1;     // 128-channel passes requested together (all of them for the
+                                                        // specialised sizes: one DRAM round trip per tile, not two)
+  for (int cb = 0; cb < D; cb += 128 * NPASS) {
+    float4 v[NPASS][4];
+#pragma unroll
+    for (int h = 0; h < NPASS; ++h) {
+      const int c = cb + h * 128 + wid * (4 * CQ) + cq * 4;
 #pragma unroll
       for (int k = 0; k < 4; ++k)
-        v[k] = qvalid ? ldg_stream(reinterpret_cast<const float4*>(z + qbase + (size_t)(c + k) * HW))
-                      : make_float4(0.f, 0.f, 0.f, 0.f);
-      float* dst = zt + (4 * tq) * ld + c;                // 4x4 transpose: 4 tokens x 4 channels
-      *reinterpret_cast<float4*>(dst) = make_float4(v[0].x, v[1].x, v[2].x, v[3].x);
-      *reinterpret_cast<float4*>(dst + ld) = make_float4(v[0].y, v[1].y, v[2].y, v[3].y);
-      *reinterpret_cast<float4*>(dst + 2 * ld) = make_float4(v[0].z, v[1].z, v[2].z, v[3].z);
-      *reinterpret_cast<float4*>(dst + 3 * ld) = make_float4(v[0].w, v[1].w, v[2].w, v[3].w);
+        v[h][k] = (qvalid && c < D) ? ldg_stream(reinterpret_cast<const float4*>(z + qbase + (size_t)(c + k) * HW))
+                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int h = 0; h < NPASS; ++h) {
+      const int c = cb + h * 128 + wid * (4 * CQ) + cq * 4;
+      if (c < D) {
+        float* dst = zt + (4 * tq) * ld + c;                // 4x4 transpose: 4 tokens x 4 channels
+        *reinterpret_cast<float4*>(dst) = make_float4(v[h][0].x, v[h][1].x, v[h][2].x, v[h][3].x);
+        *reinterpret_cast<float4*>(dst + ld) = make_float4(v[h][0].y, v[h][1].y, v[h][2].y, v[h][3].y);
+        *reinterpret_cast<float4*>(dst + 2 * ld) = make_float4(v[h][0].z, v[h][1].z, v[h][2].z, v[h][3].z);
+        *reinterpret_cast<float4*>(dst + 3 * ld) = make_float4(v[h][0].w, v[h][1].w, v[h][2].w, v[h][3].w);
+      }
     }
   }
   // Everything above only read z (an input of the whole call), so with programmatic dependent launch it overlaps
@@ -723,7 +730,7 @@ __global__ void __launch_bounds__(T * 8, DT ? 1536 / (T * 8) : 1) vq_finish_v5_k
   // gather + straight-through value + loss partial: the 4 winning rows of this warp are requested together
   float sq = 0.f;
   {
-    constexpr int G = DT ? 2 : 1;               // rows fetched together (bounded by the register budget of 6 CTAs/SM)
+    constexpr int G = DT ? 4 : 1;               // rows fetched together: one L2 round trip for the warp's 4 tokens
 #pragma unroll
     for (int i0 = 0; i0 < 4; i0 += G) {
       float4 eb[G][NV];
@@ -751,7 +758,13 @@ __global__ void __launch_bounds__(T * 8, DT ? 1536 / (T * 8) : 1) vq_finish_v5_k
       }
     }
   }
-  __syncthreads();
+  // loss: one partial per warp, summed in a fixed order by vq_loss_finalize_kernel (deterministic; an in-kernel
+  // last-CTA election cost 8.5 us of 54 on C2: four more block barriers and a device-scope fence per CTA)
+  {
+    const double wsum = warp_sum((double)sq);
+    if (lane == 0) partials[(size_t)blockIdx.x * W + wid] = wsum;
+  }
+  __syncthreads();                             // closes phase B: every token row holds its z_q
   FT_MARK(2);
   // (C) write z_q back NCHW: the transpose of (A)
   if (qvalid)
@@ -774,11 +787,19 @@ __global__ void __launch_bounds__(T * 8, DT ? 1536 / (T * 8) : 1) vq_finish_v5_k
     for (int i = 0; i < 12; ++i) g_trace_fin[blockIdx.x][i] = ft_acc[i];
 #endif
 
-  const double bsum = block_sum((double)sq, scratch);
-  double total;
-  if (publish_and_elect_last(bsum, partials, counters + kCtrLoss, gridDim.x, blockIdx.x, scratch, &total)) {
-    if (threadIdx.x == 0) write_loss(total, (long long)N * D, beta, legacy, loss);
-  }
+}
+
+// Sum of the per-warp loss partials in index order -> the reference's loss scalar.  One CTA; launched with
+// programmatic dependent launch right behind the finish kernel.
+__global__ void __launch_bounds__(256) vq_loss_finalize_kernel(const double* __restrict__ partials, int n,
+                                                                long long numel, float beta, int legacy,
+                                                                float* __restrict__ loss) {
+  __shared__ double scratch[32];
+  pdl_wait();
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < n; i += 256) acc += partials[i];
+  const double tot = block_sum(acc, scratch);
+  if (threadIdx.x == 0) write_loss(tot, numel, beta, legacy, loss);
 }
 
 int vq_finish(const float* z, const float* E, const float* ee, const float* emax, const int* cand, const VqMeta* meta,
@@ -808,6 +829,12 @@ int vq_finish(const float* z, const float* E, const float* ee, const float* emax
     cfg.numAttrs = 1;                                                                                              \
     if (cudaLaunchKernelEx(&cfg, vq_finish_v5_kernel<DT, T>, z, E, ee, emax, cand, meta, list, N, D, HW, K, beta,   \
                            legacy, zq, idx, loss, partials, counters) != cudaSuccess)                              \
+      return DCVIC_ERR_CUDA;                                                                                       \
+    cfg.gridDim = dim3(1);                                                                                         \
+    cfg.blockDim = dim3(256);                                                                                      \
+    cfg.dynamicSmemBytes = 0;                                                                                      \
+    if (cudaLaunchKernelEx(&cfg, vq_loss_finalize_kernel, (const double*)partials, ceil_div_i(N, T) * (T / 4),      \
+                           (long long)N * D, beta, legacy, loss) != cudaSuccess)                                   \
       return DCVIC_ERR_CUDA;                                                                                       \
   } while (0)
     if (tile_tokens == 32) {

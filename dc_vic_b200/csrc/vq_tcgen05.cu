@@ -37,7 +37,6 @@ namespace tc {
 constexpr int BM = 128;          // tokens per CTA tile (UMMA M = 128 * CG)
 constexpr int BN = 256;          // codes per N-tile (UMMA N)
 constexpr int BK = 64;           // channels per smem chunk: 64 fp16 = 128 B = one SWIZZLE_128B row
-constexpr int UK = 16;           // UMMA K for 16-bit inputs
 constexpr int MAX_KC = 4;        // e_dim <= 256
 constexpr int A_CHUNK_BYTES = BM * BK * 2;            // 16 KB
 constexpr int A_BUF_BYTES = MAX_KC * A_CHUNK_BYTES;   // 64 KB
