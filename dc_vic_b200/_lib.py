@@ -79,8 +79,31 @@ def ptr(t):
 
 
 def cur_stream():
+    """Raw handle of torch's current stream on the current device (no Stream object: this is on the per-call path of
+    the small in-model invocations, where host overhead is all there is)."""
     import torch
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    return C.c_void_p(torch._C._cuda_getCurrentRawStream(torch.cuda.current_device()))
+
+
+class on_device:
+    """``torch.cuda.device(dev)`` that does nothing when `dev` is already current (two cudaSetDevice calls saved)."""
+
+    def __init__(self, device):
+        import torch
+        self._idx = device.index if device.index is not None else torch.cuda.current_device()
+        self._guard = None
+
+    def __enter__(self):
+        import torch
+        if torch.cuda.current_device() != self._idx:
+            self._guard = torch.cuda.device(self._idx)
+            self._guard.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        if self._guard is not None:
+            self._guard.__exit__(*exc)
+        return False
 
 
 def require_cuda(*tensors):

@@ -136,11 +136,106 @@ __global__ void __launch_bounds__(128) vq_narrow_kernel(const float* __restrict_
   }
 }
 
+// Large codebooks (K >= 2048: the 16384x4 / 16384x8 VQGANs): one thread per token leaves most of the machine idle
+// at DC-VIC's token counts (45k tokens for a 2K image = 9 warps per SM, each scanning 16k codes serially).  Here
+// S = 8 threads share a token and take every 8th code (8 consecutive codes = 128 contiguous bytes of shared memory per
+// token group at e_dim 4), then reduce (distance, index) lexicographically with shuffles -- same distances, same
+// lowest-index tie-break, 8x the threads in flight.
+template <int D, int S>
+__global__ void __launch_bounds__(256) vq_narrow_split_kernel(const float* __restrict__ z, const float* __restrict__ E,
+                                                               int N, int HW, int K, int KT, float beta, int legacy,
+                                                               float* __restrict__ zq, int64_t* __restrict__ idx,
+                                                               float* __restrict__ loss, double* __restrict__ partials,
+                                                               unsigned* __restrict__ counters) {
+  extern __shared__ __align__(16) float smem_f[];
+  float* sE = smem_f;            // [KT][D]
+  float* sEE = smem_f + KT * D;  // [KT]
+  __shared__ double scratch[32];
+  constexpr int TOK = 256 / S;   // tokens per CTA
+  const int sub = threadIdx.x % S;
+  const int t = blockIdx.x * TOK + threadIdx.x / S;
+  const bool valid = t < N;
+  const size_t base = valid ? ((size_t)(t / HW) * D * HW + (size_t)(t % HW)) : 0;
+  float zr[D];
+  float zz = 0.f;
+#pragma unroll
+  for (int c = 0; c < D; ++c) {
+    zr[c] = valid ? z[base + (size_t)c * HW] : 0.f;
+    zz = __fadd_rn(zz, __fmul_rn(zr[c], zr[c]));
+  }
+  float best = FLT_MAX;
+  int bi = 0x7fffffff;
+  for (int k0 = 0; k0 < K; k0 += KT) {
+    const int kt = min(KT, K - k0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < kt * D; i += blockDim.x) sE[i] = E[(size_t)k0 * D + i];
+    __syncthreads();
+    for (int k = threadIdx.x; k < kt; k += blockDim.x) {
+      float a = 0.f;
+#pragma unroll
+      for (int c = 0; c < D; ++c) a = __fadd_rn(a, __fmul_rn(sE[k * D + c], sE[k * D + c]));
+      sEE[k] = a;
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int k = sub; k < kt; k += S) {
+      float dot = __fmul_rn(zr[0], sE[k * D]);
+#pragma unroll
+      for (int c = 1; c < D; ++c) dot = fmaf(zr[c], sE[k * D + c], dot);
+      const float d = fmaf(-2.f, dot, __fadd_rn(zz, sEE[k]));
+      if (d < best) {            // k ascends within a thread: the first minimum is the lowest index
+        best = d;
+        bi = k0 + k;
+      }
+    }
+  }
+#pragma unroll
+  for (int o = S / 2; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ob < best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+  }
+  float sq = 0.f;
+  if (valid) {
+    bi = min(max(bi, 0), K - 1);
+    // lane `sub` writes channel `sub` (+S, ...) of the token
+#pragma unroll
+    for (int c = 0; c < D; ++c)
+      if (c % S == sub) {
+        const float e = E[(size_t)bi * D + c];
+        const float diff = __fsub_rn(e, zr[c]);
+        zq[base + (size_t)c * HW] = __fadd_rn(zr[c], diff);
+        sq = fmaf(diff, diff, sq);
+      }
+    if (sub == 0) idx[t] = (int64_t)bi;
+  }
+  const double bsum = block_sum((double)sq, scratch);
+  double total;
+  if (publish_and_elect_last(bsum, partials, counters + kCtrLoss, gridDim.x, blockIdx.x, scratch, &total)) {
+    if (threadIdx.x == 0) write_loss(total, (long long)N * D, beta, legacy, loss);
+  }
+}
+
 int vq_narrow_forward(const float* z, const float* E, int B, int D, int HW, int K, float beta, int legacy, float* zq,
                       int64_t* idx, float* loss, double* partials, unsigned* counters, cudaStream_t s) {
   const int N = B * HW;
   const int KT = min(K, D == 4 ? 4096 : 2048);
   const size_t smem = (size_t)KT * (D + 1) * sizeof(float);
+  if (K >= 2048) {               // large codebook: 8 threads per token (32 tokens per 256-thread CTA)
+    const int g8 = ceil_div_i(N, 32);
+    if (D == 4) {
+      cudaFuncSetAttribute(vq_narrow_split_kernel<4, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      vq_narrow_split_kernel<4, 8><<<g8, 256, smem, s>>>(z, E, N, HW, K, KT, beta, legacy, zq, idx, loss, partials,
+                                                          counters);
+    } else if (D == 8) {
+      cudaFuncSetAttribute(vq_narrow_split_kernel<8, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      vq_narrow_split_kernel<8, 8><<<g8, 256, smem, s>>>(z, E, N, HW, K, KT, beta, legacy, zq, idx, loss, partials,
+                                                          counters);
+    } else {
+      return DCVIC_ERR_UNSUPPORTED;
+    }
+    return dcvic_launch_status();
+  }
   const int grid = ceil_div_i(N, 128);
   if (D == 4) {
     cudaFuncSetAttribute(vq_narrow_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -68,7 +68,7 @@ class _SteRound(torch.autograd.Function):
         _lib.require_cuda(x)
         xc = x.contiguous().float()
         out = torch.empty_like(xc)
-        with torch.cuda.device(x.device):
+        with _lib.on_device(x.device):
             _lib.check(_lib.load().dcvic_ste_round(_lib.ptr(xc), xc.numel(), _lib.ptr(out), _lib.cur_stream()),
                        "dcvic_ste_round")
         return out
@@ -129,7 +129,7 @@ class _RateBits(torch.autograd.Function):
         lc = lik.contiguous().float()
         n = lc.numel() // B
         lib = _lib.load()
-        with torch.cuda.device(lik.device):
+        with _lib.on_device(lik.device):
             bits = torch.empty(B, dtype=torch.float32, device=lik.device)
             ws = _workspace("rate", lib.dcvic_rate_workspace_bytes(B, n), lik.device)
             _lib.check(lib.dcvic_rate_bits(_lib.ptr(lc), B, n, _lib.ptr(bits), _lib.ptr(ws), ws.numel(),
@@ -144,7 +144,7 @@ class _RateBits(torch.autograd.Function):
         (lc,) = ctx.saved_tensors
         B = ctx.B
         n = lc.numel() // B
-        with torch.cuda.device(lc.device):
+        with _lib.on_device(lc.device):
             d = torch.empty_like(lc)
             gb = g_bits.contiguous().float()
             _lib.check(_lib.load().dcvic_rate_bits_backward(_lib.ptr(lc), _lib.ptr(gb), B, n, _lib.ptr(d),
@@ -230,7 +230,7 @@ class _GaussianFn(torch.autograd.Function):
         sv, ss = _batch_view(scales.detach(), B, n)
         mv, ms = (None, 0) if means is None else _batch_view(means.detach(), B, n)
         nz = None if noise is None else noise.detach().contiguous().float()
-        with torch.cuda.device(y.device):
+        with _lib.on_device(y.device):
             y_hat = torch.empty(y.shape, dtype=torch.float32, device=y.device)
             lik = torch.empty(y.shape, dtype=torch.float32, device=y.device)
             rc = lib.dcvic_gc_forward(_lib.ptr(yv), _lib.ptr(mv), _lib.ptr(sv), _lib.ptr(nz), B, n, ys, ms, ss,
@@ -248,7 +248,7 @@ class _GaussianFn(torch.autograd.Function):
         B, n, ys, ms, ss, scale_bound, lik_bound, mode, y_shape, s_shape, m_shape = ctx.meta
         lib = _lib.load()
         dev = yv.device
-        with torch.cuda.device(dev):
+        with _lib.on_device(dev):
             d_y = torch.empty(y_shape, dtype=torch.float32, device=dev)
             d_s = torch.empty(y_shape, dtype=torch.float32, device=dev)
             d_m = torch.empty(y_shape, dtype=torch.float32, device=dev) if mv is not None else None
@@ -318,7 +318,7 @@ class GaussianConditional(EntropyModel):
         _lib.require_cuda(scales)
         sc = scales.contiguous().float()
         table = self.scale_table.to(sc.device).contiguous().float()
-        with torch.cuda.device(sc.device):
+        with _lib.on_device(sc.device):
             out = torch.empty(sc.shape, dtype=torch.int32, device=sc.device)
             rc = _lib.load().dcvic_gc_build_indexes(_lib.ptr(sc), sc.numel(), _lib.ptr(table), table.numel(),
                                                     self._scale_bound, _lib.ptr(out), _lib.cur_stream())
@@ -368,7 +368,7 @@ def gaussian_rate_dual(y: Tensor, params: Tensor, noise: Tensor, scale_bound: fl
     sv, ss = _batch_view(std.detach(), B, n)
     nz = noise.detach().contiguous().float()
     dev = y.device
-    with torch.cuda.device(dev):
+    with _lib.on_device(dev):
         y_hat = torch.empty(y.shape, dtype=torch.float32, device=dev)
         lik = torch.empty_like(y_hat)
         lik_q = torch.empty_like(y_hat)
@@ -397,7 +397,7 @@ class _BottleneckFn(torch.autograd.Function):
         nz = None if noise is None else noise.detach().contiguous().float()
         ps = [p.detach().contiguous().float() for p in params] + [quantiles.detach().contiguous().float()]
         arr = (C.c_void_p * 15)(*[p.data_ptr() for p in ps])
-        with torch.cuda.device(x.device):
+        with _lib.on_device(x.device):
             x_hat = torch.empty_like(xc)
             lik = torch.empty_like(xc)
             rc = lib.dcvic_eb_forward(_lib.ptr(xc), _lib.ptr(nz), arr, B, Cc, HW, float(lik_bound), int(x_hat_mode),
@@ -417,7 +417,7 @@ class _BottleneckFn(torch.autograd.Function):
         grads = [None] * n_par
         d_x = None
         if nz is not None and g_lik is not None:
-            with torch.cuda.device(dev):
+            with _lib.on_device(dev):
                 d_x = torch.empty_like(xc)
                 grads = [torch.empty_like(p) for p in ps[:n_par]]
                 parr = (C.c_void_p * 15)(*[p.data_ptr() for p in ps])

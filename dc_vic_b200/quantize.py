@@ -56,7 +56,7 @@ class _VQForward(torch.autograd.Function):
         zc = z.detach().contiguous().float()
         wc = weight.detach().contiguous().float()
         N = B * H * W
-        with torch.cuda.device(z.device):
+        with _lib.on_device(z.device):
             z_q = torch.empty_like(zc)
             idx = torch.empty(N, dtype=torch.int64, device=z.device)
             loss = torch.empty((), dtype=torch.float32, device=z.device)
@@ -88,7 +88,7 @@ class _VQForward(torch.autograd.Function):
         B, D, H, W, K, beta, legacy = ctx.meta
         lib = _lib.load()
         need_z, need_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
-        with torch.cuda.device(zc.device):
+        with _lib.on_device(zc.device):
             dz = torch.empty_like(zc) if need_z else None
             dE = torch.empty_like(wc) if need_w else None
             if dz is None and dE is None:
@@ -113,7 +113,7 @@ def codebook_lookup(indices: torch.Tensor, weight: torch.Tensor, nchw: bool = Tr
     K, D = weight.shape
     idx = indices.contiguous().long()
     wc = weight.detach().contiguous().float()
-    with torch.cuda.device(weight.device):
+    with _lib.on_device(weight.device):
         bad = torch.zeros(1, dtype=torch.int32, device=weight.device)
         if nchw:
             if idx.dim() != 3:
@@ -137,7 +137,7 @@ def onehot_feature(indices_bhw: torch.Tensor, n_embed: int) -> torch.Tensor:
     lib = _lib.load()
     idx = indices_bhw.contiguous().long()
     B, H, W = idx.shape
-    with torch.cuda.device(idx.device):
+    with _lib.on_device(idx.device):
         out = torch.empty(B, n_embed, H, W, dtype=torch.float32, device=idx.device)
         rc = lib.dcvic_onehot_nchw(_lib.ptr(idx), B, H * W, int(n_embed), _lib.ptr(out), _lib.cur_stream())
         _lib.check(rc, "dcvic_onehot_nchw")

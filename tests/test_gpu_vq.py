@@ -276,3 +276,15 @@ def test_tensor_path_larger_codebooks():
         with torch.no_grad():
             out = m(z.to(DEV))
         check_against_oracle(z, E, out, out[2][2], allow_near_ties=False)
+
+
+@pytest.mark.parametrize("K,Dm", [(4096, 4), (2048, 8), (16384, 4)])
+def test_narrow_large_codebooks(K, Dm):
+    """The 8-threads-per-token variant of the narrow kernel (K >= 2048) against the oracle."""
+    for kind in ("D0", "D1b"):
+        z, E = vq_inputs(9, kind, 2, Dm, 12, 20, K)
+        m = make(D.VectorQuantizer2, E, sane_index_shape=True)
+        assert m.search_path() == "narrow-simt"
+        zc = z.to(DEV).requires_grad_(True)
+        out = m(zc)
+        check_against_oracle(z, E, out, out[2][2], allow_near_ties=True)
