@@ -31,6 +31,7 @@ SIGNATURES = {
     "dcvic_vq_backward": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _f, _i, _p, _p, _p]),
     "dcvic_codebook_gather": (_i, [_p, _p, _i, _i, _i, _i, _i, _p, _p, _p]),
     "dcvic_onehot_nchw": (_i, [_p, _i, _i, _i, _p, _p]),
+    "dcvic_token_decode": (_i, [_p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p]),
     "dcvic_gc_workspace_bytes": (_sz, [_i64, _i64]),
     "dcvic_gc_forward": (_i, [_p, _p, _p, _p, _i64, _i64, _i64, _i64, _i64, _f, _f, _i, _p, _p, _p, _p, _sz, _p]),
     "dcvic_gc_forward_dual": (_i, [_p, _p, _p, _p, _i64, _i64, _i64, _i64, _i64, _f, _f, _p, _p, _p, _p, _p, _p,

@@ -144,6 +144,39 @@ def onehot_feature(indices_bhw: torch.Tensor, n_embed: int) -> torch.Tensor:
     return out
 
 
+def decode_tokens(logits: torch.Tensor, weight: torch.Tensor, gt_indices: Optional[torch.Tensor] = None,
+                  want_latent: bool = True):
+    """Decoder-side token path of DC-VIC in one kernel (hyperprior_dc_vic_model.py:250-260):
+
+        out_vq_indices = torch.argmax(out_vq_logits, dim=1)                       # [B, H, W]
+        vq_accuracy    = (out_vq_indices == gt_vq_indices).float().mean()         # if gt_indices is given
+        vq_latent      = vq_indices_to_latent(out_vq_indices)                     # [B, D, H, W]
+
+    Returns ``(indices, latent | None, accuracy | None)``.  No gradient flows through argmax in the reference either
+    (the logits are trained through the code CE / MSE losses on ``out_vq_logits`` itself).
+    """
+    _lib.require_cuda(logits, weight, gt_indices)
+    if logits.dim() != 4:
+        raise ValueError(f"expected logits of shape [B, K, H, W], got {tuple(logits.shape)}")
+    lib = _lib.load()
+    B, K, H, W = logits.shape
+    K2, D = weight.shape
+    if K != K2:
+        raise ValueError(f"logits have {K} classes but the codebook has {K2} entries")
+    lg = logits.detach().contiguous().float()
+    wc = weight.detach().contiguous().float()
+    gt = None if gt_indices is None else gt_indices.contiguous().long()
+    with _lib.on_device(lg.device):
+        idx = torch.empty(B, H, W, dtype=torch.int64, device=lg.device)
+        latent = torch.empty(B, D, H, W, dtype=torch.float32, device=lg.device) if want_latent else None
+        count = torch.empty(1, dtype=torch.int32, device=lg.device) if gt is not None else None
+        rc = lib.dcvic_token_decode(_lib.ptr(lg), _lib.ptr(wc), _lib.ptr(gt), B, K, H * W, D, _lib.ptr(idx),
+                                    _lib.ptr(latent), _lib.ptr(count), _lib.cur_stream())
+        _lib.check(rc, "dcvic_token_decode")
+    acc = None if count is None else (count.float() / float(B * H * W)).reshape(())
+    return idx, latent, acc
+
+
 class _QuantizerBase(nn.Module):
     def _init_common(self, n_e, e_dim, beta):
         self.n_e = n_e

@@ -100,6 +100,13 @@ int dcvic_codebook_gather(const int64_t* idx, const float* codebook, int B, int 
  * out [B,K,HW] fp32. */
 int dcvic_onehot_nchw(const int64_t* idx, int B, int HW, int K, float* out, dcvic_stream_t stream);
 
+/* Decoder-side token path (src/models/comp_model/hyperprior_dc_vic_model.py:250-260): argmax over the vq_estimator
+ * logits [B,K,HW] (first maximal index on ties, NaN counts as maximal: torch.argmax), optional accuracy against the
+ * encoder's indices (match_count = #{idx == gt_idx}, device int32, zeroed here) and optional codebook gather
+ * latent [B,D,HW] = E[idx] ('b h w c -> b c h w').  idx int64 [B,HW]. */
+int dcvic_token_decode(const float* logits, const float* codebook, const int64_t* gt_idx, int B, int K, int HW, int D,
+                       int64_t* idx, float* latent, int* match_count, dcvic_stream_t stream);
+
 /* ------------------------------------------------------- GaussianConditional -------
  * Replaces compressai==1.2.4 GaussianConditional.forward/_likelihood/quantize as called by
  * src/models/subnet/entropy_model/gaussian_conditional.py:9-24 and

@@ -111,6 +111,14 @@ def indices_to_latent(indices_bhw: torch.Tensor, codebook: torch.Tensor) -> torc
     return F.embedding(indices_bhw, codebook).permute(0, 3, 1, 2).contiguous()
 
 
+def decode_tokens(logits: torch.Tensor, codebook: torch.Tensor, gt_indices: Optional[torch.Tensor] = None):
+    """Decoder-side token path (hyperprior_dc_vic_model.py:250-260): argmax over the class dimension,
+    accuracy against the encoder's indices, codebook lookup."""
+    idx = torch.argmax(logits, dim=1)
+    acc = None if gt_indices is None else (idx == gt_indices).float().mean()
+    return idx, indices_to_latent(idx, codebook), acc
+
+
 def onehot_feature(indices_bhw: torch.Tensor, n_embed: int) -> torch.Tensor:
     """``onehot_indices`` encoder feature (hyperprior_vic_model.py:268-271): [B,K,H,W] fp32."""
     return F.one_hot(indices_bhw, num_classes=n_embed).permute(0, 3, 1, 2).float()

@@ -288,3 +288,25 @@ def test_narrow_large_codebooks(K, Dm):
         zc = z.to(DEV).requires_grad_(True)
         out = m(zc)
         check_against_oracle(z, E, out, out[2][2], allow_near_ties=True)
+
+
+@pytest.mark.parametrize("shape", [(1, 256, 64, 96), (2, 256, 9, 7), (3, 37, 8, 12)])
+def test_decode_tokens_matches_reference_ops(shape):
+    """argmax + accuracy + codebook gather of the decoder side (hyperprior_dc_vic_model.py:250-260)."""
+    B, K, H, W = shape
+    g = torch.Generator().manual_seed(21)
+    logits = torch.randn(B, K, H, W, generator=g)
+    logits[0, 5, 0, 0] = logits[0, :, 0, 0].max() + 1.0      # exact ties: the first maximal index must win
+    logits[0, 9, 0, 0] = logits[0, 5, 0, 0]
+    logits[-1, :, -1, -1] = 0.25                              # a whole row of equal values -> index 0
+    E = torch.randn(K, 4, generator=g)
+    gt = torch.randint(0, K, (B, H, W), generator=g)
+    idx_r, lat_r, acc_r = O.decode_tokens(logits, E, gt)
+    gt[idx_r % 3 == 0] = idx_r[idx_r % 3 == 0]                # make a third of them match
+    idx_r, lat_r, acc_r = O.decode_tokens(logits, E, gt)
+    idx, lat, acc = D.decode_tokens(logits.to(DEV), E.to(DEV), gt.to(DEV))
+    assert idx.dtype == torch.int64 and torch.equal(idx.cpu(), idx_r)
+    assert torch.equal(lat.cpu(), lat_r)
+    assert abs(float(acc) - float(acc_r)) < 1e-7
+    idx2, lat2, acc2 = D.decode_tokens(logits.to(DEV), E.to(DEV), None, want_latent=False)
+    assert torch.equal(idx2.cpu(), idx_r) and lat2 is None and acc2 is None

@@ -104,3 +104,12 @@ def test_onehot_feature():
 
 def test_goldens_do_not_need_the_reference_tree():
     assert len(glob.glob(os.path.join(G, "vq_*.pt"))) >= 9
+
+
+def test_decode_tokens_oracle_is_argmax_gather():
+    g = torch.Generator().manual_seed(2)
+    logits = torch.randn(2, 16, 3, 5, generator=g)
+    E = torch.randn(16, 4, generator=g)
+    idx, lat, acc = O.decode_tokens(logits, E, torch.zeros(2, 3, 5, dtype=torch.long))
+    assert torch.equal(idx, logits.argmax(1)) and lat.shape == (2, 4, 3, 5)
+    assert torch.equal(lat[1, :, 2, 4], E[idx[1, 2, 4]]) and 0.0 <= float(acc) <= 1.0
