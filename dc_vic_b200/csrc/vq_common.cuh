@@ -17,10 +17,6 @@ struct __align__(16) VqMeta {
   short n0, n1;     // list entries of epilogue warp quad 0 / 1, or -1: scan the whole codebook for this token
   float zz;         // |z|^2 as the search computed it (its margin and the finish's threshold use the same value)
 };
-// (older description of the same data:)
-//   meta[4t + q]     float  running maximum of the FP16 score over the columns of every accumulator that went to
-//                           epilogue warp quad q (q = 0: columns 0-127, 1: columns 128-255)
-//   meta[4t + 2 + q] int    number of list entries of buffer q, or -1 if its list overflowed
 //   list[(2t + q) * kListCap + i] = { key, mask }:  key = (bits(chunk max) & ~0x7F) | chunk id,
 //                           mask bit j set <=> score of code (chunk id * 32 + j) was within the
 //                           margin of the running maximum when that chunk went by
