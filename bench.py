@@ -57,41 +57,76 @@ def peaks():
 
 
 class ClockSampler:
-    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-              "clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons while the timed region runs.  NVML is polled from a thread of this process
+    (every ~2 ms: the timed region is only a few milliseconds long, `nvidia-smi -lms` cannot start that fast);
+    `nvidia-smi` is the fallback when the NVML binding is missing."""
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20),
+               ("sw_power_cap", 0x4))
 
     def __init__(self, index: int):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.stop_flag, self.thread, self.nvml, self.handle = index, [], False, None, None, None
+        self.max_mhz = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._pump, daemon=True).start()
-        except Exception:
-            self.proc = None
-
-    def _pump(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
-
-    def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        sm, mx, reasons = [], [], set()
-        for r in self.rows:
+            import pynvml
+            pynvml.nvmlInit()
             try:
-                sm.append(float(r[0])); mx.append(float(r[1]))
+                uuid = str(torch.cuda.get_device_properties(self.index).uuid)
+                self.handle = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
             except Exception:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                self.handle = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+        self.thread = threading.Thread(target=self._poll if self.nvml else self._smi, daemon=True)
+        self.thread.start()
+
+    def _poll(self):
+        nv = self.nvml
+        while not self.stop_flag:
+            try:
+                mhz = float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM))
+                try:
+                    bits = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+                except Exception:
+                    bits = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+                self.rows.append((time.perf_counter(), mhz, bits))
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def _smi(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=10).stdout
+                r = [c.strip() for c in out.strip().split(",")]
+                bits = sum(bit for (_, bit), v in zip(self.REASONS, r[2:6]) if v.lower().startswith("active"))
+                self.max_mhz = float(r[1])
+                self.rows.append((time.perf_counter(), float(r[0]), bits))
+            except Exception:
+                time.sleep(0.05)
+
+    def stop(self, t_begin=None, t_end=None):
+        self.stop_flag = True
+        if self.thread is not None:
+            self.thread.join(timeout=15)
+        rows = self.rows
+        if t_begin is not None:
+            inside = [r for r in rows if t_begin <= r[0] <= t_end]
+            rows = inside or rows
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "samples": 0, "reasons": ["no samples"]}
+        bits = 0
+        for r in rows:
+            bits |= r[2]
+        return {"sm_mhz": statistics.median(r[1] for r in rows), "sm_max_mhz": self.max_mhz, "samples": len(rows),
+                "reasons": [name for name, bit in self.REASONS if bits & bit],
+                "source": "nvml" if self.nvml else "nvidia-smi"}
 
 
 # ----------------------------------------------------------------------------- CPU reference arm
@@ -220,15 +255,19 @@ def run_ours(args):
 
     sampler = ClockSampler(local)
     sampler.start()
+    t_clk0 = time.perf_counter()
     t_full = max_over_ranks(timed(vq_step, K_steps, W_steps, barrier))
     # the same step with the codebook prepared once (DC-VIC freezes the VQGAN codebook; the module sets this flag)
     t_frozen = max_over_ranks(timed(lambda i: vq_step(i, _lib.VQ_REUSE_PREP), K_steps, W_steps, barrier))
     # dominant kernel alone (same launches, search stage only) for the roofline
-    t_search = timed(lambda i: vq_step(i, _lib.VQ_STAGE_SEARCH_ONLY | _lib.VQ_REUSE_PREP), K_steps, W_steps, barrier)
+    # stages as differences of the same pipelined launches cut short (the kernels overlap under programmatic
+    # dependent launch, so a stage's cost is what the step grows by when it is added)
+    t_prep = timed(lambda i: vq_step(i, _lib.VQ_STAGE_PREP_ONLY), K_steps, W_steps, barrier)
     t_prep_search = timed(lambda i: vq_step(i, _lib.VQ_STAGE_SEARCH_ONLY), K_steps, W_steps, barrier)
+    t_search = max(t_prep_search - t_prep, 0.0)
     # the finish stage needs lists that belong to the same z, so it is timed as whole step minus the stages before it
     t_finish = max(t_full - t_prep_search, 0.0)
-    clocks = sampler.stop()
+    clocks = sampler.stop(t_clk0, time.perf_counter())
 
     value = world * N * K_steps / t_full
     flops = 2.0 * N * K * Dm
@@ -247,7 +286,7 @@ def run_ours(args):
                 "peak": pk["hbm"], "unit": "GB/s", "frac": finish_bytes / finish_s / 1e9 / pk["hbm"], "traffic": None,
                 "us_per_launch": finish_s * 1e6, "algorithmic": f"N*(8D+8) = {finish_bytes} B per launch",
                 "peak_source": pk["source"]}
-    stage = {"prepare_us": (t_prep_search - t_search) / K_steps * 1e6,
+    stage = {"prepare_us": t_prep / K_steps * 1e6,
              "search_us": search_s * 1e6, "finish_us": finish_s * 1e6,
              "finish_hbm_gbs": finish_bytes / finish_s / 1e9, "finish_hbm_frac": finish_bytes / finish_s / 1e9 / pk["hbm"],
              "search_tflops": flops / search_s / 1e12}
@@ -378,8 +417,8 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     args = ap.parse_args()
     if args.impl == "reference":

@@ -65,14 +65,16 @@ extern "C" int dcvic_vq_forward(const float* z_nchw, const float* codebook, int 
   if (path == 0) {
     rc = vq_narrow_forward(z_nchw, codebook, B, D, HW, K, beta, legacy, zq_nchw, idx, loss, partials, counters, s);
   } else {
-    if (!(flags & (DCVIC_VQ_REUSE_PREP | DCVIC_VQ_STAGE_FINISH_ONLY))) {
+    const bool prepared = !(flags & (DCVIC_VQ_REUSE_PREP | DCVIC_VQ_STAGE_FINISH_ONLY));
+    if (prepared) {
       rc = vq_prepare_codebook(codebook, K, D, ee, nhee, emax, path == 2 ? cb16 : nullptr, s);
       if (rc) return rc;
     }
+    if (flags & DCVIC_VQ_STAGE_PREP_ONLY) return rc;
     const bool do_search = !(flags & DCVIC_VQ_STAGE_FINISH_ONLY);
     const bool do_finish = !(flags & DCVIC_VQ_STAGE_SEARCH_ONLY);
     if (path == 2) {
-      if (do_search) rc = vq_tensor_search(z_nchw, cb16, emax, B, D, HW, K, meta, list, s);
+      if (do_search) rc = vq_tensor_search(z_nchw, cb16, emax, B, D, HW, K, prepared, meta, list, s);
       if (rc) return rc;
       if (do_finish)
         rc = vq_finish(z_nchw, codebook, ee, emax, nullptr, meta, list, B, D, HW, K, beta, legacy, zq_nchw, idx, loss,

@@ -35,7 +35,8 @@ inline VqWorkspace vq_workspace_layout(int B, int D, int HW, int K) {
   w.off_ee = take((size_t)K * sizeof(float));
   w.off_nhee = take((size_t)K * sizeof(float));
   w.off_emax = take(4 * sizeof(float));
-  w.off_partials = take((N / 4 + 8) * sizeof(double));   // one per finish warp (4 tokens each)
+  // loss partials: one per finish warp (4 tokens each), or 16 per persistent CTA of the TMA finish
+  w.off_partials = take((N / 4 + 8 + (size_t)kNumSMs * 16) * sizeof(double));
   w.off_hist = take((size_t)K * sizeof(unsigned));
   w.off_cand = take(N * sizeof(int));
   w.off_meta = take(N * sizeof(VqMeta));
@@ -74,12 +75,22 @@ int vq_exact_search(const float* z, const float* E, const float* ee, int B, int 
 int vq_finish(const float* z, const float* E, const float* ee, const float* emax, const int* cand, const VqMeta* meta,
               const uint2* list, int B, int D, int HW, int K, float beta, int legacy, float* zq, int64_t* idx,
               float* loss, double* partials, unsigned* counters, cudaStream_t s);
+int vq_launch_loss_finalize(const double* partials, int n, long long numel, float beta, int legacy, float* loss,
+                            cudaStream_t s);
 int vq_v1_extras(const int64_t* idx, int N, int K, float* onehot, float* perplexity, unsigned* hist, unsigned* counters,
                  cudaStream_t s);
 
+// vq_finish_tma.cu: the finish for H*W % 32 == 0 and e_dim in {64, 128, 192, 256} (same arguments as vq_finish)
+bool vq_finish_tma_supported(const float* z, const float* zq, int D, int HW, int K);
+int vq_finish_tma(const float* z, const float* E, const float* ee, const float* emax, const int* cand,
+                  const VqMeta* meta, const uint2* list, int B, int D, int HW, int K, float beta, int legacy,
+                  float* zq, int64_t* idx, float* loss, double* partials, unsigned* counters, cudaStream_t s);
+
 // vq_tcgen05.cu
 bool vq_tensor_supported(int D, int K);
+// after_prepare: the kernel launched just before on `s` was vq_prepare_codebook's (else the search waits for its
+// predecessor before it reads z)
 int vq_tensor_search(const float* z, const __half* cb16, const float* emax, int B, int D, int HW, int K,
-                     VqMeta* meta, uint2* list, cudaStream_t s);
+                     bool after_prepare, VqMeta* meta, uint2* list, cudaStream_t s);
 
 }  // namespace dcvic

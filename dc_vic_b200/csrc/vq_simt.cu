@@ -897,11 +897,30 @@ __global__ void __launch_bounds__(256) vq_loss_finalize_kernel(const double* __r
   if (threadIdx.x == 0) write_loss(tot, numel, beta, legacy, loss);
 }
 
+int vq_launch_loss_finalize(const double* partials, int n, long long numel, float beta, int legacy, float* loss,
+                            cudaStream_t s) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(1);
+  cfg.blockDim = dim3(256);
+  cfg.stream = s;
+  cudaLaunchAttribute pdl[1];
+  pdl[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  pdl[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = pdl;
+  cfg.numAttrs = 1;
+  if (cudaLaunchKernelEx(&cfg, vq_loss_finalize_kernel, partials, n, numel, beta, legacy, loss) != cudaSuccess)
+    return DCVIC_ERR_CUDA;
+  return dcvic_launch_status();
+}
+
 int vq_finish(const float* z, const float* E, const float* ee, const float* emax, const int* cand, const VqMeta* meta,
               const uint2* list, int B, int D, int HW, int K, float beta, int legacy, float* zq, int64_t* idx,
               float* loss, double* partials, unsigned* counters, cudaStream_t s) {
   const int N = B * HW;
   if (K > 65535 && !cand) return DCVIC_ERR_UNSUPPORTED;
+  if ((reinterpret_cast<uintptr_t>(E) & 15) == 0 && vq_finish_tma_supported(z, zq, D, HW, K))
+    return vq_finish_tma(z, E, ee, emax, cand, meta, list, B, D, HW, K, beta, legacy, zq, idx, loss, partials, counters,
+                         s);
   const bool vec = (D % 4 == 0) && (HW % 4 == 0) && ((reinterpret_cast<uintptr_t>(z) & 15) == 0) &&
                    ((reinterpret_cast<uintptr_t>(zq) & 15) == 0) && ((reinterpret_cast<uintptr_t>(E) & 15) == 0);
   if (vec) {

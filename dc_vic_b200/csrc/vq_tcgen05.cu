@@ -257,7 +257,7 @@ template <int CG>
 __global__ void __launch_bounds__(NTHREADS, 1)
 vq_tensor_search_kernel(const __grid_constant__ CUtensorMap tmap_cb, const float* __restrict__ z,
                         const float* __restrict__ emax_ptr, int N, int D, int HW, int K, int num_ptiles,
-                        VqMeta* __restrict__ meta, uint2* __restrict__ list) {
+                        int wait_first, VqMeta* __restrict__ meta, uint2* __restrict__ list) {
   using C = Cfg<CG>;
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B operands need 1024-byte alignment (same adjustment in both CTAs of a pair)
@@ -271,6 +271,10 @@ vq_tensor_search_kernel(const __grid_constant__ CUtensorMap tmap_cb, const float
   // PDL: this kernel may have started before its predecessor (codebook prepare, or the previous call's finish) ended;
   // the roles that read the predecessor's outputs wait for it below, the z loads do not.  Its own successor (finish)
   // may start as soon as SMs free up: it only touches z until it waits for this grid.
+  // wait_first: the predecessor in the stream is not one of this library's kernels (frozen codebook, no prepare
+  // launch) and may be the producer of z, so nothing here - and, through the trigger below, nothing in the finish
+  // kernel - may read z before it has completed.
+  if (wait_first) pdl_wait();
   pdl_launch_dependents();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
@@ -436,7 +440,16 @@ vq_tensor_search_kernel(const __grid_constant__ CUtensorMap tmap_cb, const float
         const uint32_t chunk0 = (uint32_t)(nt * (BN / 32) + q * (BN / 64));
         auto emit = [&](uint32_t mask, float cm, uint32_t chunk) {
           if (mask != 0u && valid) {
-            my_list[min(n, kListCap - 1)] = make_uint2((__float_as_uint(cm) & 0xFFFFFF80u) | chunk, mask);
+            const uint32_t key = (__float_as_uint(cm) & 0xFFFFFF80u) | chunk;
+            if ((n & 3) == 0 && n < kListCap) {
+              // first entry of a 32-byte sector: write the whole sector (entry + zeros), so that the finish kernel's
+              // read of it is an L2 hit and not a DRAM fill of the bytes nobody wrote
+              uint4* p = reinterpret_cast<uint4*>(my_list + n);
+              p[0] = make_uint4(key, mask, 0u, 0u);
+              p[1] = make_uint4(0u, 0u, 0u, 0u);
+            } else {
+              my_list[min(n, kListCap - 1)] = make_uint2(key, mask);
+            }
             ++n;
           }
           __syncwarp();
@@ -584,7 +597,7 @@ bool vq_tensor_supported(int D, int K) {
 
 template <int CG>
 static int launch_search(const CUtensorMap& tmap, const float* z, const float* emax, int N, int D, int HW, int K,
-                         VqMeta* meta, uint2* list, cudaStream_t s) {
+                         int wait_first, VqMeta* meta, uint2* list, cudaStream_t s) {
   using C = Cfg<CG>;
   const int num_ptiles = (N + BM * CG - 1) / (BM * CG);
   const int max_pairs = kNumSMs / CG;
@@ -607,7 +620,8 @@ static int launch_search(const CUtensorMap& tmap, const float* z, const float* e
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 2;
-  if (cudaLaunchKernelEx(&cfg, vq_tensor_search_kernel<CG>, tmap, z, emax, N, D, HW, K, num_ptiles, meta, list) != cudaSuccess)
+  if (cudaLaunchKernelEx(&cfg, vq_tensor_search_kernel<CG>, tmap, z, emax, N, D, HW, K, num_ptiles, wait_first, meta,
+                         list) != cudaSuccess)
     return DCVIC_ERR_CUDA;
   return dcvic_launch_status();
 }
@@ -621,7 +635,7 @@ namespace dcvic {
 #endif
 
 int vq_tensor_search(const float* z, const __half* cb16, const float* emax, int B, int D, int HW, int K,
-                     VqMeta* meta, uint2* list, cudaStream_t s) {
+                     bool after_prepare, VqMeta* meta, uint2* list, cudaStream_t s) {
   if (!vq_tensor_supported(D, K)) return DCVIC_ERR_UNSUPPORTED;
   static const int cta_group = [] {
     const char* e = getenv("DCVIC_VQ_CTA_GROUP");
@@ -639,8 +653,9 @@ int vq_tensor_search(const float* z, const __half* cb16, const float* emax, int 
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
     return DCVIC_ERR_CUDA;
   const int N = B * HW;
-  return cta_group == 2 ? launch_search<2>(tmap, z, emax, N, D, HW, K, meta, list, s)
-                        : launch_search<1>(tmap, z, emax, N, D, HW, K, meta, list, s);
+  const int wait_first = after_prepare ? 0 : 1;
+  return cta_group == 2 ? launch_search<2>(tmap, z, emax, N, D, HW, K, wait_first, meta, list, s)
+                        : launch_search<1>(tmap, z, emax, N, D, HW, K, wait_first, meta, list, s);
 }
 
 }  // namespace dcvic

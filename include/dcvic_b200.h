@@ -49,6 +49,7 @@ enum {
    * skipped stage are left as the previous call on the same workspace produced them */
   DCVIC_VQ_STAGE_SEARCH_ONLY = 8,  /* codebook prep + candidate search, no finish */
   DCVIC_VQ_STAGE_FINISH_ONLY = 16, /* finish (re-rank + gather + STE + loss) from the workspace's candidates */
+  DCVIC_VQ_STAGE_PREP_ONLY = 64,   /* codebook prep only */
   DCVIC_VQ_RAGGED_HW = 32   /* dcvic_vq_path only: H*W is not a multiple of 4 (or z is not 16-byte aligned), which
                                the tcgen05 search does not take; dcvic_vq_forward sets it by itself */
 };
@@ -56,7 +57,7 @@ enum {
 const char* dcvic_version(void);
 const char* dcvic_error_string(int code);
 /* Which search kernel dcvic_vq_forward would pick: 0 = narrow fused SIMT (e_dim 4/8),
- * 1 = FP32 SIMT scan, 2 = tcgen05 BF16 candidate search + FP32 re-rank. */
+ * 1 = FP32 SIMT scan, 2 = tcgen05 FP16 candidate search + FP32 re-rank. */
 int dcvic_vq_path(int D, int K, int flags);
 
 /* ------------------------------------------------------------------ VQ quantizer ----
