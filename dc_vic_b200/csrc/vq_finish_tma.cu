@@ -29,10 +29,14 @@ namespace {
 
 constexpr int FT = 32;                       // tokens per tile
 #ifndef DCVIC_FIN_NCW
-#define DCVIC_FIN_NCW 15
+#define DCVIC_FIN_NCW 12
 #endif
-constexpr int F_NCW = DCVIC_FIN_NCW;                    // consumer warps (16 warps per CTA: 128 registers per thread)
-constexpr int F_THREADS = (F_NCW + 1) * 32;  // + the producer warp
+#ifndef DCVIC_FIN_NEW
+#define DCVIC_FIN_NEW 3
+#endif
+constexpr int F_NCW = DCVIC_FIN_NCW;         // consumer warps
+constexpr int F_NEW = DCVIC_FIN_NEW;         // list-expander warps
+constexpr int F_THREADS = (F_NCW + F_NEW + 1) * 32;  // + the producer warp (16 warps: 128 registers per thread)
 
 __device__ __forceinline__ uint32_t f_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void f_mbar_init(uint32_t bar, uint32_t count) {
@@ -74,11 +78,6 @@ __device__ __forceinline__ void f_bulk_wait_read() {
 }
 __device__ __forceinline__ void f_bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void f_fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ float f_lds(uint32_t a) {
-  float v;
-  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
-  return v;
-}
 __device__ __forceinline__ float4 f_lds4(uint32_t a) {
   float4 v;
   asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
@@ -87,7 +86,6 @@ __device__ __forceinline__ float4 f_lds4(uint32_t a) {
 __device__ __forceinline__ void f_sts4(uint32_t a, const float4& v) {
   asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
-__device__ __forceinline__ void f_sts(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
 
 #ifdef DCVIC_TRACE
 __device__ unsigned long long g_trace_ftma[148][32][8];
@@ -121,14 +119,17 @@ vq_finish_tma_kernel(const __grid_constant__ CUtensorMap tm_z, const __grid_cons
   constexpr int STAGE_BYTES = D * 128;
   extern __shared__ uint8_t f_smem_raw[];
   __shared__ __align__(8) unsigned long long s_bar[2 * NST];
-  __shared__ unsigned short s_ck[F_NCW][4][kCandMax];
-  __shared__ int s_nc[F_NCW][4];               // flagged codes per token, -1: scan the whole codebook
-  __shared__ unsigned s_stat[3];
+  __shared__ __align__(8) unsigned long long s_cbar[NST];
+  __shared__ unsigned short s_ck[NST][FT][kCandMax];   // candidate codes of the tile in each stage
+  __shared__ int s_nc[NST][FT];                // flagged codes per token, -1: scan the whole codebook
+  __shared__ unsigned s_stat[4];
   // SWIZZLE_128B stages need 1024-byte alignment
   const uint32_t stage0 = (f_smem_u32(f_smem_raw) + 1023u) & ~1023u;
   const uint32_t bar0 = f_smem_u32(s_bar);
   auto full_bar = [&](int st) { return bar0 + st * 8; };
   auto done_bar = [&](int st) { return bar0 + (NST + st) * 8; };
+  const uint32_t cbar0 = f_smem_u32(s_cbar);
+  auto cand_bar = [&](int st) { return cbar0 + st * 8; };
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ntiles = N / FT;
   // tiles of this CTA: a contiguous range (its loads in flight then cover neighbouring 128-byte pieces of the same
@@ -146,13 +147,17 @@ vq_finish_tma_kernel(const __grid_constant__ CUtensorMap tm_z, const __grid_cons
   }
 
   if (threadIdx.x == 0) {
-    for (int st = 0; st < NST; ++st) { f_mbar_init(full_bar(st), 1); f_mbar_init(done_bar(st), 8); }
-    s_stat[0] = 0; s_stat[1] = 0; s_stat[2] = 0;
+    for (int st = 0; st < NST; ++st) {
+      f_mbar_init(full_bar(st), 1);
+      f_mbar_init(done_bar(st), 8);
+      f_mbar_init(cand_bar(st), 1);
+    }
+    s_stat[0] = 0; s_stat[1] = 0; s_stat[2] = 0; s_stat[3] = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
 
-  if (warp == F_NCW) {
+  if (warp == F_NCW + F_NEW) {
     // ------------------------------------------------------------ producer: TMA loads of z, TMA stores of z_q
     // z is an input of the whole call: loads start before the tensor search (the predecessor under programmatic
     // dependent launch) has finished.
@@ -192,55 +197,139 @@ vq_finish_tma_kernel(const __grid_constant__ CUtensorMap tm_z, const __grid_cons
       }
       f_bulk_wait_all();
       FTM_MARK(4);
-      FTM_PUT(F_NCW);
+      FTM_PUT(F_NCW + F_NEW);
     }
     return;
   }
 
+  if (warp >= F_NCW) {
+    // ------------------------------------------------------------ list expanders: one lane per token
+    // The tiles of stage st are expanded by warp (st mod F_NEW), each while its z is still on the way: meta record
+    // and the first 4 or 8 entries of both lists (32-byte sectors, written whole by the search; both prefetched),
+    // the rare longer tails, -> candidate codes s_ck[stage][token][], count s_nc[stage][token].
+    // (One warp per STAGE, not per tile: the parity wait on the stage's done barrier below is only valid if this
+    // warp has itself seen the previous phase complete, i.e. expanded the stage's previous tile.)
+    const int e = warp - F_NCW;
+    FTM_DECL;
+    pdl_wait();                                          // meta / lists / emax come from the preceding kernels
+    FTM_MARK(0);
+    const float emax = cand ? 0.f : __ldg(emax_ptr);
+    auto tile_token = [&](int j) { return (tile_first + j * tile_step) * FT + lane; };
+    // software pipeline over this warp's tiles: meta records two tiles ahead, list entries one tile ahead
+    auto load_meta = [&](int j, VqMeta& m, int& ck) {
+      if (j >= nloc) return;
+      if (cand) ck = __ldg(cand + tile_token(j));
+      else m = meta[tile_token(j)];
+    };
+    auto load_entries = [&](int j, const VqMeta& m, uint4 (&en)[2][4]) {   // entries 0-7 of both lists
+#pragma unroll
+      for (int q = 0; q < 2; ++q)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) en[q][i] = make_uint4(0u, 0u, 0u, 0u);
+      if (j >= nloc || cand) return;
+      const int t = tile_token(j);
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const uint4* lp = reinterpret_cast<const uint4*>(list + ((size_t)t * 2 + q) * kListCap);
+        const int n = q == 0 ? m.n0 : m.n1;
+        if (n > 0) { en[q][0] = __ldg(lp); en[q][1] = __ldg(lp + 1); }        // one 32-byte sector
+        if (n > 4) { en[q][2] = __ldg(lp + 2); en[q][3] = __ldg(lp + 3); }    // (a quarter of the lists)
+      }
+    };
+    auto next_tile = [&](int j) {                          // this warp's next tile after j (or >= nloc)
+      do { ++j; } while (j < nloc && (j % NST) % F_NEW != e);
+      return j;
+    };
+    VqMeta mt = {}, mt_n = {};
+    int cand_k = 0, cand_n = 0;
+    uint4 en[2][4], en_n[2][4];
+    const int j0 = next_tile(-1);
+    int j1 = next_tile(j0);
+    load_meta(j0, mt, cand_k);
+    load_entries(j0, mt, en);
+    load_meta(j1, mt_n, cand_n);
+    for (int j = j0; j < nloc;) {
+      const int st = j % NST;
+      const int j2 = next_tile(j1);
+      const int t = tile_token(j);
+      int w = 0;                                          // candidates found
+      bool full = !cand && (mt.n0 < 0 || mt.n1 < 0);     // overflowed list / FP16-unsafe token or codebook
+      // next tile's entries (its meta record arrived during the previous tile), the meta record after that
+      VqMeta mt_nn = {};
+      int cand_nn = 0;
+      load_entries(j1, mt_n, en_n);
+      load_meta(j2, mt_nn, cand_nn);
+      // the stage's previous tile must be through with s_ck / s_nc
+      if (j >= NST) f_mbar_wait(done_bar(st), ((j / NST) - 1) & 1);
+      FTM_MARK(1);
+      unsigned short* ck = &s_ck[st][lane][0];
+      if (cand) {
+        ck[0] = (unsigned short)min(max(cand_k, 0), K - 1);
+        w = 1;
+      } else if (!full) {
+        const float thr = fmaxf(mt.m0, mt.m1) - vq_margin(mt.zz, emax);
+        auto take = [&](unsigned key, unsigned mask) {
+          if (__uint_as_float(key | 0x7Fu) < thr) return;  // chunk maximum (rounded up) below the threshold
+          const int c0 = (int)(key & 0x7Fu) * kChunk;
+          while (mask) {
+            const int b = __ffs(mask) - 1;
+            mask &= mask - 1;
+            if (w < kCandMax) ck[w] = (unsigned short)(c0 + b);
+            ++w;
+          }
+        };
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const int n = q == 0 ? mt.n0 : mt.n1;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            if (n > 2 * i) take(en[q][i].x, en[q][i].y);
+            if (n > 2 * i + 1) take(en[q][i].z, en[q][i].w);
+          }
+          for (int i = 8; i < n; ++i) {                   // (rare)
+            const uint2 en2 = __ldg(list + ((size_t)t * 2 + q) * kListCap + i);
+            take(en2.x, en2.y);
+          }
+        }
+        if (w > kCandMax || w <= 0) full = true;
+      }
+      if (full) ck[0] = 0;
+      s_nc[st][lane] = full ? -1 : w;
+      mt = mt_n; mt_n = mt_nn;
+      cand_k = cand_n; cand_n = cand_nn;
+#pragma unroll
+      for (int q = 0; q < 2; ++q)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) en[q][i] = en_n[q][i];
+      __syncwarp();
+      if (lane == 0) f_mbar_arrive(cand_bar(st));
+      FTM_MARK(2);
+      j = j1;
+      j1 = j2;
+    }
+    FTM_PUT(warp);
+    return;
+  }
+
   // -------------------------------------------------------------- consumers
-  // Two lane mappings.  Lists: lane = 8*token + sub (8 lanes expand one token's two lists).  Arithmetic: every lane
-  // holds 4 consecutive channels per 128-channel block (c = 4*lane + 128h) of all 4 tokens of the quad: one LDG.128
-  // per codebook row and block, one LDS.128 / STS.128 per channel (the four tokens are the four words of a 16-byte
-  // piece of the swizzled stage).  Lane l visits its 4 channels in the order (j + (l >> 1)) & 3, j = 0..3, so that the
-  // 8 lanes of a quarter warp touch 8 different pieces (rows 4l + jj: (row & 7) = 4(l & 1) + jj); the codebook
-  // values are rotated once per row to that order.  Everything per token (candidate count, codes, best distance)
-  // is warp-uniform, so tokens that need no re-rank cost nothing in the re-rank loop.
+  // Every lane holds 4 consecutive channels per 128-channel block (c = 4*lane + 128h) of all 4 tokens of a quad: one
+  // LDG.128 per codebook row and block, one LDS.128 / STS.128 per channel (the four tokens are the four words of a
+  // 16-byte piece of the swizzled stage).  Lane l visits its 4 channels in the order (j + (l >> 1)) & 3, j = 0..3, so
+  // that the 8 lanes of a quarter warp touch 8 different pieces (rows 4l + jj: (row & 7) = 4(l & 1) + jj); codebook
+  // values are rotated to that order where they meet z.  Everything per token (candidate count, codes, best
+  // distance) is warp-uniform, so tokens that need no re-rank cost nothing in the re-rank loop.  Units (tile, quad)
+  // are handed out in order through a shared counter: a warp that drew a long re-rank does not hold up its CTA.
   constexpr int NH = (D + 127) / 128;                    // 128-channel blocks
-  const int cw = warp, tsub = lane >> 3, cl = lane & 7;
-  const int lq = cl >> 2, li0 = (cl & 3) * 4;          // this lane's share of the token's lists: 4 entries of list lq
+  const int cw = warp;
   const int rot = (lane >> 1) & 3;
   const bool hv[2] = {4 * lane < D, 4 * lane + 128 < D}; // which blocks this lane has (e_dim 64 / 192: not all)
   FTM_DECL;
-  pdl_wait();                                            // meta / lists / emax / ee come from the preceding kernels
+  pdl_wait();                                            // ee comes from the prepare kernel
   FTM_MARK(0);
-  const float emax = cand ? 0.f : __ldg(emax_ptr);
   const int total_units = nloc * 8;
   double dsq = 0.0;
   unsigned n_rr = 0, n_fs = 0;
-
-  // prefetch pipeline: meta records two units ahead, list entries (only the 16-byte pairs that hold entries) one
   auto unit_token0 = [&](int u) { return (tile_first + (u >> 3) * tile_step) * FT + 4 * (u & 7); };
-  VqMeta mt = {}, mt_n = {};
-  uint4 e01 = make_uint4(0u, 0u, 0u, 0u), e23 = e01;
-  int cand_k = 0;
-  auto fetch_meta = [&](int u, VqMeta& m) {
-    if (u >= total_units) return;
-    const int t = unit_token0(u) + tsub;
-    if (cand) cand_k = __ldg(cand + t);                   // (one unit ahead is enough: a single load)
-    else m = meta[t];
-  };
-  auto fetch_entries = [&](int u, const VqMeta& m, uint4& a, uint4& b2) {
-    a = make_uint4(0u, 0u, 0u, 0u);
-    b2 = a;
-    if (u >= total_units || cand) return;
-    const int t = unit_token0(u) + tsub;
-    const int n = lq == 0 ? m.n0 : m.n1;
-    const uint4* lp = reinterpret_cast<const uint4*>(list + ((size_t)t * 2 + lq) * kListCap + li0);
-    if (li0 < n) {                                        // one 32-byte sector, written whole by the search
-      a = __ldg(lp);
-      b2 = __ldg(lp + 1);
-    }
-  };
   // out[j] = v[(j + r) & 3]
   auto rotl = [](float4 v, int r) {
     if (r & 1) v = make_float4(v.y, v.z, v.w, v.x);
@@ -254,15 +343,12 @@ vq_finish_tma_kernel(const __grid_constant__ CUtensorMap tm_z, const __grid_cons
     for (int h = 0; h < NH; ++h)
       r[h] = hv[h] ? __ldg(reinterpret_cast<const float4*>(row + 128 * h)) : make_float4(0.f, 0.f, 0.f, 0.f);
   };
-  if (cand) {
-    fetch_meta(cw, mt);
-  } else {
-    fetch_meta(cw, mt);
-    fetch_entries(cw, mt, e01, e23);
-    fetch_meta(cw + F_NCW, mt_n);
-  }
 
-  for (int u = cw; u < total_units; u += F_NCW) {
+  for (;;) {
+    int u = 0;
+    if (lane == 0) u = (int)atomicAdd(&s_stat[3], 1u);
+    u = __shfl_sync(0xffffffffu, u, 0);
+    if (u >= total_units) break;
     const int j = u >> 3, q = u & 7, st = j % NST;
     const int t0 = unit_token0(u);
     // shared-memory offsets of this lane's 4 channel rows (visiting order), block 0; block h adds h * 16384
@@ -290,66 +376,14 @@ vq_finish_tma_kernel(const __grid_constant__ CUtensorMap tm_z, const __grid_cons
       continue;
     }
 #endif
-    // ---- candidates (before the tile is needed): 8 lanes per token
-    {
-      int nc = 1;
-      if (cand) {
-        if (cl == 0) s_ck[cw][tsub][0] = (unsigned short)min(max(cand_k, 0), K - 1);
-      } else {
-        const float thr = fmaxf(mt.m0, mt.m1) - vq_margin(mt.zz, emax);
-        const int n = lq == 0 ? mt.n0 : mt.n1;
-        bool full = mt.n0 < 0 || mt.n1 < 0;               // overflowed list / FP16-unsafe token or codebook
-        unsigned key[4] = {e01.x, e01.z, e23.x, e23.z};
-        unsigned msk[4] = {e01.y, e01.w, e23.y, e23.w};
-        int cnt = 0;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const bool ok = (li0 + i < n) && !(__uint_as_float(key[i] | 0x7Fu) < thr);
-          msk[i] = ok ? msk[i] : 0u;
-          cnt += __popc(msk[i]);
-        }
-        int incl = cnt;                                   // inclusive prefix over the token's 8 lanes
-#pragma unroll
-        for (int o = 1; o < 8; o <<= 1) {
-          const int v = __shfl_up_sync(0xffffffffu, incl, o, 8);
-          if (cl >= o) incl += v;
-        }
-        nc = __shfl_sync(0xffffffffu, incl, 7, 8);
-        if (nc > kCandMax || nc <= 0) full = true;
-        if (!full) {
-          int w = incl - cnt;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            unsigned m = msk[i];
-            const int c0 = (int)(key[i] & 0x7Fu) * kChunk;
-            while (m) {
-              const int b = __ffs(m) - 1;
-              m &= m - 1;
-              s_ck[cw][tsub][w++] = (unsigned short)(c0 + b);
-            }
-          }
-        } else {
-          nc = -1;
-          if (cl == 0) s_ck[cw][tsub][0] = 0;
-        }
-      }
-      if (cl == 0) s_nc[cw][tsub] = nc;
-    }
-    __syncwarp();
+    // ---- candidates of the quad's tokens (from the expander warps)
+    f_mbar_wait(cand_bar(st), (j / NST) & 1);
     FTM_MARK(1);
-    // advance the prefetch pipeline
-    if (cand) {
-      fetch_meta(u + F_NCW, mt);
-    } else {
-      mt = mt_n;
-      fetch_entries(u + F_NCW, mt, e01, e23);
-      fetch_meta(u + 2 * F_NCW, mt_n);
-    }
     int nc[4], bk[4];
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
-      nc[g] = s_nc[cw][g];
-      bk[g] = s_ck[cw][g][0];
+      nc[g] = s_nc[st][4 * q + g];
+      bk[g] = s_ck[st][4 * q + g][0];
     }
     // ---- first candidates' codebook rows (the winners for three tokens out of four), requested ahead of the tile
     float4 er[4][NH];
@@ -398,7 +432,7 @@ vq_finish_tma_kernel(const __grid_constant__ CUtensorMap tm_z, const __grid_cons
         kb = bk[g];
 #pragma unroll 1
         for (int ci = 1; ci < nc[g]; ci += 2) {            // two candidate rows in flight
-          const int k0 = s_ck[cw][g][ci], k1 = s_ck[cw][g][min(ci + 1, nc[g] - 1)];
+          const int k0 = s_ck[st][4 * q + g][ci], k1 = s_ck[st][4 * q + g][min(ci + 1, nc[g] - 1)];
           float4 e0[NH], e1[NH];
           load_row(e0, k0);
           load_row(e1, k1);

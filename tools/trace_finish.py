@@ -31,15 +31,24 @@ buf = (C.c_ulonglong * (148 * 32 * 8))()
 lib.dcvic_debug_read_ftma_trace.restype = C.c_int
 assert lib.dcvic_debug_read_ftma_trace(buf) == 0
 rows = [[[buf[(b * 32 + w) * 8 + i] for i in range(8)] for w in range(32)] for b in range(148)]
-ncw = max(w for w in range(32) if rows[0][w][7] > 0)        # the producer is the last warp that wrote
+NEW = int(os.environ.get("DCVIC_FIN_NEW", "2"))             # expander warps of the traced build
+last = max(w for w in range(32) if rows[0][w][7] > 0)       # the producer is the last warp that wrote
+ncw = last - NEW
 cons = [rows[b][w] for b in range(148) for w in range(ncw)]
-prod = [rows[b][ncw] for b in range(148)]
-cn = ["pdl wait", "expand lists", "issue rows + next lists", "wait tile", "re-rank", "z_q + arrive", "-", "total"]
+expd = [rows[b][w] for b in range(148) for w in range(ncw, last)]
+prod = [rows[b][last] for b in range(148)]
+cn = ["pdl wait", "draw unit + wait cands", "issue rows", "wait tile", "re-rank", "z_q + arrive", "-", "total"]
+en = ["pdl wait", "loads + wait stage", "expand + arrive", "-", "-", "-", "-", "total"]
 pn = ["prologue loads", "wait done", "wait store read", "issue", "drain", "-", "-", "total"]
 print("consumer warps:", ncw)
 for i, n in enumerate(cn):
     if n != "-":
         col = [r[i] for r in cons]
+        print(f"  {n:26s} median {statistics.median(col):9.0f}  max {max(col):9.0f}  min {min(col):9.0f}")
+print("expander warps:", NEW)
+for i, n in enumerate(en):
+    if n != "-":
+        col = [r[i] for r in expd]
         print(f"  {n:26s} median {statistics.median(col):9.0f}  max {max(col):9.0f}  min {min(col):9.0f}")
 print("producer thread")
 for i, n in enumerate(pn):
@@ -54,5 +63,5 @@ cta_mean = [sum(x) / len(x) for x in work]
 print(f"work per warp (total - pdl wait): mean over all {statistics.mean([v for x in work for v in x]):.0f}")
 print(f"  per CTA: slowest warp median {statistics.median(cta_max):.0f} max {max(cta_max):.0f} min {min(cta_max):.0f};"
       f" mean-warp median {statistics.median(cta_mean):.0f} max {max(cta_mean):.0f} min {min(cta_mean):.0f}")
-pw = [rows[b][ncw][7] for b in range(148)]
+pw = [rows[b][last][7] for b in range(148)]
 print(f"  producer total: median {statistics.median(pw):.0f} max {max(pw):.0f} min {min(pw):.0f}")
