@@ -268,6 +268,29 @@ def test_tensor_path_outside_fp16_range_stays_exact():
     check_against_oracle(z2, E2, out2, out2[2][2], allow_near_ties=True)
 
 
+def test_finish_ring_wraps_at_other_widths():
+    """e_dim 128 / 192 (8-stage ring of the TMA finish kernel) with enough tokens that every persistent CTA goes
+    round its ring more than once; tensor path and exact scan must agree, an image-sized sample goes to the oracle."""
+    for Dm, K, B in ((128, 512, 48), (192, 256, 48)):
+        z, E = vq_inputs(11, "D1b", B, Dm, 32, 32, K)          # 49,152 tokens = 1536 tiles > 148 x 8
+        m = make(D.VectorQuantizer2, E, sane_index_shape=True)
+        assert m.search_path() == "tcgen05"
+        zc = z.to(DEV)
+        with torch.no_grad():
+            z_q, loss, (_, _, idx) = m(zc)
+            m.search = "exact"
+            z_q2, loss2, (_, _, idx2) = m(zc)
+        differ = idx != idx2
+        assert int(differ.sum()) <= 4                          # FP32 near-ties only (different summation trees)
+        rows = zc.permute(0, 2, 3, 1).reshape(-1, Dm)
+        picked = E.to(DEV)[idx.reshape(-1)]
+        assert torch.equal(z_q.permute(0, 2, 3, 1).reshape(-1, Dm), rows + (picked - rows))
+        ref = ((picked - rows) ** 2).mean()
+        assert abs(float(loss) - float(ref + 0.25 * ref)) <= 1e-5 * float(ref)
+        n_mis, n_out, _ = O.allowed_index_mismatch(z[B - 1:], E, idx[B - 1:].cpu())   # the last image: late tiles
+        assert n_out == 0
+
+
 def test_tensor_path_larger_codebooks():
     for K, Dm in ((2048, 128), (768, 64)):
         z, E = vq_inputs(5, "D1b", 1, Dm, 16, 16, K)
