@@ -67,7 +67,7 @@ extern "C" int dcvic_vq_forward(const float* z_nchw, const float* codebook, int 
   } else {
     const bool prepared = !(flags & (DCVIC_VQ_REUSE_PREP | DCVIC_VQ_STAGE_FINISH_ONLY));
     if (prepared) {
-      rc = vq_prepare_codebook(codebook, K, D, ee, nhee, emax, path == 2 ? cb16 : nullptr, s);
+      rc = vq_prepare_codebook(codebook, K, D, ee, nhee, emax, path == 2 ? cb16 : nullptr, counters, s);
       if (rc) return rc;
     }
     if (flags & DCVIC_VQ_STAGE_PREP_ONLY) return rc;

@@ -48,7 +48,7 @@ inline VqWorkspace vq_workspace_layout(int B, int D, int HW, int K) {
 }
 
 // counters[] slots
-enum { kCtrLoss = 0, kCtrOverflow = 1, kCtrPerp = 2, kCtrRerank = 3, kCtrTotalCand = 4 };
+enum { kCtrLoss = 0, kCtrOverflow = 1, kCtrPerp = 2, kCtrRerank = 3, kCtrTotalCand = 4, kCtrPrep = 5 };
 
 // The proven bound on |fp16 score - exact score| differences that the search and the finish must agree on.
 // Both operands are rounded to nearest FP16 (relative 2^-11 each, so 2^-10 + 2^-22 per product, summed with
@@ -65,8 +65,9 @@ __host__ __device__ __forceinline__ float vq_margin(float zz, float emax) {
 }
 
 // vq_simt.cu
-int vq_prepare_codebook(const float* codebook, int K, int D, float* ee, float* nhee, float* emax,
-                        __half* cb16, cudaStream_t s);
+// scratch: K floats (per-CTA maxima of the prepare kernel)
+int vq_prepare_codebook(const float* codebook, int K, int D, float* ee, float* scratch, float* emax,
+                        __half* cb16, unsigned* counters, cudaStream_t s);
 int vq_narrow_forward(const float* z, const float* E, int B, int D, int HW, int K, float beta, int legacy, float* zq,
                       int64_t* idx, float* loss, double* partials, unsigned* counters, cudaStream_t s);
 int vq_exact_search(const float* z, const float* E, const float* ee, int B, int D, int HW, int K, int* cand,

@@ -14,51 +14,106 @@
 namespace dcvic {
 
 // ------------------------------------------------------------------ codebook prepare
-// One warp per code.  ee[k] = sum_c fl(e^2) (lane-strided partials + xor tree), nhee[k] = -ee[k]/2,
-// emax[0] = max_k |e_k| (atomicMax on the non-negative float's bit pattern), emax[1] != 0 if the codebook does
-// not fit FP16's range, cb16[k][0..D) = fp16(e), cb16[k][D..D+3) = three-way FP16 split of -ee[k]/2 (exact:
-// 3 x 11 significant bits), rest of the pad zero.
+// One warp per code.  ee[k] = sum_c fl(e^2) (lane-strided partials + xor tree), cb16[k][0..D) = fp16(e),
+// cb16[k][D..D+3) = three-way FP16 split of -ee[k]/2 (exact: 3 x 11 significant bits), rest of the pad zero.
+// emax[0] = max_k |e_k| (rounded up), emax[1] != 0 if the codebook does not fit FP16's range: per-CTA values go to
+// `scratch`, the CTA that finishes last reduces them (no atomics on floats, no memset before the kernel;
+// counters[kCtrPrep] is zero on entry and reset here).
+// Launched with programmatic dependent launch: it waits for its predecessor in the stream (which may be the
+// producer of the codebook or of z) before it reads anything, then lets the tensor search start - which may load z
+// while the codebook is being prepared.
 __global__ void __launch_bounds__(256) vq_prepare_kernel(const float* __restrict__ E, int K, int D,
-                                                          float* __restrict__ ee, float* __restrict__ nhee,
-                                                          float* __restrict__ emax, __half* __restrict__ cb16) {
-  pdl_launch_dependents();      // the tensor search may start loading z while the codebook is being prepared
-  const int lane = threadIdx.x & 31;
-  const int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (k >= K) return;
-  const float* row = E + (size_t)k * D;
-  const size_t ld = (size_t)(D + kCb16Pad);
-  float acc = 0.f;
-  bool unsafe = false;
-  for (int c = lane; c < D; c += 32) {
-    const float v = row[c];
-    acc = __fadd_rn(acc, __fmul_rn(v, v));
-    unsafe |= !(fabsf(v) < 6.0e4f);
-    if (cb16) cb16[(size_t)k * ld + c] = __float2half_rn(v);
+                                                          float* __restrict__ ee, float* __restrict__ scratch,
+                                                          float* __restrict__ emax, __half* __restrict__ cb16,
+                                                          unsigned* __restrict__ counters) {
+  __shared__ float s_m[8];
+  __shared__ int s_u[8];
+  __shared__ int s_last;
+  pdl_wait();
+  pdl_launch_dependents();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int k = blockIdx.x * 8 + wid;
+  float wm = 0.f;
+  bool wu = false;
+  if (k < K) {
+    const float* row = E + (size_t)k * D;
+    const size_t ld = (size_t)(D + kCb16Pad);
+    float acc = 0.f;
+    bool unsafe = false;
+    for (int c = lane; c < D; c += 32) {
+      const float v = row[c];
+      acc = __fadd_rn(acc, __fmul_rn(v, v));
+      unsafe |= !(fabsf(v) < 6.0e4f);
+      if (cb16) cb16[(size_t)k * ld + c] = __float2half_rn(v);
+    }
+    acc = warp_sum(acc);
+    unsafe |= !(acc < 1.2e5f);                  // -ee/2 must be representable as well
+    unsafe = __any_sync(0xffffffffu, unsafe);
+    if (lane == 0) ee[k] = acc;
+    wm = sqrtf(acc) * 1.0000002f;
+    wu = unsafe;
+    if (cb16) {
+      const float v = unsafe ? 0.f : -0.5f * acc;
+      const __half h = __float2half_rn(v);
+      const float r1 = v - __half2float(h);
+      const __half m = __float2half_rn(r1);
+      const float r2 = r1 - __half2float(m);
+      const __half l = __float2half_rn(r2);
+      for (int c = lane; c < kCb16Pad; c += 32)
+        cb16[(size_t)k * ld + D + c] = c == 0 ? h : (c == 1 ? m : (c == 2 ? l : __float2half_rn(0.f)));
+    }
   }
-  acc = warp_sum(acc);
-  unsafe |= !(acc < 1.2e5f);                    // -ee/2 must be representable as well
-  if (lane == 0) {
-    ee[k] = acc;
-    nhee[k] = -0.5f * acc;
-    atomicMax(reinterpret_cast<unsigned*>(emax), __float_as_uint(sqrtf(acc) * 1.0000002f));
+  if (lane == 0) { s_m[wid] = wm; s_u[wid] = wu ? 1 : 0; }
+  __syncthreads();
+  const unsigned grid = gridDim.x;
+  if (threadIdx.x == 0) {
+    float m = 0.f;
+    int u = 0;
+    for (int w = 0; w < 8; ++w) { m = fmaxf(m, s_m[w]); u |= s_u[w]; }   // NaN-free: fmaxf drops a NaN norm,
+    scratch[blockIdx.x] = m;                                                // and such a row is flagged unsafe
+    scratch[grid + blockIdx.x] = u ? 1.f : 0.f;
+    __threadfence();
+    s_last = atomicAdd(counters + kCtrPrep, 1u) == grid - 1;
   }
-  if (__any_sync(0xffffffffu, unsafe) && lane == 0) atomicMax(reinterpret_cast<unsigned*>(emax + 1), 1u);
-  if (cb16) {
-    const float v = unsafe ? 0.f : -0.5f * acc;
-    const __half h = __float2half_rn(v);
-    const float r1 = v - __half2float(h);
-    const __half m = __float2half_rn(r1);
-    const float r2 = r1 - __half2float(m);
-    const __half l = __float2half_rn(r2);
-    for (int c = lane; c < kCb16Pad; c += 32)
-      cb16[(size_t)k * ld + D + c] = c == 0 ? h : (c == 1 ? m : (c == 2 ? l : __float2half_rn(0.f)));
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  float m = 0.f, u = 0.f;
+  for (unsigned i = threadIdx.x; i < grid; i += 256) {
+    m = fmaxf(m, __ldcg(scratch + i));
+    u = fmaxf(u, __ldcg(scratch + grid + i));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    u = fmaxf(u, __shfl_xor_sync(0xffffffffu, u, o));
+  }
+  __syncthreads();
+  if (lane == 0) { s_m[wid] = m; s_u[wid] = u != 0.f; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int uu = 0;
+    m = 0.f;
+    for (int w = 0; w < 8; ++w) { m = fmaxf(m, s_m[w]); uu |= s_u[w]; }
+    emax[0] = m;
+    emax[1] = __uint_as_float(uu ? 1u : 0u);
+    counters[kCtrPrep] = 0u;
   }
 }
 
-int vq_prepare_codebook(const float* codebook, int K, int D, float* ee, float* nhee, float* emax, __half* cb16,
-                        cudaStream_t s) {
-  if (cudaMemsetAsync(emax, 0, 2 * sizeof(float), s) != cudaSuccess) return DCVIC_ERR_CUDA;
-  vq_prepare_kernel<<<ceil_div_i(K, 8), 256, 0, s>>>(codebook, K, D, ee, nhee, emax, cb16);
+int vq_prepare_codebook(const float* codebook, int K, int D, float* ee, float* scratch, float* emax, __half* cb16,
+                        unsigned* counters, cudaStream_t s) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(ceil_div_i(K, 8));
+  cfg.blockDim = dim3(256);
+  cfg.stream = s;
+  cudaLaunchAttribute pdl[1];
+  pdl[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  pdl[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = pdl;
+  cfg.numAttrs = 1;
+  if (cudaLaunchKernelEx(&cfg, vq_prepare_kernel, codebook, K, D, ee, scratch, emax, cb16, counters) != cudaSuccess)
+    return DCVIC_ERR_CUDA;
   return dcvic_launch_status();
 }
 
