@@ -100,22 +100,17 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
+// (The polling loop stays inside the asm block: a C++ loop around try_wait measured 2 us slower per launch.)
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t"
-      "}"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-// (a C++ loop: the compiler then places a reconvergence point behind it for warps whose lanes all wait)
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  while (!mbar_try_wait(bar, parity)) {}
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}" ::"r"(bar), "r"(parity) : "memory");
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -606,7 +601,8 @@ static int launch_search(const CUtensorMap& tmap, const float* z, const float* e
                          int wait_first, VqMeta* meta, uint2* list, cudaStream_t s) {
   using C = Cfg<CG>;
   const int num_ptiles = (N + BM * CG - 1) / (BM * CG);
-  const int max_pairs = kNumSMs / CG;
+  static const int pairs_env = getenv("DCVIC_VQ_PAIRS") ? atoi(getenv("DCVIC_VQ_PAIRS")) : 0;   // experiments
+  const int max_pairs = (pairs_env > 0 && pairs_env < kNumSMs / CG) ? pairs_env : kNumSMs / CG;
   const int grid = CG * (num_ptiles < max_pairs ? num_ptiles : max_pairs);
   const int smem = C::SMEM_BYTES + 1024;
   if (cudaFuncSetAttribute(vq_tensor_search_kernel<CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) !=
