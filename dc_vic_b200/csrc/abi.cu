@@ -74,7 +74,11 @@ extern "C" int dcvic_vq_forward(const float* z_nchw, const float* codebook, int 
     const bool do_search = !(flags & DCVIC_VQ_STAGE_FINISH_ONLY);
     const bool do_finish = !(flags & DCVIC_VQ_STAGE_SEARCH_ONLY);
     if (path == 2) {
-      if (do_search) rc = vq_tensor_search(z_nchw, cb16, emax, B, D, HW, K, prepared, meta, list, s);
+      if (do_search)
+        rc = vq_tensor_search(z_nchw, cb16, emax, B, D, HW, K, prepared,
+                              do_finish && (reinterpret_cast<uintptr_t>(codebook) & 15) == 0 &&
+                                  vq_finish_tma_supported(z_nchw, zq_nchw, D, HW, K),
+                              meta, list, s);
       if (rc) return rc;
       if (do_finish)
         rc = vq_finish(z_nchw, codebook, ee, emax, nullptr, meta, list, B, D, HW, K, beta, legacy, zq_nchw, idx, loss,

@@ -12,10 +12,15 @@ constexpr int kCb16Pad = 64;          // extra FP16 codebook columns: a 3-way sp
 constexpr int kCandMax = 24;          // FP32 re-rank candidates per token before falling back to a full scan
 
 // What the tensor search hands to the finish kernel, per token t: one VqMeta record and two lists.
+// A token tile of the search's last round may be scanned by two CTA pairs, each over half of the codebook ("split"):
+// part 0 then uses entries 0-7 of each list and the first half of the record, part 1 entries 8-15 and the second.
 struct __align__(16) VqMeta {
-  float m0, m1;     // running maximum of the FP16 score over columns 0-127 / 128-255 of every accumulator
+  float m0, m1;     // running maximum of the FP16 score over columns 0-127 / 128-255 of every accumulator (part 0)
   short n0, n1;     // list entries of epilogue warp quad 0 / 1, or -1: scan the whole codebook for this token
   float zz;         // |z|^2 as the search computed it (its margin and the finish's threshold use the same value)
+  float mb0, mb1;   // part 1 (split tiles; -inf / 0 otherwise)
+  short nb0, nb1;
+  unsigned split;   // 1: lists are two halves of 8 entries
 };
 //   list[(2t + q) * kListCap + i] = { key, mask }:  key = (bits(chunk max) & ~0x7F) | chunk id,
 //                           mask bit j set <=> score of code (chunk id * 32 + j) was within the
@@ -91,7 +96,8 @@ int vq_finish_tma(const float* z, const float* E, const float* ee, const float* 
 bool vq_tensor_supported(int D, int K);
 // after_prepare: the kernel launched just before on `s` was vq_prepare_codebook's (else the search waits for its
 // predecessor before it reads z)
+// allow_split: the finish kernel that will read meta / list understands split tiles (the TMA finish does)
 int vq_tensor_search(const float* z, const __half* cb16, const float* emax, int B, int D, int HW, int K,
-                     bool after_prepare, VqMeta* meta, uint2* list, cudaStream_t s);
+                     bool after_prepare, bool allow_split, VqMeta* meta, uint2* list, cudaStream_t s);
 
 }  // namespace dcvic

@@ -253,7 +253,8 @@ vq_finish_tma_kernel(const __grid_constant__ CUtensorMap tm_z, const __grid_cons
       const int j2 = next_tile(j1);
       const int t = tile_token(j);
       int w = 0;                                          // candidates found
-      bool full = !cand && (mt.n0 < 0 || mt.n1 < 0);     // overflowed list / FP16-unsafe token or codebook
+      // overflowed list / FP16-unsafe token or codebook
+      bool full = !cand && (mt.n0 < 0 || mt.n1 < 0 || mt.nb0 < 0 || mt.nb1 < 0);
       // next tile's entries (its meta record arrived during the previous tile), the meta record after that
       VqMeta mt_nn = {};
       int cand_nn = 0;
@@ -267,7 +268,7 @@ vq_finish_tma_kernel(const __grid_constant__ CUtensorMap tm_z, const __grid_cons
         ck[0] = (unsigned short)min(max(cand_k, 0), K - 1);
         w = 1;
       } else if (!full) {
-        const float thr = fmaxf(mt.m0, mt.m1) - vq_margin(mt.zz, emax);
+        const float thr = fmaxf(fmaxf(mt.m0, mt.m1), fmaxf(mt.mb0, mt.mb1)) - vq_margin(mt.zz, emax);
         auto take = [&](unsigned key, unsigned mask) {
           if (__uint_as_float(key | 0x7Fu) < thr) return;  // chunk maximum (rounded up) below the threshold
           const int c0 = (int)(key & 0x7Fu) * kChunk;
@@ -286,9 +287,31 @@ vq_finish_tma_kernel(const __grid_constant__ CUtensorMap tm_z, const __grid_cons
             if (n > 2 * i) take(en[q][i].x, en[q][i].y);
             if (n > 2 * i + 1) take(en[q][i].z, en[q][i].w);
           }
-          for (int i = 8; i < n; ++i) {                   // (rare)
+          for (int i = 8; i < n; ++i) {                   // (rare; never on split tiles: a half holds 8 entries)
             const uint2 en2 = __ldg(list + ((size_t)t * 2 + q) * kListCap + i);
             take(en2.x, en2.y);
+          }
+        }
+        if (mt.split) {
+          // second half of a split tile (one tile in eight on C2): entries 8.. of both lists, not prefetched
+          uint4 eb[2][4];
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            const uint4* lp = reinterpret_cast<const uint4*>(list + ((size_t)t * 2 + q) * kListCap + kListCap / 2);
+            const int n = q == 0 ? mt.nb0 : mt.nb1;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) eb[q][i] = make_uint4(0u, 0u, 0u, 0u);
+            if (n > 0) { eb[q][0] = __ldg(lp); eb[q][1] = __ldg(lp + 1); }
+            if (n > 4) { eb[q][2] = __ldg(lp + 2); eb[q][3] = __ldg(lp + 3); }
+          }
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            const int n = q == 0 ? mt.nb0 : mt.nb1;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              if (n > 2 * i) take(eb[q][i].x, eb[q][i].y);
+              if (n > 2 * i + 1) take(eb[q][i].z, eb[q][i].w);
+            }
           }
         }
         if (w > kCandMax || w <= 0) full = true;

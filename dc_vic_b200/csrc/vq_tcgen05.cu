@@ -258,7 +258,7 @@ template <int CG>
 __global__ void __launch_bounds__(NTHREADS, 1)
 vq_tensor_search_kernel(const __grid_constant__ CUtensorMap tmap_cb, const float* __restrict__ z,
                         const float* __restrict__ emax_ptr, int N, int D, int HW, int K, int num_ptiles,
-                        int wait_first, VqMeta* __restrict__ meta, uint2* __restrict__ list) {
+                        int wait_first, int split, VqMeta* __restrict__ meta, uint2* __restrict__ list) {
   using C = Cfg<CG>;
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B operands need 1024-byte alignment (same adjustment in both CTAs of a pair)
@@ -283,7 +283,17 @@ vq_tensor_search_kernel(const __grid_constant__ CUtensorMap tmap_cb, const float
   const int pair = blockIdx.x / CG, npairs = gridDim.x / CG;
   const int KC = D / BK;               // channel chunks
   const int NT = K / BN;               // N-tiles per token tile
-  const int my_tiles = (num_ptiles - pair + npairs - 1) / npairs;
+  // Schedule: `rounds` full rounds of one token tile per pair; the remaining `rem` tiles (fewer than pairs) form
+  // the last round.  With split == 2 (host: 2 * rem <= npairs) every one of them goes to TWO pairs, each scanning
+  // half of the codebook's N-tiles, so the last round takes half as long (40 of 74 pairs would idle through it on
+  // C2).  The two halves keep separate running maxima and list halves (VqMeta part 0 / part 1).
+  const int rounds = num_ptiles / npairs, rem = num_ptiles % npairs;
+  const int my_tiles = rounds + (pair < rem * split ? 1 : 0);
+  auto unit_ptile = [&](int it) { return it < rounds ? pair + it * npairs : rounds * npairs + pair / split; };
+  auto unit_part = [&](int it) { return it < rounds ? 0 : pair % split; };
+  auto unit_nt0 = [&](int it) { return (it < rounds || split == 1) ? 0 : (pair % split) * (NT / split); };
+  auto unit_nt1 = [&](int it) { return (it < rounds || split == 1) ? NT : (pair % split + 1) * (NT / split); };
+  auto unit_split = [&](int it) { return it >= rounds && split > 1; };
   // barriers that live in the leader CTA, as shared::cluster addresses
   auto leader_bar = [&](int slot) { return CG == 2 ? map_to_cta(bar(slot), 0) : bar(slot); };
   auto arrive_leader = [&](uint32_t b) { if constexpr (CG == 2) mbar_arrive_cluster(b); else mbar_arrive(b); };
@@ -340,7 +350,7 @@ vq_tensor_search_kernel(const __grid_constant__ CUtensorMap tmap_cb, const float
     [[maybe_unused]] unsigned long long tr_wait = 0, tr_work = 0;
     float4 va[8], vb[8];
     auto tile_ptr = [&](int it, bool& valid) {
-      const long long t = ((long long)(pair + it * npairs) * CG + rank) * BM + row0;
+      const long long t = ((long long)unit_ptile(it) * CG + rank) * BM + row0;
       valid = it < my_tiles && t < N;           // N and HW are multiples of 4: a quad is valid as a whole
       return z + (valid ? ((size_t)(t / HW) * D * HW + (size_t)(t % HW) + (size_t)(g * 8) * sHW) : 0);
     };
@@ -419,7 +429,10 @@ vq_tensor_search_kernel(const __grid_constant__ CUtensorMap tmap_cb, const float
     uint32_t g = 0;                               // running N-tile counter (same sequence as the MMA issuer)
     [[maybe_unused]] unsigned long long tr_zz = 0, tr_full = 0, tr_proc = 0;
     for (int it = 0; it < my_tiles; ++it) {
-      const int ptile = pair + it * npairs;
+      const int ptile = unit_ptile(it);
+      const int part = unit_part(it), nt0 = unit_nt0(it), nt1 = unit_nt1(it);
+      const bool is_split = unit_split(it);
+      const int cap = is_split ? kListCap / 2 : kListCap;   // entries this unit may write per list
       const long long t = ((long long)ptile * CG + rank) * BM + row;
       const bool valid = t < N;
       unsigned long long tr0 = TR_NOW();
@@ -429,8 +442,8 @@ vq_tensor_search_kernel(const __grid_constant__ CUtensorMap tmap_cb, const float
       const float margin = vq_margin(zz, emax);
       float m = -INFINITY;
       int n = 0;                                  // list entries written
-      uint2* my_list = list + ((size_t)(valid ? t : 0) * 2 + q) * kListCap;
-      for (int nt = 0; nt < NT; ++nt, ++g) {
+      uint2* my_list = list + ((size_t)(valid ? t : 0) * 2 + q) * kListCap + part * (kListCap / 2);
+      for (int nt = nt0; nt < nt1; ++nt, ++g) {
         const uint32_t buf = g & 1;
         tr0 = TR_NOW();
         mbar_wait(bar(C::BAR_T_FULL + buf), (g >> 1) & 1);
@@ -442,14 +455,14 @@ vq_tensor_search_kernel(const __grid_constant__ CUtensorMap tmap_cb, const float
         auto emit = [&](uint32_t mask, float cm, uint32_t chunk) {
           if (mask != 0u && valid) {
             const uint32_t key = (__float_as_uint(cm) & 0xFFFFFF80u) | chunk;
-            if ((n & 3) == 0 && n < kListCap) {
+            if ((n & 3) == 0 && n < cap) {
               // first entry of a 32-byte sector: write the whole sector (entry + zeros), so that the finish kernel's
               // read of it is an L2 hit and not a DRAM fill of the bytes nobody wrote
               uint4* p = reinterpret_cast<uint4*>(my_list + n);
               p[0] = make_uint4(key, mask, 0u, 0u);
               p[1] = make_uint4(0u, 0u, 0u, 0u);
             } else {
-              my_list[min(n, kListCap - 1)] = make_uint2(key, mask);
+              my_list[min(n, cap - 1)] = make_uint2(key, mask);
             }
             ++n;
           }
@@ -481,9 +494,19 @@ vq_tensor_search_kernel(const __grid_constant__ CUtensorMap tmap_cb, const float
         TR_ADD(tr_proc, tr0);
       }
       if (valid) {
-        const short nn = (n > kListCap || cb_unsafe || !(zz < kVqFp16Zz2Max)) ? (short)-1 : (short)n;
-        if (q == 0) { meta[t].m0 = m; meta[t].n0 = nn; meta[t].zz = zz; }
-        else        { meta[t].m1 = m; meta[t].n1 = nn; }
+        const short nn = (n > cap || cb_unsafe || !(zz < kVqFp16Zz2Max)) ? (short)-1 : (short)n;
+        VqMeta* mp = meta + t;
+        if (part == 0) {
+          if (q == 0) { mp->m0 = m; mp->n0 = nn; mp->zz = zz; mp->split = is_split ? 1u : 0u; }
+          else        { mp->m1 = m; mp->n1 = nn; }
+          if (!is_split) {                       // no second half: its fields read as "nothing flagged"
+            if (q == 0) { mp->mb0 = -INFINITY; mp->nb0 = 0; }
+            else        { mp->mb1 = -INFINITY; mp->nb1 = 0; }
+          }
+        } else {
+          if (q == 0) { mp->mb0 = m; mp->nb0 = nn; }
+          else        { mp->mb1 = m; mp->nb1 = nn; }
+        }
       }
     }
     if (part == 0 && lane == 0) { TR_PUT(2 + 4 * q, tr_zz); TR_PUT(3 + 4 * q, tr_full); TR_PUT(4 + 4 * q, tr_proc); }
@@ -495,7 +518,7 @@ vq_tensor_search_kernel(const __grid_constant__ CUtensorMap tmap_cb, const float
       int stage = 0;
       uint32_t phase = 0;
       for (int it = 0; it < my_tiles; ++it)
-        for (int nt = 0; nt < NT; ++nt)
+        for (int nt = unit_nt0(it); nt < unit_nt1(it); ++nt)
           for (int kc = -1; kc < KC; ++kc) {      // kc == -1: the -|e|^2/2 chunk (columns D .. D+63)
             mbar_wait(bar(C::BAR_B_EMPTY + stage), phase ^ 1);
             if (leader) mbar_arrive_expect_tx(bar(C::BAR_B_FULL + stage), CG * C::B_STAGE_BYTES);
@@ -515,7 +538,8 @@ vq_tensor_search_kernel(const __grid_constant__ CUtensorMap tmap_cb, const float
       [[maybe_unused]] const unsigned long long tr_start = TR_NOW();
       for (int it = 0; it < my_tiles; ++it) {
         const int abuf = it & 1;
-        for (int nt = 0; nt < NT; ++nt, ++g) {
+        const int nt0 = unit_nt0(it), nt1 = unit_nt1(it);
+        for (int nt = nt0; nt < nt1; ++nt, ++g) {
           const uint32_t buf = g & 1;
           tr0 = TR_NOW();
           if (g >= 2) mbar_wait(bar(C::BAR_T_EMPTY + buf), ((g >> 1) - 1) & 1);   // both CTAs drained this buffer
@@ -524,7 +548,7 @@ vq_tensor_search_kernel(const __grid_constant__ CUtensorMap tmap_cb, const float
           const uint32_t tmem_d = tmem_base + buf * BN;
           for (int kc = -1; kc < KC; ++kc) {      // kc == -1: the -|e|^2/2 step, which also overwrites the buffer
             tr0 = TR_NOW();
-            if (nt == 0 && kc >= 0) mbar_wait(bar(C::BAR_A_FULL + abuf * MAX_KC + kc), (it >> 1) & 1);
+            if (nt == nt0 && kc >= 0) mbar_wait(bar(C::BAR_A_FULL + abuf * MAX_KC + kc), (it >> 1) & 1);
             TR_ADD(tr_af, tr0);
             tr0 = TR_NOW();
             mbar_wait(bar(C::BAR_B_FULL + stage), phase);
@@ -598,12 +622,20 @@ bool vq_tensor_supported(int D, int K) {
 
 template <int CG>
 static int launch_search(const CUtensorMap& tmap, const float* z, const float* emax, int N, int D, int HW, int K,
-                         int wait_first, VqMeta* meta, uint2* list, cudaStream_t s) {
+                         int wait_first, bool allow_split, VqMeta* meta, uint2* list, cudaStream_t s) {
   using C = Cfg<CG>;
   const int num_ptiles = (N + BM * CG - 1) / (BM * CG);
   static const int pairs_env = getenv("DCVIC_VQ_PAIRS") ? atoi(getenv("DCVIC_VQ_PAIRS")) : 0;   // experiments
   const int max_pairs = (pairs_env > 0 && pairs_env < kNumSMs / CG) ? pairs_env : kNumSMs / CG;
-  const int grid = CG * (num_ptiles < max_pairs ? num_ptiles : max_pairs);
+  int npairs = num_ptiles < max_pairs ? num_ptiles : max_pairs;
+  // last-round split (see the kernel): two pairs per leftover tile when they fit; small inputs split every tile
+  static const bool split_off = getenv("DCVIC_VQ_SPLIT") && atoi(getenv("DCVIC_VQ_SPLIT")) == 0;
+  const int NT = K / BN;
+  const bool can_split = allow_split && !split_off && NT % 2 == 0;
+  if (can_split && 2 * num_ptiles <= max_pairs) npairs = 2 * num_ptiles;
+  const int rem = num_ptiles % npairs;
+  const int split = (can_split && rem > 0 && 2 * rem <= npairs) ? 2 : 1;
+  const int grid = CG * npairs;
   const int smem = C::SMEM_BYTES + 1024;
   if (cudaFuncSetAttribute(vq_tensor_search_kernel<CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) !=
       cudaSuccess)
@@ -622,7 +654,7 @@ static int launch_search(const CUtensorMap& tmap, const float* z, const float* e
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 2;
-  if (cudaLaunchKernelEx(&cfg, vq_tensor_search_kernel<CG>, tmap, z, emax, N, D, HW, K, num_ptiles, wait_first, meta,
+  if (cudaLaunchKernelEx(&cfg, vq_tensor_search_kernel<CG>, tmap, z, emax, N, D, HW, K, num_ptiles, wait_first, split, meta,
                          list) != cudaSuccess)
     return DCVIC_ERR_CUDA;
   return dcvic_launch_status();
@@ -637,7 +669,7 @@ namespace dcvic {
 #endif
 
 int vq_tensor_search(const float* z, const __half* cb16, const float* emax, int B, int D, int HW, int K,
-                     bool after_prepare, VqMeta* meta, uint2* list, cudaStream_t s) {
+                     bool after_prepare, bool allow_split, VqMeta* meta, uint2* list, cudaStream_t s) {
   if (!vq_tensor_supported(D, K)) return DCVIC_ERR_UNSUPPORTED;
   static const int cta_group = [] {
     const char* e = getenv("DCVIC_VQ_CTA_GROUP");
@@ -656,8 +688,8 @@ int vq_tensor_search(const float* z, const __half* cb16, const float* emax, int 
     return DCVIC_ERR_CUDA;
   const int N = B * HW;
   const int wait_first = after_prepare ? 0 : 1;
-  return cta_group == 2 ? launch_search<2>(tmap, z, emax, N, D, HW, K, wait_first, meta, list, s)
-                        : launch_search<1>(tmap, z, emax, N, D, HW, K, wait_first, meta, list, s);
+  return cta_group == 2 ? launch_search<2>(tmap, z, emax, N, D, HW, K, wait_first, allow_split, meta, list, s)
+                        : launch_search<1>(tmap, z, emax, N, D, HW, K, wait_first, allow_split, meta, list, s);
 }
 
 }  // namespace dcvic
