@@ -191,7 +191,7 @@ class _QuantizerBase(nn.Module):
 
     def freeze_codebook(self, frozen: bool = True):
         """Declare the codebook constant (DC-VIC always freezes the VQGAN,
-        src/trainer/rate_distortion_vq_code_trainer.py:62): |e|^2 and the BF16 copy used by the
+        src/trainer/rate_distortion_vq_code_trainer.py:62): |e|^2 and the FP16 copy used by the
         tensor-core search are then prepared once and reused while ``weight._version`` is unchanged."""
         self._frozen = bool(frozen)
         self._prep_key = None

@@ -36,14 +36,4 @@ for i, n in enumerate(names):
     col = [r[i] for r in rows if (i < 10 or r[13] > 0)]
     print(f"{n:18s} median {statistics.median(col):10.0f}  max {max(col):10.0f}  min {min(col):10.0f}")
 
-fb = (C.c_ulonglong * (4096 * 12))()
-lib.dcvic_debug_read_finish_trace.restype = C.c_int
-if lib.dcvic_debug_read_finish_trace(fb) == 0:
-    fn = ["stage z + lists", "re-rank", "gather", "store"]
-    rows = [[fb[b * 12 + i] for i in range(12)] for b in range(4096)]
-    rows = [r for r in rows if sum(r) > 0]
-    print("finish: CTAs traced", len(rows))
-    for i, n in enumerate(fn):
-        col = [r[i] for r in rows]
-        print(f"  {n:14s} median {statistics.median(col):9.0f}  max {max(col):9.0f}   (cycles per CTA, all its tiles)")
-    print("  total median", statistics.median([sum(r) for r in rows]))
+# (the finish kernel has its own tool: tools/trace_finish.py)
