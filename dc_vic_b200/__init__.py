@@ -8,7 +8,7 @@ from .entropy_models import (EntropyModel, EntropyBottleneck, GaussianConditiona
                              DcvicEntropyBottleneck, SteEntropyBottleneck, GaussianScaleConditional,
                              GaussianMeanScaleConditional, SteGaussianMeanScaleConditional, ste_round,
                              get_scale_table, pmf_to_quantized_cdf, likelihood_to_bit, batch_bits,
-                             gaussian_rate_dual)
+                             gaussian_rate_dual, gaussian_codec_step)
 from .register import install_compressai_shim, register_entropy_models, ENTROPY_MODEL_CLASSES
 
 __version__ = "0.1.0"

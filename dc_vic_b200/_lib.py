@@ -38,6 +38,7 @@ SIGNATURES = {
                                    _sz, _p]),
     "dcvic_gc_backward": (_i, [_p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _i64, _f, _f, _p, _p, _p, _p]),
     "dcvic_gc_build_indexes": (_i, [_p, _i64, _p, _i, _f, _p, _p]),
+    "dcvic_gc_codec_step": (_i, [_p, _p, _p, _i64, _i64, _i64, _i64, _i64, _p, _i, _f, _f, _p, _p, _p, _p, _p]),
     "dcvic_eb_workspace_bytes": (_sz, [_i, _i, _i]),
     "dcvic_eb_forward": (_i, [_p, _p, C.POINTER(_p), _i, _i, _i, _f, _i, _p, _p, _p, _p, _sz, _p]),
     "dcvic_eb_backward": (_i, [_p, _p, _p, C.POINTER(_p), _i, _i, _i, _f, _p, C.POINTER(_p), _p, _sz, _p]),

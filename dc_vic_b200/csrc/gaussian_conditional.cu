@@ -287,6 +287,45 @@ __global__ void __launch_bounds__(256) gc_build_indexes_kernel(const float* __re
   }
 }
 
+// Compress-side step of one CHARM slice (minnen20_charm_context_model.py:146-165 does these as four passes:
+// entropy_model_y(y, [mu, sigma], is_train=False), build_indexes(sigma), quantize(y, "symbols", mu)): dequantized
+// y_hat, its likelihood, the rANS symbol round(y - mu) and the scale-table index, from one read of y, mu, sigma.
+// Batched like gc_forward: per-batch strides for tensors that are channel slices of larger ones.
+__global__ void __launch_bounds__(256) gc_codec_step_kernel(const float* __restrict__ y, const float* __restrict__ mu,
+                                                             const float* __restrict__ sigma, long long n,
+                                                             long long y_bs, long long mu_bs, long long sg_bs,
+                                                             const float* __restrict__ table, int T,
+                                                             float scale_bound, float lik_bound,
+                                                             float* __restrict__ y_hat, float* __restrict__ lik,
+                                                             int32_t* __restrict__ symbols,
+                                                             int32_t* __restrict__ indexes) {
+  extern __shared__ float s_table[];
+  for (int i = threadIdx.x; i < T; i += blockDim.x) s_table[i] = table[i];
+  __syncthreads();
+  const long long b = blockIdx.y;
+  y += b * y_bs;
+  mu += b * mu_bs;
+  sigma += b * sg_bs;
+  const long long o = b * n;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+    const float yv = y[e], m = mu[e];
+    const float s = fmaxf(sigma[e], scale_bound);
+    const float q = rintf(__fsub_rn(yv, m));              // round-half-even, as torch.round
+    const float deq = __fadd_rn(q, m);
+    if (y_hat) y_hat[o + e] = deq;
+    if (lik) lik[o + e] = fmaxf(gc_lik(deq, m, s), lik_bound);
+    if (symbols) symbols[o + e] = (int32_t)q;
+    if (indexes) {
+      int lo = 0, hi = T - 1;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (s_table[mid] < s) lo = mid + 1; else hi = mid;
+      }
+      indexes[o + e] = lo;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256) ste_round_kernel(const float* __restrict__ x, long long n,
                                                          float* __restrict__ out) {
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
@@ -359,6 +398,20 @@ extern "C" int dcvic_gc_build_indexes(const float* sigma, int64_t n, const float
   DCVIC_CHECK_ARG(n > 0 && T >= 1 && T <= 4096);
   gc_build_indexes_kernel<<<min(ceil_div_i(n, 256), 8 * kNumSMs), 256, T * sizeof(float), (cudaStream_t)stream>>>(
       sigma, n, table, T, scale_bound, out);
+  return dcvic_launch_status();
+}
+
+extern "C" int dcvic_gc_codec_step(const float* y, const float* mu, const float* sigma, int64_t B, int64_t n,
+                                   int64_t y_bstride, int64_t mu_bstride, int64_t sigma_bstride, const float* table,
+                                   int T, float scale_bound, float lik_bound, float* y_hat, float* lik,
+                                   int32_t* symbols, int32_t* indexes, dcvic_stream_t stream) {
+  DCVIC_CHECK_ARG(y && mu && sigma && table);
+  DCVIC_CHECK_ARG(B > 0 && n > 0 && T >= 1 && T <= 4096 && B <= 65535);
+  DCVIC_CHECK_ARG(y_hat || lik || symbols || indexes);
+  dim3 grid((unsigned)min(ceil_div_i(n, 256), 8 * kNumSMs), (unsigned)B);
+  gc_codec_step_kernel<<<grid, 256, T * sizeof(float), (cudaStream_t)stream>>>(
+      y, mu, sigma, n, y_bstride, mu_bstride, sigma_bstride, table, T, scale_bound, lik_bound, y_hat, lik, symbols,
+      indexes);
   return dcvic_launch_status();
 }
 

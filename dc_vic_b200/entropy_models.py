@@ -383,6 +383,34 @@ def gaussian_rate_dual(y: Tensor, params: Tensor, noise: Tensor, scale_bound: fl
     return y_hat, lik, lik_q, bits, bits_q
 
 
+def gaussian_codec_step(y: Tensor, params: Tensor, scale_table: Tensor, scale_bound: float = 0.11,
+                        lik_bound: float = 1e-9):
+    """Compress-side step of one CHARM slice in one pass: what the reference computes with
+    ``entropy_model_y(y_slice, cat([mu, sigma]), is_train=False)`` (minnen20_charm_context_model.py:146) plus this
+    slice's share of ``build_indexes(y_scale)`` (:164) and of ``quantize(y, "symbols", means)`` inside ``compress``
+    (:165).  Returns ``(y_hat, likelihood, symbols int32, indexes int32)``, all shaped like ``y``."""
+    _lib.require_cuda(y, params, scale_table)
+    lib = _lib.load()
+    B = y.shape[0]
+    n = y.numel() // B
+    mean, std = params.chunk(2, 1)
+    yv, ys = _batch_view(y.detach(), B, n)
+    mv, ms = _batch_view(mean.detach(), B, n)
+    sv, ss = _batch_view(std.detach(), B, n)
+    table = scale_table.detach().to(y.device).contiguous().float()
+    dev = y.device
+    with _lib.on_device(dev):
+        y_hat = torch.empty(y.shape, dtype=torch.float32, device=dev)
+        lik = torch.empty_like(y_hat)
+        symbols = torch.empty(y.shape, dtype=torch.int32, device=dev)
+        indexes = torch.empty(y.shape, dtype=torch.int32, device=dev)
+        rc = lib.dcvic_gc_codec_step(_lib.ptr(yv), _lib.ptr(mv), _lib.ptr(sv), B, n, ys, ms, ss, _lib.ptr(table),
+                                     table.numel(), float(scale_bound), float(lik_bound), _lib.ptr(y_hat),
+                                     _lib.ptr(lik), _lib.ptr(symbols), _lib.ptr(indexes), _lib.cur_stream())
+        _lib.check(rc, "dcvic_gc_codec_step")
+    return y_hat, lik, symbols, indexes
+
+
 # ------------------------------------------------------------------------------ bottleneck
 class _BottleneckFn(torch.autograd.Function):
     N_PARAMS = 14

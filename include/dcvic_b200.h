@@ -156,6 +156,17 @@ int dcvic_gc_backward(const float* g_lik, const float* y, const float* mu, const
 int dcvic_gc_build_indexes(const float* sigma, int64_t n, const float* table, int T, float scale_bound,
                            int32_t* out, dcvic_stream_t stream);
 
+/* Compress-side step of one CHARM slice in one pass (replaces, per slice,
+ * entropy_model_y(y, [mu, sigma], is_train=False) at minnen20_charm_context_model.py:146 plus the slice's share of
+ * build_indexes (:164) and of quantize(y, "symbols", means) inside compress (:165)):
+ *   y_hat = round(y - mu) + mu, lik = max(likelihood(y_hat), lik_bound), symbols = int32(round(y - mu)),
+ *   indexes = build_indexes(sigma).  Tensors are [B, n] with per-batch strides (channel slices of larger tensors);
+ * outputs are dense [B, n]; any output may be NULL (at least one must not be). */
+int dcvic_gc_codec_step(const float* y, const float* mu, const float* sigma, int64_t B, int64_t n,
+                        int64_t y_bstride, int64_t mu_bstride, int64_t sigma_bstride, const float* table, int T,
+                        float scale_bound, float lik_bound, float* y_hat, float* lik, int32_t* symbols,
+                        int32_t* indexes, dcvic_stream_t stream);
+
 /* --------------------------------------------------------- EntropyBottleneck --------
  * Replaces compressai==1.2.4 EntropyBottleneck.forward/_likelihood/_logits_cumulative with
  * filters=(3,3,3,3) as called by src/models/subnet/entropy_model/entropy_bottleneck.py:13-28.

@@ -101,6 +101,66 @@ def test_gaussian_dual_matches_two_calls():
     assert rel_err(bits, O.batch_bits(lk_r)) < REL and rel_err(bits_q, O.batch_bits(lq_r)) < REL
 
 
+def test_codec_step_matches_the_reference_calls():
+    """One pass vs the reference's per-slice sequence (minnen20_charm_context_model.py:146,164,165): eval forward,
+    build_indexes, quantize(..., "symbols", means) - on channel slices of larger tensors (strided views)."""
+    y_all, p_all = entropy_inputs(4, B=2, C=64, H=16, W=24)
+    mu_all, sg_all = p_all.chunk(2, 1)
+    ref = O.SteGaussianMeanScaleConditional(scale_bound=0.11)
+    ref.update_scale_table(O.get_scale_table())
+    for c0 in (0, 32):
+        y, mu, sg = y_all[:, c0:c0 + 32], mu_all[:, c0:c0 + 32], sg_all[:, c0:c0 + 32]
+        params = torch.cat([mu, sg], 1)
+        with torch.no_grad():
+            yh_r, lk_r = ref(y, params, is_train=False)
+            idx_r = ref.build_indexes(sg)
+            sym_r = ref.quantize(y, "symbols", mu)
+        yd, pd = y_all.to(DEV)[:, c0:c0 + 32], torch.cat([mu_all.to(DEV)[:, c0:c0 + 32], sg_all.to(DEV)[:, c0:c0 + 32]], 1)
+        yh, lk, sym, idx = D.gaussian_codec_step(yd, pd, D.get_scale_table().to(DEV))
+        assert torch.equal(yh.cpu(), yh_r) and rel_err(lk, lk_r) < REL
+        assert sym.dtype == torch.int32 and torch.equal(sym.cpu(), sym_r.to(torch.int32))
+        assert idx.dtype == torch.int32 and torch.equal(idx.cpu(), idx_r.to(torch.int32))
+
+
+def test_slice_loop_is_cuda_graph_capturable():
+    """The entropy kernels take no host round trip, so a CHARM-like 6-slice loop (stand-in 1x1 convolutions for the
+    slice transforms) can be captured once and replayed: replay == eager, for new input contents."""
+    torch.manual_seed(5)
+    B, C, H, W, S = 2, 192, 16, 16, 6
+    cs = C // S
+    convs = [torch.nn.Conv2d(C + i * cs, 2 * cs, 1).to(DEV) for i in range(S)]
+    g = D.SteGaussianMeanScaleConditional(scale_bound=0.11).to(DEV)
+    y = torch.randn(B, C, H, W, device=DEV)
+    hyper = torch.randn(B, C, H, W, device=DEV)
+
+    def loop():
+        hats, bits = [], []
+        for i, ys in enumerate(y.chunk(S, 1)):
+            params = convs[i](torch.cat([hyper] + hats, 1))
+            y_hat, lik = g(ys, params, is_train=False)
+            hats.append(y_hat)
+            bits.append(D.batch_bits(lik))
+        return torch.cat(hats, 1), torch.stack(bits).sum(0)
+
+    with torch.no_grad():
+        for _ in range(3):                                    # warm-up on a side stream, as capture requires
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                loop()
+            torch.cuda.current_stream().wait_stream(s)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            out_hat, out_bits = loop()
+        for seed in (6, 7):
+            torch.manual_seed(seed)
+            y.copy_(torch.randn(B, C, H, W, device=DEV))
+            hyper.copy_(torch.randn(B, C, H, W, device=DEV))
+            graph.replay()
+            ref_hat, ref_bits = loop()
+            assert torch.equal(out_hat, ref_hat) and torch.equal(out_bits, ref_bits)
+
+
 def test_build_indexes_and_tables():
     table = O.get_scale_table()
     ref = O.GaussianMeanScaleConditional(scale_bound=0.11)
