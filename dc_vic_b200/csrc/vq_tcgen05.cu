@@ -41,7 +41,26 @@ constexpr int MAX_KC = 4;        // e_dim <= 256
 constexpr int A_CHUNK_BYTES = BM * BK * 2;            // 16 KB
 constexpr int A_BUF_BYTES = MAX_KC * A_CHUNK_BYTES;   // 64 KB
 constexpr int MAX_K = 4096;
+#ifndef DCVIC_SEARCH_SETS
+#define DCVIC_SEARCH_SETS 3       // register sets of operand loads in flight per producer thread (2: the older loop)
+#endif
+// Three producer sets: 20 warps (two idle ones complete the fifth warpgroup, so that every setmaxnreg is executed by a
+// whole warpgroup) launch with 96 registers each = 61,440; producers take 136, epilogue warps keep 88, the
+// TMA / MMA / idle warpgroup drops to 32:  8*32*136 + 8*32*88 + 4*32*32 = 61,440.
+#ifndef DCVIC_SEARCH_PROD_REGS
+#define DCVIC_SEARCH_PROD_REGS 136
+#endif
+#ifndef DCVIC_SEARCH_EPI_REGS
+#define DCVIC_SEARCH_EPI_REGS 88
+#endif
+#ifndef DCVIC_SEARCH_AUX_REGS
+#define DCVIC_SEARCH_AUX_REGS 32
+#endif
+#if DCVIC_SEARCH_SETS == 3
+constexpr int NTHREADS = 640;
+#else
 constexpr int NTHREADS = 576;
+#endif
 constexpr int NPROD = 8;                       // A-producer warps (warps 0-7); epilogue warps 8-15
 constexpr int WARP_TMA = 16, WARP_MMA = 17;
 constexpr int ZZ_SLOTS = 4;
@@ -360,6 +379,79 @@ vq_tensor_search_kernel(const __grid_constant__ CUtensorMap tmap_cb, const float
       for (int k = 0; k < 8; ++k)
         v[k] = valid ? ldg_stream(reinterpret_cast<const float4*>(p + (size_t)k * sHW)) : make_float4(0.f, 0.f, 0.f, 0.f);
     };
+#if DCVIC_SEARCH_SETS == 3
+    // Three register sets in flight per thread (96 KB per SM instead of 64: the producers, not the tensor pipe, set
+    // the pace of this kernel).  The steps of all this pair's tiles form one stream s = 0, 1, 2, ...
+    // (tile = s / KC, chunk = s % KC); step s lives in set s % 3: store it, then request step s + 3 into the same
+    // registers.  The extra registers come from setmaxnreg (the epilogue warps give some of theirs up).
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(DCVIC_SEARCH_PROD_REGS));
+    float4 vc[8];
+    const int total_steps = my_tiles * KC;
+    // load cursor (three steps ahead of the store cursor)
+    int lit = 0, lkc = 0;
+    bool lvalid;
+    const float* lzc = tile_ptr(0, lvalid);
+    auto load_next = [&](float4 (&v)[8]) {
+      load_step(v, lzc, lvalid, lkc);
+      if (++lkc == KC) { lkc = 0; ++lit; lzc = tile_ptr(lit, lvalid); }
+    };
+    // store cursor
+    int sit = 0, skc = 0;
+    float zz4[4] = {0.f, 0.f, 0.f, 0.f};
+    unsigned long long tr0 = 0;
+    auto store_next = [&](const float4 (&v)[8]) {
+      const int abuf = sit & 1;
+      if (skc == 0) {
+        tr0 = TR_NOW();
+        mbar_wait(bar(C::BAR_A_EMPTY + abuf), ((sit >> 1) & 1) ^ 1);
+        TR_ADD(tr_wait, tr0);
+        tr0 = TR_NOW();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) zz4[i] = 0.f;
+      }
+      uint8_t* a = smem + C::OFF_A + abuf * A_BUF_BYTES + row0 * 128 + skc * A_CHUNK_BYTES;
+      const float* f = reinterpret_cast<const float*>(v);     // f[4k + i] = channel k, token i
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        uint4 pk;
+        pk.x = pack_f16x2(f[0 + i], f[4 + i]);
+        pk.y = pack_f16x2(f[8 + i], f[12 + i]);
+        pk.z = pack_f16x2(f[16 + i], f[20 + i]);
+        pk.w = pack_f16x2(f[24 + i], f[28 + i]);
+        const int r7 = (row0 + i) & 7;
+        *reinterpret_cast<uint4*>(a + i * 128 + ((g ^ r7) << 4)) = pk;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) zz4[i] = fmaf(f[4 * k + i], f[4 * k + i], zz4[i]);
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) arrive_leader(leader_bar(C::BAR_A_FULL + abuf * MAX_KC + skc));
+      if (skc == KC - 1) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          zz4[i] += __shfl_xor_sync(0xffffffffu, zz4[i], 1);
+          zz4[i] += __shfl_xor_sync(0xffffffffu, zz4[i], 2);
+        }
+        if (cg == 0)
+          *reinterpret_cast<float4*>(s_zz + ((sit & (ZZ_SLOTS - 1)) * 2 + ch) * BM + row0) =
+              make_float4(zz4[0], zz4[1], zz4[2], zz4[3]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(C::BAR_ZZ + (sit & (ZZ_SLOTS - 1))));
+        TR_ADD(tr_work, tr0);
+      }
+      if (++skc == KC) { skc = 0; ++sit; }
+    };
+    load_next(va);
+    load_next(vb);
+    load_next(vc);
+#pragma unroll 1
+    for (int s0 = 0; s0 < total_steps; s0 += 3) {
+      store_next(va);
+      load_next(va);
+      if (s0 + 1 < total_steps) { store_next(vb); load_next(vb); }
+      if (s0 + 2 < total_steps) { store_next(vc); load_next(vc); }
+    }
+#else
     bool valid;
     const float* zc = tile_ptr(0, valid);
     load_step(va, zc, valid, 0);
@@ -416,9 +508,13 @@ vq_tensor_search_kernel(const __grid_constant__ CUtensorMap tmap_cb, const float
       if (lane == 0) mbar_arrive(bar(C::BAR_ZZ + (it & (ZZ_SLOTS - 1))));
       TR_ADD(tr_work, tr0);
     }
+#endif
     if (threadIdx.x == 0) { TR_PUT(0, tr_wait); TR_PUT(1, tr_work); }
   } else if (warp < NPROD + 8) {
     // ===================== epilogue: flag masks per 32 codes, running max per row =====================
+#if DCVIC_SEARCH_SETS == 3
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(DCVIC_SEARCH_EPI_REGS));
+#endif
     const int q = (warp - NPROD) >> 2;            // column half of every accumulator this warp quad drains
     const int part = warp & 3;                    // TMEM lane quarter this warp may access
     const int row = part * 32 + lane;
@@ -512,6 +608,9 @@ vq_tensor_search_kernel(const __grid_constant__ CUtensorMap tmap_cb, const float
     if (part == 0 && lane == 0) { TR_PUT(2 + 4 * q, tr_zz); TR_PUT(3 + 4 * q, tr_full); TR_PUT(4 + 4 * q, tr_proc); }
   } else if (warp == WARP_TMA) {
     // ===================== TMA producer: this CTA's half of every codebook tile =====================
+#if DCVIC_SEARCH_SETS == 3
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(DCVIC_SEARCH_AUX_REGS));
+#endif
     if (lane == 0) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_cb) : "memory");
       pdl_wait();                                 // the FP16 codebook is written by the prepare kernel
@@ -527,9 +626,12 @@ vq_tensor_search_kernel(const __grid_constant__ CUtensorMap tmap_cb, const float
             if (++stage == C::NSTAGE) { stage = 0; phase ^= 1; }
           }
     }
-  } else if (leader) {
-    // ===================== MMA issuer (leader CTA, one thread) =====================
-    if (lane == 0) {
+  } else {
+    // ===================== MMA issuer (leader CTA, one thread); idle warps of the last warpgroup ==========
+#if DCVIC_SEARCH_SETS == 3
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(DCVIC_SEARCH_AUX_REGS));
+#endif
+    if (warp == WARP_MMA && leader && lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
       uint32_t g = 0;   // running N-tile counter -> TMEM buffer g & 1
