@@ -941,13 +941,21 @@ __global__ void __launch_bounds__(T * 8, DT ? 1024 / (T * 8) : 1) vq_finish_v5_k
 
 // Sum of the per-warp loss partials in index order -> the reference's loss scalar.  One CTA; launched with
 // programmatic dependent launch right behind the finish kernel.
-__global__ void __launch_bounds__(256) vq_loss_finalize_kernel(const double* __restrict__ partials, int n,
-                                                                long long numel, float beta, int legacy,
-                                                                float* __restrict__ loss) {
+__global__ void __launch_bounds__(1024) vq_loss_finalize_kernel(const double* __restrict__ partials, int n,
+                                                                 long long numel, float beta, int legacy,
+                                                                 float* __restrict__ loss) {
   __shared__ double scratch[32];
   pdl_wait();
+  // fixed assignment of partials to threads and a fixed tree: the same bits on every run.  Up to eight loads in
+  // flight per thread (one dependent load per iteration made this one-CTA kernel several microseconds long).
   double acc = 0.0;
-  for (int i = threadIdx.x; i < n; i += 256) acc += partials[i];
+  for (int i0 = threadIdx.x; i0 < n; i0 += 8 * 1024) {
+    double v[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) v[r] = (i0 + r * 1024) < n ? __ldcg(partials + i0 + r * 1024) : 0.0;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) acc += v[r];
+  }
   const double tot = block_sum(acc, scratch);
   if (threadIdx.x == 0) write_loss(tot, numel, beta, legacy, loss);
 }
@@ -956,7 +964,7 @@ int vq_launch_loss_finalize(const double* partials, int n, long long numel, floa
                             cudaStream_t s) {
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(1);
-  cfg.blockDim = dim3(256);
+  cfg.blockDim = dim3(1024);
   cfg.stream = s;
   cudaLaunchAttribute pdl[1];
   pdl[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -1000,7 +1008,7 @@ int vq_finish(const float* z, const float* E, const float* ee, const float* emax
                            legacy, zq, idx, loss, partials, counters) != cudaSuccess)                              \
       return DCVIC_ERR_CUDA;                                                                                       \
     cfg.gridDim = dim3(1);                                                                                         \
-    cfg.blockDim = dim3(256);                                                                                      \
+    cfg.blockDim = dim3(1024);                                                                                     \
     cfg.dynamicSmemBytes = 0;                                                                                      \
     if (cudaLaunchKernelEx(&cfg, vq_loss_finalize_kernel, (const double*)partials, ceil_div_i(N, T) * (T / 4),      \
                            (long long)N * D, beta, legacy, loss) != cudaSuccess)                                   \
