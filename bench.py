@@ -259,14 +259,15 @@ def run_ours(args):
     t_full = max_over_ranks(timed(vq_step, K_steps, W_steps, barrier))
     # the same step with the codebook prepared once (DC-VIC freezes the VQGAN codebook; the module sets this flag)
     t_frozen = max_over_ranks(timed(lambda i: vq_step(i, _lib.VQ_REUSE_PREP), K_steps, W_steps, barrier))
-    # dominant kernel alone (same launches, search stage only) for the roofline
-    # stages as differences of the same pipelined launches cut short (the kernels overlap under programmatic
-    # dependent launch, so a stage's cost is what the step grows by when it is added)
-    t_prep = timed(lambda i: vq_step(i, _lib.VQ_STAGE_PREP_ONLY), K_steps, W_steps, barrier)
-    t_prep_search = timed(lambda i: vq_step(i, _lib.VQ_STAGE_SEARCH_ONLY), K_steps, W_steps, barrier)
-    t_search = max(t_prep_search - t_prep, 0.0)
-    # the finish stage needs lists that belong to the same z, so it is timed as whole step minus the stages before it
-    t_finish = max(t_full - t_prep_search, 0.0)
+    # Dominant kernel for the roofline: the search launched alone, back to back, codebook already prepared.  Each
+    # launch then waits for its predecessor before it reads z, so nothing of it is hidden behind another kernel:
+    # this is the kernel's own average launch duration (a conservative figure - inside the full step its first
+    # tile loads while the prepare kernel runs).  40 us of GPU work per launch keep the chain GPU-bound; a chain
+    # of prepare-only launches is host-bound and its time is not used for anything.
+    t_search = timed(lambda i: vq_step(i, _lib.VQ_STAGE_SEARCH_ONLY | _lib.VQ_REUSE_PREP), K_steps, W_steps, barrier)
+    # stages as differences of pipelined steps: what the step grows by when a stage is added
+    t_prep = max(t_full - t_frozen, 0.0)                      # codebook prepare (marginal cost inside the step)
+    t_finish = max(t_frozen - t_search, 0.0)                  # finish + loss finalize
     clocks = sampler.stop(t_clk0, time.perf_counter())
 
     value = world * N * K_steps / t_full
