@@ -262,15 +262,24 @@ using namespace tc;
 
 // Optional role timing (build with -DDCVIC_TRACE; tools/trace_run.py): cycles each warp role spends
 // waiting / working, summed over the launch, per CTA.
+// Role timing (-DDCVIC_TRACE): the MMA issuer's waits always; the other roles only with -DDCVIC_TRACE_ALL (their
+// counters cost registers that the setmaxnreg split does not have to spare, and perturb the kernel by 30 %).
 #ifdef DCVIC_TRACE
 __device__ unsigned long long g_trace[kNumSMs * 2][16];
+#define TRM_NOW() clock64()
+#define TRM_ADD(acc, t0) acc += clock64() - (t0)
+#define TR_PUT(slot, v) g_trace[blockIdx.x][slot] = (v)
+#else
+#define TRM_NOW() 0ull
+#define TRM_ADD(acc, t0) (void)(t0)
+#define TR_PUT(slot, v)
+#endif
+#if defined(DCVIC_TRACE) && defined(DCVIC_TRACE_ALL)
 #define TR_NOW() clock64()
 #define TR_ADD(acc, t0) acc += clock64() - (t0)
-#define TR_PUT(slot, v) g_trace[blockIdx.x][slot] = (v)
 #else
 #define TR_NOW() 0ull
 #define TR_ADD(acc, t0) (void)(t0)
-#define TR_PUT(slot, v)
 #endif
 
 template <int CG>
@@ -637,24 +646,24 @@ vq_tensor_search_kernel(const __grid_constant__ CUtensorMap tmap_cb, const float
       uint32_t g = 0;   // running N-tile counter -> TMEM buffer g & 1
       const uint32_t rt_one = my_tiles > 0 ? 1u : 0u;   // 1, but not a compile-time constant
       [[maybe_unused]] unsigned long long tr_te = 0, tr_af = 0, tr_bf = 0, tr0;
-      [[maybe_unused]] const unsigned long long tr_start = TR_NOW();
+      [[maybe_unused]] const unsigned long long tr_start = TRM_NOW();
       for (int it = 0; it < my_tiles; ++it) {
         const int abuf = it & 1;
         const int nt0 = unit_nt0(it), nt1 = unit_nt1(it);
         for (int nt = nt0; nt < nt1; ++nt, ++g) {
           const uint32_t buf = g & 1;
-          tr0 = TR_NOW();
+          tr0 = TRM_NOW();
           if (g >= 2) mbar_wait(bar(C::BAR_T_EMPTY + buf), ((g >> 1) - 1) & 1);   // both CTAs drained this buffer
-          TR_ADD(tr_te, tr0);
+          TRM_ADD(tr_te, tr0);
           tc_fence_after();
           const uint32_t tmem_d = tmem_base + buf * BN;
           for (int kc = -1; kc < KC; ++kc) {      // kc == -1: the -|e|^2/2 step, which also overwrites the buffer
-            tr0 = TR_NOW();
+            tr0 = TRM_NOW();
             if (nt == nt0 && kc >= 0) mbar_wait(bar(C::BAR_A_FULL + abuf * MAX_KC + kc), (it >> 1) & 1);
-            TR_ADD(tr_af, tr0);
-            tr0 = TR_NOW();
+            TRM_ADD(tr_af, tr0);
+            tr0 = TRM_NOW();
             mbar_wait(bar(C::BAR_B_FULL + stage), phase);
-            TR_ADD(tr_bf, tr0);
+            TRM_ADD(tr_bf, tr0);
             tc_fence_after();
             // Descriptors advance by 32 bytes (2 in the >>4 address field) per K=16 step.  The accumulate flags
             // are run-time values on purpose: with a literal 0 ptxas 12.9 emitted a predicated UTCHMMA whose
@@ -675,7 +684,7 @@ vq_tensor_search_kernel(const __grid_constant__ CUtensorMap tmap_cb, const float
         }
         umma_commit<CG>(bar(C::BAR_A_EMPTY + abuf));          // operand tile may be overwritten
       }
-      TR_PUT(10, tr_te); TR_PUT(11, tr_af); TR_PUT(12, tr_bf); TR_PUT(13, TR_NOW() - tr_start);
+      TR_PUT(10, tr_te); TR_PUT(11, tr_af); TR_PUT(12, tr_bf); TR_PUT(13, TRM_NOW() - tr_start);
     }
   }
 

@@ -1,6 +1,9 @@
 """Role timing of the tcgen05 search kernel (needs `python -m dc_vic_b200.build --trace` first).
     DCVIC_B200_LIB=dc_vic_b200/lib/libdcvic_b200_trace.so python tools/trace_run.py [D0|D1b]
 Prints, per role, the cycles spent waiting / working summed over the launch (median and max over CTAs).
+Only the MMA issuer's rows are filled unless the library was built with -DDCVIC_TRACE_ALL as well
+(`python -m dc_vic_b200.build --trace -DDCVIC_TRACE_ALL`); any tracing slows this kernel by 30 %: its warps have no
+registers to spare, so read the proportions, not the totals.
 """
 import ctypes as C
 import os
