@@ -291,6 +291,7 @@ __global__ void __launch_bounds__(256) gc_build_indexes_kernel(const float* __re
 // entropy_model_y(y, [mu, sigma], is_train=False), build_indexes(sigma), quantize(y, "symbols", mu)): dequantized
 // y_hat, its likelihood, the rANS symbol round(y - mu) and the scale-table index, from one read of y, mu, sigma.
 // Batched like gc_forward: per-batch strides for tensors that are channel slices of larger ones.
+template <bool VEC>
 __global__ void __launch_bounds__(256) gc_codec_step_kernel(const float* __restrict__ y, const float* __restrict__ mu,
                                                              const float* __restrict__ sigma, long long n,
                                                              long long y_bs, long long mu_bs, long long sg_bs,
@@ -307,21 +308,46 @@ __global__ void __launch_bounds__(256) gc_codec_step_kernel(const float* __restr
   mu += b * mu_bs;
   sigma += b * sg_bs;
   const long long o = b * n;
-  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
-    const float yv = y[e], m = mu[e];
-    const float s = fmaxf(sigma[e], scale_bound);
+  auto one = [&](float yv, float m, float sg, float& deq, float& lk, int& sym, int& ix) {
+    const float s = fmaxf(sg, scale_bound);
     const float q = rintf(__fsub_rn(yv, m));              // round-half-even, as torch.round
-    const float deq = __fadd_rn(q, m);
-    if (y_hat) y_hat[o + e] = deq;
-    if (lik) lik[o + e] = fmaxf(gc_lik(deq, m, s), lik_bound);
-    if (symbols) symbols[o + e] = (int32_t)q;
-    if (indexes) {
-      int lo = 0, hi = T - 1;
-      while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if (s_table[mid] < s) lo = mid + 1; else hi = mid;
-      }
-      indexes[o + e] = lo;
+    deq = __fadd_rn(q, m);
+    lk = fmaxf(gc_lik(deq, m, s), lik_bound);
+    sym = (int)q;
+    int lo = 0, hi = T - 1;                               // #{ j < T-1 : table[j] < s }
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (s_table[mid] < s) lo = mid + 1; else hi = mid;
+    }
+    ix = lo;
+  };
+  if (VEC) {                                              // n % 4 == 0, all pointers and strides 16-byte aligned
+    const long long n4 = n >> 2;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n4; e += (long long)gridDim.x * blockDim.x) {
+      const float4 yv = ldg_stream(reinterpret_cast<const float4*>(y) + e);
+      const float4 mv = ldg_stream(reinterpret_cast<const float4*>(mu) + e);
+      const float4 sv = ldg_stream(reinterpret_cast<const float4*>(sigma) + e);
+      float4 d, l;
+      int4 sy, ix;
+      one(yv.x, mv.x, sv.x, d.x, l.x, sy.x, ix.x);
+      one(yv.y, mv.y, sv.y, d.y, l.y, sy.y, ix.y);
+      one(yv.z, mv.z, sv.z, d.z, l.z, sy.z, ix.z);
+      one(yv.w, mv.w, sv.w, d.w, l.w, sy.w, ix.w);
+      const long long w = (o >> 2) + e;
+      if (y_hat) stg_stream(reinterpret_cast<float4*>(y_hat) + w, d);
+      if (lik) stg_stream(reinterpret_cast<float4*>(lik) + w, l);
+      if (symbols) reinterpret_cast<int4*>(symbols)[w] = sy;
+      if (indexes) reinterpret_cast<int4*>(indexes)[w] = ix;
+    }
+  } else {
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+      float d, l;
+      int sy, ix;
+      one(y[e], mu[e], sigma[e], d, l, sy, ix);
+      if (y_hat) y_hat[o + e] = d;
+      if (lik) lik[o + e] = l;
+      if (symbols) symbols[o + e] = sy;
+      if (indexes) indexes[o + e] = ix;
     }
   }
 }
@@ -408,10 +434,19 @@ extern "C" int dcvic_gc_codec_step(const float* y, const float* mu, const float*
   DCVIC_CHECK_ARG(y && mu && sigma && table);
   DCVIC_CHECK_ARG(B > 0 && n > 0 && T >= 1 && T <= 4096 && B <= 65535);
   DCVIC_CHECK_ARG(y_hat || lik || symbols || indexes);
-  dim3 grid((unsigned)min(ceil_div_i(n, 256), 8 * kNumSMs), (unsigned)B);
-  gc_codec_step_kernel<<<grid, 256, T * sizeof(float), (cudaStream_t)stream>>>(
-      y, mu, sigma, n, y_bstride, mu_bstride, sigma_bstride, table, T, scale_bound, lik_bound, y_hat, lik, symbols,
-      indexes);
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  const bool vec = n % 4 == 0 && y_bstride % 4 == 0 && mu_bstride % 4 == 0 && sigma_bstride % 4 == 0 && al16(y) &&
+                   al16(mu) && al16(sigma) && al16(y_hat) && al16(lik) && al16(symbols) && al16(indexes);
+  const long long per = vec ? n / 4 : n;
+  dim3 grid((unsigned)min(ceil_div_i(per, 256), 16 * kNumSMs), (unsigned)B);
+  if (vec)
+    gc_codec_step_kernel<true><<<grid, 256, T * sizeof(float), (cudaStream_t)stream>>>(
+        y, mu, sigma, n, y_bstride, mu_bstride, sigma_bstride, table, T, scale_bound, lik_bound, y_hat, lik, symbols,
+        indexes);
+  else
+    gc_codec_step_kernel<false><<<grid, 256, T * sizeof(float), (cudaStream_t)stream>>>(
+        y, mu, sigma, n, y_bstride, mu_bstride, sigma_bstride, table, T, scale_bound, lik_bound, y_hat, lik, symbols,
+        indexes);
   return dcvic_launch_status();
 }
 
