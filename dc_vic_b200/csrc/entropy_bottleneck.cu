@@ -260,6 +260,14 @@ __global__ void __launch_bounds__(64) eb_unpack_grads_kernel(const float* __rest
 constexpr int kRateThreads = 256;
 constexpr int kRateChunk = kRateThreads * 4 * 8;
 
+// log2 on the SFU (2^-22 relative error, denormals handled): the full-precision logf made this read-only reduction
+// compute-bound (20 instructions per element)
+__device__ __forceinline__ float rate_lg2(float x) {
+  float r;
+  asm("lg2.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
 __global__ void __launch_bounds__(kRateThreads) rate_partial_kernel(const float* __restrict__ lik, long long n,
                                                                      double* __restrict__ part, int vec) {
   __shared__ double scratch[32];
@@ -273,13 +281,13 @@ __global__ void __launch_bounds__(kRateThreads) rate_partial_kernel(const float*
       const long long e = start + ((long long)i * kRateThreads + threadIdx.x) * 4;
       if (e < n) {
         const float4 v = ldg_stream(reinterpret_cast<const float4*>(p + e));
-        acc += (logf(v.x) + logf(v.y)) + (logf(v.z) + logf(v.w));
+        acc += (rate_lg2(v.x) + rate_lg2(v.y)) + (rate_lg2(v.z) + rate_lg2(v.w));
       }
     }
   } else {
     for (int i = 0; i < 32; ++i) {
       const long long e = start + (long long)i * kRateThreads + threadIdx.x;
-      if (e < n) acc += logf(p[e]);
+      if (e < n) acc += rate_lg2(p[e]);
     }
   }
   const double s = block_sum((double)acc, scratch);
@@ -294,8 +302,8 @@ __global__ void __launch_bounds__(128) rate_finalize_kernel(const double* __rest
   double s = 0.0;
   for (int j = lane; j < per; j += 32) s += part[b * per + j];
   s = warp_sum(s);
-  // -(sum ln L) / ln 2, like the reference (float32 sum divided by np.log(2))
-  if (lane == 0) bits[b] = (float)(-s / 0.69314718055994530942);
+  // -(sum ln L) / ln 2 of the reference = -(sum log2 L)
+  if (lane == 0) bits[b] = (float)(-s);
 }
 
 __global__ void __launch_bounds__(256) rate_backward_kernel(const float* __restrict__ lik,
