@@ -1139,6 +1139,78 @@ __global__ void __launch_bounds__(256) vq_backward_kernel(const float* __restric
     }
 }
 
+// 128-bit version (H*W % 4 == 0, 16-byte aligned tensors): a thread moves 4 consecutive tokens of one channel per
+// load / store (lane = 4*token quad + channel offset: the 4 scalar shared-memory accesses of a float4 fall on 32
+// distinct banks across the warp), eight such loads in flight per thread.  Same arithmetic as vq_backward_kernel.
+__global__ void __launch_bounds__(256) vq_backward_vec_kernel(const float* __restrict__ g_zq,
+                                                               const float* __restrict__ g_loss,
+                                                               const float* __restrict__ z, const float* __restrict__ E,
+                                                               const int64_t* __restrict__ idx, int N, int D, int HW,
+                                                               int K, float coef_z, float coef_e,
+                                                               float* __restrict__ dz, float* __restrict__ dE) {
+  extern __shared__ __align__(16) float buf[];  // [D][33] z, then dz
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int tq = lane >> 2, cq = lane & 3;
+  const int t0 = blockIdx.x * kFinishTokens;
+  const int tokq = t0 + 4 * tq;
+  const bool qvalid = tokq < N;                 // N % 4 == 0: quads are valid as a whole
+  const size_t qbase = qvalid ? ((size_t)(tokq / HW) * D * HW + (size_t)(tokq % HW)) : 0;
+  const float gl = g_loss ? *g_loss : 0.f;
+  const float scale = 2.f / ((float)N * (float)D);
+  const float az = gl * coef_z * scale, ae = gl * coef_e * scale;
+  const int c_first = wid * 4 + cq;             // this thread's channels: c_first + 32 k
+
+  for (int c0 = c_first; c0 < D; c0 += 256) {
+    float4 v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int c = c0 + 32 * k;
+      v[k] = (qvalid && c < D) ? ldg_stream(reinterpret_cast<const float4*>(z + qbase + (size_t)c * HW))
+                               : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int c = c0 + 32 * k;
+      if (c < D) {
+        float* b = buf + c * 33 + 4 * tq;
+        b[0] = v[k].x; b[1] = v[k].y; b[2] = v[k].z; b[3] = v[k].w;
+      }
+    }
+  }
+  __syncthreads();
+  for (int tok = wid; tok < kFinishTokens; tok += 8) {
+    const int t = t0 + tok;
+    if (t >= N) break;
+    const int k = min(max((int)idx[t], 0), K - 1);
+    const float* er = E + (size_t)k * D;
+    for (int c = lane; c < D; c += 32) {
+      const float diff = buf[c * 33 + tok] - er[c];  // z - e
+      buf[c * 33 + tok] = az * diff;
+      if (dE) atomicAdd(dE + (size_t)k * D + c, -ae * diff);
+    }
+  }
+  __syncthreads();
+  if (qvalid && dz)
+    for (int c0 = c_first; c0 < D; c0 += 256) {
+      float4 g[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int c = c0 + 32 * k;
+        g[k] = (g_zq && c < D) ? ldg_stream(reinterpret_cast<const float4*>(g_zq + qbase + (size_t)c * HW))
+                               : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int c = c0 + 32 * k;
+        if (c < D) {
+          const float* b = buf + c * 33 + 4 * tq;
+          stg_stream(reinterpret_cast<float4*>(dz + qbase + (size_t)c * HW),
+                     make_float4(g[k].x + b[0], g[k].y + b[1], g[k].z + b[2], g[k].w + b[3]));
+        }
+      }
+    }
+}
+
 }  // namespace dcvic
 
 using namespace dcvic;
@@ -1157,10 +1229,12 @@ extern "C" int dcvic_vq_backward(const float* g_zq, const float* g_loss, const f
   if (dE && cudaMemsetAsync(dE, 0, (size_t)K * D * sizeof(float), s) != cudaSuccess) return DCVIC_ERR_CUDA;
   // legacy: loss = mean((sg(zq)-z)^2) + beta*mean((zq-sg(z))^2): z gets coefficient 1, E gets beta
   const float coef_z = legacy ? 1.f : beta, coef_e = legacy ? beta : 1.f;
-  if (smem > 48 * 1024)
-    cudaFuncSetAttribute(vq_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  vq_backward_kernel<<<ceil_div_i(N, kFinishTokens), 256, smem, s>>>(g_zq, g_loss, z_nchw, codebook, idx, N, D, HW, K,
-                                                                      coef_z, coef_e, dz, dE);
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  const bool vec = HW % 4 == 0 && al16(z_nchw) && al16(g_zq) && al16(dz);
+  auto kern = vec ? vq_backward_vec_kernel : vq_backward_kernel;
+  if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  kern<<<ceil_div_i(N, kFinishTokens), 256, smem, s>>>(g_zq, g_loss, z_nchw, codebook, idx, N, D, HW, K, coef_z, coef_e,
+                                                       dz, dE);
   return dcvic_launch_status();
 }
 

@@ -49,6 +49,38 @@ def bwd(i):
 
 report("VQ backward (dz + dE), C2", timeit(bwd), N * (3 * 4 * Dm + 8) + 4 * K * Dm)
 
+
+def bwd_z(i):
+    j = i % ROT
+    zq, loss, _ = outs[j]
+    torch.autograd.grad([zq, loss], [zs[j]], [gz[j], torch.ones_like(loss)], retain_graph=True)
+
+
+report("VQ backward (dz only: frozen codebook), C2", timeit(bwd_z), N * (3 * 4 * Dm + 8))
+
+# the same through the C ABI (no autograd engine in the way)
+import ctypes as C  # noqa: E402
+from dc_vic_b200 import _lib  # noqa: E402
+lib = _lib.load()
+dzs = [torch.empty(B, Dm, H, W, device=dev) for _ in range(ROT)]
+dE = torch.empty(K, Dm, device=dev)
+one = torch.ones((), device=dev)
+zd = [z.detach() for z in zs]
+idx64 = [o[2][2].reshape(-1) for o in outs]
+Ew = m.embedding.weight.detach()
+
+
+def bwd_abi(i, with_dE):
+    j = i % ROT
+    rc = lib.dcvic_vq_backward(_lib.ptr(gz[j]), _lib.ptr(one), _lib.ptr(zd[j]), _lib.ptr(Ew), _lib.ptr(idx64[j]),
+                               B, Dm, H, W, K, 0.25, 1, _lib.ptr(dzs[j]), _lib.ptr(dE) if with_dE else None,
+                               _lib.cur_stream())
+    assert rc == 0
+
+
+report("  C ABI: dz + dE", timeit(lambda i: bwd_abi(i, True)), N * (3 * 4 * Dm + 8) + 4 * K * Dm)
+report("  C ABI: dz only", timeit(lambda i: bwd_abi(i, False)), N * (3 * 4 * Dm + 8))
+
 idx = [o[2][2] for o in outs]
 with torch.no_grad():
     report("codebook gather -> NCHW, C2", timeit(lambda i: D.codebook_lookup(idx[i % ROT], m.embedding.weight)),
