@@ -302,9 +302,9 @@ vq_tensor_search_kernel(const __grid_constant__ CUtensorMap tmap_cb, const float
   // may start as soon as SMs free up: it only touches z until it waits for this grid.
   // wait_first: the predecessor in the stream is not one of this library's kernels (frozen codebook, no prepare
   // launch) and may be the producer of z, so nothing here - and, through the trigger below, nothing in the finish
-  // kernel - may read z before it has completed.
-  if (wait_first) pdl_wait();
-  pdl_launch_dependents();
+  // kernel - may read z before it has completed.  (The wait and the trigger sit behind the set-up below - barriers,
+  // constant operand chunk, TMEM allocation, cluster sync touch nothing a predecessor wrote - so that in wait_first
+  // mode the set-up still overlaps the predecessor's tail.)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
   const bool leader = rank == 0;
@@ -362,6 +362,8 @@ vq_tensor_search_kernel(const __grid_constant__ CUtensorMap tmap_cb, const float
   if constexpr (CG == 2) cluster_sync();     // peer's barriers / constant chunk are in place before anyone uses them
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
+  if (wait_first) pdl_wait();
+  pdl_launch_dependents();
 
   if (warp < NPROD) {
     // ===================== A producers: FP32 NCHW -> FP16 K-major SWIZZLE_128B =====================
