@@ -2,6 +2,7 @@
 #pragma once
 #include "common.cuh"
 #include <cuda_fp16.h>
+#include <string.h>
 
 namespace dcvic {
 
@@ -59,14 +60,31 @@ enum { kCtrLoss = 0, kCtrOverflow = 1, kCtrPerp = 2, kCtrRerank = 3, kCtrTotalCa
 // Both operands are rounded to nearest FP16 (relative 2^-11 each, so 2^-10 + 2^-22 per product, summed with
 // Cauchy-Schwarz over channels) and the bound applies to the maximum and to the candidate (x2); 2 % slack for
 // the tensor core's FP32 accumulation and the 7 mantissa bits dropped from the stored chunk maximum; an
-// absolute term for operands in FP16's subnormal range (2^-25 each, e_dim <= 256); plus a few FP32 ulps of
-// the reference distance itself (ties created by its rounding).
+// absolute term for operands in FP16's subnormal range (2^-25 each, e_dim <= 256); an absolute 4 * 2^-25 for the
+// three-way FP16 split of -|e|^2/2, whose last piece is rounded on FP16's 2^-24 subnormal grid whenever |e|^2/2 < 1/4
+// (up to 2^-25 per code, for the maximum and for the candidate, x2: it is what decides between codes for tokens
+// with |z| << |e|); plus a few FP32 ulps of the reference distance itself (ties created by its rounding).
 // Tokens with |z|^2 >= kVqFp16Zz2Max (an element could exceed FP16's range) and codebooks flagged by the
 // prepare kernel (emax[1] != 0) are not searched on the tensor cores at all: they take the full FP32 scan.
 constexpr float kVqFp16Zz2Max = 3.6e9f;       // (6e4)^2
 __host__ __device__ __forceinline__ float vq_margin(float zz, float emax) {
   const float nz = sqrtf(zz);
-  return 1.02f * 0.0019536f * nz * emax + 9.6e-7f * (nz + emax) + 1.9e-6f * (zz + emax * emax);
+  return 1.02f * 0.0019536f * nz * emax + 9.6e-7f * (nz + emax) + 1.9e-6f * (zz + emax * emax) + 1.2e-7f;
+}
+
+// Upper bound of the chunk maximum stored in a list key.  The search keeps the top 25 bits of the FP32 chunk maximum
+// (the low 7 carry the chunk id), i.e. truncates its magnitude: filling the 7 bits with ones rounds a positive value
+// up, but a NEGATIVE one (scores z.e - |e|^2/2 are negative when |z| << |e|) further down - for those the truncated
+// value itself is the upper bound.
+__host__ __device__ __forceinline__ float vq_key_upper(unsigned key) {
+  const unsigned bits = (key & 0x80000000u) ? (key & 0xFFFFFF80u) : (key | 0x7Fu);
+#ifdef __CUDA_ARCH__
+  return __uint_as_float(bits);
+#else
+  float f;
+  memcpy(&f, &bits, sizeof f);
+  return f;
+#endif
 }
 
 // vq_simt.cu

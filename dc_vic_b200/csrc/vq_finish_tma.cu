@@ -270,7 +270,7 @@ vq_finish_tma_kernel(const __grid_constant__ CUtensorMap tm_z, const __grid_cons
       } else if (!full) {
         const float thr = fmaxf(fmaxf(mt.m0, mt.m1), fmaxf(mt.mb0, mt.mb1)) - vq_margin(mt.zz, emax);
         auto take = [&](unsigned key, unsigned mask) {
-          if (__uint_as_float(key | 0x7Fu) < thr) return;  // chunk maximum (rounded up) below the threshold
+          if (vq_key_upper(key) < thr) return;               // chunk maximum (rounded towards +inf) below the threshold
           const int c0 = (int)(key & 0x7Fu) * kChunk;
           while (mask) {
             const int b = __ffs(mask) - 1;

@@ -518,7 +518,7 @@ __global__ void __launch_bounds__(256) vq_finish_kernel(const float* __restrict_
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             if (i0 + i >= n) break;
-            if (__uint_as_float(key[i] | 0x7Fu) < thr) continue;      // chunk maximum (rounded up) below threshold
+            if (vq_key_upper(key[i]) < thr) continue;                 // chunk maximum (rounded towards +inf) below threshold
             unsigned mask = msk[i];
             const int c0 = (int)(key[i] & 0x7Fu) * kChunk;
             const int pos = atomicAdd(&s_nc[tok], __popc(mask));
@@ -753,7 +753,7 @@ __global__ void __launch_bounds__(T * 8, DT ? 1024 / (T * 8) : 1) vq_finish_v5_k
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       if (li0 + i >= n) break;
-      if (__uint_as_float(key[i] | 0x7Fu) < thr) continue;      // chunk maximum (rounded up) below threshold
+      if (vq_key_upper(key[i]) < thr) continue;                 // chunk maximum (rounded towards +inf) below threshold
       unsigned mask = msk[i];
       const int c0 = (int)(key[i] & 0x7Fu) * kChunk;
       int w = atomicAdd(&s_nc[ltok], __popc(mask));

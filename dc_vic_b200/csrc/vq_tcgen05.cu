@@ -225,6 +225,19 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
                : "memory")
 
 
+// true in exactly one lane of a converged warp
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
   uint32_t r;
   asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
@@ -642,16 +655,25 @@ vq_tensor_search_kernel(const __grid_constant__ CUtensorMap tmap_cb, const float
 #if DCVIC_SEARCH_SETS == 3
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(DCVIC_SEARCH_AUX_REGS));
 #endif
-    if (warp == WARP_MMA && leader && lane == 0) {
+    if (warp == WARP_MMA && leader) {
+      // The whole warp walks the loop (warp-uniform control flow: barrier addresses, descriptors and TMEM addresses
+      // stay in uniform registers); one elected lane issues the MMAs and the commits.  With a single active lane the
+      // compiler wrapped every tcgen05 instruction in an ELECT / R2UR.BROADCAST / BRA.U.ANY loop and the ~90 dependent
+      // instructions per 64-channel chunk were on the kernel's critical path (tools/trace_run.py: the issuer was busy
+      // 2x the tensor pipe's own time).
+      const bool issuer = elect_one();
       int stage = 0;
       uint32_t phase = 0;
       uint32_t g = 0;   // running N-tile counter -> TMEM buffer g & 1
       const uint32_t rt_one = my_tiles > 0 ? 1u : 0u;   // 1, but not a compile-time constant
+      const uint32_t rt_zero = my_tiles < 0 ? 1u : 0u;  // 0, likewise
+      const uint64_t pad_desc = umma_desc_sw128(sbase + C::OFF_APAD);
       [[maybe_unused]] unsigned long long tr_te = 0, tr_af = 0, tr_bf = 0, tr0;
       [[maybe_unused]] const unsigned long long tr_start = TRM_NOW();
       for (int it = 0; it < my_tiles; ++it) {
         const int abuf = it & 1;
         const int nt0 = unit_nt0(it), nt1 = unit_nt1(it);
+        const uint64_t a_desc0 = umma_desc_sw128(sbase + C::OFF_A + abuf * A_BUF_BYTES);
         for (int nt = nt0; nt < nt1; ++nt, ++g) {
           const uint32_t buf = g & 1;
           tr0 = TRM_NOW();
@@ -659,9 +681,21 @@ vq_tensor_search_kernel(const __grid_constant__ CUtensorMap tmap_cb, const float
           TRM_ADD(tr_te, tr0);
           tc_fence_after();
           const uint32_t tmem_d = tmem_base + buf * BN;
-          for (int kc = -1; kc < KC; ++kc) {      // kc == -1: the -|e|^2/2 step, which also overwrites the buffer
+          // the -|e|^2/2 step (overwrites the buffer): constant operand chunk x pad columns of the codebook
+          {
             tr0 = TRM_NOW();
-            if (nt == nt0 && kc >= 0) mbar_wait(bar(C::BAR_A_FULL + abuf * MAX_KC + kc), (it >> 1) & 1);
+            mbar_wait(bar(C::BAR_B_FULL + stage), phase);
+            TRM_ADD(tr_bf, tr0);
+            tc_fence_after();
+            if (issuer) {
+              umma_f16<CG>(tmem_d, pad_desc, umma_desc_sw128(sbase + C::OFF_B + stage * C::B_STAGE_BYTES), rt_zero);
+              umma_commit<CG>(bar(C::BAR_B_EMPTY + stage));
+            }
+            if (++stage == C::NSTAGE) { stage = 0; phase ^= 1; }
+          }
+          for (int kc = 0; kc < KC; ++kc) {
+            tr0 = TRM_NOW();
+            if (nt == nt0) mbar_wait(bar(C::BAR_A_FULL + abuf * MAX_KC + kc), (it >> 1) & 1);
             TRM_ADD(tr_af, tr0);
             tr0 = TRM_NOW();
             mbar_wait(bar(C::BAR_B_FULL + stage), phase);
@@ -670,23 +704,23 @@ vq_tensor_search_kernel(const __grid_constant__ CUtensorMap tmap_cb, const float
             // Descriptors advance by 32 bytes (2 in the >>4 address field) per K=16 step.  The accumulate flags
             // are run-time values on purpose: with a literal 0 ptxas 12.9 emitted a predicated UTCHMMA whose
             // result was wrong in cta_group::2 (caught by the D1 / D1b parity tests).
-            const uint32_t b_addr = sbase + C::OFF_B + stage * C::B_STAGE_BYTES;
-            const uint32_t a_addr = sbase + (kc < 0 ? C::OFF_APAD : C::OFF_A + abuf * A_BUF_BYTES + kc * A_CHUNK_BYTES);
-            const uint64_t ad = umma_desc_sw128(a_addr), bd = umma_desc_sw128(b_addr);
-            umma_f16<CG>(tmem_d, ad, bd, kc < 0 ? 0u : rt_one);
-            if (kc >= 0) {
+            if (issuer) {
+              const uint64_t ad = a_desc0 + (uint64_t)((kc * A_CHUNK_BYTES) >> 4);
+              const uint64_t bd = umma_desc_sw128(sbase + C::OFF_B + stage * C::B_STAGE_BYTES);
+              umma_f16<CG>(tmem_d, ad, bd, rt_one);
               umma_f16<CG>(tmem_d, ad + 2, bd + 2, rt_one);
               umma_f16<CG>(tmem_d, ad + 4, bd + 4, rt_one);
               umma_f16<CG>(tmem_d, ad + 6, bd + 6, rt_one);
+              umma_commit<CG>(bar(C::BAR_B_EMPTY + stage));     // frees the codebook stage when these MMAs retire
             }
-            umma_commit<CG>(bar(C::BAR_B_EMPTY + stage));     // frees the codebook stage when these MMAs retire
             if (++stage == C::NSTAGE) { stage = 0; phase ^= 1; }
           }
-          umma_commit<CG>(bar(C::BAR_T_FULL + buf));          // accumulator ready for the epilogue warps
+          if (issuer) umma_commit<CG>(bar(C::BAR_T_FULL + buf));          // accumulator ready for the epilogue warps
         }
-        umma_commit<CG>(bar(C::BAR_A_EMPTY + abuf));          // operand tile may be overwritten
+        if (issuer) umma_commit<CG>(bar(C::BAR_A_EMPTY + abuf));          // operand tile may be overwritten
+        __syncwarp();
       }
-      TR_PUT(10, tr_te); TR_PUT(11, tr_af); TR_PUT(12, tr_bf); TR_PUT(13, TRM_NOW() - tr_start);
+      if (lane == 0) { TR_PUT(10, tr_te); TR_PUT(11, tr_af); TR_PUT(12, tr_bf); TR_PUT(13, TRM_NOW() - tr_start); }
     }
   }
 

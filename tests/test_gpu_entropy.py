@@ -42,6 +42,28 @@ def test_gaussian_eval_c3_slice(q):
     assert e64.max() < 2e-4, f"vs FP64 closed form: {e64.max():.3e}"
 
 
+@pytest.mark.parametrize("q", [0, 1, 2, 3, 4])
+def test_gaussian_c3_full_size_all_images(q):
+    """BASELINE config 3 at full size (64 x 320 x 32 x 32 = 20,971,520 latents), all 64 images, eval mode for every
+    q and train mode (explicit noise) for q = 2 - the q bench.py times."""
+    y, params = entropy_inputs(q)
+    ref = O.SteGaussianMeanScaleConditional(scale_bound=0.11)
+    ours = D.SteGaussianMeanScaleConditional(scale_bound=0.11).to(DEV)
+    modes = [(False, None)] + ([(True, noise_like(y, 200 + q))] if q == 2 else [])
+    yc, pc = y.to(DEV), params.to(DEV)
+    for train, nz in modes:
+        with torch.no_grad():
+            yh_r, lk_r = ref(y, params, is_train=train, noise=nz)
+            yh, lk = ours(yc, pc, is_train=train, noise=None if nz is None else nz.to(DEV))
+        assert torch.equal(yh.cpu(), yh_r)
+        worst = rel_err(lk, lk_r)
+        b_r, _ = O.likelihood_to_bit(lk_r, 64 * 512 * 512)
+        b, _ = D.likelihood_to_bit(lk, 64 * 512 * 512)
+        print(f"C3 q={q} train={train}: max rel err of the likelihood {worst:.2e}, bits {float(b):.6e} vs {float(b_r):.6e}")
+        assert worst < REL
+        assert abs(float(b) - float(b_r)) <= REL * float(b_r)
+
+
 @pytest.mark.parametrize("cls", ["GaussianMeanScaleConditional", "SteGaussianMeanScaleConditional",
                                  "GaussianScaleConditional"])
 def test_gaussian_train_with_explicit_noise(cls):

@@ -1,0 +1,454 @@
+// Probe (measurement aid, not part of the library): tcgen05.mma with the A operand in TENSOR MEMORY, cta_group::2.
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O2 -o tools/probe_ts_mma tools/probe_ts_mma.cu && tools/probe_ts_mma
+// 1. correctness: D[256 x 128] = A[256 x 64] . B[128 x 64]^T with A written to TMEM by tcgen05.st.32x32b (lane = row,
+//    two FP16 channels per 32-bit column, even channel in the low half), B K-major SWIZZLE_128B in shared memory
+//    (each CTA of the pair holds 64 of the 128 rows); integer-valued operands, exact compare with the host.
+// 2. throughput of tcgen05.ld.32x32b.x32 with 4 and 8 warps per CTA (bytes per clock and SM).
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+
+#define CK(x)                                                                    \
+  do {                                                                           \
+    cudaError_t e_ = (x);                                                        \
+    if (e_ != cudaSuccess) {                                                     \
+      printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); \
+      exit(1);                                                                   \
+    }                                                                            \
+  } while (0)
+
+constexpr int M_CTA = 128, N = 128, K = 64;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tW_LOOP:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra W_DONE;\n\tbra "
+      "W_LOOP;\n\tW_DONE:\n\t}" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
+         (2ull << 61);
+}
+constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)((2 * M_CTA) >> 4) << 24);
+
+__device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(kIdesc), "r"(accumulate)
+      : "memory");
+}
+
+#define TMEM_ST16(taddr, r)                                                                                          \
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" \
+               ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),   \
+               "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])           \
+               : "memory")
+
+#define TMEM_LD32(r, taddr)                                                                                        \
+  asm volatile(                                                                                                    \
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18," \
+      "%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"                                               \
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),  \
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),       \
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),      \
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])                    \
+      : "r"(taddr)                                                                                                 \
+      : "memory")
+
+__global__ void __launch_bounds__(128, 1)
+probe_kernel(const __half* __restrict__ A /* [256][K] */, const __half* __restrict__ B /* [N][K] */,
+             float* __restrict__ D /* [256][N] */) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ __align__(8) unsigned long long s_bar;
+  __shared__ uint32_t s_tmem;
+  const uint32_t rank = cluster_ctarank();
+  const int warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) {
+    mbar_init(smem_u32(&s_bar), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(256u));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::);
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = s_tmem;
+  const uint32_t tmem_d = tmem_base, tmem_a = tmem_base + 128;
+
+  // B: this CTA's 64 rows (codes rank*64 ..), K-major, 128-byte rows, SWIZZLE_128B
+  for (int i = threadIdx.x; i < 64 * 8; i += 128) {
+    const int row = i >> 3, piece = i & 7;
+    const uint4 v = *reinterpret_cast<const uint4*>(B + (size_t)(rank * 64 + row) * K + piece * 8);
+    *reinterpret_cast<uint4*>(smem + row * 128 + ((piece ^ (row & 7)) << 4)) = v;
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  // A: row = rank*128 + threadIdx.x -> TMEM lane threadIdx.x, columns tmem_a + c (channels 2c, 2c+1)
+  {
+    const __half* arow = A + (size_t)(rank * 128 + threadIdx.x) * K;
+    const uint32_t tl = tmem_a + ((uint32_t)(warp * 32) << 16);
+#pragma unroll
+    for (int h = 0; h < K / 32; ++h) {
+      uint32_t r[16];
+#pragma unroll
+      for (int c = 0; c < 16; ++c) r[c] = *reinterpret_cast<const uint32_t*>(arow + h * 32 + 2 * c);
+      TMEM_ST16(tl + h * 16, r);
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  cluster_sync();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  if (rank == 0 && threadIdx.x == 0) {
+    const uint64_t bd = umma_desc_sw128(smem_u32(smem));
+    const uint32_t one = (gridDim.x > 0) ? 1u : 0u, zero = (gridDim.x > 100000) ? 1u : 0u;   // run-time values
+#pragma unroll
+    for (int k = 0; k < K / 16; ++k) umma_ts(tmem_d, tmem_a + 8 * k, bd + 2 * k, k == 0 ? zero : one);
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+            smem_u32(&s_bar)),
+        "h"((uint16_t)3)
+        : "memory");
+  }
+  mbar_wait(smem_u32(&s_bar), 0);
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  {
+    const uint32_t tl = tmem_d + ((uint32_t)(warp * 32) << 16);
+    float* drow = D + (size_t)(rank * 128 + threadIdx.x) * N;
+#pragma unroll
+    for (int c = 0; c < N; c += 32) {
+      uint32_t r[32];
+      TMEM_LD32(r, tl + c);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+      for (int j = 0; j < 32; ++j) drow[c + j] = __uint_as_float(r[j]);
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  cluster_sync();
+  if (warp == 0) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u));
+  }
+}
+
+// ---- tcgen05.ld throughput: NW warps each read `iters` x 4 KB (their lane quarter, 32 columns)
+__global__ void __launch_bounds__(512, 1) ld_rate_kernel(int iters, int nwarps, unsigned long long* out, uint32_t* sink) {
+  __shared__ uint32_t s_tmem;
+  const int warp = threadIdx.x >> 5;
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(512u));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tl = s_tmem + ((uint32_t)((warp & 3) * 32) << 16) + (warp >> 2) * 64;
+  uint32_t acc = 0;
+  __syncthreads();
+  const unsigned long long t0 = clock64();
+  if (warp < nwarps) {
+    for (int i = 0; i < iters; ++i) {
+      uint32_t ra[32], rb[32];
+      TMEM_LD32(ra, tl);
+      TMEM_LD32(rb, tl + 32);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+      for (int j = 0; j < 32; ++j) acc ^= ra[j] ^ rb[j];
+    }
+  }
+  __syncthreads();
+  const unsigned long long t1 = clock64();
+  if (threadIdx.x == 0) out[blockIdx.x] = t1 - t0;
+  if (acc == 0x12345678u) sink[0] = acc;
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(s_tmem), "r"(512u));
+}
+
+
+// ---- MMA issue rate: `reps` back-to-back K=16 MMAs (cta_group::2, M=256) on fixed operands; A from shared memory (SS)
+// or from tensor memory (TS); NN = 128 or 256.  Cycles from the first issue to the arrival of the commit.
+template <int NN, int TS>
+__global__ void __launch_bounds__(128, 1) mma_rate_kernel(int reps, unsigned long long* out) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ __align__(8) unsigned long long s_bar;
+  __shared__ uint32_t s_tmem;
+  const uint32_t rank = cluster_ctarank();
+  const int warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) {
+    mbar_init(smem_u32(&s_bar), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int i = threadIdx.x; i < (32 + 16) * 1024 / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0u;
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(512u));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::);
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  cluster_sync();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = s_tmem;
+  constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(NN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+  unsigned long long t0 = 0;
+  if (rank == 0 && threadIdx.x == 0) {
+    const uint64_t bd = umma_desc_sw128(smem_u32(smem)), ad = umma_desc_sw128(smem_u32(smem) + 32 * 1024);
+    const uint32_t one = (gridDim.x > 0) ? 1u : 0u;
+    t0 = clock64();
+    for (int r = 0; r < reps; ++r) {
+      const uint32_t d = tmem_base + (r & 1) * NN * 0;   // same accumulator: a dependent chain, as in the search
+      const int k = r & 3;
+      if (TS) {
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                     "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d),
+                     "r"(tmem_base + 256 + 8 * k), "l"(bd + 2 * k), "r"(idesc), "r"(one) : "memory");
+      } else {
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                     "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d),
+                     "l"(ad + 2 * k), "l"(bd + 2 * k), "r"(idesc), "r"(one) : "memory");
+      }
+    }
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+            smem_u32(&s_bar)),
+        "h"((uint16_t)3)
+        : "memory");
+  }
+  mbar_wait(smem_u32(&s_bar), 0);
+  if (rank == 0 && threadIdx.x == 0) out[blockIdx.x / 2] = clock64() - t0;
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  cluster_sync();
+  if (warp == 0) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
+  }
+}
+
+template <int NN, int TS>
+static void run_rate(unsigned long long* dT, int nclusters) {
+  const int smem = 48 * 1024 + 1024, reps = 512;
+  CK(cudaFuncSetAttribute(mma_rate_kernel<NN, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2 * nclusters);
+  cfg.blockDim = dim3(128);
+  cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  CK(cudaLaunchKernelEx(&cfg, mma_rate_kernel<NN, TS>, reps, dT));
+  CK(cudaDeviceSynchronize());
+  unsigned long long hT[74];
+  CK(cudaMemcpy(hT, dT, sizeof(unsigned long long) * nclusters, cudaMemcpyDeviceToHost));
+  const double ideal = 256.0 * NN / 512.0;
+  printf("MMA 256x%dx16 %s, %2d pairs: %.1f cycles per MMA (ideal %.0f)\n", NN, TS ? "TS (A in TMEM)" : "SS (A in smem)",
+         nclusters, (double)hT[0] / reps, ideal);
+}
+
+// ---- shared-memory port share of the MMA: warps 4-7 of both CTAs stream conflict-free LDS.128 (bg_iters x 512 B per
+// warp) while the leader issues `reps` MMAs (reps == 0: background alone).  Prints the background's bytes per clock
+// and the MMA's cycles per instruction: the background's loss is what the MMA (and its peer's reads) take.
+template <int NN, int TS>
+__global__ void __launch_bounds__(256, 1) mma_smem_kernel(int reps, int bg_iters, unsigned long long* out, uint32_t* sink) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ __align__(8) unsigned long long s_bar;
+  __shared__ uint32_t s_tmem;
+  const uint32_t rank = cluster_ctarank();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    mbar_init(smem_u32(&s_bar), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int i = threadIdx.x; i < 96 * 1024 / 4; i += 256) reinterpret_cast<uint32_t*>(smem)[i] = 0u;
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(512u));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::);
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  cluster_sync();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = s_tmem;
+  constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(NN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+  if (warp >= 4) {
+    const uint32_t a = smem_u32(smem) + 48 * 1024 + (warp - 4) * 8192 + lane * 16;
+    uint32_t acc = 0;
+    const unsigned long long t0 = clock64();
+    for (int i = 0; i < bg_iters; ++i) {
+      uint32_t x0, x1, x2, x3;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(x0), "=r"(x1), "=r"(x2), "=r"(x3) : "r"(a + u * 512));
+        acc ^= x0 ^ x1 ^ x2 ^ x3;
+      }
+    }
+    const unsigned long long t1 = clock64();
+    if (lane == 0) out[8 + blockIdx.x * 4 + (warp - 4)] = t1 - t0;
+    if (acc == 0x12345u) sink[0] = acc;
+  } else if (reps > 0) {
+    unsigned long long t0 = 0;
+    if (rank == 0 && threadIdx.x == 0) {
+      const uint64_t bd = umma_desc_sw128(smem_u32(smem)), ad = umma_desc_sw128(smem_u32(smem) + 32 * 1024);
+      const uint32_t one = (gridDim.x > 0) ? 1u : 0u;
+      t0 = clock64();
+      for (int r = 0; r < reps; ++r) {
+        const int k = r & 3;
+        if (TS) {
+          asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                       "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_base),
+                       "r"(tmem_base + 256 + 8 * k), "l"(bd + 2 * k), "r"(idesc), "r"(one) : "memory");
+        } else {
+          asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                       "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_base),
+                       "l"(ad + 2 * k), "l"(bd + 2 * k), "r"(idesc), "r"(one) : "memory");
+        }
+      }
+      asm volatile(
+          "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+              smem_u32(&s_bar)),
+          "h"((uint16_t)3)
+          : "memory");
+    }
+    if (warp == 0) {
+      mbar_wait(smem_u32(&s_bar), 0);
+      if (rank == 0 && threadIdx.x == 0) out[0] = clock64() - t0;
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  cluster_sync();
+  if (warp == 0) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
+  }
+}
+
+template <int NN, int TS>
+static void run_smem(unsigned long long* dT, uint32_t* dS, int reps) {
+  const int smem = 96 * 1024 + 1024, bg_iters = 4000;
+  CK(cudaFuncSetAttribute(mma_smem_kernel<NN, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2);
+  cfg.blockDim = dim3(256);
+  cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  CK(cudaMemset(dT, 0, 16 * 8));
+  CK(cudaLaunchKernelEx(&cfg, mma_smem_kernel<NN, TS>, reps, bg_iters, dT, dS));
+  CK(cudaDeviceSynchronize());
+  unsigned long long hT[16];
+  CK(cudaMemcpy(hT, dT, sizeof(hT), cudaMemcpyDeviceToHost));
+  double bg[2];
+  for (int c = 0; c < 2; ++c) {
+    unsigned long long mx = 0;
+    for (int w = 0; w < 4; ++w) mx = hT[8 + c * 4 + w] > mx ? hT[8 + c * 4 + w] : mx;
+    bg[c] = 4.0 * bg_iters * 8 * 512 / (double)mx;
+  }
+  printf("smem share, MMA 256x%dx16 %s reps=%5d: background LDS %.1f / %.1f B/clk (leader / peer CTA), MMA %.1f cycles each\n",
+         NN, TS ? "TS" : "SS", reps, bg[0], bg[1], reps ? (double)hT[0] / reps : 0.0);
+}
+
+int main() {
+  const int M = 2 * M_CTA;
+  __half *hA = (__half*)malloc(M * K * 2), *hB = (__half*)malloc(N * K * 2);
+  float* ref = (float*)malloc(M * N * 4);
+  srand(1);
+  for (int i = 0; i < M * K; ++i) hA[i] = __float2half((float)(rand() % 9 - 4));
+  for (int i = 0; i < N * K; ++i) hB[i] = __float2half((float)(rand() % 7 - 3));
+  for (int m = 0; m < M; ++m)
+    for (int n = 0; n < N; ++n) {
+      float s = 0.f;
+      for (int k = 0; k < K; ++k) s += __half2float(hA[m * K + k]) * __half2float(hB[n * K + k]);
+      ref[m * N + n] = s;
+    }
+  __half *dA, *dB;
+  float* dD;
+  CK(cudaMalloc(&dA, M * K * 2));
+  CK(cudaMalloc(&dB, N * K * 2));
+  CK(cudaMalloc(&dD, M * N * 4));
+  CK(cudaMemcpy(dA, hA, M * K * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dB, hB, N * K * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemset(dD, 0xFF, M * N * 4));
+  const int smem = 64 * 128 + 1024;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2);
+  cfg.blockDim = dim3(128);
+  cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  CK(cudaLaunchKernelEx(&cfg, probe_kernel, (const __half*)dA, (const __half*)dB, dD));
+  CK(cudaDeviceSynchronize());
+  float* out = (float*)malloc(M * N * 4);
+  CK(cudaMemcpy(out, dD, M * N * 4, cudaMemcpyDeviceToHost));
+  int bad = 0;
+  for (int i = 0; i < M * N; ++i)
+    if (out[i] != ref[i]) {
+      if (bad < 8) printf("mismatch m=%d n=%d got %g want %g\n", i / N, i % N, out[i], ref[i]);
+      ++bad;
+    }
+  printf("TS-MMA cta_group::2 A-in-TMEM: %d mismatches of %d -> %s\n", bad, M * N, bad ? "FAIL" : "OK");
+
+  unsigned long long* dT;
+  uint32_t* dS;
+  CK(cudaMalloc(&dT, 148 * 8));
+  CK(cudaMalloc(&dS, 4));
+  for (int nw : {4, 8, 16}) {
+    const int iters = 2000;
+    ld_rate_kernel<<<148, 512>>>(iters, nw, dT, dS);
+    CK(cudaDeviceSynchronize());
+    unsigned long long hT[148];
+    CK(cudaMemcpy(hT, dT, sizeof(hT), cudaMemcpyDeviceToHost));
+    const double bytes = (double)nw * iters * 2 * 4096;
+    printf("tcgen05.ld x32: %2d warps: %.1f B/clk/SM (%.0f cycles)\n", nw, bytes / (double)hT[0], (double)hT[0]);
+  }
+  for (int nc : {1, 74}) {
+    run_rate<256, 0>(dT, nc);
+    run_rate<256, 1>(dT, nc);
+    run_rate<128, 0>(dT, nc);
+    run_rate<128, 1>(dT, nc);
+  }
+  run_smem<256, 0>(dT, dS, 0);
+  run_smem<256, 0>(dT, dS, 3000);
+  run_smem<256, 1>(dT, dS, 3000);
+  run_smem<128, 0>(dT, dS, 6000);
+  run_smem<128, 1>(dT, dS, 6000);
+  return bad ? 1 : 0;
+}
