@@ -35,7 +35,8 @@ from . import _lib
 __all__ = ["LowerBound", "EntropyModel", "GaussianConditional", "EntropyBottleneck", "DcvicEntropyBottleneck",
            "SteEntropyBottleneck", "GaussianScaleConditional", "GaussianMeanScaleConditional",
            "SteGaussianMeanScaleConditional", "ste_round", "get_scale_table", "pmf_to_quantized_cdf",
-           "likelihood_to_bit", "batch_bits", "gaussian_rate_dual"]
+           "likelihood_to_bit", "batch_bits", "gaussian_rate_dual", "gaussian_codec_step", "DevicePinned",
+           "FUSED_FORWARDS"]
 
 _WS = {}
 
@@ -164,7 +165,50 @@ def batch_bits(likelihood: Tensor) -> Tensor:
 
 
 # ------------------------------------------------------------------------------ base
-class EntropyModel(nn.Module):
+def _module_device(module) -> torch.device:
+    for t in module.buffers():
+        return t.device
+    for t in module.parameters():
+        return t.device
+    return torch.device("cpu")
+
+
+class DevicePinned:
+    """Keeps a CUDA-resident entropy model on its GPU when the host code moves it to the CPU, and lets it take CPU
+    tensors.  DC-VIC's ``codec_setup`` does ``entropy_model_z.to("cpu")`` / ``entropy_model_y.to("cpu")`` and then
+    feeds ``y.cpu()``, ``z.cpu()`` (hyperprior_dc_vic_model.py:65-73,308-328): with this mixin the call sites stay
+    as they are, the arithmetic still runs in the CUDA kernels (there is no CPU implementation in this package),
+    inputs are uploaded and results returned on the caller's device.  Set ``allow_cpu_move = True`` on an instance to
+    get torch's normal behaviour back (its forward will then refuse to run)."""
+
+    allow_cpu_move = False
+
+    def _apply(self, fn, *args, **kwargs):
+        if not self.allow_cpu_move:
+            dev = _module_device(self)
+            if dev.type == "cuda":
+                try:
+                    target = fn(torch.empty(0, device=dev)).device
+                except Exception:      # not a device/dtype conversion: let torch handle it
+                    target = dev
+                if target.type == "cpu":
+                    return self
+        return super()._apply(fn, *args, **kwargs)
+
+    def _upload(self, *tensors):
+        """-> (device the caller works on, the tensors on this module's GPU)."""
+        dev = _module_device(self)
+        home = next((t.device for t in tensors if t is not None), dev)
+        if dev.type != "cuda":
+            return home, tensors
+        return home, tuple(None if t is None else (t if t.device == dev else t.to(dev)) for t in tensors)
+
+    @staticmethod
+    def _download(home, *tensors):
+        return tuple(t if (t is None or t.device == home) else t.to(home) for t in tensors)
+
+
+class EntropyModel(DevicePinned, nn.Module):
     """compressai.entropy_models.EntropyModel surface used by DC-VIC (base_model.py:88-104)."""
 
     def __init__(self, likelihood_bound: float = 1e-9, entropy_coder=None, entropy_coder_precision: int = 16):
@@ -182,15 +226,16 @@ class EntropyModel(nn.Module):
     def quantize(self, inputs: Tensor, mode: str, means: Optional[Tensor] = None) -> Tensor:
         if mode not in ("noise", "dequantize", "symbols"):
             raise ValueError(f'Invalid quantization mode: "{mode}"')
+        home, (inputs, means) = self._upload(inputs, means)
         _lib.require_cuda(inputs)
         if mode == "noise":
             noise = torch.empty_like(inputs).uniform_(-0.5, 0.5)
-            return inputs + noise
+            return self._download(home, inputs + noise)[0]
         x = inputs if means is None else inputs - means
         r = _SteRound.apply(x.detach())          # value == round(x), one kernel
         if mode == "dequantize":
-            return r if means is None else r + means
-        return r.int()
+            return self._download(home, r if means is None else r + means)[0]
+        return self._download(home, r.int())[0]
 
     @staticmethod
     def dequantize(inputs: Tensor, means: Optional[Tensor] = None, dtype: torch.dtype = torch.float) -> Tensor:
@@ -315,6 +360,7 @@ class GaussianConditional(EntropyModel):
         return _GaussianFn.apply(inputs, scales, means, noise, self._scale_bound, self._likelihood_bound, 0)
 
     def build_indexes(self, scales: Tensor) -> Tensor:
+        home, (scales,) = self._upload(scales)
         _lib.require_cuda(scales)
         sc = scales.contiguous().float()
         table = self.scale_table.to(sc.device).contiguous().float()
@@ -323,7 +369,7 @@ class GaussianConditional(EntropyModel):
             rc = _lib.load().dcvic_gc_build_indexes(_lib.ptr(sc), sc.numel(), _lib.ptr(table), table.numel(),
                                                     self._scale_bound, _lib.ptr(out), _lib.cur_stream())
             _lib.check(rc, "dcvic_gc_build_indexes")
-        return out
+        return self._download(home, out)[0]
 
     def update_scale_table(self, scale_table, force: bool = False) -> bool:
         if self._offset.numel() > 0 and not force:
@@ -523,19 +569,12 @@ class EntropyBottleneck(EntropyModel):
                 logits = logits + torch.tanh(factor) * torch.tanh(logits)
         return logits
 
-    def _draw_noise(self, x: Tensor) -> Tensor:
-        # the reference draws the noise on the permuted [C, 1, B*HW] view; draw it there so the RNG
-        # stream is consumed identically, then bring it back to NCHW
-        Cc, B = x.shape[1], x.shape[0]
-        nz = torch.empty(Cc, 1, x.numel() // Cc, device=x.device, dtype=torch.float32).uniform_(-0.5, 0.5)
-        return nz.view(Cc, B, *x.shape[2:]).transpose(0, 1).contiguous()
-
     def forward(self, x: Tensor, training: Optional[bool] = None, noise: Optional[Tensor] = None,
                 _x_hat_mode: int = 0) -> Tuple[Tensor, Tensor]:
         if training is None:
             training = self.training
         if training and noise is None:
-            noise = self._draw_noise(x)
+            noise = _bottleneck_noise(x)
         if not training:
             noise = None
         return _BottleneckFn.apply(x, noise, self._likelihood_bound, _x_hat_mode, self.quantiles,
@@ -569,56 +608,141 @@ class EntropyBottleneck(EntropyModel):
 
 
 # ------------------------------------------------------------- DC-VIC wrappers (registry names)
-class DcvicEntropyBottleneck(EntropyBottleneck):
-    """``EntropyBottleneck`` of entropy_bottleneck.py:13-16 (forward(x, is_train))."""
+# The fused forwards are MIXINS without state of their own: they only need the attributes every CompressAI-shaped
+# module has (parameters ``_matrix{i}`` / ``_bias{i}`` / ``_factor{i}`` / ``quantiles``, ``likelihood_lower_bound``,
+# ``lower_bound_scale``).  ``register.register_entropy_models`` puts them IN FRONT of the reference's own wrapper
+# classes (``type(name, (mixin, reference_class), {})``), so that the class built from ``ENTROPYMODEL_REGISTRY`` is a
+# subclass of ``src.models.subnet.entropy_model.entropy_bottleneck.EntropyBottleneck`` /
+# ``compressai.entropy_models.GaussianConditional`` and ``base_model.py:76-104,128-130``'s isinstance checks hold;
+# below they are combined with this file's own base classes for stand-alone use.
+def _bound_of(module, cache_name: str, private_name: str, bound_module_name: str, default: float) -> float:
+    v = getattr(module, private_name, None)
+    if v is not None:
+        return v
+    v = module.__dict__.get(cache_name)
+    if v is None:
+        lb = getattr(module, bound_module_name, None)
+        v = float(lb.bound) if lb is not None else default       # (one host read, then cached)
+        module.__dict__[cache_name] = v
+    return v
 
-    def forward(self, x: Tensor, is_train: bool, noise: Optional[Tensor] = None) -> Tuple[Tensor, Tensor]:
-        return super().forward(x, training=is_train, noise=noise)
+
+def _lik_bound_of(module) -> float:
+    if not getattr(module, "use_likelihood_bound", True):
+        return 0.0
+    return _bound_of(module, "_dcvic_lik_bound", "_likelihood_bound", "likelihood_lower_bound", 1e-9)
 
 
-class SteEntropyBottleneck(DcvicEntropyBottleneck):
-    """entropy_bottleneck.py:19-28: training output is ``ste_round(x - med) + med``."""
+def _scale_bound_of(module) -> float:
+    return _bound_of(module, "_dcvic_scale_bound", "_scale_bound", "lower_bound_scale", 0.11)
+
+
+def _bottleneck_noise(x: Tensor) -> Tensor:
+    # the reference draws the noise on the permuted [C, 1, B*HW] view; draw it there so the RNG
+    # stream is consumed identically, then bring it back to NCHW
+    Cc, B = x.shape[1], x.shape[0]
+    nz = torch.empty(Cc, 1, x.numel() // Cc, device=x.device, dtype=torch.float32).uniform_(-0.5, 0.5)
+    return nz.view(Cc, B, *x.shape[2:]).transpose(0, 1).contiguous()
+
+
+def _bottleneck_params(module):
+    return [getattr(module, f"_matrix{i}") for i in range(5)] + [getattr(module, f"_bias{i}") for i in range(5)] + \
+           [getattr(module, f"_factor{i}") for i in range(4)]
+
+
+class FusedBottleneckForward(DevicePinned):
+    """``EntropyBottleneck.forward(x, is_train)`` of entropy_bottleneck.py:13-16 as one kernel."""
+
+    _x_hat_mode = 0          # 0: x + noise (training) / round about the median (eval)
 
     def forward(self, x: Tensor, is_train: bool = True, noise: Optional[Tensor] = None) -> Tuple[Tensor, Tensor]:
+        home, (x, noise) = self._upload(x, noise)
+        if is_train and noise is None:
+            noise = _bottleneck_noise(x)
         if not is_train:
-            return EntropyBottleneck.forward(self, x, training=False)
-        return EntropyBottleneck.forward(self, x, training=True, noise=noise, _x_hat_mode=1)
+            noise = None
+        out = _BottleneckFn.apply(x, noise, _lik_bound_of(self), self._x_hat_mode if is_train else 0,
+                                  self.quantiles, *_bottleneck_params(self))
+        return self._download(home, *out)
 
 
-class GaussianScaleConditional(GaussianConditional):
+class FusedSteBottleneckForward(FusedBottleneckForward):
+    """entropy_bottleneck.py:19-28: the training output is ``ste_round(x - med) + med``."""
+
+    _x_hat_mode = 1
+
+
+class _FusedGaussianForward(DevicePinned):
+    _y_hat_mode = 0          # 0: y + noise (training); 1: ste_round(y - mu) + mu (training).  Eval: round about mu.
+    _has_means = True
+
+    def forward(self, y: Tensor, params: Tensor, is_train: bool = True,
+                noise: Optional[Tensor] = None) -> Tuple[Tensor, Tensor]:
+        home, (y, params, noise) = self._upload(y, params, noise)
+        if self._has_means:
+            mean, std = params.chunk(2, 1)
+        else:
+            mean, std = None, params
+        if is_train and noise is None:
+            noise = torch.empty_like(y).uniform_(-0.5, 0.5)        # same RNG call as EntropyModel.quantize("noise")
+        if not is_train:
+            noise = None
+        out = _GaussianFn.apply(y, std, mean, noise, _scale_bound_of(self), _lik_bound_of(self), self._y_hat_mode)
+        return self._download(home, *out)
+
+
+class FusedGaussianScaleForward(_FusedGaussianForward):
+    """gaussian_conditional.py:9-15 (``forward(y, scales, is_train)``, no means)."""
+
+    _has_means = False
+
+
+class FusedGaussianMeanScaleForward(_FusedGaussianForward):
+    """gaussian_conditional.py:17-24."""
+
+
+class FusedSteGaussianMeanScaleForward(_FusedGaussianForward):
+    """ste_gaussian_conditional.py:9-23: y_hat is the STE-rounded value in training, the plain de-quantized value in
+    eval; the likelihood is the parent's (noisy in training)."""
+
+    _y_hat_mode = 1
+
+
+FUSED_FORWARDS = {
+    "EntropyBottleneck": FusedBottleneckForward,
+    "SteEntropyBottleneck": FusedSteBottleneckForward,
+    "GaussianScaleConditional": FusedGaussianScaleForward,
+    "GaussianMeanScaleConditional": FusedGaussianMeanScaleForward,
+    "SteGaussianMeanScaleConditional": FusedSteGaussianMeanScaleForward,
+}
+
+
+class DcvicEntropyBottleneck(FusedBottleneckForward, EntropyBottleneck):
+    """``EntropyBottleneck`` of entropy_bottleneck.py:13-16 (forward(x, is_train))."""
+
+
+class SteEntropyBottleneck(FusedSteBottleneckForward, DcvicEntropyBottleneck):
+    """entropy_bottleneck.py:19-28."""
+
+
+class GaussianScaleConditional(FusedGaussianScaleForward, GaussianConditional):
     """gaussian_conditional.py:9-15."""
 
     def __init__(self, scale_bound=None):
         super().__init__(scale_table=None, scale_bound=scale_bound)
 
-    def forward(self, y: Tensor, params: Tensor, is_train: bool = True, noise: Optional[Tensor] = None):
-        return super().forward(y, scales=params, means=None, training=is_train, noise=noise)
 
-
-class GaussianMeanScaleConditional(GaussianConditional):
+class GaussianMeanScaleConditional(FusedGaussianMeanScaleForward, GaussianConditional):
     """gaussian_conditional.py:17-24."""
 
     def __init__(self, scale_bound=None):
         super().__init__(scale_table=None, scale_bound=scale_bound)
 
-    def forward(self, y: Tensor, params: Tensor, is_train: bool = True, noise: Optional[Tensor] = None):
-        mean, std = params.chunk(2, 1)
-        return super().forward(y, scales=std, means=mean, training=is_train, noise=noise)
 
-
-class SteGaussianMeanScaleConditional(GaussianMeanScaleConditional):
-    """ste_gaussian_conditional.py:9-23: y_hat is the STE-rounded value in training, the plain
-    de-quantized value in eval; the likelihood is the parent's (noisy in training)."""
+class SteGaussianMeanScaleConditional(FusedSteGaussianMeanScaleForward, GaussianMeanScaleConditional):
+    """ste_gaussian_conditional.py:9-23."""
 
     def __init__(self, scale_bound=None, entropy_quant_type: str = "noise", **kwargs) -> None:
         super().__init__(scale_bound=scale_bound)
         assert entropy_quant_type == "noise"
         self.entropy_quant_type = entropy_quant_type
-
-    def forward(self, y: Tensor, params: Tensor, is_train: bool = True, noise: Optional[Tensor] = None):
-        mean, std = params.chunk(2, 1)
-        if is_train and noise is None:
-            noise = torch.empty_like(y).uniform_(-0.5, 0.5)
-        if not is_train:
-            noise = None
-        return _GaussianFn.apply(y, std, mean, noise, self._scale_bound, self._likelihood_bound, 1)

@@ -14,9 +14,9 @@ There is no CPU or PyTorch fallback: CPU tensors raise.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional
 
-import numpy as np
 import torch
 import torch.nn as nn
 
@@ -26,16 +26,21 @@ __all__ = ["VectorQuantizer", "VectorQuantizer2", "codebook_lookup", "onehot_fea
 
 
 class _Workspace:
-    """Zero-initialised device scratch, cached per (device, stream, shape)."""
+    """Zero-initialised device scratch, one buffer per (device, stream) that grows to the largest size asked for
+    (evaluating on variable-size images must not keep one buffer per distinct shape alive)."""
 
     def __init__(self):
         self._cache = {}
 
-    def get(self, key, nbytes: int, device) -> torch.Tensor:
-        stream = torch.cuda.current_stream(device).cuda_stream
-        k = (device.index, stream) + tuple(key)
+    def get(self, nbytes: int, device):
+        """-> (buffer, fresh): fresh means newly allocated (zero-filled; nothing prepared in it yet)."""
+        stream = torch._C._cuda_getCurrentRawStream(device.index if device.index is not None
+                                                    else torch.cuda.current_device())
+        k = (device.index, stream)
         buf = self._cache.get(k)
         if buf is None or buf.numel() < nbytes:
+            buf = None                      # release the smaller one first
+            self._cache.pop(k, None)
             buf = torch.zeros(max(int(nbytes), 256), dtype=torch.uint8, device=device)
             self._cache[k] = buf
             return buf, True
@@ -65,8 +70,10 @@ class _VQForward(torch.autograd.Function):
             nbytes = lib.dcvic_vq_workspace_bytes(B, D, H, W, K)
             if nbytes == 0:
                 raise RuntimeError("dcvic_vq_workspace_bytes rejected the shape")
-            ws, fresh = owner._ws.get((B, D, H, W, K), nbytes, z.device)
-            key = (wc.data_ptr(), weight._version, ws.data_ptr())
+            ws, fresh = owner._ws.get(nbytes, z.device)
+            # what the prepared |e|^2 / FP16 codebook inside `ws` belongs to (the workspace layout depends on the
+            # token count, so a different shape re-prepares)
+            key = (wc.data_ptr(), weight._version, ws.data_ptr(), B * H * W, D, K)
             if owner._frozen and not fresh and owner._prep_key == key:
                 flags |= _lib.VQ_REUSE_PREP
             rc = lib.dcvic_vq_forward(_lib.ptr(zc), _lib.ptr(wc), B, D, H, W, K, float(beta), int(bool(legacy)),
@@ -102,19 +109,51 @@ class _VQForward(torch.autograd.Function):
         return dz, dE, None, None, None, None, None
 
 
+_CHECK_INDICES = os.environ.get("DCVIC_CHECK_INDICES", "0") == "1"
+
+
+class _Gather(torch.autograd.Function):
+    """Differentiable wrt the codebook like ``nn.Embedding`` (quantize.py:92-107 / :314-329 go through
+    ``self.embedding``); the gradient is a scatter-add of the incoming rows (torch ``index_add_``: DC-VIC's codebook
+    is frozen, so this is off the hot path)."""
+
+    @staticmethod
+    def forward(ctx, weight, indices, nchw):
+        out = _gather_rows(indices, weight, nchw)
+        ctx.save_for_backward(indices)
+        ctx.meta = (tuple(weight.shape), bool(nchw))
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (indices,) = ctx.saved_tensors
+        (K, D), nchw = ctx.meta
+        rows = g.permute(0, 2, 3, 1).reshape(-1, D) if nchw else g.reshape(-1, D)
+        dE = torch.zeros(K, D, dtype=g.dtype, device=g.device).index_add_(0, indices.reshape(-1).clamp(0, K - 1), rows)
+        return dE, None, None
+
+
 def codebook_lookup(indices: torch.Tensor, weight: torch.Tensor, nchw: bool = True) -> torch.Tensor:
     """``embedding(indices)`` [+ 'b h w c -> b c h w'] in one gather kernel.
 
     ``indices`` [B, H, W] (nchw=True -> [B, D, H, W]) or any shape (nchw=False -> [..., D]).
     Mirrors vq_indices_to_latent (src/models/comp_model/hyperprior_vic_model.py:165-168).
+    Out-of-range indices are clamped by the kernel (``nn.Embedding`` raises); set DCVIC_CHECK_INDICES=1 to read the
+    kernel's out-of-range counter back (one host sync) and raise IndexError.
     """
+    if weight.requires_grad and torch.is_grad_enabled():
+        return _Gather.apply(weight, indices, nchw)
+    return _gather_rows(indices, weight, nchw)
+
+
+def _gather_rows(indices: torch.Tensor, weight: torch.Tensor, nchw: bool) -> torch.Tensor:
     _lib.require_cuda(indices, weight)
     lib = _lib.load()
     K, D = weight.shape
     idx = indices.contiguous().long()
     wc = weight.detach().contiguous().float()
     with _lib.on_device(weight.device):
-        bad = torch.zeros(1, dtype=torch.int32, device=weight.device)
+        bad = torch.zeros(1, dtype=torch.int32, device=weight.device) if _CHECK_INDICES else None
         if nchw:
             if idx.dim() != 3:
                 raise ValueError("nchw lookup expects indices of shape [B, H, W]")
@@ -128,6 +167,8 @@ def codebook_lookup(indices: torch.Tensor, weight: torch.Tensor, nchw: bool = Tr
             rc = lib.dcvic_codebook_gather(_lib.ptr(idx), _lib.ptr(wc), 1, n, D, K, 0, _lib.ptr(out), _lib.ptr(bad),
                                            _lib.cur_stream())
         _lib.check(rc, "dcvic_codebook_gather")
+        if bad is not None and int(bad) != 0:
+            raise IndexError(f"codebook_lookup: {int(bad)} indices outside [0, {K})")
     return out
 
 
@@ -192,10 +233,26 @@ class _QuantizerBase(nn.Module):
     def freeze_codebook(self, frozen: bool = True):
         """Declare the codebook constant (DC-VIC always freezes the VQGAN,
         src/trainer/rate_distortion_vq_code_trainer.py:62): |e|^2 and the FP16 copy used by the
-        tensor-core search are then prepared once and reused while ``weight._version`` is unchanged."""
+        tensor-core search are then prepared once and reused while the weight tensor, its ``_version`` and the
+        workspace are unchanged.  In-place writes THROUGH ``weight.data`` (``.data.copy_``, EMA updates, loading a
+        state dict into an existing parameter bumps ``_version``, ``.data`` writes do not) are invisible to that
+        check: call ``invalidate_codebook()`` after them."""
         self._frozen = bool(frozen)
         self._prep_key = None
         return self
+
+    def invalidate_codebook(self):
+        """Forget the prepared copies of a frozen codebook (next forward prepares them again)."""
+        self._prep_key = None
+        return self
+
+    @property
+    def codebook_frozen(self) -> bool:
+        return self._frozen
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        super()._load_from_state_dict(*args, **kwargs)
+        self._prep_key = None
 
     def _flags(self) -> int:
         return {"auto": 0, "exact": _lib.VQ_FORCE_EXACT, "tensor": _lib.VQ_FORCE_TENSOR}[self.search]
@@ -234,58 +291,26 @@ class VectorQuantizer2(_QuantizerBase):
         super().__init__()
         self._init_common(n_e, e_dim, beta)
         self.legacy = legacy
-        self.remap = remap
-        if self.remap is not None:
-            self.register_buffer("used", torch.tensor(np.load(self.remap)))
-            self.re_embed = self.used.shape[0]
-            self.unknown_index = unknown_index  # "random" or "extra" or integer
-            if self.unknown_index == "extra":
-                self.unknown_index = self.re_embed
-                self.re_embed = self.re_embed + 1
-        else:
-            self.re_embed = n_e
+        if remap is not None:
+            # quantize.py:221-269 (index remapping onto a "used" subset): no DC-VIC config sets it
+            raise NotImplementedError("VectorQuantizer2(remap=...) is not part of the DC-VIC hot path and is not "
+                                      "implemented; build the quantizer with remap=None")
+        self.remap = None
+        self.unknown_index = unknown_index
+        self.re_embed = n_e
         self.sane_index_shape = sane_index_shape
-
-    # remap helpers (quantize.py:245-269): index bookkeeping, host-side torch ops, unused by DC-VIC
-    def remap_to_used(self, inds):
-        ishape = inds.shape
-        assert len(ishape) > 1
-        inds = inds.reshape(ishape[0], -1)
-        used = self.used.to(inds)
-        match = (inds[:, :, None] == used[None, None, ...]).long()
-        new = match.argmax(-1)
-        unknown = match.sum(2) < 1
-        if self.unknown_index == "random":
-            new[unknown] = torch.randint(0, self.re_embed, size=new[unknown].shape).to(device=new.device)
-        else:
-            new[unknown] = self.unknown_index
-        return new.reshape(ishape)
-
-    def unmap_to_all(self, inds):
-        ishape = inds.shape
-        assert len(ishape) > 1
-        inds = inds.reshape(ishape[0], -1)
-        used = self.used.to(inds)
-        if self.re_embed > self.used.shape[0]:  # extra token
-            inds[inds >= self.used.shape[0]] = 0
-        back = torch.gather(used[None, :][inds.shape[0] * [0], :], 1, inds)
-        return back.reshape(ishape)
 
     def forward(self, z, temp=None, rescale_logits=False, return_logits=False):
         assert temp is None or temp == 1.0, "Only for interface compatible with Gumbel"
         assert rescale_logits is False, "Only for interface compatible with Gumbel"
         assert return_logits is False, "Only for interface compatible with Gumbel"
         z_q, loss, idx = _VQForward.apply(z, self.embedding.weight, self.beta, self.legacy, False, self._flags(), self)
-        if self.remap is not None:
-            idx = self.remap_to_used(idx.reshape(z.shape[0], -1)).reshape(-1, 1)
         if self.sane_index_shape:
             idx = idx.reshape(z_q.shape[0], z_q.shape[2], z_q.shape[3])
         return z_q, loss, (None, None, idx)
 
     def get_codebook_entry(self, indices, shape):
         # shape specifying (batch, height, width, channel)
-        if self.remap is not None:
-            indices = self.unmap_to_all(indices.reshape(shape[0], -1)).reshape(-1)
         if shape is not None:
             return codebook_lookup(indices.reshape(shape[0], shape[1], shape[2]), self.embedding.weight, nchw=True)
         return codebook_lookup(indices.reshape(-1), self.embedding.weight, nchw=False)
@@ -298,11 +323,14 @@ class VectorQuantizer2(_QuantizerBase):
                   sane_index_shape=getattr(ref, "sane_index_shape", False), legacy=getattr(ref, "legacy", True))
         new.embedding.weight.data = ref.embedding.weight.data.clone()
         new.embedding.weight.requires_grad_(ref.embedding.weight.requires_grad)
+        if not ref.embedding.weight.requires_grad:
+            new.freeze_codebook()      # DC-VIC: vq_model.requires_grad_(False) (rate_distortion_vq_code_trainer.py:62)
         return new.to(ref.embedding.weight.device)
 
 
 def swap_quantizer(vq_model: nn.Module) -> nn.Module:
     """``vq_model.quantize = VectorQuantizer2.from_reference(vq_model.quantize)`` -- the VQ plugin
-    boundary of DC-VIC is this attribute (ldm/models/autoencoder.py:39-41)."""
+    boundary of DC-VIC is this attribute (ldm/models/autoencoder.py:39-41).  A codebook that does not require grad
+    (DC-VIC always freezes the VQGAN) is declared frozen, so its |e|^2 / FP16 copies are prepared once."""
     vq_model.quantize = VectorQuantizer2.from_reference(vq_model.quantize)
     return vq_model
