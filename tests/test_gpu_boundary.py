@@ -38,7 +38,7 @@ def test_fused_subclass_of_a_reference_wrapper_matches_it_and_the_oracle():
     ref.load_state_dict({k: v.cpu() for k, v in fused.state_dict().items()})
     x = 3 * torch.randn(2, 8, 4, 6)
     with torch.no_grad():
-        a, b, c = fused(x.to(DEV), False), plain(x.to(DEV), False), ref(x, is_train=False)
+        a, b, c = fused(x.to(DEV), False), plain(x.to(DEV), False), ref(x, training=False)
     assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
     assert torch.equal(a[0].cpu(), c[0]) and float(((a[1].cpu() - c[1]).abs() / c[1]).max()) < 1e-4
     assert float(fused.loss()) > 0
