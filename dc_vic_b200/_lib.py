@@ -13,7 +13,7 @@ from .build import LIB_PATH
 
 OK = 0
 VQ_REUSE_PREP, VQ_FORCE_EXACT, VQ_FORCE_TENSOR = 1, 2, 4
-VQ_STAGE_SEARCH_ONLY, VQ_STAGE_FINISH_ONLY, VQ_STAGE_PREP_ONLY = 8, 16, 64
+VQ_STAGE_SEARCH_ONLY, VQ_STAGE_FINISH_ONLY, VQ_STAGE_PREP_ONLY, VQ_TWO_KERNELS = 8, 16, 64, 128
 GC_PRECISE = 2
 
 _lock = threading.Lock()

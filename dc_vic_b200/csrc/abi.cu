@@ -73,7 +73,11 @@ extern "C" int dcvic_vq_forward(const float* z_nchw, const float* codebook, int 
     if (flags & DCVIC_VQ_STAGE_PREP_ONLY) return rc;
     const bool do_search = !(flags & DCVIC_VQ_STAGE_FINISH_ONLY);
     const bool do_finish = !(flags & DCVIC_VQ_STAGE_SEARCH_ONLY);
-    if (path == 2) {
+    if (path == 2 && do_search && do_finish && !(flags & DCVIC_VQ_TWO_KERNELS) &&
+        vq_fused_supported(z_nchw, zq_nchw, codebook, D, HW, K)) {
+      rc = vq_fused_forward(z_nchw, codebook, ee, emax, cb16, B, D, HW, K, prepared, beta, legacy, zq_nchw, idx, loss,
+                            partials, counters, s);
+    } else if (path == 2) {
       if (do_search)
         rc = vq_tensor_search(z_nchw, cb16, emax, B, D, HW, K, prepared,
                               do_finish && (reinterpret_cast<uintptr_t>(codebook) & 15) == 0 &&

@@ -118,4 +118,11 @@ bool vq_tensor_supported(int D, int K);
 int vq_tensor_search(const float* z, const __half* cb16, const float* emax, int B, int D, int HW, int K,
                      bool after_prepare, bool allow_split, VqMeta* meta, uint2* list, cudaStream_t s);
 
+// vq_fused.cu: the single-pass wide forward (search + re-rank + gather + straight-through value + loss in one
+// persistent kernel) for e_dim in {64, 128, 192, 256}, K % 128 == 0, K <= 2048, H*W % 32 == 0
+bool vq_fused_supported(const float* z, const float* zq, const float* E, int D, int HW, int K);
+int vq_fused_forward(const float* z, const float* E, const float* ee, const float* emax, const __half* cb16, int B,
+                     int D, int HW, int K, bool after_prepare, float beta, int legacy, float* zq, int64_t* idx,
+                     float* loss, double* partials, unsigned* counters, cudaStream_t s);
+
 }  // namespace dcvic

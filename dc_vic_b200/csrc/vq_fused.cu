@@ -1,0 +1,844 @@
+// Single-pass wide VQ forward on sm_100a: tcgen05 candidate search, FP32 re-rank, codebook gather, straight-through
+// value, loss partials and indices in ONE persistent kernel.  z is fetched from HBM once (the second read, for the
+// straight-through value, follows ~one tile time later and is an L2 hit), z_q is written once, and neither the
+// distance matrix nor any candidate list ever leaves the SM.
+//
+// Reference semantics: taming/modules/vqvae/quantize.py:271-312 (d = |z|^2 + |e|^2 - 2 z.e, argmin with the lowest
+// index on ties, z_q = z + (e - z), loss from mean((e - z)^2)).  Same arithmetic contract as the two-kernel path
+// (vq_tcgen05.cu + vq_finish_tma.cu): FP16 x FP16 -> FP32 scores s = z.e - |e|^2/2 on the tensor cores flag every
+// code within a PROVEN margin (vq_margin) of the row maximum; the flagged codes are re-ranked in FP32 in the
+// reference's operation order.
+//
+// One CTA pair (cta_group::2, UMMA 256 x 128 x 16) per 256-token tile, 128 tokens (4 groups of 32) per CTA, 24 warps:
+//   warp 0      TMA: this CTA's half of every FP16 codebook chunk [64 codes x 64 ch] into an 8-stage ring
+//   warp 1      TMA: z chunks [64 ch x 32 tokens] FP32, straight from NCHW, into an 8-stage conversion ring
+//   warp 2      TMA: finish ring - loads z groups [e_dim x 32 tokens] (L2 hits), stores z_q from the same stages
+//   warp 3      MMA issuer (leader CTA; warp-uniform loop, one elected lane).  The A operand lives in TENSOR MEMORY
+//               (tcgen05.mma with [a_tmem]): shared memory only carries the codebook ring, the two z rings and the
+//               candidate bookkeeping, and the MMA's operand reads take a quarter of what the SS form takes.
+//   warps 4-7   converters: lane = token.  FP32 chunk from the ring -> FP16 pairs -> tcgen05.st into the A buffer
+//               (double-buffered: 2 x 128 columns), |z|^2 per token
+//   warps 8-15  epilogue: two column halves x four lane quarters of every 128-column accumulator (double-buffered:
+//               2 x 128 columns).  tcgen05.ld 32 scores per row, running maximum, one flag mask per 32 codes; flagged
+//               chunks go to a 4-entry list per (token, half) in shared memory (entries that a later, larger maximum
+//               rules out are dropped on the fly).  -|e|^2/2 enters as the accumulator's INITIAL value: after a warp
+//               has drained its slice it writes the bias of the N-tile that will use the buffer next (tcgen05.st), so
+//               every MMA accumulates and no extra K-step, operand chunk or per-score add is needed.  At the end of a
+//               tile the lists are compacted into at most 8 candidate codes per token.
+//   warps 16-23 consumers (the finish): (group, token quad) units.  First candidates' codebook rows are requested
+//               before the group's z has arrived; tokens with more than one candidate are re-ranked in FP32
+//               ((|z|^2 + |e|^2) - 2 z.e, lowest index on ties); z + (e - z) overwrites z in the stage; loss partials.
+#include <cuda.h>
+#include <float.h>
+#include <stdlib.h>
+
+#include "vq_common.cuh"
+#include "sm100_ptx.cuh"
+
+namespace dcvic {
+namespace fz {
+
+using namespace tc;
+
+constexpr int BM = 128;   // tokens per CTA tile
+constexpr int BN = 128;   // codes per N-tile (UMMA N); 64 per CTA of the pair
+constexpr int BK = 64;    // channels per chunk (64 fp16 = one SWIZZLE_128B row)
+constexpr int GT = 32;    // tokens per group (one TMA box column block, one finish stage)
+constexpr int NG = BM / GT;
+#ifndef DCVIC_FZ_NB
+#define DCVIC_FZ_NB 8
+#endif
+#ifndef DCVIC_FZ_NZ
+#define DCVIC_FZ_NZ 8
+#endif
+#ifndef DCVIC_FZ_NF
+#define DCVIC_FZ_NF 2
+#endif
+constexpr int NB = DCVIC_FZ_NB;     // codebook ring stages (8 KB each)
+constexpr int NZ = DCVIC_FZ_NZ;     // conversion ring stages (8 KB each), a multiple of 4
+constexpr int NF = DCVIC_FZ_NF;     // finish ring stages (e_dim * 128 B each)
+constexpr int B_STAGE = (BN / 2) * BK * 2;   // 8 KB
+constexpr int Z_STAGE = BK * GT * 4;         // 8 KB
+constexpr int LIST_CAP = 4;         // list entries per (token, column half)
+constexpr int CK_MAX = 8;           // candidate codes per token after compaction; more -> whole-codebook scan
+constexpr int MAX_K = 2048;         // bias table in shared memory
+constexpr int NCONS = 8;
+constexpr int W_TMAB = 0, W_ZLOAD = 1, W_FIN = 2, W_MMA = 3, W_CONV0 = 4, W_EPI0 = 8, W_CONS0 = 16;
+constexpr int NTHREADS = 768;
+// registers: 24 warps launch with 80 each = 61,440, and setmaxnreg can only move registers WITHIN that launch
+// allocation (a total above it leaves the last warpgroup waiting for ever): TMA / MMA warps drop to 32, converters
+// to 56, epilogue warps take 88, consumers 104: 128 * (32 + 56 + 2 * 88 + 2 * 104) = 60,416
+#define FZ_REGS_AUX 32
+#define FZ_REGS_CONV 56
+#define FZ_REGS_EPI 88
+#define FZ_REGS_CONS 104
+
+static_assert(NZ % NG == 0, "every converter warp owns fixed stages of the conversion ring");
+
+struct Smem {
+  // dynamic shared memory map (base aligned to 1024 B); the finish stages are sized for e_dim = 256
+  static constexpr int OFF_B = 0;
+  static constexpr int OFF_Z = OFF_B + NB * B_STAGE;
+  static constexpr int OFF_F = OFF_Z + NZ * Z_STAGE;
+  __host__ __device__ static constexpr int off_bias(int D) { return OFF_F + NF * D * 128; }
+  __host__ __device__ static constexpr int off_list(int D) { return off_bias(D) + MAX_K * 4; }              // [BM][2][LIST_CAP] uint2
+  __host__ __device__ static constexpr int off_ck(int D) { return off_list(D) + BM * 2 * LIST_CAP * 8; }    // [2][BM][CK_MAX] u16
+  __host__ __device__ static constexpr int off_nc(int D) { return off_ck(D) + 2 * BM * CK_MAX * 2; }        // [2][BM] int
+  __host__ __device__ static constexpr int off_zz(int D) { return off_nc(D) + 2 * BM * 4; }                 // [2][BM] float
+  __host__ __device__ static constexpr int off_m(int D) { return off_zz(D) + 2 * BM * 4; }                  // [BM][2] float
+  __host__ __device__ static constexpr int off_ln(int D) { return off_m(D) + BM * 2 * 4; }                  // [BM][2] int
+  __host__ __device__ static constexpr int off_bar(int D) { return off_ln(D) + BM * 2 * 4; }
+  // barrier slots (8 bytes each)
+  static constexpr int BAR_B_FULL = 0;                      // [NB] leader only
+  static constexpr int BAR_B_EMPTY = BAR_B_FULL + NB;       // [NB]
+  static constexpr int BAR_Z_FULL = BAR_B_EMPTY + NB;       // [NZ]
+  static constexpr int BAR_Z_EMPTY = BAR_Z_FULL + NZ;       // [NZ]
+  static constexpr int BAR_A_FULL = BAR_Z_EMPTY + NZ;       // [2][4] leader only
+  static constexpr int BAR_A_EMPTY = BAR_A_FULL + 8;        // [2]
+  static constexpr int BAR_T_FULL = BAR_A_EMPTY + 2;        // [2]
+  static constexpr int BAR_T_EMPTY = BAR_T_FULL + 2;        // [2] leader only
+  static constexpr int BAR_ZZ = BAR_T_EMPTY + 2;            // [2]
+  static constexpr int BAR_C_FULL = BAR_ZZ + 2;             // [2]
+  static constexpr int BAR_C_EMPTY = BAR_C_FULL + 2;        // [2]
+  static constexpr int BAR_F_FULL = BAR_C_EMPTY + 2;        // [NF]
+  static constexpr int BAR_F_DONE = BAR_F_FULL + NF;        // [NF]
+  static constexpr int BAR_COUNT = BAR_F_DONE + NF;
+  __host__ __device__ static constexpr int off_tmem(int D) { return off_bar(D) + BAR_COUNT * 8; }   // [0] TMEM base, [1] tiles converted x 4
+  __host__ __device__ static constexpr int bytes(int D) { return off_tmem(D) + 16; }
+};
+static_assert(Smem::bytes(256) + 1024 <= 232448, "shared memory budget");
+
+__device__ __forceinline__ void tma_load_2d_cta(uint32_t dst, const CUtensorMap* map, int x, int y, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+          dst),
+      "l"(map), "r"(x), "r"(y), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, int x, int y, uint32_t src) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(map), "r"(x),
+               "r"(y), "r"(src)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ float lds32(uint32_t a) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ float4 lds128(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t a, const float4& v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// Progress marks for tools/debug_fused.py (-DDCVIC_FZ_DEBUG builds only): every warp's lane 0 writes
+// (code << 16 | value) to a mapped host buffer, which the host can read while the kernel is still running (or hung).
+#ifdef DCVIC_FZ_DEBUG
+__device__ volatile int* g_fz_dbg = nullptr;
+#define FZ_DBG(code, val)                                                                      \
+  do {                                                                                         \
+    if (g_fz_dbg && (threadIdx.x & 31) == 0)                                                   \
+      g_fz_dbg[(blockIdx.x * 24 + (threadIdx.x >> 5)) * 2] = ((code) << 20) | ((val) & 0xFFFFF); \
+  } while (0)
+#define FZ_DBG2(val)                                                                           \
+  do {                                                                                         \
+    if (g_fz_dbg && (threadIdx.x & 31) == 0)                                                   \
+      g_fz_dbg[(blockIdx.x * 24 + (threadIdx.x >> 5)) * 2 + 1] = (val);                        \
+  } while (0)
+#else
+#define FZ_DBG(code, val)
+#define FZ_DBG2(val)
+#endif
+
+// kind::f16 instruction descriptor: D = F32, A = B = F16, both K-major, N = 128, M = 256 (cta_group::2)
+constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
+
+// D[tmem] (+)= A[tmem] . B[smem]^T
+__device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(kIdesc), "r"(accumulate)
+      : "memory");
+}
+
+template <int D>
+__global__ void __launch_bounds__(NTHREADS, 1)
+vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant__ CUtensorMap tm_zc,
+                const __grid_constant__ CUtensorMap tm_zf, const __grid_constant__ CUtensorMap tm_zq,
+                const float* __restrict__ E, const float* __restrict__ ee, const float* __restrict__ emax_ptr, int N, int HW, int K, int num_ptiles, int wait_first,
+                int64_t* __restrict__ idx, double* __restrict__ partials, unsigned* __restrict__ counters) {
+  constexpr int KC = D / BK;                 // channel chunks per tile
+  constexpr int F_STAGE = D * 128;           // finish stage: [D channels][32 tokens] FP32
+  constexpr int NH = (D + 127) / 128;        // 128-channel blocks (consumer lanes hold 4 channels of each)
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t bar0 = sbase + Smem::off_bar(D);
+  auto bar = [&](int slot) { return bar0 + slot * 8; };
+  float* s_bias = reinterpret_cast<float*>(smem + Smem::off_bias(D));
+  uint2* s_list = reinterpret_cast<uint2*>(smem + Smem::off_list(D));
+  unsigned short* s_ck = reinterpret_cast<unsigned short*>(smem + Smem::off_ck(D));
+  int* s_nc = reinterpret_cast<int*>(smem + Smem::off_nc(D));
+  float* s_zz = reinterpret_cast<float*>(smem + Smem::off_zz(D));
+  float* s_m = reinterpret_cast<float*>(smem + Smem::off_m(D));
+  int* s_ln = reinterpret_cast<int*>(smem + Smem::off_ln(D));
+  volatile uint32_t* s_tmem = reinterpret_cast<volatile uint32_t*>(smem + Smem::off_tmem(D));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const int NT = K / BN;
+  const int my_tiles = pair < num_ptiles ? (num_ptiles - pair + npairs - 1) / npairs : 0;
+  // first token of this CTA's half of its it-th tile
+  auto tile_token0 = [&](int it) { return ((long long)(pair + it * npairs) * 2 + rank) * BM; };
+  auto leader_bar = [&](int slot) { return map_to_cta(bar(slot), 0); };
+
+  if (threadIdx.x == 0) {
+    s_tmem[1] = 0u;
+    for (int s = 0; s < NB; ++s) { mbar_init(bar(Smem::BAR_B_FULL + s), 1); mbar_init(bar(Smem::BAR_B_EMPTY + s), 1); }
+    for (int s = 0; s < NZ; ++s) { mbar_init(bar(Smem::BAR_Z_FULL + s), 1); mbar_init(bar(Smem::BAR_Z_EMPTY + s), 1); }
+    for (int c = 0; c < 8; ++c) mbar_init(bar(Smem::BAR_A_FULL + c), 2 * NG);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(bar(Smem::BAR_A_EMPTY + b), 1);
+      mbar_init(bar(Smem::BAR_T_FULL + b), 1);
+      mbar_init(bar(Smem::BAR_T_EMPTY + b), 16);
+      mbar_init(bar(Smem::BAR_ZZ + b), NG);
+      mbar_init(bar(Smem::BAR_C_FULL + b), 4);
+      mbar_init(bar(Smem::BAR_C_EMPTY + b), NCONS);
+    }
+    for (int s = 0; s < NF; ++s) { mbar_init(bar(Smem::BAR_F_FULL + s), 1); mbar_init(bar(Smem::BAR_F_DONE + s), NCONS); }
+    fence_barrier_init();
+  }
+  if (warp == W_MMA) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + Smem::off_tmem(D)),
+                 "r"(512u));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::);
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync();
+  tc_fence_after();
+  const uint32_t tmem_base = *s_tmem;
+  const uint32_t tmem_acc = tmem_base, tmem_a = tmem_base + 2 * BN;
+  // PDL: see vq_tcgen05.cu.  wait_first: the predecessor in the stream may be the producer of z.
+  if (wait_first) pdl_wait();
+  pdl_launch_dependents();
+
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(FZ_REGS_AUX));
+    if (warp == W_TMAB) {
+      // ===================== codebook ring: this CTA's 64 codes of every [128 codes x 64 ch] chunk =====================
+      if (lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_cb) : "memory");
+        pdl_wait();                                 // the FP16 codebook is written by the prepare kernel
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int it = 0; it < my_tiles; ++it)
+          for (int nt = 0; nt < NT; ++nt)
+            for (int kc = 0; kc < KC; ++kc) {
+              FZ_DBG(1, (it * NT + nt) * KC + kc);
+              mbar_wait(bar(Smem::BAR_B_EMPTY + stage), phase ^ 1);
+              if (leader) mbar_arrive_expect_tx(bar(Smem::BAR_B_FULL + stage), 2 * B_STAGE);
+              tma_load_2d<2>(sbase + Smem::OFF_B + stage * B_STAGE, &tm_cb, kc * BK, nt * BN + (int)rank * (BN / 2),
+                             leader_bar(Smem::BAR_B_FULL + stage));
+              if (++stage == NB) { stage = 0; phase ^= 1; }
+            }
+      }
+    } else if (warp == W_ZLOAD) {
+      // ===================== conversion ring: z chunks [64 ch x 32 tokens], order (tile, chunk, group) ================
+      if (lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_zc) : "memory");
+        int s = 0;
+        for (int it = 0; it < my_tiles; ++it) {
+          const long long t0 = tile_token0(it);
+          for (int kc = 0; kc < KC; ++kc)
+            for (int g = 0; g < NG; ++g, ++s) {
+              const int st = s % NZ;
+              FZ_DBG(2, s);
+              mbar_wait(bar(Smem::BAR_Z_EMPTY + st), ((s / NZ) & 1) ^ 1);
+              const long long tg = t0 + g * GT;         // (groups beyond N: out-of-bounds box, zero fill)
+              mbar_arrive_expect_tx(bar(Smem::BAR_Z_FULL + st), Z_STAGE);
+              tma_load_2d_cta(sbase + Smem::OFF_Z + st * Z_STAGE, &tm_zc, (int)(tg % HW), (int)(tg / HW) * D + kc * BK,
+                              bar(Smem::BAR_Z_FULL + st));
+            }
+        }
+      }
+    } else if (warp == W_FIN) {
+      // ===================== finish ring: load z groups (after their tile has been converted: L2 hits), store z_q ====
+      if (lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_zf) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_zq) : "memory");
+        const int total = my_tiles * NG;
+        auto coords = [&](int j, int& x, int& y) {
+          const long long tg = tile_token0(j / NG) + (j % NG) * GT;
+          x = (int)(tg % HW);
+          y = (int)(tg / HW) * D;
+        };
+        auto load = [&](int j) {
+          const int it = j / NG, st = j % NF;
+          // tile `it` has been converted, i.e. its z is in L2 (a monotonic counter, not the ZZ barrier: this thread
+          // may trail the converters by more than one phase of it; a heuristic for the cache, not a data dependence)
+          FZ_DBG(3, j);
+          while (s_tmem[1] < (uint32_t)(NG * (it + 1))) __nanosleep(64);
+          int x, y;
+          coords(j, x, y);
+          mbar_arrive_expect_tx(bar(Smem::BAR_F_FULL + st), F_STAGE);
+          tma_load_2d_cta(sbase + Smem::OFF_F + st * F_STAGE, &tm_zf, x, y, bar(Smem::BAR_F_FULL + st));
+        };
+        for (int j = 0; j < total && j < NF; ++j) load(j);
+        for (int j = 0; j < total; ++j) {
+          const int st = j % NF;
+          FZ_DBG(4, j);
+          mbar_wait(bar(Smem::BAR_F_DONE + st), (j / NF) & 1);
+          int x, y;
+          coords(j, x, y);
+          tma_store_2d(&tm_zq, x, y, sbase + Smem::OFF_F + st * F_STAGE);
+          bulk_commit();
+          if (j + NF < total) {
+            bulk_wait_read_all();                    // the stage has been read out: refill it
+            load(j + NF);
+          }
+        }
+        bulk_wait_all();
+      }
+    } else if (leader) {
+      // ===================== MMA issuer: whole warp walks the loop, one elected lane issues =====================
+      const bool issuer = elect_one();
+      const uint32_t rt_one = my_tiles > 0 ? 1u : 0u;   // 1, but not a compile-time constant (see vq_tcgen05.cu)
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t g = 0;
+      for (int it = 0; it < my_tiles; ++it) {
+        const int abuf = it & 1;
+        const uint32_t a0 = tmem_a + abuf * (BM);        // 128 columns per A buffer
+        for (int nt = 0; nt < NT; ++nt, ++g) {
+          const uint32_t buf = g & 1;
+          FZ_DBG(5, g);
+          mbar_wait(bar(Smem::BAR_T_EMPTY + buf), (g >> 1) & 1);      // drained and re-initialised with the bias
+          tc_fence_after();
+          const uint32_t d = tmem_acc + buf * BN;
+#pragma unroll 1
+          for (int kc = 0; kc < KC; ++kc) {
+            FZ_DBG(6, g * 8 + kc);
+            if (nt == 0) mbar_wait(bar(Smem::BAR_A_FULL + abuf * 4 + kc), (it >> 1) & 1);
+            FZ_DBG(7, g * 8 + kc);
+            mbar_wait(bar(Smem::BAR_B_FULL + stage), phase);
+            tc_fence_after();
+            if (issuer) {
+              const uint64_t bd = umma_desc_sw128(sbase + Smem::OFF_B + stage * B_STAGE);
+              const uint32_t a = a0 + kc * (BK / 2);
+              umma_ts(d, a, bd, rt_one);
+              umma_ts(d, a + 8, bd + 2, rt_one);
+              umma_ts(d, a + 16, bd + 4, rt_one);
+              umma_ts(d, a + 24, bd + 6, rt_one);
+              umma_commit<2>(bar(Smem::BAR_B_EMPTY + stage));
+            }
+            if (++stage == NB) { stage = 0; phase ^= 1; }
+          }
+          if (issuer) umma_commit<2>(bar(Smem::BAR_T_FULL + buf));
+        }
+        if (issuer) umma_commit<2>(bar(Smem::BAR_A_EMPTY + abuf));
+        __syncwarp();
+      }
+    }
+  } else if (warp < W_EPI0) {
+    // ===================== converters: FP32 ring stage -> FP16 A operand in tensor memory =====================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(FZ_REGS_CONV));
+    const int g = warp - W_CONV0;                    // token group == TMEM lane quarter (warp % 4)
+    const int row = g * GT + lane;
+    const uint32_t tl = tmem_a + ((uint32_t)(g * 32) << 16);
+    const uint32_t lane_off = ((uint32_t)(lane & 3)) << 2;
+    const uint32_t lq = (uint32_t)(lane >> 2);
+    for (int it = 0; it < my_tiles; ++it) {
+      const int abuf = it & 1;
+      FZ_DBG(8, it);
+      mbar_wait(bar(Smem::BAR_A_EMPTY + abuf), ((it >> 1) & 1) ^ 1);   // the MMAs of tile it-2 have read this buffer
+      tc_fence_after();
+      float zz = 0.f;
+#pragma unroll 1
+      for (int kc = 0; kc < KC; ++kc) {
+        const int s = (it * KC + kc) * NG + g;
+        const int st = s % NZ;
+        FZ_DBG(9, s);
+        mbar_wait(bar(Smem::BAR_Z_FULL + st), (s / NZ) & 1);
+        const uint32_t zb = sbase + Smem::OFF_Z + st * Z_STAGE + lane_off;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {                 // 32 channels -> 16 columns per store
+          uint32_t r[16];
+#pragma unroll
+          for (int c = 0; c < 32; c += 2) {
+            const int ch = h * 32 + c;
+            const float v0 = lds32(zb + ch * 128 + ((lq ^ (uint32_t)(ch & 7)) << 4));
+            const float v1 = lds32(zb + (ch + 1) * 128 + ((lq ^ (uint32_t)((ch + 1) & 7)) << 4));
+            zz = fmaf(v0, v0, zz);
+            zz = fmaf(v1, v1, zz);
+            r[c >> 1] = pack_f16x2(v0, v1);
+          }
+          TMEM_ST16(tl + abuf * BM + kc * (BK / 2) + h * 16, r);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(Smem::BAR_Z_EMPTY + st));     // every lane's loads have been consumed
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(leader_bar(Smem::BAR_A_FULL + abuf * 4 + kc));
+      }
+      s_zz[abuf * BM + row] = zz;
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(bar(Smem::BAR_ZZ + abuf));
+        atomicAdd(const_cast<uint32_t*>(s_tmem) + 1, 1u);
+      }
+    }
+  } else if (warp < W_CONS0) {
+    // ===================== epilogue: flag masks per 32 codes, running maximum per row, candidate lists ==========
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(FZ_REGS_EPI));
+    const int q = (warp - W_EPI0) >> 2;              // column half of every accumulator
+    const int part = warp & 3;                       // TMEM lane quarter
+    const int row = part * 32 + lane;
+    const int et = threadIdx.x - W_EPI0 * 32;        // 0..255
+    const uint32_t tlane = tmem_acc + ((uint32_t)(part * 32) << 16) + q * (BN / 2);
+    FZ_DBG(20, 0);
+    pdl_wait();                                      // emax, -|e|^2/2 (prepare kernel)
+    FZ_DBG(21, 0);
+    const float emax = emax_ptr[0];
+    const bool cb_unsafe = __float_as_uint(emax_ptr[1]) != 0u;
+    for (int k = et; k < K; k += 256) s_bias[k] = -0.5f * ee[k];     // exact
+    named_bar_sync(1, 256);
+    const uint32_t bias_base = sbase + Smem::off_bias(D) + q * (BN / 2) * 4;
+    // accumulator slice <- bias of N-tile nt (this warp's 64 columns)
+    auto init_slice = [&](uint32_t taddr, int nt, uint32_t (&r)[32], int half) {
+      const uint32_t a = bias_base + (nt * BN + half * 32) * 4;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float4 v = lds128(a + i * 16);
+        r[4 * i] = __float_as_uint(v.x); r[4 * i + 1] = __float_as_uint(v.y);
+        r[4 * i + 2] = __float_as_uint(v.z); r[4 * i + 3] = __float_as_uint(v.w);
+      }
+      TMEM_ST32(taddr + half * 32, r);
+    };
+    {
+      uint32_t r[32];
+      for (int b = 0; b < 2; ++b) {
+        init_slice(tlane + b * BN, b % NT, r, 0);
+        init_slice(tlane + b * BN, b % NT, r, 1);
+      }
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive_cluster(leader_bar(Smem::BAR_T_EMPTY + 0));
+        mbar_arrive_cluster(leader_bar(Smem::BAR_T_EMPTY + 1));
+      }
+    }
+    uint2* my_list = s_list + (row * 2 + q) * LIST_CAP;
+    uint32_t g = 0;
+    for (int it = 0; it < my_tiles; ++it) {
+      const int abuf = it & 1;
+      const long long t = tile_token0(it) + row;
+      const bool valid = t < N;
+      FZ_DBG(10, it);
+      mbar_wait(bar(Smem::BAR_ZZ + abuf), (it >> 1) & 1);
+      const float zz = s_zz[abuf * BM + row];
+      const float margin = vq_margin(zz, emax);
+      float m = -INFINITY;
+      int n = 0;                                     // list entries; -1: overflow (whole-codebook scan)
+      auto emit = [&](uint32_t mask, float cm, float m_old, uint32_t chunk) {
+        if (mask != 0u) {
+          if (cm > m_old + margin) n = 0;            // every earlier entry is out of reach of the new maximum
+          if (n >= 0) {
+            if (n < LIST_CAP) { my_list[n] = make_uint2((__float_as_uint(cm) & 0xFFFFFF80u) | chunk, mask); ++n; }
+            else n = -1;
+          }
+        }
+      };
+      for (int nt = 0; nt < NT; ++nt, ++g) {
+        const uint32_t buf = g & 1;
+        FZ_DBG(11, g);
+        mbar_wait(bar(Smem::BAR_T_FULL + buf), (g >> 1) & 1);
+        tc_fence_after();
+        const uint32_t taddr = tlane + buf * BN;
+        const uint32_t chunk0 = (uint32_t)(nt * (BN / 32) + q * (BN / 64));
+        const int nt_next = (nt + 2) % NT;           // the N-tile that uses this buffer next (g + 2)
+        uint32_t ra[32], rb[32];
+        float cm, m_old;
+        uint32_t mask;
+        TMEM_LD32(ra, taddr);
+        TMEM_LD32(rb, taddr + 32);
+        TMEM_WAIT_LD32(ra);
+        TMEM_WAIT_LD32(rb);
+        m_old = m;
+        mask = chunk_flags(ra, margin, m, cm);
+        emit(mask, cm, m_old, chunk0);
+        init_slice(taddr, nt_next, ra, 0);
+        m_old = m;
+        mask = chunk_flags(rb, margin, m, cm);
+        emit(mask, cm, m_old, chunk0 + 1);
+        init_slice(taddr, nt_next, rb, 1);
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(leader_bar(Smem::BAR_T_EMPTY + buf));
+      }
+      // ---- end of tile: both halves publish (maximum, entries), the q == 0 thread of every row compacts
+      s_m[row * 2 + q] = m;
+      s_ln[row * 2 + q] = n;
+      FZ_DBG(12, it);
+      named_bar_sync(1, 256);
+      if (q == 0) {
+        const int par = it & 1;
+        FZ_DBG(13, it);
+        if (it >= 2) mbar_wait(bar(Smem::BAR_C_EMPTY + par), ((it >> 1) - 1) & 1);   // consumers are done with tile it-2
+        const float m1 = s_m[row * 2 + 1];
+        const int n1 = s_ln[row * 2 + 1];
+        bool full = cb_unsafe || !(zz < kVqFp16Zz2Max) || n < 0 || n1 < 0;
+        const float thr = fmaxf(m, m1) - margin;
+        unsigned short* ck = s_ck + (par * BM + row) * CK_MAX;
+        int w = 0;
+        if (!full) {
+#pragma unroll
+          for (int qq = 0; qq < 2; ++qq) {
+            const int nn = qq == 0 ? n : n1;
+            const uint2* lp = s_list + (row * 2 + qq) * LIST_CAP;
+#pragma unroll
+            for (int i = 0; i < LIST_CAP; ++i) {
+              if (i < nn) {
+                const uint2 en = lp[i];
+                if (!(vq_key_upper(en.x) < thr)) {
+                  const int c0 = (int)(en.x & 0x7Fu) * kChunk;
+                  uint32_t mk = en.y;
+                  while (mk) {
+                    const int b = __ffs(mk) - 1;
+                    mk &= mk - 1;
+                    if (w < CK_MAX) ck[w] = (unsigned short)(c0 + b);
+                    ++w;
+                  }
+                }
+              }
+            }
+          }
+          if (w > CK_MAX || w <= 0) full = true;
+        }
+        if (full) ck[0] = 0;
+        s_nc[par * BM + row] = valid ? (full ? -1 : w) : 0;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(Smem::BAR_C_FULL + par));
+      }
+      FZ_DBG(14, it);
+      named_bar_sync(2, 256);                         // lists may be overwritten by the next tile
+    }
+  } else {
+    // ===================== consumers: FP32 re-rank, z + (e - z) in place, loss, indices =====================
+    FZ_DBG(22, 0);
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(FZ_REGS_CONS));
+    FZ_DBG(23, 0);
+    // Lane l holds 4 consecutive channels per 128-channel block (c = 4l + 128h) of the 4 tokens of its quad: one
+    // LDG.128 per codebook row and block, one LDS.128 / STS.128 per channel.  Lane l visits its 4 channels in the
+    // order (j + (l >> 1)) & 3 so that a quarter warp touches 8 different 16-byte pieces of the swizzled stage
+    // (see vq_finish_tma.cu, whose consumer this is).
+    const int cw = warp - W_CONS0;                   // token quad inside every group
+    const int rot = (lane >> 1) & 3;
+    const bool hv[2] = {4 * lane < D, 4 * lane + 128 < D};
+    pdl_wait();                                      // |e|^2 comes from the prepare kernel
+    double dsq = 0.0;
+    unsigned n_rr = 0, n_fs = 0;
+    auto rotl = [](float4 v, int r) {
+      if (r & 1) v = make_float4(v.y, v.z, v.w, v.x);
+      if (r & 2) v = make_float4(v.z, v.w, v.x, v.y);
+      return v;
+    };
+    auto load_row = [&](float4 (&r)[NH], int k) {
+      const float* rowp = E + (size_t)k * D + 4 * lane;
+#pragma unroll
+      for (int h = 0; h < NH; ++h)
+        r[h] = hv[h] ? __ldg(reinterpret_cast<const float4*>(rowp + 128 * h)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+    const int total = my_tiles * NG;
+    for (int j = 0; j < total; ++j) {
+      const int it = j / NG, g = j % NG, par = it & 1, st = j % NF;
+      FZ_DBG(15, j);
+      if (g == 0) mbar_wait(bar(Smem::BAR_C_FULL + par), (it >> 1) & 1);
+      const int r0 = g * GT + 4 * cw;                // first row (token of the CTA tile) of this unit
+      const long long t0 = tile_token0(it) + r0;
+      int nc[4], bk[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        nc[i] = s_nc[par * BM + r0 + i];
+        bk[i] = s_ck[(par * BM + r0 + i) * CK_MAX];
+      }
+      const bool live = nc[0] != 0;                  // (a quad is valid or invalid as a whole: N % 4 == 0)
+      uint32_t zo[4];
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        const int rowc = 4 * lane + ((jj + rot) & 3);
+        zo[jj] = sbase + Smem::OFF_F + st * F_STAGE + rowc * 128 + ((cw ^ (rowc & 7)) << 4);
+      }
+      float4 er[4][NH];
+      if (live) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) load_row(er[i], bk[i]);
+      }
+      FZ_DBG(16, j);
+      mbar_wait(bar(Smem::BAR_F_FULL + st), (j / NF) & 1);
+      FZ_DBG(17, j);
+      if (live) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if (nc[i] == 1) continue;                  // warp-uniform
+          float4 zg[NH];
+          float zz = 0.f;
+#pragma unroll
+          for (int h = 0; h < NH; ++h) {
+            float v[4] = {0.f, 0.f, 0.f, 0.f};
+            if (hv[h]) {
+#pragma unroll
+              for (int jj = 0; jj < 4; ++jj) {
+                const float4 a = lds128(zo[jj] + h * 16384);
+                v[jj] = i == 0 ? a.x : i == 1 ? a.y : i == 2 ? a.z : a.w;
+              }
+            }
+            zg[h] = rotl(make_float4(v[0], v[1], v[2], v[3]), (4 - rot) & 3);   // back to channel order
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) zz = __fadd_rn(zz, __fmul_rn(v[jj], v[jj]));
+          }
+          zz = warp_sum(zz);
+          auto dot = [&](const float4 (&r)[NH]) {
+            float dp = 0.f;
+#pragma unroll
+            for (int h = 0; h < NH; ++h) {
+              dp = fmaf(zg[h].x, r[h].x, dp); dp = fmaf(zg[h].y, r[h].y, dp);
+              dp = fmaf(zg[h].z, r[h].z, dp); dp = fmaf(zg[h].w, r[h].w, dp);
+            }
+            return warp_sum(dp);
+          };
+          float bd = FLT_MAX;
+          int kb = 0x7fffffff;
+          if (nc[i] > 1) {
+            ++n_rr;
+            bd = fmaf(-2.f, dot(er[i]), __fadd_rn(zz, __ldg(ee + bk[i])));
+            kb = bk[i];
+            const unsigned short* ck = s_ck + (par * BM + r0 + i) * CK_MAX;
+#pragma unroll 1
+            for (int ci = 1; ci < nc[i]; ++ci) {
+              const int k0 = ck[ci];
+              float4 e0[NH];
+              load_row(e0, k0);
+              const float d0 = fmaf(-2.f, dot(e0), __fadd_rn(zz, __ldg(ee + k0)));
+              if (d0 < bd || (d0 == bd && k0 < kb)) {
+                bd = d0;
+                kb = k0;
+#pragma unroll
+                for (int h = 0; h < NH; ++h) er[i][h] = e0[h];
+              }
+            }
+          } else {
+            // whole-codebook scan (overflowed list or FP16-unsafe input; rare): two rows in flight
+            ++n_fs;
+#pragma unroll 1
+            for (int k = 0; k < K; k += 2) {
+              float4 e0[NH], e1[NH];
+              const int k1 = min(k + 1, K - 1);
+              load_row(e0, k);
+              load_row(e1, k1);
+              const float d0 = fmaf(-2.f, dot(e0), __fadd_rn(zz, __ldg(ee + k)));
+              const float d1 = fmaf(-2.f, dot(e1), __fadd_rn(zz, __ldg(ee + k1)));
+              if (d0 < bd || (d0 == bd && k < kb)) { bd = d0; kb = k; }
+              if (d1 < bd || (d1 == bd && k1 < kb)) { bd = d1; kb = k1; }
+            }
+            load_row(er[i], kb);
+          }
+          bk[i] = kb;
+        }
+        // ---- z_q = z + (e - z) in place, loss partial
+        float sq = 0.f;
+#pragma unroll
+        for (int h = 0; h < NH; ++h) {
+          if (!hv[h]) continue;
+          const float4 v0 = rotl(er[0][h], rot), v1 = rotl(er[1][h], rot), v2 = rotl(er[2][h], rot),
+                       v3 = rotl(er[3][h], rot);      // visiting order
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) {
+            const float4 a = lds128(zo[jj] + h * 16384);
+            const float e0 = jj == 0 ? v0.x : jj == 1 ? v0.y : jj == 2 ? v0.z : v0.w;
+            const float e1 = jj == 0 ? v1.x : jj == 1 ? v1.y : jj == 2 ? v1.z : v1.w;
+            const float e2 = jj == 0 ? v2.x : jj == 1 ? v2.y : jj == 2 ? v2.z : v2.w;
+            const float e3 = jj == 0 ? v3.x : jj == 1 ? v3.y : jj == 2 ? v3.z : v3.w;
+            const float d0 = __fsub_rn(e0, a.x), d1 = __fsub_rn(e1, a.y), d2 = __fsub_rn(e2, a.z),
+                        d3 = __fsub_rn(e3, a.w);
+            sts128(zo[jj] + h * 16384,
+                   make_float4(__fadd_rn(a.x, d0), __fadd_rn(a.y, d1), __fadd_rn(a.z, d2), __fadd_rn(a.w, d3)));
+            sq = fmaf(d0, d0, sq); sq = fmaf(d1, d1, sq); sq = fmaf(d2, d2, sq); sq = fmaf(d3, d3, sq);
+          }
+        }
+        dsq += (double)sq;
+        if (lane < 4) idx[t0 + lane] = (int64_t)(lane == 0 ? bk[0] : lane == 1 ? bk[1] : lane == 2 ? bk[2] : bk[3]);
+      }
+      fence_proxy_async();                          // generic-proxy writes of the stage -> visible to the TMA store
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(bar(Smem::BAR_F_DONE + st));
+        if (g == NG - 1) mbar_arrive(bar(Smem::BAR_C_EMPTY + par));
+      }
+    }
+    // loss: one partial per consumer warp, summed in index order by vq_loss_finalize_kernel (deterministic)
+    {
+      const double wsum = warp_sum(dsq);
+      if (lane == 0) partials[(size_t)blockIdx.x * NCONS + cw] = wsum;
+    }
+    if (lane == 0) {
+      if (n_rr) atomicAdd(counters + kCtrRerank, n_rr);
+      if (n_fs) atomicAdd(counters + kCtrOverflow, n_fs);
+    }
+  }
+
+  FZ_DBG(30, 0);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync();            // no CTA leaves while its peer may still touch its shared memory / barriers
+  if (warp == W_MMA) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
+  }
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn cached = [] {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess) {
+      cudaGetLastError();
+      return (EncodeTiledFn) nullptr;
+    }
+    return reinterpret_cast<EncodeTiledFn>(fn);
+  }();
+  return cached;
+}
+
+static bool map_2d(CUtensorMap* tm, CUtensorMapDataType dt, int esize, const void* base, uint64_t inner, uint64_t outer,
+                   uint64_t pitch_bytes, uint32_t box_inner, uint32_t box_outer) {
+  EncodeTiledFn encode = encode_fn();
+  if (!encode) return false;
+  (void)esize;
+  const cuuint64_t gdim[2] = {inner, outer};
+  const cuuint64_t gstride[1] = {pitch_bytes};
+  const cuuint32_t box[2] = {box_inner, box_outer};
+  const cuuint32_t estr[2] = {1, 1};
+  return encode(tm, dt, 2, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int D>
+static int launch(const CUtensorMap& tcb, const CUtensorMap& tzc, const CUtensorMap& tzf, const CUtensorMap& tzq,
+                  const float* E, const float* ee, const float* emax, int N, int HW, int K,
+                  int wait_first, int64_t* idx, double* partials, unsigned* counters, int* grid_out, cudaStream_t s) {
+  const int smem = Smem::bytes(D) + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(vq_fused_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+      return DCVIC_ERR_CUDA;
+    attr_set = true;
+  }
+  const int num_ptiles = (N + 2 * BM - 1) / (2 * BM);
+  const int max_pairs = kNumSMs / 2;
+  const int npairs = num_ptiles < max_pairs ? num_ptiles : max_pairs;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2 * npairs);
+  cfg.blockDim = dim3(NTHREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 2;
+  *grid_out = 2 * npairs;
+  if (cudaLaunchKernelEx(&cfg, vq_fused_kernel<D>, tcb, tzc, tzf, tzq, E, ee, emax, N, HW, K, num_ptiles,
+                         wait_first, idx, partials, counters) != cudaSuccess)
+    return DCVIC_ERR_CUDA;
+  return dcvic_launch_status();
+}
+
+}  // namespace fz
+
+#ifdef DCVIC_FZ_DEBUG
+}  // namespace dcvic
+extern "C" int dcvic_debug_set_fz_progress(int* mapped) {
+  return cudaMemcpyToSymbol(dcvic::fz::g_fz_dbg, &mapped, sizeof(mapped)) == cudaSuccess ? 0 : -4;
+}
+namespace dcvic {
+#endif
+
+bool vq_fused_supported(const float* z, const float* zq, const float* E, int D, int HW, int K) {
+  static const bool disabled = getenv("DCVIC_VQ_FUSED") && atoi(getenv("DCVIC_VQ_FUSED")) == 0;
+  if (disabled) return false;
+  if (!(D == 64 || D == 128 || D == 192 || D == 256)) return false;
+  if (K % fz::BN != 0 || K < fz::BN || K > fz::MAX_K) return false;
+  if (HW % fz::GT != 0) return false;
+  if ((reinterpret_cast<uintptr_t>(z) & 15) || (reinterpret_cast<uintptr_t>(zq) & 15) ||
+      (reinterpret_cast<uintptr_t>(E) & 15))
+    return false;
+  static const bool sm100 = [] {
+    int dev = 0, major = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) {
+      cudaGetLastError();
+      return false;
+    }
+    return major == 10;
+  }();
+  return sm100 && fz::encode_fn() != nullptr;
+}
+
+int vq_fused_forward(const float* z, const float* E, const float* ee, const float* emax,
+                     const __half* cb16, int B, int D, int HW, int K, bool after_prepare, float beta, int legacy,
+                     float* zq, int64_t* idx, float* loss, double* partials, unsigned* counters, cudaStream_t s) {
+  using namespace fz;
+  CUtensorMap tcb, tzc, tzf, tzq;
+  const int N = B * HW;
+  if (!map_2d(&tcb, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, cb16, (uint64_t)(D + kCb16Pad), (uint64_t)K,
+              (uint64_t)(D + kCb16Pad) * 2, BK, BN / 2) ||
+      !map_2d(&tzc, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, z, (uint64_t)HW, (uint64_t)B * D, (uint64_t)HW * 4, GT, BK) ||
+      !map_2d(&tzf, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, z, (uint64_t)HW, (uint64_t)B * D, (uint64_t)HW * 4, GT, D) ||
+      !map_2d(&tzq, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, zq, (uint64_t)HW, (uint64_t)B * D, (uint64_t)HW * 4, GT, D))
+    return DCVIC_ERR_CUDA;
+  const int wait_first = after_prepare ? 0 : 1;
+  int grid = 0, rc;
+#define DCVIC_FZ(DD) \
+  launch<DD>(tcb, tzc, tzf, tzq, E, ee, emax, N, HW, K, wait_first, idx, partials, counters, &grid, s)
+  switch (D) {
+    case 64: rc = DCVIC_FZ(64); break;
+    case 128: rc = DCVIC_FZ(128); break;
+    case 192: rc = DCVIC_FZ(192); break;
+    case 256: rc = DCVIC_FZ(256); break;
+    default: return DCVIC_ERR_UNSUPPORTED;
+  }
+#undef DCVIC_FZ
+  if (rc) return rc;
+  return vq_launch_loss_finalize(partials, grid * NCONS, (long long)N * D, beta, legacy, loss, s);
+}
+
+}  // namespace dcvic

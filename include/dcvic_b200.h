@@ -50,6 +50,7 @@ enum {
   DCVIC_VQ_STAGE_SEARCH_ONLY = 8,  /* codebook prep + candidate search, no finish */
   DCVIC_VQ_STAGE_FINISH_ONLY = 16, /* finish (re-rank + gather + STE + loss) from the workspace's candidates */
   DCVIC_VQ_STAGE_PREP_ONLY = 64,   /* codebook prep only */
+  DCVIC_VQ_TWO_KERNELS = 128,      /* wide path: separate search and finish kernels instead of the single-pass kernel */
   DCVIC_VQ_RAGGED_HW = 32   /* dcvic_vq_path only: H*W is not a multiple of 4 (or z is not 16-byte aligned), which
                                the tcgen05 search does not take; dcvic_vq_forward sets it by itself */
 };

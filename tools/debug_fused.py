@@ -1,0 +1,57 @@
+"""Where does the single-pass VQ kernel stand?  (needs `python -m dc_vic_b200.build --variant fzdbg -DDCVIC_FZ_DEBUG`)
+    python tools/debug_fused.py [B H W D K] [kind]
+Launches one forward, waits a few seconds, and - finished or hung - prints every warp's last progress mark
+(code, value), read from a mapped host buffer.  Exits by os._exit so that a hung kernel cannot hold the process."""
+import ctypes as C
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+os.environ.setdefault("DCVIC_B200_LIB", os.path.join(ROOT, "dc_vic_b200", "lib", "libdcvic_b200_fzdbg.so"))
+import torch  # noqa: E402
+import dc_vic_b200 as D  # noqa: E402
+from dc_vic_b200 import _lib  # noqa: E402
+from synth import vq_inputs  # noqa: E402
+
+args = [int(a) for a in sys.argv[1:6]] if len(sys.argv) >= 6 else [1, 16, 16, 256, 1024]
+kind = sys.argv[6] if len(sys.argv) > 6 else "D1b"
+B, H, W, Dm, K = args
+z, E = vq_inputs(3, kind, B, Dm, H, W, K)
+lib = _lib.load()
+prog = torch.zeros(148 * 24 * 2, dtype=torch.int32).pin_memory()
+lib.dcvic_debug_set_fz_progress.restype = C.c_int
+lib.dcvic_debug_set_fz_progress.argtypes = [C.c_void_p]
+assert lib.dcvic_debug_set_fz_progress(C.c_void_p(prog.data_ptr())) == 0
+m = D.VectorQuantizer2(K, Dm, 0.25, sane_index_shape=True).to("cuda:0")
+m.embedding.weight.data.copy_(E)
+zc = z.to("cuda:0")
+torch.cuda.synchronize()
+with torch.no_grad():
+    out = m(zc)
+ev = torch.cuda.Event()
+ev.record()
+t0 = time.time()
+while not ev.query() and time.time() - t0 < 5.0:
+    time.sleep(0.05)
+done = ev.query()
+NAMES = {0: "-", 1: "tmaB wait B_EMPTY", 2: "zload wait Z_EMPTY", 3: "fin wait converted", 4: "fin wait F_DONE",
+         5: "mma wait T_EMPTY", 6: "mma wait A_FULL", 7: "mma wait B_FULL", 8: "conv wait A_EMPTY", 9: "conv wait Z_FULL",
+         10: "epi wait ZZ", 11: "epi wait T_FULL", 12: "epi bar1", 13: "epi wait C_EMPTY", 14: "epi bar2",
+         15: "cons wait C_FULL", 16: "cons wait F_FULL", 17: "cons work", 20: "epi pdl", 21: "epi after pdl",
+         22: "cons setmaxnreg", 23: "cons after setmaxnreg", 30: "at exit"}
+print("finished" if done else "HUNG", "after", round(time.time() - t0, 2), "s")
+grid = min(148, 2 * ((B * H * W + 255) // 256))
+for b in range(min(grid, 4)):
+    print(f"CTA {b}:")
+    for w in range(24):
+        v = int(prog[(b * 24 + w) * 2])
+        print(f"  warp {w:2d}: {NAMES.get(v >> 20, v >> 20):24s} {v & 0xFFFFF}")
+if done:
+    from oracle import vq_oracle as O
+    n_mis, n_out, n_tie = O.allowed_index_mismatch(z, E, out[2][2].cpu())
+    print("mismatches", n_mis, "outside clause", n_out, "near ties", n_tie)
+sys.stdout.flush()
+os._exit(0 if done else 1)
