@@ -72,6 +72,19 @@ __host__ __device__ __forceinline__ float vq_margin(float zz, float emax) {
   return 1.02f * 0.0019536f * nz * emax + 9.6e-7f * (nz + emax) + 1.9e-6f * (zz + emax * emax) + 1.2e-7f;
 }
 
+// The single-pass kernel's margin: the same bound from MEASURED rounding residuals instead of worst-case ones.
+// With h = fp16(z), g_k = fp16(e_k), dz = |z - h|, de = max_k |e_k - g_k| (both computed exactly, so FP16 subnormals
+// need no term of their own):  |z.e_k - h.g_k| <= dz (|e_k| + de) + |z| de  (Cauchy-Schwarz), the FP16 x FP16 products
+// are exact in FP32 and their FP32 accumulation over D terms is off by at most D 2^-23 |z| |e_k|; the bound applies
+// to the maximum and to the candidate (x2).  On top: 4 ulps of the reference's own FP32 distance (so that every code
+// the reference's rounding could prefer is re-ranked; anything closer than that is a documented near-tie, 1e-6
+// relative being 8 ulps) and 2 % slack.  -|e|^2/2 is added exactly there.
+__host__ __device__ __forceinline__ float vq_margin_measured(float zz, float dz2, float emax, float demax, int D) {
+  const float nz = sqrtf(zz), dz = sqrtf(dz2) * 1.000001f;
+  return 2.04f * (dz * (emax + demax) + nz * demax) + (float)D * 2.4e-7f * nz * emax + 4.8e-7f * (zz + emax * emax) +
+         1.0e-30f;
+}
+
 // Upper bound of the chunk maximum stored in a list key.  The search keeps the top 25 bits of the FP32 chunk maximum
 // (the low 7 carry the chunk id), i.e. truncates its magnitude: filling the 7 bits with ones rounds a positive value
 // up, but a NEGATIVE one (scores z.e - |e|^2/2 are negative when |z| << |e|) further down - for those the truncated

@@ -16,15 +16,17 @@
 //   warp 3      MMA issuer (leader CTA; warp-uniform loop, one elected lane).  The A operand lives in TENSOR MEMORY
 //               (tcgen05.mma with [a_tmem]): shared memory only carries the codebook ring, the two z rings and the
 //               candidate bookkeeping, and the MMA's operand reads take a quarter of what the SS form takes.
-//   warps 4-7   converters: lane = token.  FP32 chunk from the ring -> FP16 pairs -> tcgen05.st into the A buffer
-//               (double-buffered: 2 x 128 columns), |z|^2 per token
+//   warps 4-7   converters: lane = token.  FP32 chunk from the ring -> FP16 pairs -> tcgen05.st into the A operand
+//               (double-buffered: 2 x 128 columns, so a tile is converted while its predecessor multiplies), |z|^2
+//               per token
 //   warps 8-15  epilogue: two column halves x four lane quarters of every 128-column accumulator (double-buffered:
-//               2 x 128 columns).  tcgen05.ld 32 scores per row, running maximum, one flag mask per 32 codes; flagged
-//               chunks go to a 4-entry list per (token, half) in shared memory (entries that a later, larger maximum
-//               rules out are dropped on the fly).  -|e|^2/2 enters as the accumulator's INITIAL value: after a warp
-//               has drained its slice it writes the bias of the N-tile that will use the buffer next (tcgen05.st), so
-//               every MMA accumulates and no extra K-step, operand chunk or per-score add is needed.  At the end of a
-//               tile the lists are compacted into at most 8 candidate codes per token.
+//               2 x 128 columns).  tcgen05.ld 32 scores per row - the accumulator goes back to the MMA as soon as a
+//               warp's scores are in registers -, running maximum, one flag mask per 32 codes; flagged chunks go to an
+//               8-entry list per (token, half) in shared memory (entries that a later, larger maximum rules out are
+//               dropped on the fly).  -|e|^2/2 is added here, exactly, from a table in shared memory (tensor memory is
+//               full: 2 x 128 accumulator + 2 x 128 operand columns leave no room for the constant operand of an extra
+//               K-step, and re-initialising the accumulators by tcgen05.st kept them from the MMA for too long).  At
+//               the end of a tile the lists are compacted into at most 8 candidate codes per token.
 //   warps 16-23 consumers (the finish): (group, token quad) units.  First candidates' codebook rows are requested
 //               before the group's z has arrived; tokens with more than one candidate are re-ranked in FP32
 //               ((|z|^2 + |e|^2) - 2 z.e, lowest index on ties); z + (e - z) overwrites z in the stage; loss partials.
@@ -46,7 +48,7 @@ constexpr int BK = 64;    // channels per chunk (64 fp16 = one SWIZZLE_128B row)
 constexpr int GT = 32;    // tokens per group (one TMA box column block, one finish stage)
 constexpr int NG = BM / GT;
 #ifndef DCVIC_FZ_NB
-#define DCVIC_FZ_NB 8
+#define DCVIC_FZ_NB 4
 #endif
 #ifndef DCVIC_FZ_NZ
 #define DCVIC_FZ_NZ 8
@@ -54,15 +56,17 @@ constexpr int NG = BM / GT;
 #ifndef DCVIC_FZ_NF
 #define DCVIC_FZ_NF 2
 #endif
-constexpr int NB = DCVIC_FZ_NB;     // codebook ring stages (8 KB each)
-constexpr int NZ = DCVIC_FZ_NZ;     // conversion ring stages (8 KB each), a multiple of 4
+constexpr int NB = DCVIC_FZ_NB;     // codebook ring stages: half an N-tile slab each (see b_chunks_a)
+constexpr int NZ = DCVIC_FZ_NZ;     // conversion ring stages (8 KB each), a multiple of 4: every stage always serves the
+                                    // same converter warp, which therefore meets its barrier phases in order
 constexpr int NF = DCVIC_FZ_NF;     // finish ring stages (e_dim * 128 B each)
-constexpr int B_STAGE = (BN / 2) * BK * 2;   // 8 KB
+constexpr int B_CHUNK = (BN / 2) * BK * 2;   // 8 KB: this CTA's 64 codes x 64 channels
 constexpr int Z_STAGE = BK * GT * 4;         // 8 KB
-constexpr int LIST_CAP = 4;         // list entries per (token, column half)
-constexpr int CK_MAX = 8;           // candidate codes per token after compaction; more -> whole-codebook scan
-constexpr int MAX_K = 2048;         // bias table in shared memory
+constexpr int LIST_CAP = 8;        // list entries per (token, column half)
+constexpr int CK_MAX = 16;         // candidate codes per token after compaction; more -> whole-codebook scan
+constexpr int MAX_K = 1024;         // -|e|^2/2 table in shared memory (larger codebooks take the two-kernel path)
 constexpr int NCONS = 8;
+static_assert(NZ % NG == 0, "a conversion-ring stage must always belong to the same converter warp");
 constexpr int W_TMAB = 0, W_ZLOAD = 1, W_FIN = 2, W_MMA = 3, W_CONV0 = 4, W_EPI0 = 8, W_CONS0 = 16;
 constexpr int NTHREADS = 768;
 // registers: 24 warps launch with 80 each = 61,440, and setmaxnreg can only move registers WITHIN that launch
@@ -73,19 +77,23 @@ constexpr int NTHREADS = 768;
 #define FZ_REGS_EPI 88
 #define FZ_REGS_CONS 104
 
-static_assert(NZ % NG == 0, "every converter warp owns fixed stages of the conversion ring");
 
 struct Smem {
   // dynamic shared memory map (base aligned to 1024 B); the finish stages are sized for e_dim = 256
-  static constexpr int OFF_B = 0;
-  static constexpr int OFF_Z = OFF_B + NB * B_STAGE;
+  static constexpr int OFF_Z = 0;
   static constexpr int OFF_F = OFF_Z + NZ * Z_STAGE;
-  __host__ __device__ static constexpr int off_bias(int D) { return OFF_F + NF * D * 128; }
-  __host__ __device__ static constexpr int off_list(int D) { return off_bias(D) + MAX_K * 4; }              // [BM][2][LIST_CAP] uint2
+  __host__ __device__ static constexpr int off_b(int D) { return OFF_F + NF * D * 128; }
+  // an N-tile's codebook slab = KC channel chunks, brought by two 3-D boxes: chunks [0, nA) and [nA, KC); a ring
+  // stage holds the larger one
+  __host__ __device__ static constexpr int b_chunks_a(int D) { return (D / BK + 1) / 2; }
+  __host__ __device__ static constexpr int b_stage(int D) { return b_chunks_a(D) * B_CHUNK; }
+  __host__ __device__ static constexpr int off_bias(int D) { return off_b(D) + NB * b_stage(D); }          // [MAX_K] float
+  __host__ __device__ static constexpr int off_list(int D) { return off_bias(D) + MAX_K * 4; }             // [BM][2][LIST_CAP] uint2
   __host__ __device__ static constexpr int off_ck(int D) { return off_list(D) + BM * 2 * LIST_CAP * 8; }    // [2][BM][CK_MAX] u16
   __host__ __device__ static constexpr int off_nc(int D) { return off_ck(D) + 2 * BM * CK_MAX * 2; }        // [2][BM] int
   __host__ __device__ static constexpr int off_zz(int D) { return off_nc(D) + 2 * BM * 4; }                 // [2][BM] float
-  __host__ __device__ static constexpr int off_m(int D) { return off_zz(D) + 2 * BM * 4; }                  // [BM][2] float
+  __host__ __device__ static constexpr int off_dz(int D) { return off_zz(D) + 2 * BM * 4; }                 // [2][BM] float
+  __host__ __device__ static constexpr int off_m(int D) { return off_dz(D) + 2 * BM * 4; }                  // [BM][2] float
   __host__ __device__ static constexpr int off_ln(int D) { return off_m(D) + BM * 2 * 4; }                  // [BM][2] int
   __host__ __device__ static constexpr int off_bar(int D) { return off_ln(D) + BM * 2 * 4; }
   // barrier slots (8 bytes each)
@@ -93,8 +101,8 @@ struct Smem {
   static constexpr int BAR_B_EMPTY = BAR_B_FULL + NB;       // [NB]
   static constexpr int BAR_Z_FULL = BAR_B_EMPTY + NB;       // [NZ]
   static constexpr int BAR_Z_EMPTY = BAR_Z_FULL + NZ;       // [NZ]
-  static constexpr int BAR_A_FULL = BAR_Z_EMPTY + NZ;       // [2][4] leader only
-  static constexpr int BAR_A_EMPTY = BAR_A_FULL + 8;        // [2]
+  static constexpr int BAR_A_FULL = BAR_Z_EMPTY + NZ;       // [2][4] leader only: chunk kc of A buffer b is written
+  static constexpr int BAR_A_EMPTY = BAR_A_FULL + 8;        // [2] the tile's MMAs have read A buffer b
   static constexpr int BAR_T_FULL = BAR_A_EMPTY + 2;        // [2]
   static constexpr int BAR_T_EMPTY = BAR_T_FULL + 2;        // [2] leader only
   static constexpr int BAR_ZZ = BAR_T_EMPTY + 2;            // [2]
@@ -147,16 +155,33 @@ __device__ volatile int* g_fz_dbg = nullptr;
 #define FZ_DBG(code, val)                                                                      \
   do {                                                                                         \
     if (g_fz_dbg && (threadIdx.x & 31) == 0)                                                   \
-      g_fz_dbg[(blockIdx.x * 24 + (threadIdx.x >> 5)) * 2] = ((code) << 20) | ((val) & 0xFFFFF); \
+      g_fz_dbg[(blockIdx.x * 24 + (threadIdx.x >> 5)) * 8] = ((code) << 20) | ((val) & 0xFFFFF); \
   } while (0)
-#define FZ_DBG2(val)                                                                           \
-  do {                                                                                         \
-    if (g_fz_dbg && (threadIdx.x & 31) == 0)                                                   \
-      g_fz_dbg[(blockIdx.x * 24 + (threadIdx.x >> 5)) * 2 + 1] = (val);                        \
+// cycle accounting per warp: FZ_T() marks "now"; FZ_ACC(k) adds the cycles since the last mark to slot k (1..6);
+// FZ_PUT() writes the slots (and the warp's total in slot 7)
+#define FZ_TDECL long long fz_t = clock64(), fz_t0 = fz_t, fz_acc[7] = {0, 0, 0, 0, 0, 0, 0}
+#define FZ_T() fz_t = clock64()
+#define FZ_ACC(k)                       \
+  do {                                  \
+    const long long now_ = clock64();   \
+    fz_acc[k] += now_ - fz_t;           \
+    fz_t = now_;                        \
+  } while (0)
+#define FZ_PUT()                                                                                 \
+  do {                                                                                           \
+    if (g_fz_dbg && (threadIdx.x & 31) == 0) {                                                   \
+      fz_acc[0] = clock64() - fz_t0;                                                             \
+      for (int k_ = 1; k_ < 7; ++k_)                                                             \
+        g_fz_dbg[(blockIdx.x * 24 + (threadIdx.x >> 5)) * 8 + k_] = (int)(fz_acc[k_] >> 3);      \
+      g_fz_dbg[(blockIdx.x * 24 + (threadIdx.x >> 5)) * 8 + 7] = (int)(fz_acc[0] >> 3);          \
+    }                                                                                            \
   } while (0)
 #else
 #define FZ_DBG(code, val)
-#define FZ_DBG2(val)
+#define FZ_TDECL
+#define FZ_T()
+#define FZ_ACC(k)
+#define FZ_PUT()
 #endif
 
 // kind::f16 instruction descriptor: D = F32, A = B = F16, both K-major, N = 128, M = 256 (cta_group::2)
@@ -175,12 +200,16 @@ __device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64
 
 template <int D>
 __global__ void __launch_bounds__(NTHREADS, 1)
-vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant__ CUtensorMap tm_zc,
+vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant__ CUtensorMap tm_cb2,
+                const __grid_constant__ CUtensorMap tm_zc,
                 const __grid_constant__ CUtensorMap tm_zf, const __grid_constant__ CUtensorMap tm_zq,
                 const float* __restrict__ E, const float* __restrict__ ee, const float* __restrict__ emax_ptr, int N, int HW, int K, int num_ptiles, int wait_first,
                 int64_t* __restrict__ idx, double* __restrict__ partials, unsigned* __restrict__ counters) {
   constexpr int KC = D / BK;                 // channel chunks per tile
   constexpr int F_STAGE = D * 128;           // finish stage: [D channels][32 tokens] FP32
+  constexpr int NA = Smem::b_chunks_a(D);    // chunks in the first box of an N-tile's slab, KC - NA in the second
+  constexpr int B_STAGE = Smem::b_stage(D);
+  constexpr int OFF_B = Smem::off_b(D);
   constexpr int NH = (D + 127) / 128;        // 128-channel blocks (consumer lanes hold 4 channels of each)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -192,6 +221,7 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant
   unsigned short* s_ck = reinterpret_cast<unsigned short*>(smem + Smem::off_ck(D));
   int* s_nc = reinterpret_cast<int*>(smem + Smem::off_nc(D));
   float* s_zz = reinterpret_cast<float*>(smem + Smem::off_zz(D));
+  float* s_dz = reinterpret_cast<float*>(smem + Smem::off_dz(D));     // |z - fp16(z)|^2 per token
   float* s_m = reinterpret_cast<float*>(smem + Smem::off_m(D));
   int* s_ln = reinterpret_cast<int*>(smem + Smem::off_ln(D));
   volatile uint32_t* s_tmem = reinterpret_cast<volatile uint32_t*>(smem + Smem::off_tmem(D));
@@ -208,6 +238,7 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant
 
   if (threadIdx.x == 0) {
     s_tmem[1] = 0u;
+    s_tmem[2] = 0u;
     for (int s = 0; s < NB; ++s) { mbar_init(bar(Smem::BAR_B_FULL + s), 1); mbar_init(bar(Smem::BAR_B_EMPTY + s), 1); }
     for (int s = 0; s < NZ; ++s) { mbar_init(bar(Smem::BAR_Z_FULL + s), 1); mbar_init(bar(Smem::BAR_Z_EMPTY + s), 1); }
     for (int c = 0; c < 8; ++c) mbar_init(bar(Smem::BAR_A_FULL + c), 2 * NG);
@@ -217,9 +248,9 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant
       mbar_init(bar(Smem::BAR_T_EMPTY + b), 16);
       mbar_init(bar(Smem::BAR_ZZ + b), NG);
       mbar_init(bar(Smem::BAR_C_FULL + b), 4);
-      mbar_init(bar(Smem::BAR_C_EMPTY + b), NCONS);
+      mbar_init(bar(Smem::BAR_C_EMPTY + b), NG * 8);          // one arrival per (group, quad) unit
     }
-    for (int s = 0; s < NF; ++s) { mbar_init(bar(Smem::BAR_F_FULL + s), 1); mbar_init(bar(Smem::BAR_F_DONE + s), NCONS); }
+    for (int s = 0; s < NF; ++s) { mbar_init(bar(Smem::BAR_F_FULL + s), 1); mbar_init(bar(Smem::BAR_F_DONE + s), 8); }
     fence_barrier_init();
   }
   if (warp == W_MMA) {
@@ -232,6 +263,7 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant
   cluster_sync();
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
+  // tensor memory: accumulators 2 x 128 columns | A operand 2 x 128 columns
   const uint32_t tmem_acc = tmem_base, tmem_a = tmem_base + 2 * BN;
   // PDL: see vq_tcgen05.cu.  wait_first: the predecessor in the stream may be the producer of z.
   if (wait_first) pdl_wait();
@@ -246,35 +278,53 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant
         pdl_wait();                                 // the FP16 codebook is written by the prepare kernel
         int stage = 0;
         uint32_t phase = 0;
+        FZ_TDECL;
+        // two 3-D boxes per N-tile: [64 ch] x [this CTA's 64 codes] x [NA | KC - NA chunks] of the chunk-major FP16
+        // codebook (a request costs the issuing thread ~235 cycles whatever its size - tools/probe_tma.cu -, so 8 KB
+        // boxes could not feed an MMA that eats one every 218 cycles)
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_cb2) : "memory");
         for (int it = 0; it < my_tiles; ++it)
           for (int nt = 0; nt < NT; ++nt)
-            for (int kc = 0; kc < KC; ++kc) {
-              FZ_DBG(1, (it * NT + nt) * KC + kc);
+#pragma unroll
+            for (int part = 0; part < (KC > NA ? 2 : 1); ++part) {
+              FZ_DBG(1, (it * NT + nt) * 2 + part);
+              FZ_T();
               mbar_wait(bar(Smem::BAR_B_EMPTY + stage), phase ^ 1);
-              if (leader) mbar_arrive_expect_tx(bar(Smem::BAR_B_FULL + stage), 2 * B_STAGE);
-              tma_load_2d<2>(sbase + Smem::OFF_B + stage * B_STAGE, &tm_cb, kc * BK, nt * BN + (int)rank * (BN / 2),
-                             leader_bar(Smem::BAR_B_FULL + stage));
+              FZ_ACC(1);
+              const int nch = part == 0 ? NA : KC - NA;
+              if (leader) mbar_arrive_expect_tx(bar(Smem::BAR_B_FULL + stage), 2 * nch * B_CHUNK);
+              asm volatile(
+                  "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, "
+                  "{%2, %3, %4}], [%5];" ::"r"(sbase + OFF_B + stage * B_STAGE),
+                  "l"(part == 0 ? &tm_cb : &tm_cb2), "r"(0), "r"(nt * BN + (int)rank * (BN / 2)), "r"(part == 0 ? 0 : NA),
+                  "r"(leader_bar(Smem::BAR_B_FULL + stage))
+                  : "memory");
               if (++stage == NB) { stage = 0; phase ^= 1; }
             }
+        FZ_PUT();
       }
     } else if (warp == W_ZLOAD) {
       // ===================== conversion ring: z chunks [64 ch x 32 tokens], order (tile, chunk, group) ================
       if (lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_zc) : "memory");
         int s = 0;
+        FZ_TDECL;
         for (int it = 0; it < my_tiles; ++it) {
           const long long t0 = tile_token0(it);
           for (int kc = 0; kc < KC; ++kc)
             for (int g = 0; g < NG; ++g, ++s) {
               const int st = s % NZ;
               FZ_DBG(2, s);
+              FZ_T();
               mbar_wait(bar(Smem::BAR_Z_EMPTY + st), ((s / NZ) & 1) ^ 1);
+              FZ_ACC(1);
               const long long tg = t0 + g * GT;         // (groups beyond N: out-of-bounds box, zero fill)
               mbar_arrive_expect_tx(bar(Smem::BAR_Z_FULL + st), Z_STAGE);
               tma_load_2d_cta(sbase + Smem::OFF_Z + st * Z_STAGE, &tm_zc, (int)(tg % HW), (int)(tg / HW) * D + kc * BK,
                               bar(Smem::BAR_Z_FULL + st));
             }
         }
+        FZ_PUT();
       }
     } else if (warp == W_FIN) {
       // ===================== finish ring: load z groups (after their tile has been converted: L2 hits), store z_q ====
@@ -282,6 +332,7 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_zf) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_zq) : "memory");
         const int total = my_tiles * NG;
+        FZ_TDECL;
         auto coords = [&](int j, int& x, int& y) {
           const long long tg = tile_token0(j / NG) + (j % NG) * GT;
           x = (int)(tg % HW);
@@ -292,7 +343,9 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant
           // tile `it` has been converted, i.e. its z is in L2 (a monotonic counter, not the ZZ barrier: this thread
           // may trail the converters by more than one phase of it; a heuristic for the cache, not a data dependence)
           FZ_DBG(3, j);
+          FZ_T();
           while (s_tmem[1] < (uint32_t)(NG * (it + 1))) __nanosleep(64);
+          FZ_ACC(1);
           int x, y;
           coords(j, x, y);
           mbar_arrive_expect_tx(bar(Smem::BAR_F_FULL + st), F_STAGE);
@@ -302,17 +355,24 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant
         for (int j = 0; j < total; ++j) {
           const int st = j % NF;
           FZ_DBG(4, j);
+          FZ_T();
           mbar_wait(bar(Smem::BAR_F_DONE + st), (j / NF) & 1);
+          FZ_ACC(2);
           int x, y;
           coords(j, x, y);
           tma_store_2d(&tm_zq, x, y, sbase + Smem::OFF_F + st * F_STAGE);
           bulk_commit();
           if (j + NF < total) {
+            FZ_T();
             bulk_wait_read_all();                    // the stage has been read out: refill it
+            FZ_ACC(3);
             load(j + NF);
           }
         }
+        FZ_T();
         bulk_wait_all();
+        FZ_ACC(4);
+        FZ_PUT();
       }
     } else if (leader) {
       // ===================== MMA issuer: whole warp walks the loop, one elected lane issues =====================
@@ -321,31 +381,44 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant
       int stage = 0;
       uint32_t phase = 0;
       uint32_t g = 0;
+      FZ_TDECL;
+      const uint32_t rt_zero = my_tiles < 0 ? 1u : 0u;  // 0, likewise
       for (int it = 0; it < my_tiles; ++it) {
         const int abuf = it & 1;
-        const uint32_t a0 = tmem_a + abuf * (BM);        // 128 columns per A buffer
+        const uint32_t a0 = tmem_a + abuf * BM;           // 128 columns per A buffer
         for (int nt = 0; nt < NT; ++nt, ++g) {
           const uint32_t buf = g & 1;
           FZ_DBG(5, g);
-          mbar_wait(bar(Smem::BAR_T_EMPTY + buf), (g >> 1) & 1);      // drained and re-initialised with the bias
+          FZ_T();
+          if (g >= 2) mbar_wait(bar(Smem::BAR_T_EMPTY + buf), ((g >> 1) - 1) & 1);   // both CTAs hold its scores in registers
+          FZ_ACC(1);
           tc_fence_after();
           const uint32_t d = tmem_acc + buf * BN;
-#pragma unroll 1
-          for (int kc = 0; kc < KC; ++kc) {
-            FZ_DBG(6, g * 8 + kc);
-            if (nt == 0) mbar_wait(bar(Smem::BAR_A_FULL + abuf * 4 + kc), (it >> 1) & 1);
-            FZ_DBG(7, g * 8 + kc);
+#pragma unroll
+          for (int part = 0; part < (KC > NA ? 2 : 1); ++part) {
+            FZ_T();
             mbar_wait(bar(Smem::BAR_B_FULL + stage), phase);
+            FZ_ACC(3);
             tc_fence_after();
-            if (issuer) {
-              const uint64_t bd = umma_desc_sw128(sbase + Smem::OFF_B + stage * B_STAGE);
-              const uint32_t a = a0 + kc * (BK / 2);
-              umma_ts(d, a, bd, rt_one);
-              umma_ts(d, a + 8, bd + 2, rt_one);
-              umma_ts(d, a + 16, bd + 4, rt_one);
-              umma_ts(d, a + 24, bd + 6, rt_one);
-              umma_commit<2>(bar(Smem::BAR_B_EMPTY + stage));
+            const uint32_t slab = sbase + OFF_B + stage * B_STAGE;
+            const int c0 = part == 0 ? 0 : NA, c1 = part == 0 ? NA : KC;
+#pragma unroll 1
+            for (int c = c0; c < c1; ++c) {
+              FZ_DBG(6, g * 8 + c);
+              FZ_T();
+              if (nt == 0) mbar_wait(bar(Smem::BAR_A_FULL + abuf * 4 + c), (it >> 1) & 1);
+              FZ_ACC(2);
+              tc_fence_after();
+              if (issuer) {
+                const uint64_t bd = umma_desc_sw128(slab + (c - c0) * B_CHUNK);
+                const uint32_t a = a0 + c * (BK / 2);
+                umma_ts(d, a, bd, c == 0 ? rt_zero : rt_one);     // the N-tile's first MMA overwrites the buffer
+                umma_ts(d, a + 8, bd + 2, rt_one);
+                umma_ts(d, a + 16, bd + 4, rt_one);
+                umma_ts(d, a + 24, bd + 6, rt_one);
+              }
             }
+            if (issuer) umma_commit<2>(bar(Smem::BAR_B_EMPTY + stage));
             if (++stage == NB) { stage = 0; phase ^= 1; }
           }
           if (issuer) umma_commit<2>(bar(Smem::BAR_T_FULL + buf));
@@ -353,6 +426,7 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant
         if (issuer) umma_commit<2>(bar(Smem::BAR_A_EMPTY + abuf));
         __syncwarp();
       }
+      FZ_PUT();
     }
   } else if (warp < W_EPI0) {
     // ===================== converters: FP32 ring stage -> FP16 A operand in tensor memory =====================
@@ -362,18 +436,23 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant
     const uint32_t tl = tmem_a + ((uint32_t)(g * 32) << 16);
     const uint32_t lane_off = ((uint32_t)(lane & 3)) << 2;
     const uint32_t lq = (uint32_t)(lane >> 2);
+    FZ_TDECL;
     for (int it = 0; it < my_tiles; ++it) {
       const int abuf = it & 1;
       FZ_DBG(8, it);
+      FZ_T();
       mbar_wait(bar(Smem::BAR_A_EMPTY + abuf), ((it >> 1) & 1) ^ 1);   // the MMAs of tile it-2 have read this buffer
+      FZ_ACC(1);
       tc_fence_after();
-      float zz = 0.f;
+      float zz = 0.f, dz2 = 0.f;
 #pragma unroll 1
       for (int kc = 0; kc < KC; ++kc) {
         const int s = (it * KC + kc) * NG + g;
         const int st = s % NZ;
         FZ_DBG(9, s);
+        FZ_T();
         mbar_wait(bar(Smem::BAR_Z_FULL + st), (s / NZ) & 1);
+        FZ_ACC(2);
         const uint32_t zb = sbase + Smem::OFF_Z + st * Z_STAGE + lane_off;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {                 // 32 channels -> 16 columns per store
@@ -385,7 +464,13 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant
             const float v1 = lds32(zb + (ch + 1) * 128 + ((lq ^ (uint32_t)((ch + 1) & 7)) << 4));
             zz = fmaf(v0, v0, zz);
             zz = fmaf(v1, v1, zz);
-            r[c >> 1] = pack_f16x2(v0, v1);
+            const uint32_t pk = pack_f16x2(v0, v1);
+            r[c >> 1] = pk;
+            // the rounding residual of this pair (exact in FP32): the margin uses its measured norm
+            const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&pk));
+            const float d0 = v0 - hf.x, d1 = v1 - hf.y;
+            dz2 = fmaf(d0, d0, dz2);
+            dz2 = fmaf(d1, d1, dz2);
           }
           TMEM_ST16(tl + abuf * BM + kc * (BK / 2) + h * 16, r);
         }
@@ -397,68 +482,72 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant
         if (lane == 0) mbar_arrive_cluster(leader_bar(Smem::BAR_A_FULL + abuf * 4 + kc));
       }
       s_zz[abuf * BM + row] = zz;
+      s_dz[abuf * BM + row] = dz2;
       __syncwarp();
       if (lane == 0) {
         mbar_arrive(bar(Smem::BAR_ZZ + abuf));
         atomicAdd(const_cast<uint32_t*>(s_tmem) + 1, 1u);
       }
     }
+    FZ_PUT();
   } else if (warp < W_CONS0) {
     // ===================== epilogue: flag masks per 32 codes, running maximum per row, candidate lists ==========
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(FZ_REGS_EPI));
     const int q = (warp - W_EPI0) >> 2;              // column half of every accumulator
     const int part = warp & 3;                       // TMEM lane quarter
     const int row = part * 32 + lane;
-    const int et = threadIdx.x - W_EPI0 * 32;        // 0..255
     const uint32_t tlane = tmem_acc + ((uint32_t)(part * 32) << 16) + q * (BN / 2);
     FZ_DBG(20, 0);
     pdl_wait();                                      // emax, -|e|^2/2 (prepare kernel)
     FZ_DBG(21, 0);
     const float emax = emax_ptr[0];
     const bool cb_unsafe = __float_as_uint(emax_ptr[1]) != 0u;
-    for (int k = et; k < K; k += 256) s_bias[k] = -0.5f * ee[k];     // exact
+    const float demax = emax_ptr[2];
+    for (int k = threadIdx.x - W_EPI0 * 32; k < K; k += 256) s_bias[k] = -0.5f * ee[k];     // exact
     named_bar_sync(1, 256);
     const uint32_t bias_base = sbase + Smem::off_bias(D) + q * (BN / 2) * 4;
-    // accumulator slice <- bias of N-tile nt (this warp's 64 columns)
-    auto init_slice = [&](uint32_t taddr, int nt, uint32_t (&r)[32], int half) {
-      const uint32_t a = bias_base + (nt * BN + half * 32) * 4;
+    // scores of one 32-code chunk += -|e|^2/2 of its codes (the same 32 values for every row: broadcast loads)
+    auto add_bias = [&](uint32_t (&r)[32], uint32_t a) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const float4 v = lds128(a + i * 16);
-        r[4 * i] = __float_as_uint(v.x); r[4 * i + 1] = __float_as_uint(v.y);
-        r[4 * i + 2] = __float_as_uint(v.z); r[4 * i + 3] = __float_as_uint(v.w);
+        const float4 b = lds128(a + i * 16);
+        r[4 * i] = __float_as_uint(__fadd_rn(__uint_as_float(r[4 * i]), b.x));
+        r[4 * i + 1] = __float_as_uint(__fadd_rn(__uint_as_float(r[4 * i + 1]), b.y));
+        r[4 * i + 2] = __float_as_uint(__fadd_rn(__uint_as_float(r[4 * i + 2]), b.z));
+        r[4 * i + 3] = __float_as_uint(__fadd_rn(__uint_as_float(r[4 * i + 3]), b.w));
       }
-      TMEM_ST32(taddr + half * 32, r);
     };
-    {
-      uint32_t r[32];
-      for (int b = 0; b < 2; ++b) {
-        init_slice(tlane + b * BN, b % NT, r, 0);
-        init_slice(tlane + b * BN, b % NT, r, 1);
-      }
-      tmem_wait_st();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        mbar_arrive_cluster(leader_bar(Smem::BAR_T_EMPTY + 0));
-        mbar_arrive_cluster(leader_bar(Smem::BAR_T_EMPTY + 1));
-      }
-    }
     uint2* my_list = s_list + (row * 2 + q) * LIST_CAP;
     uint32_t g = 0;
+    FZ_TDECL;
     for (int it = 0; it < my_tiles; ++it) {
       const int abuf = it & 1;
       const long long t = tile_token0(it) + row;
       const bool valid = t < N;
       FZ_DBG(10, it);
+      FZ_T();
       mbar_wait(bar(Smem::BAR_ZZ + abuf), (it >> 1) & 1);
+      FZ_ACC(1);
       const float zz = s_zz[abuf * BM + row];
-      const float margin = vq_margin(zz, emax);
+      const float margin = vq_margin_measured(zz, s_dz[abuf * BM + row], emax, demax, D);
       float m = -INFINITY;
       int n = 0;                                     // list entries; -1: overflow (whole-codebook scan)
+      // A flagged chunk joins the list.  Entries a later maximum has put out of reach are dropped: all of them at
+      // once when this chunk's maximum beats the previous running maximum by more than the margin, one by one (only
+      // when the list is full) when the running maximum has crept away from them in small steps.
       auto emit = [&](uint32_t mask, float cm, float m_old, uint32_t chunk) {
         if (mask != 0u) {
-          if (cm > m_old + margin) n = 0;            // every earlier entry is out of reach of the new maximum
+          if (cm > m_old + margin) n = 0;
+          if (n == LIST_CAP) {
+            const float keep = m - margin;
+            int w = 0;
+#pragma unroll
+            for (int i = 0; i < LIST_CAP; ++i) {
+              const uint2 en = my_list[i];
+              if (!(vq_key_upper(en.x) < keep)) { my_list[w] = en; ++w; }
+            }
+            n = w;
+          }
           if (n >= 0) {
             if (n < LIST_CAP) { my_list[n] = make_uint2((__float_as_uint(cm) & 0xFFFFFF80u) | chunk, mask); ++n; }
             else n = -1;
@@ -468,11 +557,12 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant
       for (int nt = 0; nt < NT; ++nt, ++g) {
         const uint32_t buf = g & 1;
         FZ_DBG(11, g);
+        FZ_T();
         mbar_wait(bar(Smem::BAR_T_FULL + buf), (g >> 1) & 1);
+        FZ_ACC(2);
         tc_fence_after();
         const uint32_t taddr = tlane + buf * BN;
         const uint32_t chunk0 = (uint32_t)(nt * (BN / 32) + q * (BN / 64));
-        const int nt_next = (nt + 2) % NT;           // the N-tile that uses this buffer next (g + 2)
         uint32_t ra[32], rb[32];
         float cm, m_old;
         uint32_t mask;
@@ -480,38 +570,43 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant
         TMEM_LD32(rb, taddr + 32);
         TMEM_WAIT_LD32(ra);
         TMEM_WAIT_LD32(rb);
-        m_old = m;
-        mask = chunk_flags(ra, margin, m, cm);
-        emit(mask, cm, m_old, chunk0);
-        init_slice(taddr, nt_next, ra, 0);
-        m_old = m;
-        mask = chunk_flags(rb, margin, m, cm);
-        emit(mask, cm, m_old, chunk0 + 1);
-        init_slice(taddr, nt_next, rb, 1);
-        tmem_wait_st();
+        // every score of this warp's slice is in registers: the accumulator can be overwritten
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(leader_bar(Smem::BAR_T_EMPTY + buf));
+        add_bias(ra, bias_base + nt * (BN * 4));
+        add_bias(rb, bias_base + nt * (BN * 4) + 128);
+        m_old = m;
+        mask = chunk_flags(ra, margin, m, cm);
+        emit(mask, cm, m_old, chunk0);
+        m_old = m;
+        mask = chunk_flags(rb, margin, m, cm);
+        emit(mask, cm, m_old, chunk0 + 1);
+        FZ_ACC(3);
       }
       // ---- end of tile: both halves publish (maximum, entries), the q == 0 thread of every row compacts
       s_m[row * 2 + q] = m;
       s_ln[row * 2 + q] = n;
       FZ_DBG(12, it);
+      FZ_T();
       named_bar_sync(1, 256);
+      FZ_ACC(4);
       if (q == 0) {
         const int par = it & 1;
         FZ_DBG(13, it);
         if (it >= 2) mbar_wait(bar(Smem::BAR_C_EMPTY + par), ((it >> 1) - 1) & 1);   // consumers are done with tile it-2
+        FZ_ACC(5);
         const float m1 = s_m[row * 2 + 1];
         const int n1 = s_ln[row * 2 + 1];
-        bool full = cb_unsafe || !(zz < kVqFp16Zz2Max) || n < 0 || n1 < 0;
         const float thr = fmaxf(m, m1) - margin;
+        // (a half whose list overflowed only matters if its maximum is within reach of the row's)
+        bool full = cb_unsafe || !(zz < kVqFp16Zz2Max) || (n < 0 && !(m < thr)) || (n1 < 0 && !(m1 < thr));
         unsigned short* ck = s_ck + (par * BM + row) * CK_MAX;
         int w = 0;
         if (!full) {
 #pragma unroll
           for (int qq = 0; qq < 2; ++qq) {
-            const int nn = qq == 0 ? n : n1;
+            const int nn = (qq == 0 ? m : m1) < thr ? 0 : (qq == 0 ? n : n1);
             const uint2* lp = s_list + (row * 2 + qq) * LIST_CAP;
 #pragma unroll
             for (int i = 0; i < LIST_CAP; ++i) {
@@ -530,7 +625,12 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant
               }
             }
           }
-          if (w > CK_MAX || w <= 0) full = true;
+          if (w > CK_MAX || w <= 0) {
+            full = true;
+            if (valid) atomicAdd(counters + (w <= 0 ? 8 : 7), 1u);     // diagnostics: why a token is scanned in full
+          }
+        } else if (valid) {
+          atomicAdd(counters + ((n < 0 || n1 < 0) ? 6 : 9), 1u);
         }
         if (full) ck[0] = 0;
         s_nc[par * BM + row] = valid ? (full ? -1 : w) : 0;
@@ -538,8 +638,11 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant
         if (lane == 0) mbar_arrive(bar(Smem::BAR_C_FULL + par));
       }
       FZ_DBG(14, it);
+      FZ_T();
       named_bar_sync(2, 256);                         // lists may be overwritten by the next tile
+      FZ_ACC(6);
     }
+    FZ_PUT();
   } else {
     // ===================== consumers: FP32 re-rank, z + (e - z) in place, loss, indices =====================
     FZ_DBG(22, 0);
@@ -549,7 +652,7 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant
     // LDG.128 per codebook row and block, one LDS.128 / STS.128 per channel.  Lane l visits its 4 channels in the
     // order (j + (l >> 1)) & 3 so that a quarter warp touches 8 different 16-byte pieces of the swizzled stage
     // (see vq_finish_tma.cu, whose consumer this is).
-    const int cw = warp - W_CONS0;                   // token quad inside every group
+    const int cwarp = warp - W_CONS0;
     const int rot = (lane >> 1) & 3;
     const bool hv[2] = {4 * lane < D, 4 * lane + 128 < D};
     pdl_wait();                                      // |e|^2 comes from the prepare kernel
@@ -566,11 +669,21 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant
       for (int h = 0; h < NH; ++h)
         r[h] = hv[h] ? __ldg(reinterpret_cast<const float4*>(rowp + 128 * h)) : make_float4(0.f, 0.f, 0.f, 0.f);
     };
-    const int total = my_tiles * NG;
-    for (int j = 0; j < total; ++j) {
+    const int total_units = my_tiles * NG * 8;
+    FZ_TDECL;
+    // (group, token quad) units are handed out in order through a shared counter: a warp that drew long re-ranks does
+    // not hold up its CTA
+    for (;;) {
+      int u = 0;
+      if (lane == 0) u = (int)atomicAdd(const_cast<uint32_t*>(s_tmem) + 2, 1u);
+      u = __shfl_sync(0xffffffffu, u, 0);
+      if (u >= total_units) break;
+      const int j = u >> 3, cw = u & 7;              // group (in this CTA's sequence), token quad inside it
       const int it = j / NG, g = j % NG, par = it & 1, st = j % NF;
       FZ_DBG(15, j);
-      if (g == 0) mbar_wait(bar(Smem::BAR_C_FULL + par), (it >> 1) & 1);
+      FZ_T();
+      mbar_wait(bar(Smem::BAR_C_FULL + par), (it >> 1) & 1);
+      FZ_ACC(1);
       const int r0 = g * GT + 4 * cw;                // first row (token of the CTA tile) of this unit
       const long long t0 = tile_token0(it) + r0;
       int nc[4], bk[4];
@@ -592,7 +705,9 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant
         for (int i = 0; i < 4; ++i) load_row(er[i], bk[i]);
       }
       FZ_DBG(16, j);
+      FZ_ACC(2);
       mbar_wait(bar(Smem::BAR_F_FULL + st), (j / NF) & 1);
+      FZ_ACC(3);
       FZ_DBG(17, j);
       if (live) {
 #pragma unroll
@@ -662,8 +777,15 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant
           }
           bk[i] = kb;
         }
+        FZ_ACC(4);
         // ---- z_q = z + (e - z) in place, loss partial
         float sq = 0.f;
+        float4 za[NH][4];                             // all loads first: one round trip to shared memory per unit
+#pragma unroll
+        for (int h = 0; h < NH; ++h)
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj)
+            za[h][jj] = hv[h] ? lds128(zo[jj] + h * 16384) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int h = 0; h < NH; ++h) {
           if (!hv[h]) continue;
@@ -671,7 +793,7 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant
                        v3 = rotl(er[3][h], rot);      // visiting order
 #pragma unroll
           for (int jj = 0; jj < 4; ++jj) {
-            const float4 a = lds128(zo[jj] + h * 16384);
+            const float4 a = za[h][jj];
             const float e0 = jj == 0 ? v0.x : jj == 1 ? v0.y : jj == 2 ? v0.z : v0.w;
             const float e1 = jj == 0 ? v1.x : jj == 1 ? v1.y : jj == 2 ? v1.z : v1.w;
             const float e2 = jj == 0 ? v2.x : jj == 1 ? v2.y : jj == 2 ? v2.z : v2.w;
@@ -690,13 +812,15 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant
       __syncwarp();
       if (lane == 0) {
         mbar_arrive(bar(Smem::BAR_F_DONE + st));
-        if (g == NG - 1) mbar_arrive(bar(Smem::BAR_C_EMPTY + par));
+        mbar_arrive(bar(Smem::BAR_C_EMPTY + par));
       }
+      FZ_ACC(5);
     }
+    FZ_PUT();
     // loss: one partial per consumer warp, summed in index order by vq_loss_finalize_kernel (deterministic)
     {
       const double wsum = warp_sum(dsq);
-      if (lane == 0) partials[(size_t)blockIdx.x * NCONS + cw] = wsum;
+      if (lane == 0) partials[(size_t)blockIdx.x * NCONS + cwarp] = wsum;
     }
     if (lane == 0) {
       if (n_rr) atomicAdd(counters + kCtrRerank, n_rr);
@@ -748,7 +872,7 @@ static bool map_2d(CUtensorMap* tm, CUtensorMapDataType dt, int esize, const voi
 }
 
 template <int D>
-static int launch(const CUtensorMap& tcb, const CUtensorMap& tzc, const CUtensorMap& tzf, const CUtensorMap& tzq,
+static int launch(const CUtensorMap& tcb, const CUtensorMap& tcb2, const CUtensorMap& tzc, const CUtensorMap& tzf, const CUtensorMap& tzq,
                   const float* E, const float* ee, const float* emax, int N, int HW, int K,
                   int wait_first, int64_t* idx, double* partials, unsigned* counters, int* grid_out, cudaStream_t s) {
   const int smem = Smem::bytes(D) + 1024;
@@ -776,7 +900,7 @@ static int launch(const CUtensorMap& tcb, const CUtensorMap& tzc, const CUtensor
   cfg.attrs = attr;
   cfg.numAttrs = 2;
   *grid_out = 2 * npairs;
-  if (cudaLaunchKernelEx(&cfg, vq_fused_kernel<D>, tcb, tzc, tzf, tzq, E, ee, emax, N, HW, K, num_ptiles,
+  if (cudaLaunchKernelEx(&cfg, vq_fused_kernel<D>, tcb, tcb2, tzc, tzf, tzq, E, ee, emax, N, HW, K, num_ptiles,
                          wait_first, idx, partials, counters) != cudaSuccess)
     return DCVIC_ERR_CUDA;
   return dcvic_launch_status();
@@ -817,18 +941,33 @@ int vq_fused_forward(const float* z, const float* E, const float* ee, const floa
                      const __half* cb16, int B, int D, int HW, int K, bool after_prepare, float beta, int legacy,
                      float* zq, int64_t* idx, float* loss, double* partials, unsigned* counters, cudaStream_t s) {
   using namespace fz;
-  CUtensorMap tcb, tzc, tzf, tzq;
+  CUtensorMap tcb, tcb2, tzc, tzf, tzq;
   const int N = B * HW;
-  if (!map_2d(&tcb, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, cb16, (uint64_t)(D + kCb16Pad), (uint64_t)K,
-              (uint64_t)(D + kCb16Pad) * 2, BK, BN / 2) ||
-      !map_2d(&tzc, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, z, (uint64_t)HW, (uint64_t)B * D, (uint64_t)HW * 4, GT, BK) ||
+  {
+    EncodeTiledFn encode = encode_fn();
+    if (!encode) return DCVIC_ERR_DEVICE;
+    const int nchunk = D / BK + 1;      // (the chunk-major codebook also carries the pad chunk of the two-kernel path)
+    const cuuint64_t gdim[3] = {(cuuint64_t)BK, (cuuint64_t)K, (cuuint64_t)nchunk};
+    const cuuint64_t gstride[2] = {(cuuint64_t)BK * 2, (cuuint64_t)K * BK * 2};
+    const int na = Smem::b_chunks_a(D);
+    const cuuint32_t estr[3] = {1, 1, 1};
+    for (int part = 0; part < 2; ++part) {
+      const int nz = part == 0 ? na : (D / BK - na > 0 ? D / BK - na : 1);
+      const cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)(BN / 2), (cuuint32_t)nz};
+      if (encode(part == 0 ? &tcb : &tcb2, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<__half*>(cb16), gdim, gstride,
+                 box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return DCVIC_ERR_CUDA;
+    }
+  }
+  if (!map_2d(&tzc, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, z, (uint64_t)HW, (uint64_t)B * D, (uint64_t)HW * 4, GT, BK) ||
       !map_2d(&tzf, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, z, (uint64_t)HW, (uint64_t)B * D, (uint64_t)HW * 4, GT, D) ||
       !map_2d(&tzq, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, zq, (uint64_t)HW, (uint64_t)B * D, (uint64_t)HW * 4, GT, D))
     return DCVIC_ERR_CUDA;
   const int wait_first = after_prepare ? 0 : 1;
   int grid = 0, rc;
 #define DCVIC_FZ(DD) \
-  launch<DD>(tcb, tzc, tzf, tzq, E, ee, emax, N, HW, K, wait_first, idx, partials, counters, &grid, s)
+  launch<DD>(tcb, tcb2, tzc, tzf, tzq, E, ee, emax, N, HW, K, wait_first, idx, partials, counters, &grid, s)
   switch (D) {
     case 64: rc = DCVIC_FZ(64); break;
     case 128: rc = DCVIC_FZ(128); break;

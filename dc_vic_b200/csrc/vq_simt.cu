@@ -14,8 +14,10 @@
 namespace dcvic {
 
 // ------------------------------------------------------------------ codebook prepare
-// One warp per code.  ee[k] = sum_c fl(e^2) (lane-strided partials + xor tree), cb16[k][0..D) = fp16(e),
-// cb16[k][D..D+3) = three-way FP16 split of -ee[k]/2 (exact: 3 x 11 significant bits), rest of the pad zero.
+// One warp per code.  ee[k] = sum_c fl(e^2) (lane-strided partials + xor tree); FP16 codebook in CHUNK-MAJOR layout
+// cb16[chunk][k][64] (chunk = 64 channels: every chunk is a dense [K x 128 B] matrix, so one 3-D TMA box brings all
+// chunks of a code range): columns 0..D-1 = fp16(e), columns D..D+2 (the first three of the pad chunk) = three-way
+// FP16 split of -ee[k]/2 (3 x 11 significant bits; exact down to FP16's 2^-24 grid), rest of the pad zero.
 // emax[0] = max_k |e_k| (rounded up), emax[1] != 0 if the codebook does not fit FP16's range: per-CTA values go to
 // `scratch`, the CTA that finishes last reduces them (no atomics on floats, no memset before the kernel;
 // counters[kCtrPrep] is zero on entry and reset here).
@@ -27,26 +29,32 @@ __global__ void __launch_bounds__(256) vq_prepare_kernel(const float* __restrict
                                                           float* __restrict__ emax, __half* __restrict__ cb16,
                                                           unsigned* __restrict__ counters) {
   __shared__ float s_m[8];
+  __shared__ float s_r[8];
   __shared__ int s_u[8];
   __shared__ int s_last;
   pdl_wait();
   pdl_launch_dependents();
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int k = blockIdx.x * 8 + wid;
-  float wm = 0.f;
+  float wm = 0.f, wr = 0.f;
   bool wu = false;
   if (k < K) {
     const float* row = E + (size_t)k * D;
-    const size_t ld = (size_t)(D + kCb16Pad);
-    float acc = 0.f;
+    auto at = [&](int c) { return ((size_t)(c >> 6) * K + k) * 64 + (c & 63); };   // chunk-major position
+    float acc = 0.f, res = 0.f;
     bool unsafe = false;
     for (int c = lane; c < D; c += 32) {
       const float v = row[c];
       acc = __fadd_rn(acc, __fmul_rn(v, v));
       unsafe |= !(fabsf(v) < 6.0e4f);
-      if (cb16) cb16[(size_t)k * ld + c] = __float2half_rn(v);
+      const __half hv = __float2half_rn(v);
+      const float dv = v - __half2float(hv);          // exact: the FP16 rounding residual of this element
+      res = fmaf(dv, dv, res);
+      if (cb16) cb16[at(c)] = hv;
     }
     acc = warp_sum(acc);
+    res = warp_sum(res);
+    wr = sqrtf(res) * 1.000001f;                      // |e_k - fp16(e_k)|, rounded up
     unsafe |= !(acc < 1.2e5f);                  // -ee/2 must be representable as well
     unsafe = __any_sync(0xffffffffu, unsafe);
     if (lane == 0) ee[k] = acc;
@@ -60,43 +68,48 @@ __global__ void __launch_bounds__(256) vq_prepare_kernel(const float* __restrict
       const float r2 = r1 - __half2float(m);
       const __half l = __float2half_rn(r2);
       for (int c = lane; c < kCb16Pad; c += 32)
-        cb16[(size_t)k * ld + D + c] = c == 0 ? h : (c == 1 ? m : (c == 2 ? l : __float2half_rn(0.f)));
+        cb16[at(D + c)] = c == 0 ? h : (c == 1 ? m : (c == 2 ? l : __float2half_rn(0.f)));
     }
   }
-  if (lane == 0) { s_m[wid] = wm; s_u[wid] = wu ? 1 : 0; }
+  if (lane == 0) { s_m[wid] = wm; s_r[wid] = wr; s_u[wid] = wu ? 1 : 0; }
   __syncthreads();
   const unsigned grid = gridDim.x;
   if (threadIdx.x == 0) {
-    float m = 0.f;
+    float m = 0.f, r = 0.f;
     int u = 0;
-    for (int w = 0; w < 8; ++w) { m = fmaxf(m, s_m[w]); u |= s_u[w]; }   // NaN-free: fmaxf drops a NaN norm,
-    scratch[blockIdx.x] = m;                                                // and such a row is flagged unsafe
+    for (int w = 0; w < 8; ++w) { m = fmaxf(m, s_m[w]); r = fmaxf(r, s_r[w]); u |= s_u[w]; }   // NaN-free: fmaxf drops
+    scratch[blockIdx.x] = m;                                                // a NaN norm, and such a row is flagged unsafe
     scratch[grid + blockIdx.x] = u ? 1.f : 0.f;
+    scratch[2 * grid + blockIdx.x] = r;
     __threadfence();
     s_last = atomicAdd(counters + kCtrPrep, 1u) == grid - 1;
   }
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  float m = 0.f, u = 0.f;
+  float m = 0.f, u = 0.f, r = 0.f;
   for (unsigned i = threadIdx.x; i < grid; i += 256) {
     m = fmaxf(m, __ldcg(scratch + i));
     u = fmaxf(u, __ldcg(scratch + grid + i));
+    r = fmaxf(r, __ldcg(scratch + 2 * grid + i));
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
     u = fmaxf(u, __shfl_xor_sync(0xffffffffu, u, o));
+    r = fmaxf(r, __shfl_xor_sync(0xffffffffu, r, o));
   }
   __syncthreads();
-  if (lane == 0) { s_m[wid] = m; s_u[wid] = u != 0.f; }
+  if (lane == 0) { s_m[wid] = m; s_r[wid] = r; s_u[wid] = u != 0.f; }
   __syncthreads();
   if (threadIdx.x == 0) {
     int uu = 0;
     m = 0.f;
-    for (int w = 0; w < 8; ++w) { m = fmaxf(m, s_m[w]); uu |= s_u[w]; }
+    r = 0.f;
+    for (int w = 0; w < 8; ++w) { m = fmaxf(m, s_m[w]); r = fmaxf(r, s_r[w]); uu |= s_u[w]; }
     emax[0] = m;
     emax[1] = __uint_as_float(uu ? 1u : 0u);
+    emax[2] = r;                                   // max_k |e_k - fp16(e_k)|: the single-pass kernel's margin
     counters[kCtrPrep] = 0u;
   }
 }

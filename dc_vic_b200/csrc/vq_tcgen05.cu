@@ -493,8 +493,9 @@ vq_tensor_search_kernel(const __grid_constant__ CUtensorMap tmap_cb, const float
           for (int kc = -1; kc < KC; ++kc) {      // kc == -1: the -|e|^2/2 chunk (columns D .. D+63)
             mbar_wait(bar(C::BAR_B_EMPTY + stage), phase ^ 1);
             if (leader) mbar_arrive_expect_tx(bar(C::BAR_B_FULL + stage), CG * C::B_STAGE_BYTES);
-            tma_load_2d<CG>(sbase + C::OFF_B + stage * C::B_STAGE_BYTES, &tmap_cb, kc < 0 ? D : kc * BK,
-                            nt * BN + (int)rank * (BN / CG), leader_bar(C::BAR_B_FULL + stage));
+            // chunk-major FP16 codebook: rows [chunk * K, (chunk + 1) * K) of a 64-column matrix; the pad is chunk KC
+            tma_load_2d<CG>(sbase + C::OFF_B + stage * C::B_STAGE_BYTES, &tmap_cb, 0,
+                            (kc < 0 ? KC : kc) * K + nt * BN + (int)rank * (BN / CG), leader_bar(C::BAR_B_FULL + stage));
             if (++stage == C::NSTAGE) { stage = 0; phase ^= 1; }
           }
     }
@@ -673,8 +674,8 @@ int vq_tensor_search(const float* z, const __half* cb16, const float* emax, int 
   EncodeTiledFn encode = encode_tiled_fn();
   if (!encode) return DCVIC_ERR_DEVICE;
   CUtensorMap tmap;
-  const cuuint64_t gdim[2] = {(cuuint64_t)(D + kCb16Pad), (cuuint64_t)K};
-  const cuuint64_t gstride[1] = {(cuuint64_t)(D + kCb16Pad) * sizeof(__half)};
+  const cuuint64_t gdim[2] = {(cuuint64_t)BK, (cuuint64_t)K * (cuuint64_t)((D + kCb16Pad) / BK)};
+  const cuuint64_t gstride[1] = {(cuuint64_t)BK * sizeof(__half)};
   const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)(BN / cta_group)};
   const cuuint32_t estr[2] = {1, 1};
   if (encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(cb16), gdim, gstride, box, estr,

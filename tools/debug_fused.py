@@ -18,18 +18,23 @@ from synth import vq_inputs  # noqa: E402
 
 args = [int(a) for a in sys.argv[1:6]] if len(sys.argv) >= 6 else [1, 16, 16, 256, 1024]
 kind = sys.argv[6] if len(sys.argv) > 6 else "D1b"
+frozen = len(sys.argv) > 7 and sys.argv[7] == "frozen"      # second call on a frozen codebook (no prepare kernel)
 B, H, W, Dm, K = args
 z, E = vq_inputs(3, kind, B, Dm, H, W, K)
 lib = _lib.load()
-prog = torch.zeros(148 * 24 * 2, dtype=torch.int32).pin_memory()
-lib.dcvic_debug_set_fz_progress.restype = C.c_int
-lib.dcvic_debug_set_fz_progress.argtypes = [C.c_void_p]
-assert lib.dcvic_debug_set_fz_progress(C.c_void_p(prog.data_ptr())) == 0
+prog = torch.zeros(148 * 24 * 8, dtype=torch.int32).pin_memory()
+if hasattr(lib, "dcvic_debug_set_fz_progress"):       # (timing runs use the normal library: DCVIC_B200_LIB=...)
+    lib.dcvic_debug_set_fz_progress.restype = C.c_int
+    lib.dcvic_debug_set_fz_progress.argtypes = [C.c_void_p]
+    assert lib.dcvic_debug_set_fz_progress(C.c_void_p(prog.data_ptr())) == 0
 m = D.VectorQuantizer2(K, Dm, 0.25, sane_index_shape=True).to("cuda:0")
 m.embedding.weight.data.copy_(E)
 zc = z.to("cuda:0")
 torch.cuda.synchronize()
 with torch.no_grad():
+    if frozen:
+        m.freeze_codebook()
+        m(zc)
     out = m(zc)
 ev = torch.cuda.Event()
 ev.record()
@@ -44,12 +49,44 @@ NAMES = {0: "-", 1: "tmaB wait B_EMPTY", 2: "zload wait Z_EMPTY", 3: "fin wait c
          22: "cons setmaxnreg", 23: "cons after setmaxnreg", 30: "at exit"}
 print("finished" if done else "HUNG", "after", round(time.time() - t0, 2), "s")
 grid = min(148, 2 * ((B * H * W + 255) // 256))
-for b in range(min(grid, 4)):
+ROLES = {0: ("tmaB", ["wait B_EMPTY"]), 1: ("zload", ["wait Z_EMPTY"]),
+         2: ("fin", ["wait converted", "wait F_DONE", "wait read-out", "drain"]),
+         3: ("mma", ["wait T_EMPTY", "wait A_FULL", "wait B_FULL"]),
+         4: ("conv", ["wait A_EMPTY", "wait Z_FULL"]),
+         8: ("epi", ["wait ZZ", "wait T_FULL", "drain+flags+init", "bar1", "compact(+C_EMPTY)", "bar2"]),
+         16: ("cons", ["wait C_FULL", "rows issue", "wait F_FULL", "re-rank", "z_q+arrive"])}
+for b in range(min(grid, 2)):
     print(f"CTA {b}:")
     for w in range(24):
-        v = int(prog[(b * 24 + w) * 2])
-        print(f"  warp {w:2d}: {NAMES.get(v >> 20, v >> 20):24s} {v & 0xFFFFF}")
+        rec = [int(x) for x in prog[(b * 24 + w) * 8:(b * 24 + w) * 8 + 8]]
+        v = rec[0]
+        role = ROLES[max(k for k in ROLES if k <= w)]
+        cyc = "  ".join(f"{n} {rec[1 + i] * 8}" for i, n in enumerate(role[1]))
+        print(f"  warp {w:2d} {role[0]:5s}: {NAMES.get(v >> 20, v >> 20):20s} {v & 0xFFFFF:6d} | total {rec[7] * 8}  {cyc}")
+if not done:
+    shown = 0
+    for b in range(grid):
+        for w in range(24):
+            rec = [int(x) for x in prog[(b * 24 + w) * 8:(b * 24 + w) * 8 + 8]]
+            if (rec[0] >> 20) != 30 and shown < 80:
+                role = ROLES[max(k for k in ROLES if k <= w)]
+                print(f"  STUCK CTA {b:3d} warp {w:2d} {role[0]:5s}: {NAMES.get(rec[0] >> 20, rec[0] >> 20):20s} {rec[0] & 0xFFFFF}")
+                shown += 1
 if done:
+    ws = list(m._ws._cache.values())[0]
+    ctr = ws[:64].view(torch.int32).cpu().tolist()
+    print("counters: overflow/full scans", ctr[1], "re-ranked tokens", ctr[3], "of", B * H * W,
+          "| list overflow", ctr[6], "more than CK_MAX candidates", ctr[7], "no candidate", ctr[8], "unsafe", ctr[9])
+    with torch.no_grad():
+        for _ in range(3):
+            m(zc)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            m(zc)
+        e1.record()
+        torch.cuda.synchronize()
+    print("forward: %.1f us" % (e0.elapsed_time(e1) * 100))
     from oracle import vq_oracle as O
     n_mis, n_out, n_tie = O.allowed_index_mismatch(z, E, out[2][2].cpu())
     print("mismatches", n_mis, "outside clause", n_out, "near ties", n_tie)
