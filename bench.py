@@ -7,7 +7,10 @@ One "step" = one pass of the hot path over one batch of synthetic input:
   headline workload (BASELINE.json configs[1]): VectorQuantizer2 forward, codebook 1024x256,
   z = 64x256x32x32 FP32 (65,536 tokens) per GPU -> metric vq_tokens_per_sec.
   secondary block "entropy" (configs[2]): SteGaussianMeanScaleConditional eval forward +
-  per-sample rate on 64x320x32x32 latents -> latents/s.
+  per-sample rate on 64x320x32x32 latents at q = 0..4 -> latents/s; EntropyBottleneck and the backward kernels.
+  "in_model": the shapes DC-VIC itself runs (256x4 codebook, 32-channel CHARM slices, 192-channel hyper-latent),
+  per call eager vs CUDA-graph replay, CPU port beside it.
+  "exchange" (N > 1): the training configuration's gradient all-reduce on NCCL, overlapped with the VQ backward.
 N > 1: launched by torchrun, one rank per GPU, every rank runs the same per-GPU workload on its
 own batch shard (weak scaling, no data-path collective); time = max over ranks.
 `--impl reference` times the reference's own CPU implementation of the path (the torch-CPU
@@ -38,13 +41,33 @@ GC_WORKLOAD = "SteGaussianMeanScaleConditional eval forward + per-sample rate on
 
 
 def ncu_traffic(kernel):
-    """dram bytes per launch of `kernel` from the committed ncu capture (profiles/), or None."""
-    p = os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")
+    """DRAM bytes per launch of `kernel`: a STATIC figure read from the committed ncu capture of this code
+    (profiles/r2_ncu_traffic.json, `ncu --set full`), not a measurement of this run; None if absent."""
+    for name in ("r2_ncu_traffic.json", "r1_ncu_traffic.json"):
+        try:
+            d = json.load(open(os.path.join(ROOT, "profiles", name)))[kernel]
+            return d["dram_bytes_read"] + d["dram_bytes_write"]
+        except Exception:
+            continue
+    return None
+
+
+def bind_to_gpu_numa_node(index: int):
+    """Pin this process (and the pinned buffers it allocates afterwards) to the CPUs NVML reports as local to the
+    GPU: with 8 ranks on the default node the host side of the H2D / D2H copies was the end-to-end limiter."""
     try:
-        d = json.load(open(p))[kernel]
-        return d["dram_bytes_read"] + d["dram_bytes_write"]
-    except Exception:
-        return None
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = [64 * w + b for w, mask in enumerate(words) for b in range(64) if (int(mask) >> b) & 1]
+        cpus = [c for c in cpus if c < (os.cpu_count() or 1)]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return {"cpus": len(cpus), "first": cpus[0], "last": cpus[-1]}
+    except Exception as e:       # noqa: BLE001
+        return {"error": str(e)[:80]}
+    return None
 
 
 def peaks():
@@ -141,7 +164,7 @@ def cpu_vq_reference(steps: int, warmup: int):
     B, D, H, W, K = VQ_SHAPE
     z, E = vq_inputs(0, "D0", B, D, H, W, K)
     with torch.no_grad():
-        for _ in range(max(1, min(warmup, 2))):
+        for _ in range(max(0, warmup)):
             VO.vq2_forward(z, E)
         t0 = time.perf_counter()
         for _ in range(steps):
@@ -171,10 +194,10 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 10))
+    steps = max(1, args.steps)          # ~0.1 s per step on 16 cores: the default 200 steps take ~20 s
     val, dt, cores = cpu_vq_reference(steps, args.warmup)
     line = {"impl": "reference", "metric": "vq_tokens_per_sec", "value": val, "unit": "tokens/s", "n_gpus": args.gpus,
-            "steps": steps, "warmup": min(args.warmup, 2), "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "steps": steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
             "config": {"workload": VQ_WORKLOAD, "where": "host CPU, torch FP32, all threads"},
             "cpu_baseline": {"value": val, "unit": "tokens/s", "cores": cores, "kind": "port",
@@ -204,14 +227,15 @@ def timed(fn, steps, warmup, barrier):
 def run_ours(args):
     import torch.distributed as dist
     import dc_vic_b200 as D
-    from dc_vic_b200 import _lib
-    from synth import vq_inputs, entropy_inputs
+    from dc_vic_b200 import _lib, parallel as P
+    from synth import vq_inputs, entropy_inputs, noise_like
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    numa = bind_to_gpu_numa_node(local)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -233,6 +257,8 @@ def run_ours(args):
     K_steps, W_steps = args.steps, max(args.warmup, 3)
     B, Dm, H, W, K = VQ_SHAPE
     N = B * H * W
+    stream = torch.cuda.current_stream()
+    sraw = C.c_void_p(stream.cuda_stream)
 
     # ---------------- VQ: device-resident throughput through the C ABI -------------------------
     ROT = 4   # rotate over 4 input/output sets: 4 x (67 + 67) MB > 126 MB L2, so no step re-reads a warm L2
@@ -244,53 +270,67 @@ def run_ours(args):
     loss = torch.empty((), device=dev)
     ws = torch.zeros(lib.dcvic_vq_workspace_bytes(B, Dm, H, W, K), dtype=torch.uint8, device=dev)
     path = {0: "narrow-simt", 1: "exact-simt", 2: "tcgen05"}[lib.dcvic_vq_path(Dm, K, 0)]
-    stream = torch.cuda.current_stream()
 
     def vq_step(i, flags=0):
         j = i % ROT
         rc = lib.dcvic_vq_forward(_lib.ptr(zs[j]), _lib.ptr(Ec), B, Dm, H, W, K, 0.25, 1, _lib.ptr(zqs[j]),
-                                  _lib.ptr(idxs[j]), _lib.ptr(loss), None, None, flags, _lib.ptr(ws), ws.numel(),
-                                  C.c_void_p(stream.cuda_stream))
+                                  _lib.ptr(idxs[j]), _lib.ptr(loss), None, None, flags, _lib.ptr(ws), ws.numel(), sraw)
         _lib.check(rc, "dcvic_vq_forward")
 
     sampler = ClockSampler(local)
     sampler.start()
     t_clk0 = time.perf_counter()
     t_full = max_over_ranks(timed(vq_step, K_steps, W_steps, barrier))
-    # the same step with the codebook prepared once (DC-VIC freezes the VQGAN codebook; the module sets this flag)
+    # the same step with the codebook prepared once (DC-VIC freezes the VQGAN codebook; the module sets this flag):
+    # prepare kernel gone, what remains is the single-pass kernel + the 1-CTA loss finalize kernel
     t_frozen = max_over_ranks(timed(lambda i: vq_step(i, _lib.VQ_REUSE_PREP), K_steps, W_steps, barrier))
-    # Dominant kernel for the roofline: the search launched alone, back to back, codebook already prepared.  Each
-    # launch then waits for its predecessor before it reads z, so nothing of it is hidden behind another kernel:
-    # this is the kernel's own average launch duration (a conservative figure - inside the full step its first
-    # tile loads while the prepare kernel runs).  40 us of GPU work per launch keep the chain GPU-bound; a chain
-    # of prepare-only launches is host-bound and its time is not used for anything.
-    t_search = timed(lambda i: vq_step(i, _lib.VQ_STAGE_SEARCH_ONLY | _lib.VQ_REUSE_PREP), K_steps, W_steps, barrier)
-    # stages as differences of pipelined steps: what the step grows by when a stage is added
-    t_prep = max(t_full - t_frozen, 0.0)                      # codebook prepare (marginal cost inside the step)
-    t_finish = max(t_frozen - t_search, 0.0)                  # finish + loss finalize
+    # the round-1 structure (separate search and finish kernels) on the same inputs, for comparison
+    t_two = timed(lambda i: vq_step(i, _lib.VQ_TWO_KERNELS), K_steps, W_steps, barrier)
+    t_search = timed(lambda i: vq_step(i, _lib.VQ_STAGE_SEARCH_ONLY | _lib.VQ_REUSE_PREP | _lib.VQ_TWO_KERNELS),
+                     K_steps, W_steps, barrier)
     clocks = sampler.stop(t_clk0, time.perf_counter())
+    # sustained: the same step back to back for >= 2 s (power / thermal steady state), against the sustained peak
+    n_sus = max(K_steps, int(2.2 / max(t_full / K_steps, 1e-6)))
+    sampler2 = ClockSampler(local)
+    sampler2.start()
+    t_s0 = time.perf_counter()
+    t_sus = max_over_ranks(timed(vq_step, n_sus, 3, barrier))
+    clocks_sus = sampler2.stop(t_s0, time.perf_counter())
 
     value = world * N * K_steps / t_full
     flops = 2.0 * N * K * Dm
-    search_s = t_search / K_steps
-    finish_s = t_finish / K_steps
-    finish_bytes = N * (4 * Dm + 4 * Dm + 8)
-    if path == "tcgen05" or search_s >= finish_s:
-        roof = {"kernel": "vq_tensor_search" if path == "tcgen05" else "vq_exact_kernel", "bound": "tensor",
-                "achieved": flops / search_s / 1e12, "peak": pk["bf16"], "unit": "TFLOP/s",
-                "frac": flops / search_s / 1e12 / pk["bf16"],
-                "traffic": ncu_traffic("vq_tensor_search_kernel") if path == "tcgen05" else None,
-                "us_per_launch": search_s * 1e6,
-                "algorithmic": f"2*N*K*D = {flops:.4g} flop per launch", "peak_source": pk["source"] + ", bf16 burst"}
-    else:
-        roof = {"kernel": "vq_finish_kernel", "bound": "hbm", "achieved": finish_bytes / finish_s / 1e9,
-                "peak": pk["hbm"], "unit": "GB/s", "frac": finish_bytes / finish_s / 1e9 / pk["hbm"], "traffic": None,
-                "us_per_launch": finish_s * 1e6, "algorithmic": f"N*(8D+8) = {finish_bytes} B per launch",
-                "peak_source": pk["source"]}
-    stage = {"prepare_us": t_prep / K_steps * 1e6,
-             "search_us": search_s * 1e6, "finish_us": finish_s * 1e6,
-             "finish_hbm_gbs": finish_bytes / finish_s / 1e9, "finish_hbm_frac": finish_bytes / finish_s / 1e9 / pk["hbm"],
-             "search_tflops": flops / search_s / 1e12}
+    fwd_bytes = N * (4 * Dm + 4 * Dm + 8) + K * Dm * 4
+    kern_s = t_frozen / K_steps
+    fused = path == "tcgen05"
+    roof = {"kernel": "vq_fused_kernel (whole forward: search + re-rank + gather + z_q + loss in one launch)" if fused
+            else "vq_exact_kernel",
+            "bound": "tensor", "achieved": flops / kern_s / 1e12, "peak": pk["bf16"], "unit": "TFLOP/s",
+            "frac": flops / kern_s / 1e12 / pk["bf16"],
+            "traffic": ncu_traffic("vq_fused_kernel"), "traffic_source": "static: ncu --set full capture of this code, profiles/",
+            "us_per_launch": kern_s * 1e6,
+            "us_per_launch_note": "frozen-codebook step = this kernel + the 1-CTA loss finalize kernel (~2 us), launches back to back",
+            "algorithmic": f"2*N*K*D = {flops:.4g} flop and N*(8D+8)+4KD = {fwd_bytes} B per launch",
+            "whole_forward_frac_tensor": flops / (t_full / K_steps) / 1e12 / pk["bf16"],
+            "whole_forward_frac_hbm": fwd_bytes / (t_full / K_steps) / 1e9 / pk["hbm"],
+            "hbm_frac_of_kernel": fwd_bytes / kern_s / 1e9 / pk["hbm"],
+            "sustained": {"seconds": t_sus, "steps": n_sus, "tokens_per_s": world * N * n_sus / t_sus,
+                          "frac_of_sustained_peak": flops / (t_sus / n_sus) / 1e12 / (pk["bf16_sustained"] or pk["bf16"]),
+                          "peak": pk["bf16_sustained"], "clocks": clocks_sus},
+            "peak_source": pk["source"] + ", bf16 burst"}
+    stage = {"prepare_us": max(t_full - t_frozen, 0.0) / K_steps * 1e6, "single_pass_plus_finalize_us": kern_s * 1e6,
+             "two_kernel_forward_us": t_two / K_steps * 1e6, "two_kernel_search_us": t_search / K_steps * 1e6,
+             "two_kernel_search_frac": flops / (t_search / K_steps) / 1e12 / pk["bf16"]}
+
+    # ---------------- host <-> device copy bandwidth of this rank (what bounds the end-to-end number) ---------
+    hbuf = torch.empty(64 << 20, dtype=torch.uint8).pin_memory()
+    dbuf = torch.empty(64 << 20, dtype=torch.uint8, device=dev)
+
+    def copy_gbs(dst, src):
+        t = timed(lambda i: dst.copy_(src, non_blocking=True), 8, 2, barrier)
+        return 8 * dst.numel() / max_over_ranks(t) / 1e9
+
+    h2d_gbs, d2h_gbs = copy_gbs(dbuf, hbuf), copy_gbs(hbuf, dbuf)
+    del hbuf, dbuf
 
     # ---------------- VQ end to end: module API, pinned host buffers in and out -----------------
     # Every step copies its input from pinned host memory and its results (z_q, indices, loss) back, inside the timed
@@ -341,84 +381,266 @@ def run_ours(args):
     t_e2e = max_over_ranks(e2e_run(e2e_steps))
     barrier()
     z_host, zq_host, idx_host = lanes[0].z_host, lanes[0].zq_host, lanes[0].idx_host
-    e2e = {"value": world * N * e2e_steps / t_e2e, "unit": "tokens/s", "h2d_bytes_per_step": z_host.numel() * 4,
-           "d2h_bytes_per_step": zq_host.numel() * 4 + idx_host.numel() * 8 + 4, "ms_per_step": t_e2e / e2e_steps * 1e3,
+    h2d_b, d2h_b = z_host.numel() * 4, zq_host.numel() * 4 + idx_host.numel() * 8 + 4
+    e2e = {"value": world * N * e2e_steps / t_e2e, "unit": "tokens/s", "h2d_bytes_per_step": h2d_b,
+           "d2h_bytes_per_step": d2h_b, "ms_per_step": t_e2e / e2e_steps * 1e3,
+           "per_rank_copy_gbs": {"h2d": h2d_gbs, "d2h": d2h_gbs, "note": "64 MB pinned copies, slowest rank, all ranks at once"},
+           "copy_bound_ms_per_step": max(h2d_b / h2d_gbs, d2h_b / d2h_gbs) / 1e6,
+           "numa_binding": numa,
            "api": "dc_vic_b200.VectorQuantizer2.forward on pinned host tensors (H2D z, D2H z_q + indices + loss), "
                   "steps alternating over two streams so upload and download overlap"}
+    del lanes
 
     # ---------------- entropy model (secondary block) -------------------------------------------
-    yb, pb = entropy_inputs(2)
-    yc, pc = yb.to(dev), pb.to(dev)
-    n_lat = yc.numel()
-    gb, gn = GC_SHAPE[0], n_lat // GC_SHAPE[0]
-    y_hat, lik = torch.empty_like(yc), torch.empty_like(yc)
-    bits = torch.empty(gb, device=dev)
-    gws = torch.zeros(lib.dcvic_gc_workspace_bytes(gb, gn), dtype=torch.uint8, device=dev)
+    GROT = 2
+    gb = GC_SHAPE[0]
+    entropy_q = {}
+    gc_e2e_line = None
+    for q in range(5):
+        yb, pb = entropy_inputs(q)
+        yc, pc = yb.to(dev), pb.to(dev)
+        n_lat = yc.numel()
+        gn = n_lat // gb
+        outs = [(torch.empty_like(yc), torch.empty_like(yc)) for _ in range(GROT)]   # rotated: 2 x 168 MB > L2
+        bits = torch.empty(gb, device=dev)
+        gws = torch.zeros(lib.dcvic_gc_workspace_bytes(gb, gn), dtype=torch.uint8, device=dev)
 
-    def gc_step(i):
-        rc = lib.dcvic_gc_forward(_lib.ptr(yc), _lib.ptr(pc), C.c_void_p(pc.data_ptr() + gn * 4), None, gb, gn, gn,
-                                  2 * gn, 2 * gn, 0.11, 1e-9, 1, _lib.ptr(y_hat), _lib.ptr(lik), _lib.ptr(bits),
-                                  _lib.ptr(gws), gws.numel(), C.c_void_p(stream.cuda_stream))
-        _lib.check(rc, "dcvic_gc_forward")
+        def gc_step(i):
+            y_hat, lik = outs[i % GROT]
+            rc = lib.dcvic_gc_forward(_lib.ptr(yc), _lib.ptr(pc), C.c_void_p(pc.data_ptr() + gn * 4), None, gb, gn, gn,
+                                      2 * gn, 2 * gn, 0.11, 1e-9, 1, _lib.ptr(y_hat), _lib.ptr(lik), _lib.ptr(bits),
+                                      _lib.ptr(gws), gws.numel(), sraw)
+            _lib.check(rc, "dcvic_gc_forward")
 
-    t_gc = max_over_ranks(timed(gc_step, K_steps, W_steps, barrier))
-    gc_s = t_gc / K_steps
-    gc_bytes = 20.0 * n_lat
-    gcm = D.SteGaussianMeanScaleConditional(scale_bound=0.11).to(dev)
-    y_host, p_host = yb.pin_memory(), pb.pin_memory()
-    yh_host, lk_host = torch.empty_like(y_host).pin_memory(), torch.empty_like(y_host).pin_memory()
-    yd, pd = torch.empty_like(yc), torch.empty_like(pc)
+        steps_q = K_steps if q == 2 else max(5, K_steps // 4)
+        gc_s = max_over_ranks(timed(gc_step, steps_q, W_steps, barrier)) / steps_q
+        entropy_q[f"q{q}"] = {"us": gc_s * 1e6, "latents_per_s": world * n_lat / gc_s,
+                              "hbm_frac": 20.0 * n_lat / gc_s / 1e9 / pk["hbm"]}
+        if q == 2:
+            gc_q2_s = gc_s
+            # backward of the same op (d/dy, d/dmu, d/dsigma: reads g, y, mu, sigma, writes three gradients = 28 B/latent)
+            g_l = torch.randn_like(yc)
+            d_y, d_m, d_s = torch.empty_like(yc), torch.empty_like(yc), torch.empty_like(yc)
 
-    def gc_e2e(i):
-        yd.copy_(y_host, non_blocking=True)
-        pd.copy_(p_host, non_blocking=True)
+            def gcb_step(i):
+                rc = lib.dcvic_gc_backward(_lib.ptr(g_l), _lib.ptr(yc), _lib.ptr(pc), C.c_void_p(pc.data_ptr() + gn * 4),
+                                           None, gb, gn, gn, 2 * gn, 2 * gn, 0.11, 1e-9, _lib.ptr(d_y), _lib.ptr(d_m),
+                                           _lib.ptr(d_s), sraw)
+                _lib.check(rc, "dcvic_gc_backward")
+
+            gcb_s = timed(gcb_step, 5, 2, barrier) / 5
+            gcm = D.SteGaussianMeanScaleConditional(scale_bound=0.11).to(dev)
+            y_host, p_host = yb.pin_memory(), pb.pin_memory()
+            yh_host, lk_host = torch.empty_like(y_host).pin_memory(), torch.empty_like(y_host).pin_memory()
+            yd, pd = torch.empty_like(yc), torch.empty_like(pc)
+
+            def gc_e2e(i):
+                yd.copy_(y_host, non_blocking=True)
+                pd.copy_(p_host, non_blocking=True)
+                with torch.no_grad():
+                    a, b = gcm(yd, pd, is_train=False)
+                    _ = D.batch_bits(b)
+                yh_host.copy_(a, non_blocking=True)
+                lk_host.copy_(b, non_blocking=True)
+
+            t_gce = max_over_ranks(timed(gc_e2e, 5, 2, barrier))
+            gc_e2e_line = {"value": world * n_lat * 5 / t_gce, "unit": "latents/s",
+                           "h2d_bytes_per_step": (y_host.numel() + p_host.numel()) * 4,
+                           "d2h_bytes_per_step": 2 * y_host.numel() * 4}
+            gc_backward = {"us": gcb_s * 1e6, "hbm_frac": 28.0 * n_lat / gcb_s / 1e9 / pk["hbm"],
+                           "algorithmic": "28 B/latent (read g, y, mu, sigma; write dy, dmu, dsigma)"}
+            del g_l, d_y, d_m, d_s, yd, pd, y_host, p_host, yh_host, lk_host
+        del yc, pc, outs
+    n_lat = GC_SHAPE[0] * GC_SHAPE[1] * GC_SHAPE[2] * GC_SHAPE[3]
+    # EntropyBottleneck on the hyper-latent of the same batch at ELIC scale (64 x 192 x 64 x 64 = 50 M) and at C3's own
+    # size (64 x 192 x 8 x 8), forward (12 B/latent) and backward
+    eb = D.SteEntropyBottleneck(channels=192).to(dev)
+    torch.manual_seed(7)
+    with torch.no_grad():
+        for n_, p_ in eb.named_parameters():
+            if "_factor" in n_ or "_bias" in n_:
+                p_.add_(0.3 * torch.randn_like(p_))
+    ebn = {}
+    for tag, shape in (("64x192x64x64", (64, 192, 64, 64)), ("64x192x8x8", (64, 192, 8, 8))):
+        x = 3 * torch.randn(*shape, device=dev)
         with torch.no_grad():
-            a, b = gcm(yd, pd, is_train=False)
-            _ = D.batch_bits(b)
-        yh_host.copy_(a, non_blocking=True)
-        lk_host.copy_(b, non_blocking=True)
+            t_f = timed(lambda i: eb(x, is_train=False), 5, 2, barrier) / 5
+        nz = torch.rand_like(x) - 0.5
+        xg = x.clone().requires_grad_(True)
 
-    t_gce = max_over_ranks(timed(gc_e2e, 5, 2, barrier))
-    entropy = {"metric": "bpp_estimate_latents_per_sec", "value": world * n_lat / gc_s, "unit": "latents/s",
-               "ms_per_step": gc_s * 1e3, "config": {"workload": GC_WORKLOAD},
-               "roofline": {"kernel": "gc_forward_kernel", "bound": "hbm", "achieved": gc_bytes / gc_s / 1e9,
-                            "peak": pk["hbm"], "unit": "GB/s", "frac": gc_bytes / gc_s / 1e9 / pk["hbm"],
-                            "traffic": ncu_traffic("gc_forward_kernel"), "algorithmic": "20 B/latent (read y, mu, sigma; write y_hat, likelihood)",
+        def eb_fb(i):
+            xg.grad = None
+            a, lk = eb(xg, is_train=True, noise=nz)
+            lk.sum().backward()
+
+        t_fb = timed(eb_fb, 3, 1, barrier) / 3
+        ebn[tag] = {"forward_us": t_f * 1e6, "forward_hbm_frac": 12.0 * x.numel() / t_f / 1e9 / pk["hbm"],
+                    "forward_latents_per_s": x.numel() / t_f, "forward_plus_backward_us": t_fb * 1e6}
+        del x, nz, xg
+    entropy = {"metric": "bpp_estimate_latents_per_sec", "value": world * n_lat / gc_q2_s, "unit": "latents/s",
+               "ms_per_step": gc_q2_s * 1e3, "config": {"workload": GC_WORKLOAD, "l2": "outputs rotated over 2 buffer sets"},
+               "roofline": {"kernel": "gc_forward_kernel", "bound": "hbm", "achieved": 20.0 * n_lat / gc_q2_s / 1e9,
+                            "peak": pk["hbm"], "unit": "GB/s", "frac": 20.0 * n_lat / gc_q2_s / 1e9 / pk["hbm"],
+                            "traffic": ncu_traffic("gc_forward_kernel"), "traffic_source": "static: ncu capture, profiles/",
+                            "algorithmic": "20 B/latent (read y, mu, sigma; write y_hat, likelihood)",
                             "peak_source": pk["source"]},
-               "e2e": {"value": world * n_lat * 5 / t_gce, "unit": "latents/s",
-                       "h2d_bytes_per_step": (y_host.numel() + p_host.numel()) * 4,
-                       "d2h_bytes_per_step": 2 * y_host.numel() * 4}}
+               "per_q": entropy_q, "gc_backward": gc_backward, "entropy_bottleneck": ebn, "e2e": gc_e2e_line}
+
+    # ---------------- the shapes DC-VIC itself runs: host-bound per call, so eager vs graph replay ----
+    def per_call_us(fn, n=200):
+        for _ in range(10):
+            fn()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(n):
+            fn()
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t0) / n * 1e6
+
+    def graphed(fn):
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                fn()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            fn()
+        return g.replay
+
+    in_model = {}
+    with torch.no_grad():
+        for tag, (bb, hh, ww) in (("kodim03_6144_tokens", (1, 64, 96)), ("2k_45056_tokens", (1, 176, 256)),
+                                  ("train_6x256sq_6144_tokens", (6, 32, 32))):
+            zq_, Eq_ = vq_inputs(2, "D1b", bb, 4, hh, ww, 256)
+            mq = D.VectorQuantizer2(256, 4, 0.25, sane_index_shape=True).to(dev)
+            mq.embedding.weight.data.copy_(Eq_)
+            mq.freeze_codebook()
+            zd = zq_.to(dev)
+            f = lambda: mq(zd)                                           # noqa: E731
+            in_model[f"vq_256x4_{tag}"] = {"eager_us": per_call_us(f), "graph_replay_us": per_call_us(graphed(f))}
+        for tag, (bb, hh, ww) in (("kodim03_1x32x32x48", (1, 32, 48)), ("train_6x32x16x16", (6, 16, 16))):
+            ys = [torch.randn(bb, 32, hh, ww, device=dev) for _ in range(6)]
+            ps = [torch.cat([torch.randn(bb, 32, hh, ww, device=dev), torch.randn(bb, 32, hh, ww, device=dev).exp()], 1)
+                  for _ in range(6)]
+            nzs = [torch.rand(bb, 32, hh, ww, device=dev) - 0.5 for _ in range(6)]
+
+            def slice_loop():
+                out = None
+                for k in range(6):      # the 6 CHARM slices: noisy + quantized likelihood + rate from one pass each
+                    out = D.gaussian_rate_dual(ys[k], ps[k], nzs[k])
+                return out
+
+            one = lambda: D.gaussian_rate_dual(ys[0], ps[0], nzs[0])    # noqa: E731
+            in_model[f"charm_6_slices_{tag}"] = {"eager_us": per_call_us(slice_loop, 100),
+                                                  "graph_replay_us": per_call_us(graphed(slice_loop), 100),
+                                                  "one_kernel_graph_us": per_call_us(graphed(one), 100)}
+        ebm = D.SteEntropyBottleneck(channels=192).to(dev)
+        xz = 3 * torch.randn(1, 192, 8, 12, device=dev)
+        f = lambda: ebm(xz, is_train=False)                              # noqa: E731
+        in_model["entropy_bottleneck_1x192x8x12"] = {"eager_us": per_call_us(f), "graph_replay_us": per_call_us(graphed(f))}
+
+    # ---------------- training configuration: gradient exchange on NCCL ----------------
+    exchange = None
+    if world > 1:
+        # gradients of a stand-alone VQGAN / stage 1-1 step: codebook dE (written straight into the flat bucket by the
+        # backward kernel) + the entropy parameters, ONE all-reduce on a side stream; dz of the next micro-batch overlaps
+        buckets = [P.GradBucket(dev, [("codebook", (K, Dm)), ("entropy_params", (11136,)), ("quantiles", (192, 1, 3))])
+                   for _ in range(2)]
+        g_zq = torch.randn(B, Dm, H, W, device=dev)
+        g_loss = torch.ones((), device=dev)
+        dz = torch.empty_like(g_zq)
+        vq_step(0)
+        idx0 = idxs[0]
+
+        def bwd(i, exchange_grads):
+            bk = buckets[i % 2]
+            bk.wait()                                    # its previous all-reduce has finished with the buffer
+            rc = lib.dcvic_vq_backward(_lib.ptr(g_zq), _lib.ptr(g_loss), _lib.ptr(zs[0]), _lib.ptr(Ec), _lib.ptr(idx0),
+                                       B, Dm, H, W, K, 0.25, 1, _lib.ptr(dz), _lib.ptr(bk.view("codebook")), sraw)
+            _lib.check(rc, "dcvic_vq_backward")
+            if exchange_grads:
+                bk.allreduce_async()
+
+        t_b = max_over_ranks(timed(lambda i: bwd(i, False), 10, 3, barrier)) / 10
+        t_bx = max_over_ranks(timed(lambda i: bwd(i, True), 10, 3, barrier)) / 10
+        for bk in buckets:
+            bk.wait()
+        nb = buckets[0].nbytes()
+        t_ar = max_over_ranks(timed(lambda i: dist.all_reduce(buckets[0].flat), 10, 3, barrier)) / 10
+        big = torch.zeros(33_460_000, device=dev)       # faithful stage 3: decoder + vq_estimator + fusion grads (134 MB)
+        t_big = max_over_ranks(timed(lambda i: dist.all_reduce(big), 5, 2, barrier)) / 5
+        busf = 2.0 * (world - 1) / world
+        exchange = {"backend": "nccl", "world": world, "bucket_bytes": nb,
+                    "vq_backward_us": t_b * 1e6, "vq_backward_with_overlapped_allreduce_us": t_bx * 1e6,
+                    "allreduce_alone_us": t_ar * 1e6, "allreduce_bus_gbs": busf * nb / t_ar / 1e9,
+                    "stage3_grads_134MB_allreduce_us": t_big * 1e6, "stage3_grads_bus_gbs": busf * big.numel() * 4 / t_big / 1e9,
+                    "note": "dE is written into the flat bucket by dcvic_vq_backward; the collective runs on a side stream "
+                            "while the next micro-batch's backward runs"}
+        del big
 
     if rank == 0:
         cpu_val, _, cores = cpu_vq_reference(3, 1)
         gc_cpu, _ = cpu_gc_reference(2)
         entropy["cpu_baseline"] = {"value": gc_cpu, "unit": "latents/s", "cores": cores, "kind": "port",
                                    "sample": "8 of 64 images (2.6M latents) x 2, CompressAI-1.2.4 restatement, torch CPU"}
-        # prepare, search, finish, loss finalize (see profiles/r1_launches.csv)
-        launches_per_step = 4 if path != "narrow-simt" else 1
+        in_model["cpu_port_us"] = cpu_in_model()
+        # prepare, single-pass forward, loss finalize (see profiles/)
+        launches_per_step = 3 if path == "tcgen05" else (4 if path != "narrow-simt" else 1)
         line = {"metric": "vq_tokens_per_sec", "value": value, "unit": "tokens/s", "n_gpus": world, "steps": K_steps,
                 "warmup": W_steps, "ms_per_step": t_full / K_steps * 1e3, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
                 "config": {"workload": VQ_WORKLOAD, "search_path": path,
-                           "arithmetic": "fp16 tcgen05 candidate search (fp32 accumulate) + fp32 re-rank" if path == "tcgen05" else "fp32 SIMT",
+                           "arithmetic": "fp16 tcgen05 candidate search (fp32 accumulate) + fp32 re-rank, one kernel" if path == "tcgen05" else "fp32 SIMT",
                            "l2": f"inputs/outputs rotated over {ROT} buffer sets (536 MB > 126 MB L2)",
                            "codebook_prep": "inside every timed step (value_frozen_codebook: prepared once)",
-                           "launch": "programmatic dependent launch between prepare, search, finish and loss finalize", "sharding": "batch (images) per rank, no collective"},
+                           "launch": "programmatic dependent launch between prepare, the single-pass kernel and loss finalize",
+                           "sharding": "batch (images) per rank, no collective"},
                 "value_frozen_codebook": world * N * K_steps / t_frozen,
                 "roofline": roof, "stages": stage,
                 "cpu_baseline": {"value": cpu_val, "unit": "tokens/s", "cores": cores, "kind": "port",
                                  "sample": "full 65,536-token batch x 3 (oracle port of taming VectorQuantizer2, torch CPU)"},
-                "e2e": e2e, "gpu_launches": launches_per_step * K_steps, "clocks": clocks, "entropy": entropy}
+                "e2e": e2e, "gpu_launches": launches_per_step * K_steps, "clocks": clocks, "entropy": entropy,
+                "in_model": in_model, "exchange": exchange}
         sys.stdout.flush()
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
+def cpu_in_model():
+    """CPU port (oracle) timings of the in-model shapes, per call, all host threads."""
+    from oracle import vq_oracle as VO, entropy_oracle as EO
+    from synth import vq_inputs
+    out = {}
+    with torch.no_grad():
+        for tag, (bb, hh, ww) in (("kodim03_6144_tokens", (1, 64, 96)), ("2k_45056_tokens", (1, 176, 256))):
+            z, E = vq_inputs(2, "D1b", bb, 4, hh, ww, 256)
+            VO.vq2_forward(z, E)
+            t0 = time.perf_counter()
+            for _ in range(5):
+                VO.vq2_forward(z, E)
+            out[f"vq_256x4_{tag}"] = (time.perf_counter() - t0) / 5 * 1e6
+        m = EO.SteGaussianMeanScaleConditional(scale_bound=0.11)
+        y = torch.randn(1, 32, 32, 48)
+        p = torch.cat([torch.randn(1, 32, 32, 48), torch.randn(1, 32, 32, 48).exp()], 1)
+        nz = torch.rand(1, 32, 32, 48) - 0.5
+        m(y, p, is_train=True, noise=nz)
+        t0 = time.perf_counter()
+        for _ in range(5):
+            for _k in range(6):
+                m(y, p, is_train=True, noise=nz)
+                m(y, p, is_train=False)
+        out["charm_6_slices_kodim03_1x32x32x48"] = (time.perf_counter() - t0) / 5 * 1e6
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=200)      # (the reference arm: ~0.1 s per step)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     args = ap.parse_args()

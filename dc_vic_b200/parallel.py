@@ -87,6 +87,63 @@ def allreduce_gradients(params: Iterable[torch.nn.Parameter], world: int | None 
     return n_coll
 
 
+class GradBucket:
+    """A persistent flat FP32 gradient buffer with named views, all-reduced as ONE collective.
+
+    SURVEY 8(e): the kernels that produce gradients write straight into the bucket (``dcvic_vq_backward`` takes any
+    ``dE`` pointer, so the codebook gradient's scatter-add lands in ``view("codebook")``; the entropy-parameter
+    gradients are copied into their views), and the all-reduce is launched on a SIDE stream as soon as the producing
+    kernels are enqueued, so it overlaps whatever the compute stream does next (``dz`` of the next micro-batch, the
+    decoder's backward).  ``wait()`` makes the compute stream wait for the collective before the views are read."""
+
+    def __init__(self, device, fields, group=None, average: bool = True):
+        self.device = torch.device(device)
+        self.group, self.average = group, average
+        self.offsets, off = {}, 0
+        for name, shape in fields:
+            n = 1
+            for d in shape:
+                n *= int(d)
+            self.offsets[name] = (off, n, tuple(int(d) for d in shape))
+            off += (n + 3) // 4 * 4                      # 16-byte aligned views (128-bit kernels write them)
+        self.flat = torch.zeros(max(off, 1), dtype=torch.float32, device=self.device)
+        self._side = torch.cuda.Stream(device=self.device) if self.device.type == "cuda" else None
+        self._done = None
+        self._work = None
+
+    def view(self, name: str) -> torch.Tensor:
+        off, n, shape = self.offsets[name]
+        return self.flat[off:off + n].view(shape)
+
+    def nbytes(self) -> int:
+        return self.flat.numel() * 4
+
+    def allreduce_async(self) -> None:
+        """Enqueue the all-reduce behind everything already enqueued on the current stream."""
+        if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(self.group) == 1:
+            return
+        world = dist.get_world_size(self.group)
+        if self._side is None:                            # CPU tensors (gloo in the tests): synchronous
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
+            if self.average:
+                self.flat.div_(world)
+            return
+        ready = torch.cuda.Event()
+        ready.record(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(self._side):
+            self._side.wait_event(ready)
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
+            if self.average:
+                self.flat.div_(world)
+            self._done = torch.cuda.Event()
+            self._done.record(self._side)
+
+    def wait(self) -> None:
+        if self._done is not None:
+            torch.cuda.current_stream(self.device).wait_event(self._done)
+            self._done = None
+
+
 def max_over_ranks(value: float, device: torch.device | str = "cpu", group=None) -> float:
     """Device-timed durations are reported as the maximum over ranks."""
     if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:

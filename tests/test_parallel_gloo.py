@@ -61,6 +61,23 @@ def _worker(rank, world, port, out):
         mine = P.shard_batch(lik, rank, world)
         tot = P.sum_over_ranks([float(-torch.log2(mine).sum())])[0]
         ok = ok and abs(tot - float(-torch.log2(lik).sum())) < 1e-9 * abs(tot) + 1e-9
+        # the flat bucket the gradient kernels write into (codebook dE + entropy-parameter grads), one collective
+        b = P.GradBucket("cpu", [("codebook", (16, 4)), ("entropy", (7,)), ("quantiles", (5, 1, 3))])
+        gb = torch.Generator().manual_seed(300 + rank)
+        b.view("codebook").copy_(torch.randn(16, 4, generator=gb))
+        b.view("entropy").copy_(torch.randn(7, generator=gb))
+        b.view("quantiles").copy_(torch.randn(5, 1, 3, generator=gb))
+        b.allreduce_async()
+        b.wait()
+        exp = {k: torch.zeros(v[2]) for k, v in b.offsets.items()}
+        for r in range(world):
+            ge = torch.Generator().manual_seed(300 + r)
+            exp["codebook"] += torch.randn(16, 4, generator=ge)
+            exp["entropy"] += torch.randn(7, generator=ge)
+            exp["quantiles"] += torch.randn(5, 1, 3, generator=ge)
+        for k in exp:
+            ok = ok and torch.allclose(b.view(k), exp[k] / world, atol=1e-6)
+        ok = ok and b.offsets["entropy"][0] % 4 == 0 and b.offsets["quantiles"][0] % 4 == 0
         out[rank] = bool(ok)
     finally:
         dist.destroy_process_group()
