@@ -9,6 +9,7 @@
 namespace dcvic {
 
 constexpr int kEbParams = 58;
+constexpr int EXPP = 59, EXPM = 62;   // e^{+m0_j}, e^{-m0_j} (first-layer matrix): slots 59-61, 62-64 of the shared table
 constexpr int M0 = 0, M1 = 3, M2 = 12, M3 = 21, M4 = 30, B0 = 33, B1 = 36, B2 = 39, B3 = 42, B4 = 45, F0 = 46,
               F1 = 49, F2 = 52, F3 = 55, MED = 58;
 constexpr int kEbThreads = 256;
@@ -23,6 +24,25 @@ struct EbGradPtrs {
 
 __device__ __forceinline__ float softplus_f(float x) { return x > 20.f ? x : log1pf(expf(x)); }
 __device__ __forceinline__ float sigmoid_f(float x) { return 1.f / (1.f + expf(-x)); }
+
+// Per-element transcendentals of the hot kernels on the SFU: ex2.approx (2^-22 relative) and rcp.approx (1 ulp), i.e.
+// ~2e-7 ABSOLUTE error on tanh and ~3e-7 relative on the sigmoid - two orders below the 1e-4 budget on likelihoods
+// (tanh.approx itself, 5e-4 relative, is not: the likelihood is a difference of two nearby logits).  The library
+// tanhf / expf (fast-math off) made these kernels instruction-bound: 24 tanh + 2 sigmoid per latent.
+__device__ __forceinline__ float eb_ex2(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float eb_rcp(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+// tanh(a) = 1 - 2 / (e^{2a} + 1), given E = e^{2a} (inf -> 1, 0 -> -1)
+__device__ __forceinline__ float eb_tanh_from_exp(float E) { return fmaf(-2.f, eb_rcp(E + 1.f), 1.f); }
+__device__ __forceinline__ float eb_tanh(float a) { return eb_tanh_from_exp(eb_ex2(a * 2.8853900817779268f)); }
+__device__ __forceinline__ float eb_sigmoid(float x) { return eb_rcp(1.f + eb_ex2(x * -1.4426950408889634f)); }
 
 // raw parameter (channel c, slot s) -> value; s indexes the packed 58-slot layout
 __device__ __forceinline__ float eb_raw_param(const EbParamPtrs& P, int c, int s) {
@@ -48,9 +68,49 @@ __device__ __forceinline__ void eb_load_params(const EbParamPtrs& P, int c, floa
       sp[MED] = P.p[14][c * 3 + 1];
     } else {
       const float raw = eb_raw_param(P, c, s);
-      sp[s] = (s < B0) ? softplus_f(raw) : ((s >= F0) ? tanhf(raw) : raw);
+      const float v = (s < B0) ? softplus_f(raw) : ((s >= F0) ? tanhf(raw) : raw);
+      sp[s] = v;
+      if (s < M1) { sp[EXPP + s] = expf(v); sp[EXPM + s] = expf(-v); }
     }
   }
+}
+
+// logits_cumulative at x - 1/2 and x + 1/2 at once.  First layer: a(x +- 1/2) = (m x + b) +- m / 2, so
+// e^{2 a(x +- 1/2)} = e^{2 (m x + b)} e^{+-m}: one exponential serves both evaluations.
+__device__ __forceinline__ void eb_logits_pair(const float* sp, float x, float& lower, float& upper) {
+  float hl[3], hu[3];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    const float a = fmaf(sp[M0 + j], x, sp[B0 + j]);
+    const float E = eb_ex2(a * 2.8853900817779268f);
+    const float half = 0.5f * sp[M0 + j];
+    const float al = a - half, au = a + half;
+    hl[j] = fmaf(sp[F0 + j], eb_tanh_from_exp(E * sp[EXPM + j]), al);
+    hu[j] = fmaf(sp[F0 + j], eb_tanh_from_exp(E * sp[EXPP + j]), au);
+  }
+#pragma unroll
+  for (int layer = 0; layer < 3; ++layer) {
+    const int m = M1 + 9 * layer, b = B1 + 3 * layer, f = F1 + 3 * layer;
+    float gl[3], gu[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const float m0 = sp[m + 3 * j], m1 = sp[m + 3 * j + 1], m2 = sp[m + 3 * j + 2], bb = sp[b + j], ff = sp[f + j];
+      const float al = fmaf(m2, hl[2], fmaf(m1, hl[1], m0 * hl[0])) + bb;
+      const float au = fmaf(m2, hu[2], fmaf(m1, hu[1], m0 * hu[0])) + bb;
+      gl[j] = fmaf(ff, eb_tanh(al), al);
+      gu[j] = fmaf(ff, eb_tanh(au), au);
+    }
+#pragma unroll
+    for (int j = 0; j < 3; ++j) { hl[j] = gl[j]; hu[j] = gu[j]; }
+  }
+  lower = fmaf(sp[M4 + 2], hl[2], fmaf(sp[M4 + 1], hl[1], sp[M4] * hl[0])) + sp[B4];
+  upper = fmaf(sp[M4 + 2], hu[2], fmaf(sp[M4 + 1], hu[1], sp[M4] * hu[0])) + sp[B4];
+}
+
+__device__ __forceinline__ float eb_lik_fast(float lower, float upper) {
+  const float sum = lower + upper;
+  const float sgn = (sum > 0.f) ? -1.f : ((sum < 0.f) ? 1.f : 0.f);  // -sign(lower+upper)
+  return fabsf(eb_sigmoid(sgn * upper) - eb_sigmoid(sgn * lower));
 }
 
 // logits_cumulative for one scalar input
@@ -86,32 +146,58 @@ __device__ __forceinline__ float eb_lik_from_logits(float lower, float upper) {
   return fabsf(sigmoid_f(sgn * upper) - sigmoid_f(sgn * lower));
 }
 
+template <int VEC>
 __global__ void __launch_bounds__(kEbThreads) eb_forward_kernel(const float* __restrict__ x,
                                                                  const float* __restrict__ noise, EbParamPtrs P,
                                                                  int B, int C, int HW, float lik_bound, int x_hat_mode,
                                                                  float* __restrict__ x_hat, float* __restrict__ lik) {
-  __shared__ float sp[64];
+  __shared__ float sp[72];
   const int c = blockIdx.y;
   eb_load_params(P, c, sp);
   __syncthreads();
   const float med = sp[MED];
   const long long per_ch = (long long)B * HW;
-  const long long e0 = (long long)blockIdx.x * (kEbThreads * kEbPerThread);
-#pragma unroll
-  for (int i = 0; i < kEbPerThread; ++i) {
-    const long long e = e0 + (long long)i * kEbThreads + threadIdx.x;
-    if (e >= per_ch) break;
-    const long long b = e / HW, p = e % HW;
+  // VEC == 4 (H*W % 4 == 0, 16-byte aligned tensors): one 128-bit load / store per thread and tensor, four latents
+  // of one (image, channel) row; otherwise one latent per thread and step
+  const long long e0 = ((long long)blockIdx.x * kEbThreads + threadIdx.x) * kEbPerThread;
+  if (VEC == 4) {
+    if (e0 >= per_ch) return;
+    const long long b = e0 / HW, p = e0 % HW;
     const size_t o = ((size_t)b * C + c) * HW + p;
-    const float v = x[o];
-    const float deq = __fadd_rn(rintf(__fsub_rn(v, med)), med);
-    const float outputs = noise ? __fadd_rn(v, noise[o]) : deq;
-    if (lik) {
-      const float lower = eb_logits(sp, outputs - 0.5f);
-      const float upper = eb_logits(sp, outputs + 0.5f);
-      lik[o] = fmaxf(eb_lik_from_logits(lower, upper), lik_bound);
+    const float4 v4 = ldg_stream(reinterpret_cast<const float4*>(x + o));
+    float4 n4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (noise) n4 = ldg_stream(reinterpret_cast<const float4*>(noise + o));
+    const float v[4] = {v4.x, v4.y, v4.z, v4.w}, nz[4] = {n4.x, n4.y, n4.z, n4.w};
+    float xh[4], lk[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float deq = __fadd_rn(rintf(__fsub_rn(v[i], med)), med);
+      const float outputs = noise ? __fadd_rn(v[i], nz[i]) : deq;
+      xh[i] = (x_hat_mode == 1) ? deq : outputs;
+      float lower, upper;
+      eb_logits_pair(sp, outputs, lower, upper);
+      lk[i] = fmaxf(eb_lik_fast(lower, upper), lik_bound);
     }
-    if (x_hat) x_hat[o] = (x_hat_mode == 1) ? deq : outputs;
+    if (lik) stg_stream(reinterpret_cast<float4*>(lik + o), make_float4(lk[0], lk[1], lk[2], lk[3]));
+    if (x_hat) stg_stream(reinterpret_cast<float4*>(x_hat + o), make_float4(xh[0], xh[1], xh[2], xh[3]));
+  } else {
+    const long long eb0 = (long long)blockIdx.x * (kEbThreads * kEbPerThread);
+#pragma unroll
+    for (int i = 0; i < kEbPerThread; ++i) {
+      const long long e = eb0 + (long long)i * kEbThreads + threadIdx.x;
+      if (e >= per_ch) break;
+      const long long b = e / HW, p = e % HW;
+      const size_t o = ((size_t)b * C + c) * HW + p;
+      const float v = x[o];
+      const float deq = __fadd_rn(rintf(__fsub_rn(v, med)), med);
+      const float outputs = noise ? __fadd_rn(v, noise[o]) : deq;
+      if (lik) {
+        float lower, upper;
+        eb_logits_pair(sp, outputs, lower, upper);
+        lik[o] = fmaxf(eb_lik_fast(lower, upper), lik_bound);
+      }
+      if (x_hat) x_hat[o] = (x_hat_mode == 1) ? deq : outputs;
+    }
   }
 }
 
@@ -123,7 +209,7 @@ __device__ __forceinline__ float eb_logits_backward(const float* sp, float x, fl
 #pragma unroll
   for (int j = 0; j < 3; ++j) {
     const float a = fmaf(sp[M0 + j], x, sp[B0 + j]);
-    t[0][j] = tanhf(a);
+    t[0][j] = eb_tanh(a);
     hin[0][j] = fmaf(sp[F0 + j], t[0][j], a);
   }
 #pragma unroll
@@ -135,7 +221,7 @@ __device__ __forceinline__ float eb_logits_backward(const float* sp, float x, fl
       a = fmaf(sp[m + 3 * j + 1], hin[layer][1], a);
       a = fmaf(sp[m + 3 * j + 2], hin[layer][2], a);
       a += sp[b + j];
-      t[layer + 1][j] = tanhf(a);
+      t[layer + 1][j] = eb_tanh(a);
       hin[layer + 1][j] = fmaf(sp[f + j], t[layer + 1][j], a);
     }
   }
@@ -184,7 +270,7 @@ __global__ void __launch_bounds__(kEbThreads) eb_backward_kernel(const float* __
                                                                   int B, int C, int HW, float lik_bound,
                                                                   float* __restrict__ d_x,
                                                                   float* __restrict__ packed /*[C][58]*/) {
-  __shared__ float sp[64];
+  __shared__ float sp[72];
   __shared__ float red[kEbThreads / 32][kEbParams];
   const int c = blockIdx.y;
   eb_load_params(P, c, sp);
@@ -199,11 +285,11 @@ __global__ void __launch_bounds__(kEbThreads) eb_backward_kernel(const float* __
     const size_t o = ((size_t)b * C + c) * HW + p;
     const float outputs = __fadd_rn(x[o], noise[o]);
     const float xl = outputs - 0.5f, xu = outputs + 0.5f;
-    const float lower = eb_logits(sp, xl);
-    const float upper = eb_logits(sp, xu);
+    float lower, upper;
+    eb_logits_pair(sp, outputs, lower, upper);
     const float sum = lower + upper;
     const float sgn = (sum > 0.f) ? -1.f : ((sum < 0.f) ? 1.f : 0.f);
-    const float A = sigmoid_f(sgn * upper), Bv = sigmoid_f(sgn * lower);
+    const float A = eb_sigmoid(sgn * upper), Bv = eb_sigmoid(sgn * lower);
     const float diff = A - Bv;
     const float L = fabsf(diff);
     float go = g_lik[o];
@@ -372,8 +458,14 @@ extern "C" int dcvic_eb_forward(const float* x, const float* noise, const float*
   for (int i = 0; i < 15; ++i) P.p[i] = params[i];
   const long long per_ch = (long long)B * HW;
   dim3 grid(ceil_div_i(per_ch, kEbThreads * kEbPerThread), C);
-  eb_forward_kernel<<<grid, kEbThreads, 0, (cudaStream_t)stream>>>(x, noise, P, B, C, HW, lik_bound, x_hat_mode,
-                                                                    x_hat, lik);
+  auto misaligned = [](const void* p) { return p && (reinterpret_cast<uintptr_t>(p) & 15) != 0; };
+  const bool vec = HW % 4 == 0 && !misaligned(x) && !misaligned(noise) && !misaligned(x_hat) && !misaligned(lik);
+  if (vec)
+    eb_forward_kernel<4><<<grid, kEbThreads, 0, (cudaStream_t)stream>>>(x, noise, P, B, C, HW, lik_bound, x_hat_mode,
+                                                                         x_hat, lik);
+  else
+    eb_forward_kernel<1><<<grid, kEbThreads, 0, (cudaStream_t)stream>>>(x, noise, P, B, C, HW, lik_bound, x_hat_mode,
+                                                                         x_hat, lik);
   if (dcvic_launch_status() != DCVIC_OK) return DCVIC_ERR_CUDA;
   if (bits) {
     const size_t packed = align_up((size_t)C * kEbParams * sizeof(float), 256);

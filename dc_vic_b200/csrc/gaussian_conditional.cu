@@ -231,6 +231,29 @@ static int gc_launch(GcArgs a, long long B, float* bits, float* bits_q, void* wo
 // L = Phi(u) - Phi(l), u = (.5 - v)/s, l = (-.5 - v)/s, v = |y + noise - mu|, s = max(sigma, bound)
 //   dL/dv = (phi(l) - phi(u))/s ; dL/dx = sign(x - mu) dL/dv ; dL/dmu = -dL/dx
 //   dL/ds = (l phi(l) - u phi(u))/s ; LowerBound rules gate both bounds.
+// One latent: the SFU forms of the forward kernel (Chebyshev erfc, ex2 for the pdf, rcp for 1/s); the likelihood is
+// only needed for the LowerBound gate.
+__device__ __forceinline__ void gc_backward_element(const GcArgs& a, float yv, float m, float raw, float nzv, bool train,
+                                                    float go, float& dx, float& ds) {
+  const float s = fmaxf(raw, a.scale_bound);
+  // eval mode: outputs = round(y - mu) + mu, whose derivative wrt y and (net) mu is zero
+  const float x = train ? __fadd_rn(yv, nzv) : __fadd_rn(rintf(__fsub_rn(yv, m)), m);
+  const float diff = __fsub_rn(x, m);
+  const float v = fabsf(diff);
+  const float inv_s = rcp_ftz(s);
+  const float u = (0.5f - v) * inv_s, l = (-0.5f - v) * inv_s;
+  const float L = gc_lik(x, m, s);
+  if (!(L >= a.lik_bound || go < 0.f)) go = 0.f;  // likelihood LowerBound
+  const float pu = kInvSqrt2Pi * ex2_ftz(-0.72134752044448170368f * u * u);   // exp(-u^2 / 2)
+  const float pl = kInvSqrt2Pi * ex2_ftz(-0.72134752044448170368f * l * l);
+  const float dv = (pl - pu) * inv_s;
+  const float sgn = (diff > 0.f) ? 1.f : ((diff < 0.f) ? -1.f : 0.f);
+  dx = train ? go * sgn * dv : 0.f;
+  ds = go * (l * pl - u * pu) * inv_s;
+  if (!(raw >= a.scale_bound || ds < 0.f)) ds = 0.f;  // scale LowerBound
+}
+
+template <bool VEC>
 __global__ void __launch_bounds__(256) gc_backward_kernel(const float* __restrict__ g_lik, GcArgs a,
                                                            float* __restrict__ d_y, float* __restrict__ d_mu,
                                                            float* __restrict__ d_sigma) {
@@ -240,32 +263,36 @@ __global__ void __launch_bounds__(256) gc_backward_kernel(const float* __restric
   const float* sg = a.sigma + b * a.sg_bs;
   const float* nz = a.noise ? a.noise + b * a.n : nullptr;
   const float* g = g_lik + b * a.n;
-  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < a.n;
-       e += (long long)gridDim.x * blockDim.x) {
-    const float m = mu ? mu[e] : 0.f;
-    const float raw = sg[e];
-    const float s = fmaxf(raw, a.scale_bound);
-    // eval mode: outputs = round(y - mu) + mu, whose derivative wrt y and (net) mu is zero
-    const float x = nz ? __fadd_rn(y[e], nz[e]) : __fadd_rn(rintf(__fsub_rn(y[e], m)), m);
-    const float diff = __fsub_rn(x, m);
-    const float v = fabsf(diff);
-    const float u = __fdiv_rn(__fsub_rn(0.5f, v), s);
-    const float l = __fdiv_rn(__fsub_rn(-0.5f, v), s);
-    const float L = __fsub_rn(0.5f * erfcf(kNegInvSqrt2 * u), 0.5f * erfcf(kNegInvSqrt2 * l));
-    float go = g[e];
-    if (!(L >= a.lik_bound || go < 0.f)) go = 0.f;  // likelihood LowerBound
-    const float pu = kInvSqrt2Pi * __expf(-0.5f * u * u);
-    const float pl = kInvSqrt2Pi * __expf(-0.5f * l * l);
-    const float inv_s = 1.f / s;
-    const float dv = (pl - pu) * inv_s;
-    const float sgn = (diff > 0.f) ? 1.f : ((diff < 0.f) ? -1.f : 0.f);
-    const float dx = nz ? go * sgn * dv : 0.f;
-    float ds = go * (l * pl - u * pu) * inv_s;
-    if (!(raw >= a.scale_bound || ds < 0.f)) ds = 0.f;  // scale LowerBound
-    const long long o = b * a.n + e;
-    if (d_y) d_y[o] = dx;
-    if (d_mu) d_mu[o] = -dx;
-    if (d_sigma) d_sigma[o] = ds;
+  const bool train = nz != nullptr;
+  if (VEC) {
+    // 128-bit loads / stores: 28 B per latent (g, y, mu, sigma in; dy, dmu, dsigma out), HBM-bound
+    for (long long e = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; e < a.n;
+         e += (long long)gridDim.x * blockDim.x * 4) {
+      const float4 y4 = ldg_stream(reinterpret_cast<const float4*>(y + e));
+      const float4 s4 = ldg_stream(reinterpret_cast<const float4*>(sg + e));
+      const float4 g4 = ldg_stream(reinterpret_cast<const float4*>(g + e));
+      const float4 m4 = mu ? ldg_stream(reinterpret_cast<const float4*>(mu + e)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 n4 = nz ? ldg_stream(reinterpret_cast<const float4*>(nz + e)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 dx, ds;
+      gc_backward_element(a, y4.x, m4.x, s4.x, n4.x, train, g4.x, dx.x, ds.x);
+      gc_backward_element(a, y4.y, m4.y, s4.y, n4.y, train, g4.y, dx.y, ds.y);
+      gc_backward_element(a, y4.z, m4.z, s4.z, n4.z, train, g4.z, dx.z, ds.z);
+      gc_backward_element(a, y4.w, m4.w, s4.w, n4.w, train, g4.w, dx.w, ds.w);
+      const long long o = b * a.n + e;
+      if (d_y) stg_stream(reinterpret_cast<float4*>(d_y + o), dx);
+      if (d_mu) stg_stream(reinterpret_cast<float4*>(d_mu + o), make_float4(-dx.x, -dx.y, -dx.z, -dx.w));
+      if (d_sigma) stg_stream(reinterpret_cast<float4*>(d_sigma + o), ds);
+    }
+  } else {
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < a.n;
+         e += (long long)gridDim.x * blockDim.x) {
+      float dx, ds;
+      gc_backward_element(a, y[e], mu ? mu[e] : 0.f, sg[e], nz ? nz[e] : 0.f, train, g[e], dx, ds);
+      const long long o = b * a.n + e;
+      if (d_y) d_y[o] = dx;
+      if (d_mu) d_mu[o] = -dx;
+      if (d_sigma) d_sigma[o] = ds;
+    }
   }
 }
 
@@ -413,8 +440,16 @@ extern "C" int dcvic_gc_backward(const float* g_lik, const float* y, const float
   DCVIC_CHECK_ARG(d_y || d_mu || d_sigma);
   GcArgs a{y, mu, sigma, noise, n, y_bstride, mu_bstride, sigma_bstride, scale_bound, lik_bound, 0,
            nullptr, nullptr, nullptr, nullptr, nullptr};
-  dim3 grid(min(ceil_div_i(n, 256), 2048), (unsigned)B);
-  gc_backward_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(g_lik, a, d_y, d_mu, d_sigma);
+  auto mis = [](const void* p) { return p && (reinterpret_cast<uintptr_t>(p) & 15) != 0; };
+  const bool vec = n % 4 == 0 && y_bstride % 4 == 0 && mu_bstride % 4 == 0 && sigma_bstride % 4 == 0 && !mis(g_lik) &&
+                   !mis(y) && !mis(mu) && !mis(sigma) && !mis(noise) && !mis(d_y) && !mis(d_mu) && !mis(d_sigma);
+  if (vec) {
+    dim3 grid(min(ceil_div_i(n, 1024), 4 * kNumSMs), (unsigned)B);
+    gc_backward_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(g_lik, a, d_y, d_mu, d_sigma);
+  } else {
+    dim3 grid(min(ceil_div_i(n, 256), 2048), (unsigned)B);
+    gc_backward_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(g_lik, a, d_y, d_mu, d_sigma);
+  }
   return dcvic_launch_status();
 }
 
