@@ -255,10 +255,50 @@ class EntropyModel(DevicePinned, nn.Module):
             cdf[i, : row.numel()] = row
         return cdf
 
-    def compress(self, *a, **k):
-        raise NotImplementedError("rANS bitstream coding is outside this build's scope (SURVEY 8(f) rank 2)")
+    # ---- bitstreams (CompressAI 1.2.4 EntropyModel.compress / decompress; call sites
+    # hyperprior_dc_vic_model.py:308-328,378-387).  Symbols are produced and range-coded on the GPU (dc_vic_b200.rans:
+    # one warp per image, no .tolist() marshaling); only the finished byte strings travel to the host.
+    def _check_tables(self):
+        if self._quantized_cdf.numel() == 0 or self._offset.numel() == 0 or self._cdf_length.numel() == 0:
+            raise ValueError("Uninitialized CDFs. Run update() first")
+        if self._quantized_cdf.dim() != 2:
+            raise ValueError(f"Invalid CDF size {self._quantized_cdf.size()}")
 
-    decompress = compress
+    def compress(self, inputs: Tensor, indexes: Tensor, means: Optional[Tensor] = None):
+        from . import rans
+        if inputs.dim() < 2:
+            raise ValueError("Invalid `inputs` size. Expected a tensor with at least 2 dimensions.")
+        if inputs.size() != indexes.size():
+            raise ValueError("`inputs` and `indexes` should have the same size.")
+        self._check_tables()
+        _, (inputs, indexes, means) = self._upload(inputs, indexes, means)
+        symbols = self.quantize(inputs, "symbols", means)
+        dev = symbols.device
+        tab = rans._Tables(self._quantized_cdf.to(dev), self._cdf_length.reshape(-1).to(dev),
+                           self._offset.reshape(-1).to(dev), dev)
+        B = symbols.shape[0]
+        return rans.encode_batch([symbols[i].reshape(-1) for i in range(B)],
+                                 [indexes[i].reshape(-1).int() for i in range(B)], tab)
+
+    def decompress(self, strings, indexes: Tensor, dtype: torch.dtype = torch.float, means: Optional[Tensor] = None):
+        from . import rans
+        if not isinstance(strings, (tuple, list)):
+            raise ValueError("Invalid `strings` parameter type.")
+        if not len(strings) == indexes.size(0):
+            raise ValueError("Invalid strings or indexes parameters")
+        if indexes.dim() < 2:
+            raise ValueError("Invalid `indexes` size. Expected a tensor with at least 2 dimensions.")
+        self._check_tables()
+        home, (indexes, means) = self._upload(indexes, means)
+        dev = indexes.device
+        outputs = torch.empty(indexes.size(), dtype=torch.int32, device=dev)
+        for i, s in enumerate(strings):
+            dec = rans.RansDecoder()
+            dec.set_stream(s)
+            outputs[i] = dec.decode_stream_tensor(indexes[i].reshape(-1).int(), self._quantized_cdf.to(dev),
+                                                  self._cdf_length.reshape(-1).to(dev),
+                                                  self._offset.reshape(-1).to(dev)).view(outputs[i].shape)
+        return self._download(home, self.dequantize(outputs, means, dtype))[0]
 
 
 # ------------------------------------------------------------------------------ Gaussian
@@ -583,6 +623,34 @@ class EntropyBottleneck(EntropyModel):
     def loss(self) -> Tensor:
         logits = self._logits_cumulative(self.quantiles, stop_gradient=True)
         return torch.abs(logits - self.target).sum()
+
+    @staticmethod
+    def _build_indexes(size):
+        dims = len(size)
+        N, Cc = size[0], size[1]
+        view_dims = np.ones((dims,), dtype=np.int64)
+        view_dims[1] = -1
+        indexes = torch.arange(Cc).view(*view_dims)
+        return indexes.int().repeat(N, 1, *size[2:])
+
+    @staticmethod
+    def _extend_ndims(tensor, n):
+        return tensor.reshape(-1, *([1] * n)) if n > 0 else tensor.reshape(-1)
+
+    def compress(self, x: Tensor):
+        indexes = self._build_indexes(x.size()).to(self._quantized_cdf.device)
+        medians = self._get_medians().detach()
+        spatial_dims = len(x.size()) - 2
+        medians = self._extend_ndims(medians, spatial_dims)
+        medians = medians.expand(x.size(0), *([-1] * (spatial_dims + 1)))
+        return super().compress(x, indexes, medians)
+
+    def decompress(self, strings, size):
+        output_size = (len(strings), self._quantized_cdf.size(0), *size)
+        indexes = self._build_indexes(output_size).to(self._quantized_cdf.device)
+        medians = self._extend_ndims(self._get_medians().detach(), len(size))
+        medians = medians.expand(len(strings), *([-1] * (len(size) + 1)))
+        return super().decompress(strings, indexes, medians.dtype, medians)
 
     def update(self, force: bool = False) -> bool:
         if self._offset.numel() > 0 and not force:

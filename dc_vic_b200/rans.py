@@ -11,6 +11,7 @@ from __future__ import annotations
 
 from typing import List, Sequence
 
+import numpy as np
 import torch
 
 from . import _lib
@@ -47,12 +48,29 @@ class _Tables:
         self.offsets = _as_i32(offsets, device)
 
 
+_TABLE_CACHE = {}
+
+
+def _tables_cached(cdfs, cdf_lengths, offsets, device) -> _Tables:
+    """The CHARM decode loop passes the SAME Python list of CDF rows for every slice
+    (minnen20_charm_context_model.py:175-177): upload it once."""
+    if isinstance(cdfs, torch.Tensor):
+        return _Tables(cdfs, cdf_lengths, offsets, device)
+    key = (id(cdfs), id(cdf_lengths), id(offsets), str(device))
+    hit = _TABLE_CACHE.get(key)
+    if hit is None or hit[0] is not cdfs:
+        _TABLE_CACHE.clear()
+        hit = (cdfs, _Tables(cdfs, cdf_lengths, offsets, device))
+        _TABLE_CACHE[key] = hit
+    return hit[1]
+
+
 def encode_with_indexes(symbols, indexes, cdfs, cdf_lengths, offsets) -> bytes:
     """One rANS stream over ``symbols`` (any shape, flattened in C order) -> the bytes CompressAI's
     ``RansEncoder.encode_with_indexes`` produces."""
     dev = _device()
     sym, idx = _as_i32(symbols, dev).reshape(-1), _as_i32(indexes, dev).reshape(-1)
-    tab = _Tables(cdfs, cdf_lengths, offsets, dev)
+    tab = _tables_cached(cdfs, cdf_lengths, offsets, dev)
     return encode_batch([sym], [idx], tab)[0]
 
 
@@ -77,13 +95,13 @@ def encode_batch(symbols: Sequence[torch.Tensor], indexes: Sequence[torch.Tensor
                                    _lib.ptr(out), _lib.ptr(out_starts), _lib.ptr(nwords), _lib.cur_stream())
         _lib.check(rc, "dcvic_rans_encode")
     nw = nwords.cpu().tolist()
-    host = out.cpu().numpy()
+    ends = out_starts.cpu().tolist()
     res = []
     for s in range(S):
-        o = int(out_starts[s]) if S > 1 else 0
-        # the kernel writes the words of stream s backwards from the end of its slot (the encoder runs in reverse)
-        end = o + cap_words[s]
-        res.append(host[end - nw[s]: end].tobytes())
+        # the kernel writes the words of stream s backwards from the end of its slot (the encoder runs in reverse);
+        # only the words that were written travel to the host
+        end = int(ends[s + 1])
+        res.append(out[end - nw[s]: end].cpu().numpy().tobytes())
     return res
 
 
@@ -129,12 +147,9 @@ class RansDecoder:
 
     def set_stream(self, stream: bytes) -> None:
         dev = _device()
-        import numpy as np
-        arr = np.frombuffer(stream, dtype=np.uint32).astype(np.int64).astype(np.int32, casting="unsafe") \
-            if len(stream) % 4 == 0 else None
-        if arr is None:
-            raise ValueError("rANS stream length must be a multiple of 4 bytes")
-        self._words = torch.from_numpy(arr.copy()).to(dev)
+        if len(stream) % 4 != 0 or len(stream) < 8:
+            raise ValueError("a rans64 stream is a whole number (>= 2) of 32-bit words")
+        self._words = torch.from_numpy(np.frombuffer(stream, dtype=np.int32).copy()).to(dev)
         self._state = torch.zeros(4, dtype=torch.int64, device=dev)      # [state, word position, initialised, -]
 
     def decode_stream_tensor(self, indexes, cdfs, cdf_lengths, offsets) -> torch.Tensor:
@@ -142,7 +157,7 @@ class RansDecoder:
             raise RuntimeError("RansDecoder.set_stream was not called")
         dev = self._words.device
         idx = _as_i32(indexes, dev).reshape(-1)
-        tab = indexes_tables = _Tables(cdfs, cdf_lengths, offsets, dev)
+        tab = _tables_cached(cdfs, cdf_lengths, offsets, dev)
         out = torch.empty(idx.numel(), dtype=torch.int32, device=dev)
         lib = _lib.load()
         with _lib.on_device(dev):

@@ -209,6 +209,22 @@ int dcvic_ste_round(const float* x, int64_t n, float* out, dcvic_stream_t stream
  * every symbol width >= 1. */
 int dcvic_pmf_to_quantized_cdf(const float* pmf, int n, int precision, int32_t* cdf);
 
+/* Range-ANS coder: compressai.ans' rans64 streams (CompressAI 1.2.4 rans_interface.cpp; call sites
+ * src/models/comp_model/hyperprior_dc_vic_model.py:308-328,378-387, minnen20_charm_context_model.py:175-202), bit-exact
+ * with oracle/rans_oracle.c.  All pointers are device pointers.
+ * encode: n_streams independent streams; stream s codes symbols[starts[s] .. starts[s+1]) with the CDF rows selected by
+ *   indexes[] (cdf [rows, width] int32, cdf_sizes / offsets per row).  Its 32-bit words are written BACKWARDS from
+ *   out_words[out_starts[s+1]] (the caller sizes the slot: 4 words per symbol + 8 always suffice); n_words[s] receives
+ *   how many: the stream is out_words[out_starts[s+1] - n_words[s] .. out_starts[s+1]).
+ * decode: advances ONE stream by n symbols; state[4] (int64, zero before the first call) carries the coder state and
+ *   the read position between calls, as RansDecoder.set_stream / decode_stream do. */
+int dcvic_rans_encode(const int32_t* symbols, const int32_t* indexes, const int64_t* starts, int n_streams,
+                      const int32_t* cdf, int rows, int width, const int32_t* cdf_sizes, const int32_t* offsets,
+                      uint32_t* out_words, const int64_t* out_starts, int32_t* n_words, dcvic_stream_t stream);
+int dcvic_rans_decode(const uint32_t* words, int64_t n_words, int64_t* state, const int32_t* indexes, int64_t n,
+                      const int32_t* cdf, int rows, int width, const int32_t* cdf_sizes, const int32_t* offsets,
+                      int32_t* out_symbols, dcvic_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
