@@ -47,6 +47,7 @@ SIGNATURES = {
     "dcvic_rate_bits_backward": (_i, [_p, _p, _i64, _i64, _p, _p]),
     "dcvic_ste_round": (_i, [_p, _i64, _p, _p]),
     "dcvic_pmf_to_quantized_cdf": (_i, [C.POINTER(C.c_float), _i, _i, C.POINTER(C.c_int32)]),
+    "dcvic_pmf_to_quantized_cdf_rows": (_i, [_p, _i, _i, _p, _p, _i, _p, _p, _p]),
     "dcvic_rans_encode": (_i, [_p, _p, _p, _i, _p, _i, _i, _p, _p, _p, _p, _p, _p]),
     "dcvic_rans_decode": (_i, [_p, _i64, _p, _p, _i64, _p, _i, _i, _p, _p, _p, _p]),
 }

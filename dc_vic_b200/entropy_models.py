@@ -247,6 +247,22 @@ class EntropyModel(DevicePinned, nn.Module):
         return outputs
 
     def _pmf_to_cdf(self, pmf, tail_mass, pmf_length, max_length):
+        if pmf.is_cuda:
+            # the whole table on the device, one thread per row (dcvic_pmf_to_quantized_cdf_rows)
+            dev = pmf.device
+            pm = pmf.detach().float().contiguous()
+            rows, width = pm.shape[0], pm.shape[1]
+            tm = tail_mass.detach().float().reshape(-1).contiguous().to(dev)
+            ln = pmf_length.detach().int().reshape(-1).contiguous().to(dev)
+            with _lib.on_device(dev):
+                cdf = torch.empty(rows, width + 2, dtype=torch.int32, device=dev)
+                status = torch.zeros(1, dtype=torch.int32, device=dev)
+                rc = _lib.load().dcvic_pmf_to_quantized_cdf_rows(_lib.ptr(pm), rows, width, _lib.ptr(tm), _lib.ptr(ln),
+                                                                 self.entropy_coder_precision, _lib.ptr(cdf),
+                                                                 _lib.ptr(status), _lib.cur_stream())
+                _lib.check(rc, "dcvic_pmf_to_quantized_cdf_rows")
+            _lib.check(int(status), "dcvic_pmf_to_quantized_cdf_rows (row)")
+            return cdf[:, : max_length + 2].contiguous()
         pmf, tail_mass, pmf_length = pmf.cpu(), tail_mass.cpu(), pmf_length.cpu()
         cdf = torch.zeros((len(pmf_length), max_length + 2), dtype=torch.int32)
         for i, p in enumerate(pmf):

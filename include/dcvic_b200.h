@@ -209,6 +209,13 @@ int dcvic_ste_round(const float* x, int64_t n, float* out, dcvic_stream_t stream
  * every symbol width >= 1. */
 int dcvic_pmf_to_quantized_cdf(const float* pmf, int n, int precision, int32_t* cdf);
 
+/* The same construction for a whole table ON THE DEVICE (EntropyBottleneck.update / GaussianConditional.update ->
+ * EntropyModel._pmf_to_cdf): pmf [rows, width] FP32 as the likelihood kernel left it, tail_mass [rows], lengths [rows];
+ * cdf [rows, width + 2] int32 (zero beyond lengths[r] + 2); *status (device int32, zero on entry) receives a negative
+ * code if a row is invalid.  One thread per row. */
+int dcvic_pmf_to_quantized_cdf_rows(const float* pmf, int rows, int width, const float* tail_mass, const int32_t* lengths,
+                                    int precision, int32_t* cdf, int32_t* status, dcvic_stream_t stream);
+
 /* Range-ANS coder: compressai.ans' rans64 streams (CompressAI 1.2.4 rans_interface.cpp; call sites
  * src/models/comp_model/hyperprior_dc_vic_model.py:308-328,378-387, minnen20_charm_context_model.py:175-202), bit-exact
  * with oracle/rans_oracle.c.  All pointers are device pointers.

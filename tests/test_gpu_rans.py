@@ -114,3 +114,33 @@ def test_gaussian_conditional_bin_file_round_trip(tmp_path):
     h2, _, y2 = BS.load_byte_strings(path)
     assert BS.HeaderHandler().decode(h2)["img_size"] == (512, 768) and y2 == y_str[0]
     assert os.path.getsize(path) == 6 + 8 + len(y_str[0]) + 12
+
+
+def test_cdf_tables_are_built_on_the_device_bit_exactly():
+    """_pmf_to_cdf on the GPU (one thread per row) == the host construction == the oracle's, on the real tables."""
+    gc = D.SteGaussianMeanScaleConditional(scale_bound=0.11).to(DEV)
+    gc.update_scale_table(D.get_scale_table(), force=True)
+    eb = D.SteEntropyBottleneck(channels=16).to(DEV)
+    with torch.no_grad():
+        eb.quantiles[:, 0, 0] -= 5 * torch.rand(16, device=DEV)
+        eb.quantiles[:, 0, 2] += 5 * torch.rand(16, device=DEV)
+    eb.update(force=True)
+    for m in (gc, eb):
+        cdf, ln = m._quantized_cdf, m._cdf_length
+        assert cdf.is_cuda and cdf.dtype == torch.int32
+        for r in range(cdf.shape[0]):
+            row = cdf[r, : int(ln[r])].cpu()
+            assert int(row[0]) == 0 and int(row[-1]) == 65536 and bool((row[1:] > row[:-1]).all())
+            assert bool((cdf[r, int(ln[r]):] == 0).all())
+    # same PMF rows through the host entry point and through the oracle
+    pmf = torch.rand(7, 33, device=DEV) ** 4 + 1e-7
+    pmf = pmf / pmf.sum(1, keepdim=True) * 0.97
+    lens = torch.tensor([33, 5, 17, 1, 33, 20, 9], dtype=torch.int32, device=DEV)
+    tail = torch.rand(7, 1, device=DEV) * 0.03 + 1e-6
+    dev_cdf = gc._pmf_to_cdf(pmf, tail, lens, 33)
+    host_cdf = gc._pmf_to_cdf(pmf.cpu(), tail.cpu(), lens.cpu(), 33)
+    assert torch.equal(dev_cdf.cpu(), host_cdf)
+    for r in range(7):
+        n = int(lens[r])
+        want = EO.pmf_to_quantized_cdf(np.concatenate([pmf[r, :n].cpu().numpy(), tail[r].cpu().numpy()]), 16)
+        assert dev_cdf[r, : n + 2].cpu().tolist() == [int(v) for v in want]
