@@ -3,7 +3,8 @@ the VQGAN codebook quantizer and the CompressAI-style rate/entropy model, behind
 reference's own module interfaces.  Hand-written CUDA behind a C ABI (include/dcvic_b200.h);
 PyTorch is plumbing (device memory, streams, autograd glue, torch.distributed)."""
 from .quantize import (VectorQuantizer, VectorQuantizer2, codebook_lookup, onehot_feature, swap_quantizer,
-                       decode_tokens)
+                       decode_tokens, CrossEntropyLoss, FocalCrossEntropyLoss)
+from . import tiling, bitstream, rans, parallel
 from .entropy_models import (EntropyModel, EntropyBottleneck, GaussianConditional, LowerBound,
                              DcvicEntropyBottleneck, SteEntropyBottleneck, GaussianScaleConditional,
                              GaussianMeanScaleConditional, SteGaussianMeanScaleConditional, ste_round,

@@ -32,6 +32,8 @@ SIGNATURES = {
     "dcvic_codebook_gather": (_i, [_p, _p, _i, _i, _i, _i, _i, _p, _p, _p]),
     "dcvic_onehot_nchw": (_i, [_p, _i, _i, _i, _p, _p]),
     "dcvic_token_decode": (_i, [_p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p]),
+    "dcvic_token_decode_ex": (_i, [_p, _p, _p, _i, _i, _i, _i, _p, _p, _i, _f, _p, _p, _p, _p, _p, _p]),
+    "dcvic_token_ce_backward": (_i, [_p, _p, _p, _p, _i, _i, _i, _f, _f, _p, _p]),
     "dcvic_gc_workspace_bytes": (_sz, [_i64, _i64]),
     "dcvic_gc_forward": (_i, [_p, _p, _p, _p, _i64, _i64, _i64, _i64, _i64, _f, _f, _i, _p, _p, _p, _p, _sz, _p]),
     "dcvic_gc_forward_dual": (_i, [_p, _p, _p, _p, _i64, _i64, _i64, _i64, _i64, _f, _f, _p, _p, _p, _p, _p, _p,
@@ -48,6 +50,8 @@ SIGNATURES = {
     "dcvic_ste_round": (_i, [_p, _i64, _p, _p]),
     "dcvic_pmf_to_quantized_cdf": (_i, [C.POINTER(C.c_float), _i, _i, C.POINTER(C.c_int32)]),
     "dcvic_pmf_to_quantized_cdf_rows": (_i, [_p, _i, _i, _p, _p, _i, _p, _p, _p]),
+    "dcvic_tile_gather": (_i, [_p, _i, _i, _i, _i, _p, _i, _i, _i, _i, _p, _p]),
+    "dcvic_tile_stitch": (_i, [_p, _i, _i, _i, _i, _p, _i, _i, _p, _i, _i, _p]),
     "dcvic_rans_encode": (_i, [_p, _p, _p, _i, _p, _i, _i, _p, _p, _p, _p, _p, _p]),
     "dcvic_rans_decode": (_i, [_p, _i64, _p, _p, _i64, _p, _i, _i, _p, _p, _p, _p]),
 }

@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libdcvic_b200.so")
-SOURCES = ["abi.cu", "vq_simt.cu", "vq_tcgen05.cu", "gaussian_conditional.cu", "entropy_bottleneck.cu", "codec_tables.cu", "token_decode.cu", "vq_finish_tma.cu", "vq_fused.cu", "rans.cu"]
+SOURCES = ["abi.cu", "vq_simt.cu", "vq_tcgen05.cu", "gaussian_conditional.cu", "entropy_bottleneck.cu", "codec_tables.cu", "token_decode.cu", "vq_finish_tma.cu", "vq_fused.cu", "rans.cu", "tiling.cu"]
 HEADERS = ["common.cuh", "vq_common.cuh", "sm100_ptx.cuh", "../../include/dcvic_b200.h"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "--use_fast_math=false"]

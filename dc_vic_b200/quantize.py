@@ -22,7 +22,8 @@ import torch.nn as nn
 
 from . import _lib
 
-__all__ = ["VectorQuantizer", "VectorQuantizer2", "codebook_lookup", "onehot_feature", "swap_quantizer"]
+__all__ = ["VectorQuantizer", "VectorQuantizer2", "codebook_lookup", "onehot_feature", "swap_quantizer", "decode_tokens",
+           "CrossEntropyLoss", "FocalCrossEntropyLoss"]
 
 
 class _Workspace:
@@ -185,18 +186,8 @@ def onehot_feature(indices_bhw: torch.Tensor, n_embed: int) -> torch.Tensor:
     return out
 
 
-def decode_tokens(logits: torch.Tensor, weight: torch.Tensor, gt_indices: Optional[torch.Tensor] = None,
-                  want_latent: bool = True):
-    """Decoder-side token path of DC-VIC in one kernel (hyperprior_dc_vic_model.py:250-260):
-
-        out_vq_indices = torch.argmax(out_vq_logits, dim=1)                       # [B, H, W]
-        vq_accuracy    = (out_vq_indices == gt_vq_indices).float().mean()         # if gt_indices is given
-        vq_latent      = vq_indices_to_latent(out_vq_indices)                     # [B, D, H, W]
-
-    Returns ``(indices, latent | None, accuracy | None)``.  No gradient flows through argmax in the reference either
-    (the logits are trained through the code CE / MSE losses on ``out_vq_logits`` itself).
-    """
-    _lib.require_cuda(logits, weight, gt_indices)
+def _token_decode(logits, weight, gt, want_latent, pq_w, pq_b, gamma, want_lse, want_loss):
+    _lib.require_cuda(logits, weight, gt, pq_w, pq_b)
     if logits.dim() != 4:
         raise ValueError(f"expected logits of shape [B, K, H, W], got {tuple(logits.shape)}")
     lib = _lib.load()
@@ -206,16 +197,108 @@ def decode_tokens(logits: torch.Tensor, weight: torch.Tensor, gt_indices: Option
         raise ValueError(f"logits have {K} classes but the codebook has {K2} entries")
     lg = logits.detach().contiguous().float()
     wc = weight.detach().contiguous().float()
-    gt = None if gt_indices is None else gt_indices.contiguous().long()
+    gtc = None if gt is None else gt.contiguous().long()
+    D_out = D
+    if pq_w is not None:
+        pq_w = pq_w.detach().reshape(pq_w.shape[0], -1).contiguous().float()
+        if pq_w.shape[1] != D:
+            raise ValueError(f"post_quant_conv expects {pq_w.shape[1]} input channels, the codebook has e_dim={D}")
+        D_out = pq_w.shape[0]
+        pq_b = None if pq_b is None else pq_b.detach().contiguous().float()
     with _lib.on_device(lg.device):
         idx = torch.empty(B, H, W, dtype=torch.int64, device=lg.device)
-        latent = torch.empty(B, D, H, W, dtype=torch.float32, device=lg.device) if want_latent else None
-        count = torch.empty(1, dtype=torch.int32, device=lg.device) if gt is not None else None
-        rc = lib.dcvic_token_decode(_lib.ptr(lg), _lib.ptr(wc), _lib.ptr(gt), B, K, H * W, D, _lib.ptr(idx),
-                                    _lib.ptr(latent), _lib.ptr(count), _lib.cur_stream())
-        _lib.check(rc, "dcvic_token_decode")
+        latent = torch.empty(B, D_out, H, W, dtype=torch.float32, device=lg.device) if want_latent else None
+        count = torch.empty(1, dtype=torch.int32, device=lg.device) if gtc is not None else None
+        lse = torch.empty(B, H, W, dtype=torch.float32, device=lg.device) if want_lse else None
+        sums = torch.empty(2, dtype=torch.float64, device=lg.device) if want_loss else None
+        rc = lib.dcvic_token_decode_ex(_lib.ptr(lg), _lib.ptr(wc), _lib.ptr(gtc), B, K, H * W, D, _lib.ptr(pq_w),
+                                       _lib.ptr(pq_b), D_out, float(gamma), _lib.ptr(idx), _lib.ptr(latent),
+                                       _lib.ptr(count), _lib.ptr(lse), _lib.ptr(sums), _lib.cur_stream())
+        _lib.check(rc, "dcvic_token_decode_ex")
+    return idx, latent, count, lse, sums, lg, gtc
+
+
+def decode_tokens(logits: torch.Tensor, weight: torch.Tensor, gt_indices: Optional[torch.Tensor] = None,
+                  want_latent: bool = True, post_quant_conv: Optional[nn.Module] = None):
+    """Decoder-side token path of DC-VIC in one kernel (hyperprior_dc_vic_model.py:250-260):
+
+        out_vq_indices = torch.argmax(out_vq_logits, dim=1)                       # [B, H, W]
+        vq_accuracy    = (out_vq_indices == gt_vq_indices).float().mean()         # if gt_indices is given
+        vq_latent      = vq_indices_to_latent(out_vq_indices)                     # [B, D, H, W]
+        vq_latent      = vq_model.post_quant_conv(vq_latent)                      # if post_quant_conv (a 1x1 Conv2d)
+
+    Returns ``(indices, latent | None, accuracy | None)``.  No gradient flows through argmax in the reference either
+    (the logits are trained through the code CE / MSE losses on ``out_vq_logits`` itself).
+    """
+    pq_w = pq_b = None
+    if post_quant_conv is not None:
+        if tuple(post_quant_conv.weight.shape[2:]) != (1, 1):
+            raise ValueError("post_quant_conv must be a 1x1 convolution (ldm/models/autoencoder.py:41)")
+        pq_w, pq_b = post_quant_conv.weight, post_quant_conv.bias
+    B, K, H, W = logits.shape
+    idx, latent, count, _, _, _, _ = _token_decode(logits, weight, gt_indices, want_latent, pq_w, pq_b, 0.0, False, False)
     acc = None if count is None else (count.float() / float(B * H * W)).reshape(())
     return idx, latent, acc
+
+
+class _CodeCE(torch.autograd.Function):
+    """Mean (or summed) code cross entropy / focal cross entropy over [B, K, H, W] logits, one pass forward (riding
+    on the arg-max scan), one pass backward."""
+
+    @staticmethod
+    def forward(ctx, logits, target, gamma, loss_weight, reduction, weight_for_shape):
+        idx, _, _, lse, sums, lg, gtc = _token_decode(logits, weight_for_shape, target, False, None, None, gamma, True,
+                                                      True)
+        B, K, H, W = logits.shape
+        n = B * H * W
+        scale = loss_weight / n if reduction == "mean" else loss_weight
+        ctx.save_for_backward(lg, gtc, lse)
+        ctx.meta = (B, K, H * W, float(gamma), float(scale))
+        return (sums[1 if gamma != 0.0 else 0] * scale).float()
+
+    @staticmethod
+    def backward(ctx, g):
+        lg, gtc, lse = ctx.saved_tensors
+        B, K, HW, gamma, scale = ctx.meta
+        with _lib.on_device(lg.device):
+            d = torch.empty_like(lg)
+            gl = g.detach().reshape(1).contiguous().float()
+            rc = _lib.load().dcvic_token_ce_backward(_lib.ptr(lg), _lib.ptr(gtc), _lib.ptr(lse), _lib.ptr(gl), B, K, HW,
+                                                     gamma, scale, _lib.ptr(d), _lib.cur_stream())
+            _lib.check(rc, "dcvic_token_ce_backward")
+        return d, None, None, None, None, None
+
+
+class CrossEntropyLoss(nn.Module):
+    """src/losses/cross_entropy_loss.py:9-31 (the code CE loss on the vq_estimator logits), default ``ce_kwargs``."""
+
+    def __init__(self, loss_weight: float, ce_kwargs: Optional[dict] = None) -> None:
+        super().__init__()
+        if ce_kwargs:
+            raise NotImplementedError("class weights / label smoothing / ignore_index are not used by DC-VIC's configs")
+        self.loss_weight = loss_weight
+
+    def forward(self, input: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+        dummy = torch.empty(input.shape[1], 1, device=input.device)
+        return _CodeCE.apply(input, target, 0.0, float(self.loss_weight), "mean", dummy)
+
+
+class FocalCrossEntropyLoss(nn.Module):
+    """src/losses/cross_entropy_loss.py:33-52."""
+
+    def __init__(self, loss_weight: float, gamma: float, reduction: str = "mean", **kwargs) -> None:
+        super().__init__()
+        if kwargs:
+            raise NotImplementedError("extra nn.CrossEntropyLoss arguments are not used by DC-VIC's configs")
+        if reduction not in ("mean", "sum"):
+            raise NotImplementedError("reduction='none' is not implemented (the trainers use 'mean')")
+        self.loss_weight, self.gamma, self.reduction = loss_weight, gamma, reduction
+
+    def forward(self, input: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+        dummy = torch.empty(input.shape[1], 1, device=input.device)
+        if self.gamma == 0:
+            return _CodeCE.apply(input, target, 0.0, float(self.loss_weight), self.reduction, dummy)
+        return _CodeCE.apply(input, target, float(self.gamma), float(self.loss_weight), self.reduction, dummy)
 
 
 class _QuantizerBase(nn.Module):

@@ -209,6 +209,20 @@ int dcvic_ste_round(const float* x, int64_t n, float* out, dcvic_stream_t stream
  * every symbol width >= 1. */
 int dcvic_pmf_to_quantized_cdf(const float* pmf, int n, int precision, int32_t* cdf);
 
+/* dcvic_token_decode with the rest of the decoder-side token path fused in:
+ *  - pq_weight [D_out, D] / pq_bias [D_out] (nullable): ldm VQModel.post_quant_conv, the 1x1 conv applied to the looked-up
+ *    latent (hyperprior_dc_vic_model.py:259-260); latent is then [B, D_out, HW];
+ *  - loss_sums (device double[2], nullable; needs gt_idx): sum over tokens of the code cross entropy and of the focal
+ *    term (1 - p_t)^gamma CE (src/losses/cross_entropy_loss.py:9-52; the losses are these sums / (B*HW) * loss_weight);
+ *  - lse [B*HW] (nullable): log-sum-exp of every token's logits, input of dcvic_token_ce_backward.
+ * dcvic_token_ce_backward: d_logits [B,K,HW] = g_loss[0] * scale * coef_t * (softmax - onehot(target)), coef_t = 1 for
+ * gamma = 0 (plain CE), the focal factor otherwise; scale = loss_weight / (B*HW) for the mean reduction. */
+int dcvic_token_decode_ex(const float* logits, const float* codebook, const int64_t* gt_idx, int B, int K, int HW, int D,
+                          const float* pq_weight, const float* pq_bias, int D_out, float gamma, int64_t* idx,
+                          float* latent, int* match_count, float* lse, double* loss_sums, dcvic_stream_t stream);
+int dcvic_token_ce_backward(const float* logits, const int64_t* gt_idx, const float* lse, const float* g_loss, int B,
+                            int K, int HW, float gamma, float scale, float* d_logits, dcvic_stream_t stream);
+
 /* The same construction for a whole table ON THE DEVICE (EntropyBottleneck.update / GaussianConditional.update ->
  * EntropyModel._pmf_to_cdf): pmf [rows, width] FP32 as the likelihood kernel left it, tail_mass [rows], lengths [rows];
  * cdf [rows, width + 2] int32 (zero beyond lengths[r] + 2); *status (device int32, zero on entry) receives a negative
@@ -231,6 +245,17 @@ int dcvic_rans_encode(const int32_t* symbols, const int32_t* indexes, const int6
 int dcvic_rans_decode(const uint32_t* words, int64_t n_words, int64_t* state, const int32_t* indexes, int64_t n,
                       const int32_t* cdf, int rows, int width, const int32_t* cdf_sizes, const int32_t* offsets,
                       int32_t* out_symbols, dcvic_stream_t stream);
+
+/* Tiling driver for images beyond 1024 px (src/models/comp_model/hyperprior_vic_model.py:190-246
+ * `_vq_encode_split`, :413-473 `decode_split`): windows of all tiles in one batch, keep-windows stitched on the device.
+ * gather: out [(T*N), C, ph, pw] <- in [N, C, H, W] at origins[t] = {y0, x0} (device int32 [T][2]).
+ * stitch: out [N, C, H, W] <- tiles [(T*N), C, ph, pw]; windows[t] = {y0, x0, top, bottom, left, right} (device int32
+ *   [T][6]) in OUTPUT coordinates: rows [top, bottom) x columns [left, right) of the output come from tile t, whose
+ *   own origin in the output is (y0, x0).  vec_ok != 0: every origin / window column is a multiple of 4. */
+int dcvic_tile_gather(const float* in, int N, int C, int H, int W, const int32_t* origins, int T, int ph, int pw,
+                      int vec_ok, float* out, dcvic_stream_t stream);
+int dcvic_tile_stitch(const float* tiles, int N, int C, int ph, int pw, const int32_t* windows, int T, int vec_ok,
+                      float* out, int H, int W, dcvic_stream_t stream);
 
 #ifdef __cplusplus
 }

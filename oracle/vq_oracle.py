@@ -119,6 +119,27 @@ def decode_tokens(logits: torch.Tensor, codebook: torch.Tensor, gt_indices: Opti
     return idx, indices_to_latent(idx, codebook), acc
 
 
+def post_quant_latent(idx: torch.Tensor, codebook: torch.Tensor, pq_weight: torch.Tensor, pq_bias) -> torch.Tensor:
+    """Lookup followed by ldm VQModel.post_quant_conv, a 1x1 Conv2d (hyperprior_dc_vic_model.py:258-260;
+    ldm/models/autoencoder.py:41)."""
+    return F.conv2d(indices_to_latent(idx, codebook), pq_weight.reshape(pq_weight.shape[0], -1, 1, 1), pq_bias)
+
+
+def code_cross_entropy(logits: torch.Tensor, target: torch.Tensor, loss_weight: float = 1.0) -> torch.Tensor:
+    """src/losses/cross_entropy_loss.py:9-31 (CrossEntropyLoss, default ce_kwargs)."""
+    return loss_weight * F.cross_entropy(logits, target)
+
+
+def code_focal_cross_entropy(logits: torch.Tensor, target: torch.Tensor, loss_weight: float, gamma: float,
+                             reduction: str = "mean") -> torch.Tensor:
+    """src/losses/cross_entropy_loss.py:33-52 (FocalCrossEntropyLoss)."""
+    ce_loss = F.cross_entropy(logits, target, reduction="none")
+    pt = F.softmax(logits, dim=1).gather(1, target.unsqueeze(1)).squeeze(1)
+    focal = ((1 - pt) ** gamma) * ce_loss
+    val = focal.mean() if reduction == "mean" else (focal.sum() if reduction == "sum" else focal)
+    return loss_weight * val
+
+
 def onehot_feature(indices_bhw: torch.Tensor, n_embed: int) -> torch.Tensor:
     """``onehot_indices`` encoder feature (hyperprior_vic_model.py:268-271): [B,K,H,W] fp32."""
     return F.one_hot(indices_bhw, num_classes=n_embed).permute(0, 3, 1, 2).float()

@@ -380,3 +380,39 @@ def test_c2_all_tokens_against_the_oracle(kind):
     assert torch.equal(z_q.cpu(), ste)
     mse = ((picked - rows) ** 2).mean()
     assert abs(float(loss) - float(mse + 0.25 * mse)) <= 1e-5 * float(mse)
+
+
+def test_decode_tokens_with_post_quant_conv_and_code_losses():
+    """The rest of the decoder-side token path: lookup + post_quant_conv in the decode kernel
+    (hyperprior_dc_vic_model.py:258-260) and the code CE / focal loss with its gradient
+    (src/losses/cross_entropy_loss.py:9-52)."""
+    g = torch.Generator().manual_seed(31)
+    for (B, K, H, W, Dm) in ((1, 256, 64, 96, 4), (6, 256, 32, 32, 4), (2, 37, 9, 7, 8)):
+        logits = 3 * torch.randn(B, K, H, W, generator=g)
+        E = torch.randn(K, Dm, generator=g)
+        gt = torch.randint(0, K, (B, H, W), generator=g)
+        pq = torch.nn.Conv2d(Dm, Dm, 1)
+        with torch.no_grad():
+            pq.weight.copy_(torch.randn(Dm, Dm, 1, 1, generator=g))
+            pq.bias.copy_(torch.randn(Dm, generator=g))
+        idx_r = torch.argmax(logits, 1)
+        lat_r = O.post_quant_latent(idx_r, E, pq.weight.detach(), pq.bias.detach())
+        idx, lat, acc = D.decode_tokens(logits.to(DEV), E.to(DEV), gt.to(DEV), post_quant_conv=pq.to(DEV))
+        assert torch.equal(idx.cpu(), idx_r)
+        assert torch.allclose(lat.cpu(), lat_r, rtol=1e-6, atol=1e-6)          # 4 fused multiply-adds vs cuDNN's order
+        assert abs(float(acc) - float((idx_r == gt).float().mean())) < 1e-7
+        for gamma, red in ((0.0, "mean"), (2.0, "mean"), (1.0, "sum"), (0.5, "mean")):
+            lr = logits.clone().requires_grad_(True)
+            if gamma == 0.0:
+                ref = O.code_cross_entropy(lr, gt, 0.7)
+                ours_m = D.CrossEntropyLoss(0.7)
+            else:
+                ref = O.code_focal_cross_entropy(lr, gt, 0.7, gamma, red)
+                ours_m = D.FocalCrossEntropyLoss(0.7, gamma, red)
+            ref.backward()
+            lo = logits.to(DEV).requires_grad_(True)
+            ours = ours_m(lo, gt.to(DEV))
+            (2.0 * ours).backward()
+            assert abs(float(ours) - float(ref)) <= 2e-5 * abs(float(ref)), (gamma, red, float(ours), float(ref))
+            scale = float(lr.grad.abs().max())
+            assert float((lo.grad.cpu() - 2.0 * lr.grad).abs().max()) <= 2e-4 * scale + 1e-9
