@@ -56,6 +56,17 @@ __device__ __forceinline__ float erfc_pos(float z) {   // z >= 0
 __device__ __forceinline__ float gc_lik(float outputs, float mu, float s) {
   const float v = fabsf(__fsub_rn(outputs, mu));
   const float r = 0.70710678118654752440f * rcp_ftz(s);
+  // Large sigma (h = b - a = 1/(sigma sqrt 2) < 1/64, sigma > 45): erfc(a) - erfc(b) is the difference of two values
+  // whose ARGUMENTS are already rounded - an ulp of a is worth a sigma sqrt(2) 1e-7 ~ 1e-4 of the result at
+  // sigma = 256, a = 3, for the reference's FP32 evaluation as well.  The integral of exp(-t^2) over [c - h/2, c + h/2]
+  // from its midpoint expansion (h^6 term < 1e-9) has no such cancellation:
+  //   L = h/sqrt(pi) exp(-c^2) [1 + h^2 (4c^2 - 2)/24 + h^4 (16c^4 - 48c^2 + 12)/1920],  c = v / (sigma sqrt 2).
+  if (r < 0.015625f) {
+    const float c2 = (v * r) * (v * r), h2 = r * r;
+    const float corr = fmaf(h2, fmaf(h2, fmaf(c2, fmaf(c2, 16.f, -48.f), 12.f) * (1.f / 1920.f),
+                                     fmaf(c2, 4.f, -2.f) * (1.f / 24.f)), 1.f);
+    return 0.56418958354775628695f * r * ex2_ftz(-1.4426950408889634f * c2) * corr;
+  }
   const float a = (v - 0.5f) * r, b = (v + 0.5f) * r;
   const float ea = erfc_pos(fabsf(a));
   const float up = a < 0.f ? 2.f - ea : ea;

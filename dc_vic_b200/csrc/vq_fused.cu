@@ -517,7 +517,9 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant
         r[4 * i + 3] = __float_as_uint(__fadd_rn(__uint_as_float(r[4 * i + 3]), b.w));
       }
     };
-    uint2* my_list = s_list + (row * 2 + q) * LIST_CAP;
+    // list entry i of (row, half q) lives at s_list[(q * LIST_CAP + i) * BM + row]: the 32 rows of a warp are 32
+    // consecutive 8-byte slots (the row-major layout put them 128 bytes apart: 32-way bank conflicts on every append)
+    uint2* my_list = s_list + (q * LIST_CAP) * BM + row;
     uint32_t g = 0;
     FZ_TDECL;
     for (int it = 0; it < my_tiles; ++it) {
@@ -543,13 +545,13 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant
             int w = 0;
 #pragma unroll
             for (int i = 0; i < LIST_CAP; ++i) {
-              const uint2 en = my_list[i];
-              if (!(vq_key_upper(en.x) < keep)) { my_list[w] = en; ++w; }
+              const uint2 en = my_list[i * BM];
+              if (!(vq_key_upper(en.x) < keep)) { my_list[w * BM] = en; ++w; }
             }
             n = w;
           }
           if (n >= 0) {
-            if (n < LIST_CAP) { my_list[n] = make_uint2((__float_as_uint(cm) & 0xFFFFFF80u) | chunk, mask); ++n; }
+            if (n < LIST_CAP) { my_list[n * BM] = make_uint2((__float_as_uint(cm) & 0xFFFFFF80u) | chunk, mask); ++n; }
             else n = -1;
           }
         }
@@ -607,11 +609,11 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant
 #pragma unroll
           for (int qq = 0; qq < 2; ++qq) {
             const int nn = (qq == 0 ? m : m1) < thr ? 0 : (qq == 0 ? n : n1);
-            const uint2* lp = s_list + (row * 2 + qq) * LIST_CAP;
+            const uint2* lp = s_list + (qq * LIST_CAP) * BM + row;
 #pragma unroll
             for (int i = 0; i < LIST_CAP; ++i) {
               if (i < nn) {
-                const uint2 en = lp[i];
+                const uint2 en = lp[i * BM];
                 if (!(vq_key_upper(en.x) < thr)) {
                   const int c0 = (int)(en.x & 0x7Fu) * kChunk;
                   uint32_t mk = en.y;
