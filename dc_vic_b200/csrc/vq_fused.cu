@@ -9,8 +9,8 @@
 // code within a PROVEN margin (vq_margin) of the row maximum; the flagged codes are re-ranked in FP32 in the
 // reference's operation order.
 //
-// One CTA pair (cta_group::2, UMMA 256 x 128 x 16) per 256-token tile, 128 tokens (4 groups of 32) per CTA, 24 warps:
-//   warp 0      TMA: this CTA's half of every FP16 codebook chunk [64 codes x 64 ch] into an 8-stage ring
+// One CTA pair (cta_group::2, UMMA 256 x 128 x 16) per 256-token tile, 128 tokens (4 groups of 32) per CTA, 32 warps:
+//   warp 0      TMA: this CTA's half of every N-tile's FP16 codebook slab (two 3-D boxes of the chunk-major codebook)
 //   warp 1      TMA: z chunks [64 ch x 32 tokens] FP32, straight from NCHW, into an 8-stage conversion ring
 //   warp 2      TMA: finish ring - loads z groups [e_dim x 32 tokens] (L2 hits), stores z_q from the same stages
 //   warp 3      MMA issuer (leader CTA; warp-uniform loop, one elected lane).  The A operand lives in TENSOR MEMORY
@@ -18,16 +18,17 @@
 //               candidate bookkeeping, and the MMA's operand reads take a quarter of what the SS form takes.
 //   warps 4-7   converters: lane = token.  FP32 chunk from the ring -> FP16 pairs -> tcgen05.st into the A operand
 //               (double-buffered: 2 x 128 columns, so a tile is converted while its predecessor multiplies), |z|^2
-//               per token
-//   warps 8-15  epilogue: two column halves x four lane quarters of every 128-column accumulator (double-buffered:
-//               2 x 128 columns).  tcgen05.ld 32 scores per row - the accumulator goes back to the MMA as soon as a
-//               warp's scores are in registers -, running maximum, one flag mask per 32 codes; flagged chunks go to an
-//               8-entry list per (token, half) in shared memory (entries that a later, larger maximum rules out are
-//               dropped on the fly).  -|e|^2/2 is added here, exactly, from a table in shared memory (tensor memory is
-//               full: 2 x 128 accumulator + 2 x 128 operand columns leave no room for the constant operand of an extra
-//               K-step, and re-initialising the accumulators by tcgen05.st kept them from the MMA for too long).  At
-//               the end of a tile the lists are compacted into at most 8 candidate codes per token.
-//   warps 16-23 consumers (the finish): (group, token quad) units.  First candidates' codebook rows are requested
+//               and the rounding residual per token
+//   warps 8-23  epilogue: four column quarters x four lane quarters of every 128-column accumulator (double-buffered:
+//               2 x 128 columns): ONE 32-code chunk per warp and N-tile.  tcgen05.ld 32 scores per row - the
+//               accumulator goes back to the MMA as soon as a warp's scores are in registers -, -|e|^2/2 added exactly
+//               from a table in shared memory (tensor memory is full: no room for the constant operand of an extra
+//               K-step), running maximum, one flag mask per chunk; flagged chunks go to a 4-entry list per (token,
+//               quarter) in shared memory (entries that a later, larger maximum rules out are dropped on the fly).
+//               At the end of a tile the four quarters of a row exchange their maxima and append their surviving
+//               codes to the token's candidate array (atomic slot counter).  Sixteen warps at 64 registers instead
+//               of eight at 88 with two chunks each: the epilogue's latency per N-tile was what paced the kernel.
+//   warps 24-31 consumers (the finish): (group, token quad) units.  First candidates' codebook rows are requested
 //               before the group's z has arrived; tokens with more than one candidate are re-ranked in FP32
 //               ((|z|^2 + |e|^2) - 2 z.e, lowest index on ties); z + (e - z) overwrites z in the stage; loss partials.
 #include <cuda.h>
@@ -62,20 +63,23 @@ constexpr int NZ = DCVIC_FZ_NZ;     // conversion ring stages (8 KB each), a mul
 constexpr int NF = DCVIC_FZ_NF;     // finish ring stages (e_dim * 128 B each)
 constexpr int B_CHUNK = (BN / 2) * BK * 2;   // 8 KB: this CTA's 64 codes x 64 channels
 constexpr int Z_STAGE = BK * GT * 4;         // 8 KB
-constexpr int LIST_CAP = 8;        // list entries per (token, column half)
+constexpr int LIST_CAP = 4;        // list entries per (token, column quarter)
 constexpr int CK_MAX = 16;         // candidate codes per token after compaction; more -> whole-codebook scan
 constexpr int MAX_K = 1024;         // -|e|^2/2 table in shared memory (larger codebooks take the two-kernel path)
 constexpr int NCONS = 8;
+constexpr int NEPI = 16;           // epilogue warps: 4 column quarters x 4 TMEM lane quarters
+constexpr int kFullFlag = 1 << 16; // added to a token's candidate count: whole-codebook scan
 static_assert(NZ % NG == 0, "a conversion-ring stage must always belong to the same converter warp");
-constexpr int W_TMAB = 0, W_ZLOAD = 1, W_FIN = 2, W_MMA = 3, W_CONV0 = 4, W_EPI0 = 8, W_CONS0 = 16;
-constexpr int NTHREADS = 768;
-// registers: 24 warps launch with 80 each = 61,440, and setmaxnreg can only move registers WITHIN that launch
-// allocation (a total above it leaves the last warpgroup waiting for ever): TMA / MMA warps drop to 32, converters
-// to 56, epilogue warps take 88, consumers 104: 128 * (32 + 56 + 2 * 88 + 2 * 104) = 60,416
-#define FZ_REGS_AUX 32
-#define FZ_REGS_CONV 56
-#define FZ_REGS_EPI 88
-#define FZ_REGS_CONS 104
+constexpr int W_TMAB = 0, W_ZLOAD = 1, W_FIN = 2, W_MMA = 3, W_CONV0 = 4, W_EPI0 = 8, W_CONS0 = W_EPI0 + NEPI;
+constexpr int NWARPS = W_CONS0 + NCONS;
+constexpr int NTHREADS = NWARPS * 32;
+// registers: 32 warps launch with 64 each = the whole file, and setmaxnreg can only move registers WITHIN the launch
+// allocation (a total above it leaves the last warpgroup waiting for ever): TMA / MMA warps drop to 24, converters
+// to 40, the epilogue warps keep their 64, consumers take 96: 128 * (24 + 40 + 4 * 64 + 2 * 96) = 65,536
+#define FZ_REGS_AUX 24
+#define FZ_REGS_CONV 40
+#define FZ_REGS_CONS 96
+static_assert(NTHREADS == 1024, "register budget above assumes 32 warps");
 
 
 struct Smem {
@@ -88,14 +92,13 @@ struct Smem {
   __host__ __device__ static constexpr int b_chunks_a(int D) { return (D / BK + 1) / 2; }
   __host__ __device__ static constexpr int b_stage(int D) { return b_chunks_a(D) * B_CHUNK; }
   __host__ __device__ static constexpr int off_bias(int D) { return off_b(D) + NB * b_stage(D); }          // [MAX_K] float
-  __host__ __device__ static constexpr int off_list(int D) { return off_bias(D) + MAX_K * 4; }             // [BM][2][LIST_CAP] uint2
-  __host__ __device__ static constexpr int off_ck(int D) { return off_list(D) + BM * 2 * LIST_CAP * 8; }    // [2][BM][CK_MAX] u16
+  __host__ __device__ static constexpr int off_list(int D) { return off_bias(D) + MAX_K * 4; }             // [4][LIST_CAP][BM] uint2
+  __host__ __device__ static constexpr int off_ck(int D) { return off_list(D) + BM * 4 * LIST_CAP * 8; }    // [2][BM][CK_MAX] u16
   __host__ __device__ static constexpr int off_nc(int D) { return off_ck(D) + 2 * BM * CK_MAX * 2; }        // [2][BM] int
   __host__ __device__ static constexpr int off_zz(int D) { return off_nc(D) + 2 * BM * 4; }                 // [2][BM] float
   __host__ __device__ static constexpr int off_dz(int D) { return off_zz(D) + 2 * BM * 4; }                 // [2][BM] float
-  __host__ __device__ static constexpr int off_m(int D) { return off_dz(D) + 2 * BM * 4; }                  // [BM][2] float
-  __host__ __device__ static constexpr int off_ln(int D) { return off_m(D) + BM * 2 * 4; }                  // [BM][2] int
-  __host__ __device__ static constexpr int off_bar(int D) { return off_ln(D) + BM * 2 * 4; }
+  __host__ __device__ static constexpr int off_m(int D) { return off_dz(D) + 2 * BM * 4; }                  // [BM][4] float
+  __host__ __device__ static constexpr int off_bar(int D) { return off_m(D) + BM * 4 * 4; }
   // barrier slots (8 bytes each)
   static constexpr int BAR_B_FULL = 0;                      // [NB] leader only
   static constexpr int BAR_B_EMPTY = BAR_B_FULL + NB;       // [NB]
@@ -152,11 +155,27 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 // (code << 16 | value) to a mapped host buffer, which the host can read while the kernel is still running (or hung).
 #ifdef DCVIC_FZ_DEBUG
 __device__ volatile int* g_fz_dbg = nullptr;
+constexpr int FZ_REC = 48;          // ints per warp: [0] progress, [1..6] cycle slots, [7] total, [8..47] time marks
+#define FZ_SLOT(k) g_fz_dbg[(blockIdx.x * 32 + (threadIdx.x >> 5)) * FZ_REC + (k)]
+#if defined(DCVIC_FZ_TIMING_ONLY) || defined(DCVIC_FZ_MARKS_ONLY)
+#define FZ_DBG(code, val)           // (a posted host write per step perturbs the timing)
+#else
 #define FZ_DBG(code, val)                                                                      \
   do {                                                                                         \
-    if (g_fz_dbg && (threadIdx.x & 31) == 0)                                                   \
-      g_fz_dbg[(blockIdx.x * 24 + (threadIdx.x >> 5)) * 8] = ((code) << 20) | ((val) & 0xFFFFF); \
+    if (g_fz_dbg && (threadIdx.x & 31) == 0) FZ_SLOT(0) = ((code) << 20) | ((val) & 0xFFFFF);  \
   } while (0)
+#endif
+// time marks: the SM clock (low 32 bits) when a warp passes a point; tools/debug_fused.py draws the tile timeline
+#define FZ_MARK(k)                                                                             \
+  do {                                                                                         \
+    if (g_fz_dbg && (threadIdx.x & 31) == 0 && (k) < 40) FZ_SLOT(8 + (k)) = (int)clock64();    \
+  } while (0)
+#ifdef DCVIC_FZ_MARKS_ONLY
+#define FZ_TDECL
+#define FZ_T()
+#define FZ_ACC(k)
+#define FZ_PUT()
+#else
 // cycle accounting per warp: FZ_T() marks "now"; FZ_ACC(k) adds the cycles since the last mark to slot k (1..6);
 // FZ_PUT() writes the slots (and the warp's total in slot 7)
 #define FZ_TDECL long long fz_t = clock64(), fz_t0 = fz_t, fz_acc[7] = {0, 0, 0, 0, 0, 0, 0}
@@ -167,17 +186,18 @@ __device__ volatile int* g_fz_dbg = nullptr;
     fz_acc[k] += now_ - fz_t;           \
     fz_t = now_;                        \
   } while (0)
-#define FZ_PUT()                                                                                 \
-  do {                                                                                           \
-    if (g_fz_dbg && (threadIdx.x & 31) == 0) {                                                   \
-      fz_acc[0] = clock64() - fz_t0;                                                             \
-      for (int k_ = 1; k_ < 7; ++k_)                                                             \
-        g_fz_dbg[(blockIdx.x * 24 + (threadIdx.x >> 5)) * 8 + k_] = (int)(fz_acc[k_] >> 3);      \
-      g_fz_dbg[(blockIdx.x * 24 + (threadIdx.x >> 5)) * 8 + 7] = (int)(fz_acc[0] >> 3);          \
-    }                                                                                            \
+#define FZ_PUT()                                                            \
+  do {                                                                      \
+    if (g_fz_dbg && (threadIdx.x & 31) == 0) {                              \
+      fz_acc[0] = clock64() - fz_t0;                                        \
+      for (int k_ = 1; k_ < 7; ++k_) FZ_SLOT(k_) = (int)(fz_acc[k_] >> 3);  \
+      FZ_SLOT(7) = (int)(fz_acc[0] >> 3);                                   \
+    }                                                                       \
   } while (0)
+#endif
 #else
 #define FZ_DBG(code, val)
+#define FZ_MARK(k)
 #define FZ_TDECL
 #define FZ_T()
 #define FZ_ACC(k)
@@ -223,7 +243,6 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant
   float* s_zz = reinterpret_cast<float*>(smem + Smem::off_zz(D));
   float* s_dz = reinterpret_cast<float*>(smem + Smem::off_dz(D));     // |z - fp16(z)|^2 per token
   float* s_m = reinterpret_cast<float*>(smem + Smem::off_m(D));
-  int* s_ln = reinterpret_cast<int*>(smem + Smem::off_ln(D));
   volatile uint32_t* s_tmem = reinterpret_cast<volatile uint32_t*>(smem + Smem::off_tmem(D));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -233,7 +252,8 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant
   const int NT = K / BN;
   const int my_tiles = pair < num_ptiles ? (num_ptiles - pair + npairs - 1) / npairs : 0;
   // first token of this CTA's half of its it-th tile
-  auto tile_token0 = [&](int it) { return ((long long)(pair + it * npairs) * 2 + rank) * BM; };
+  // (< N + 2 * BM: 32-bit unsigned arithmetic throughout - the TMA / MMA warps live on 24 registers)
+  auto tile_token0 = [&](int it) { return ((uint32_t)(pair + it * npairs) * 2u + rank) * (uint32_t)BM; };
   auto leader_bar = [&](int slot) { return map_to_cta(bar(slot), 0); };
 
   if (threadIdx.x == 0) {
@@ -245,14 +265,15 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant
     for (int b = 0; b < 2; ++b) {
       mbar_init(bar(Smem::BAR_A_EMPTY + b), 1);
       mbar_init(bar(Smem::BAR_T_FULL + b), 1);
-      mbar_init(bar(Smem::BAR_T_EMPTY + b), 16);
+      mbar_init(bar(Smem::BAR_T_EMPTY + b), 2 * NEPI);
       mbar_init(bar(Smem::BAR_ZZ + b), NG);
-      mbar_init(bar(Smem::BAR_C_FULL + b), 4);
+      mbar_init(bar(Smem::BAR_C_FULL + b), NEPI);
       mbar_init(bar(Smem::BAR_C_EMPTY + b), NG * 8);          // one arrival per (group, quad) unit
     }
     for (int s = 0; s < NF; ++s) { mbar_init(bar(Smem::BAR_F_FULL + s), 1); mbar_init(bar(Smem::BAR_F_DONE + s), 8); }
     fence_barrier_init();
   }
+  if (threadIdx.x < 2 * BM) s_nc[threadIdx.x] = 0;     // candidate counters (atomic appends; the consumers re-zero them)
   if (warp == W_MMA) {
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + Smem::off_tmem(D)),
                  "r"(512u));
@@ -262,6 +283,7 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant
   __syncthreads();
   cluster_sync();
   tc_fence_after();
+  FZ_MARK(0);
   const uint32_t tmem_base = *s_tmem;
   // tensor memory: accumulators 2 x 128 columns | A operand 2 x 128 columns
   const uint32_t tmem_acc = tmem_base, tmem_a = tmem_base + 2 * BN;
@@ -310,19 +332,23 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant
         int s = 0;
         FZ_TDECL;
         for (int it = 0; it < my_tiles; ++it) {
-          const long long t0 = tile_token0(it);
+          const uint32_t t0 = tile_token0(it);
+#pragma unroll 1
           for (int kc = 0; kc < KC; ++kc)
+#pragma unroll 1
             for (int g = 0; g < NG; ++g, ++s) {
               const int st = s % NZ;
               FZ_DBG(2, s);
               FZ_T();
               mbar_wait(bar(Smem::BAR_Z_EMPTY + st), ((s / NZ) & 1) ^ 1);
               FZ_ACC(1);
-              const long long tg = t0 + g * GT;         // (groups beyond N: out-of-bounds box, zero fill)
+              const uint32_t tg = t0 + g * GT;          // (groups beyond N: out-of-bounds box, zero fill)
               mbar_arrive_expect_tx(bar(Smem::BAR_Z_FULL + st), Z_STAGE);
-              tma_load_2d_cta(sbase + Smem::OFF_Z + st * Z_STAGE, &tm_zc, (int)(tg % HW), (int)(tg / HW) * D + kc * BK,
+              tma_load_2d_cta(sbase + Smem::OFF_Z + st * Z_STAGE, &tm_zc, (int)(tg % (uint32_t)HW),
+                              (int)(tg / (uint32_t)HW) * D + kc * BK,
                               bar(Smem::BAR_Z_FULL + st));
             }
+          FZ_MARK(3 + it * 4);
         }
         FZ_PUT();
       }
@@ -334,9 +360,9 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant
         const int total = my_tiles * NG;
         FZ_TDECL;
         auto coords = [&](int j, int& x, int& y) {
-          const long long tg = tile_token0(j / NG) + (j % NG) * GT;
-          x = (int)(tg % HW);
-          y = (int)(tg / HW) * D;
+          const uint32_t tg = tile_token0(j / NG) + (j % NG) * GT;
+          x = (int)(tg % (uint32_t)HW);
+          y = (int)(tg / (uint32_t)HW) * D;
         };
         auto load = [&](int j) {
           const int it = j / NG, st = j % NF;
@@ -350,6 +376,7 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant
           coords(j, x, y);
           mbar_arrive_expect_tx(bar(Smem::BAR_F_FULL + st), F_STAGE);
           tma_load_2d_cta(sbase + Smem::OFF_F + st * F_STAGE, &tm_zf, x, y, bar(Smem::BAR_F_FULL + st));
+          if (j % NG == 0) FZ_MARK(1 + it * 4);
         };
         for (int j = 0; j < total && j < NF; ++j) load(j);
         for (int j = 0; j < total; ++j) {
@@ -362,6 +389,8 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant
           coords(j, x, y);
           tma_store_2d(&tm_zq, x, y, sbase + Smem::OFF_F + st * F_STAGE);
           bulk_commit();
+          if (j % NG == 0) FZ_MARK(2 + (j / NG) * 4);
+          if (j % NG == NG - 1) FZ_MARK(3 + (j / NG) * 4);
           if (j + NF < total) {
             FZ_T();
             bulk_wait_read_all();                    // the stage has been read out: refill it
@@ -378,11 +407,15 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant
       // ===================== MMA issuer: whole warp walks the loop, one elected lane issues =====================
       const bool issuer = elect_one();
       const uint32_t rt_one = my_tiles > 0 ? 1u : 0u;   // 1, but not a compile-time constant (see vq_tcgen05.cu)
+      const uint32_t rt_zero = my_tiles < 0 ? 1u : 0u;  // 0, likewise
+      // The loop below is the kernel's pacemaker and shares its scheduler with seven busy warps: it is kept to the
+      // fewest instructions per MMA (descriptors advance by constants, channel chunks unrolled, one divergent region
+      // per codebook box).
+      const uint64_t bd_ring = umma_desc_sw128(sbase + OFF_B);     // stage 0; a stage further: + B_STAGE / 16
       int stage = 0;
       uint32_t phase = 0;
       uint32_t g = 0;
       FZ_TDECL;
-      const uint32_t rt_zero = my_tiles < 0 ? 1u : 0u;  // 0, likewise
       for (int it = 0; it < my_tiles; ++it) {
         const int abuf = it & 1;
         const uint32_t a0 = tmem_a + abuf * BM;           // 128 columns per A buffer
@@ -392,38 +425,44 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant
           FZ_T();
           if (g >= 2) mbar_wait(bar(Smem::BAR_T_EMPTY + buf), ((g >> 1) - 1) & 1);   // both CTAs hold its scores in registers
           FZ_ACC(1);
-          tc_fence_after();
           const uint32_t d = tmem_acc + buf * BN;
 #pragma unroll
           for (int part = 0; part < (KC > NA ? 2 : 1); ++part) {
+            constexpr int c0s[2] = {0, NA}, c1s[2] = {NA, KC};
+            const int c0 = c0s[part], c1 = c1s[part];
             FZ_T();
             mbar_wait(bar(Smem::BAR_B_FULL + stage), phase);
             FZ_ACC(3);
-            tc_fence_after();
-            const uint32_t slab = sbase + OFF_B + stage * B_STAGE;
-            const int c0 = part == 0 ? 0 : NA, c1 = part == 0 ? NA : KC;
-#pragma unroll 1
-            for (int c = c0; c < c1; ++c) {
-              FZ_DBG(6, g * 8 + c);
+            if (nt == 0) {                                 // the tile's A operand arrives chunk by chunk
               FZ_T();
-              if (nt == 0) mbar_wait(bar(Smem::BAR_A_FULL + abuf * 4 + c), (it >> 1) & 1);
+#pragma unroll
+              for (int c = c0; c < c1; ++c) {
+                mbar_wait(bar(Smem::BAR_A_FULL + abuf * 4 + c), (it >> 1) & 1);
+                if (c == 0) FZ_MARK(1 + it * 4);
+                if (c == KC - 1) FZ_MARK(2 + it * 4);
+              }
               FZ_ACC(2);
-              tc_fence_after();
-              if (issuer) {
-                const uint64_t bd = umma_desc_sw128(slab + (c - c0) * B_CHUNK);
+            }
+            tc_fence_after();
+            if (issuer) {
+              const uint64_t bds = bd_ring + (uint64_t)(uint32_t)(stage * (B_STAGE >> 4));
+#pragma unroll
+              for (int c = c0; c < c1; ++c) {
+                const uint64_t bd = bds + (uint64_t)((c - c0) * (B_CHUNK >> 4));
                 const uint32_t a = a0 + c * (BK / 2);
                 umma_ts(d, a, bd, c == 0 ? rt_zero : rt_one);     // the N-tile's first MMA overwrites the buffer
                 umma_ts(d, a + 8, bd + 2, rt_one);
                 umma_ts(d, a + 16, bd + 4, rt_one);
                 umma_ts(d, a + 24, bd + 6, rt_one);
               }
+              umma_commit<2>(bar(Smem::BAR_B_EMPTY + stage));
+              if (part == (KC > NA ? 1 : 0)) umma_commit<2>(bar(Smem::BAR_T_FULL + buf));
             }
-            if (issuer) umma_commit<2>(bar(Smem::BAR_B_EMPTY + stage));
             if (++stage == NB) { stage = 0; phase ^= 1; }
           }
-          if (issuer) umma_commit<2>(bar(Smem::BAR_T_FULL + buf));
         }
         if (issuer) umma_commit<2>(bar(Smem::BAR_A_EMPTY + abuf));
+        FZ_MARK(3 + it * 4);
         __syncwarp();
       }
       FZ_PUT();
@@ -443,6 +482,7 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant
       FZ_T();
       mbar_wait(bar(Smem::BAR_A_EMPTY + abuf), ((it >> 1) & 1) ^ 1);   // the MMAs of tile it-2 have read this buffer
       FZ_ACC(1);
+      FZ_MARK(1 + it * 4);
       tc_fence_after();
       float zz = 0.f, dz2 = 0.f;
 #pragma unroll 1
@@ -453,6 +493,7 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant
         FZ_T();
         mbar_wait(bar(Smem::BAR_Z_FULL + st), (s / NZ) & 1);
         FZ_ACC(2);
+        if (kc == 0) FZ_MARK(2 + it * 4);
         const uint32_t zb = sbase + Smem::OFF_Z + st * Z_STAGE + lane_off;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {                 // 32 channels -> 16 columns per store
@@ -488,24 +529,25 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant
         mbar_arrive(bar(Smem::BAR_ZZ + abuf));
         atomicAdd(const_cast<uint32_t*>(s_tmem) + 1, 1u);
       }
+      FZ_MARK(3 + it * 4);
     }
     FZ_PUT();
   } else if (warp < W_CONS0) {
     // ===================== epilogue: flag masks per 32 codes, running maximum per row, candidate lists ==========
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(FZ_REGS_EPI));
-    const int q = (warp - W_EPI0) >> 2;              // column half of every accumulator
+    // (these warps keep the 64 registers of the launch)
+    const int q = (warp - W_EPI0) >> 2;              // column quarter of every accumulator: one 32-code chunk per N-tile
     const int part = warp & 3;                       // TMEM lane quarter
     const int row = part * 32 + lane;
-    const uint32_t tlane = tmem_acc + ((uint32_t)(part * 32) << 16) + q * (BN / 2);
+    const uint32_t tlane = tmem_acc + ((uint32_t)(part * 32) << 16) + q * kChunk;
     FZ_DBG(20, 0);
     pdl_wait();                                      // emax, -|e|^2/2 (prepare kernel)
     FZ_DBG(21, 0);
     const float emax = emax_ptr[0];
     const bool cb_unsafe = __float_as_uint(emax_ptr[1]) != 0u;
     const float demax = emax_ptr[2];
-    for (int k = threadIdx.x - W_EPI0 * 32; k < K; k += 256) s_bias[k] = -0.5f * ee[k];     // exact
-    named_bar_sync(1, 256);
-    const uint32_t bias_base = sbase + Smem::off_bias(D) + q * (BN / 2) * 4;
+    for (int k = threadIdx.x - W_EPI0 * 32; k < K; k += NEPI * 32) s_bias[k] = -0.5f * ee[k];     // exact
+    named_bar_sync(5, NEPI * 32);
+    const uint32_t bias_base = sbase + Smem::off_bias(D) + q * kChunk * 4;
     // scores of one 32-code chunk += -|e|^2/2 of its codes (the same 32 values for every row: broadcast loads)
     auto add_bias = [&](uint32_t (&r)[32], uint32_t a) {
 #pragma unroll
@@ -517,22 +559,21 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant
         r[4 * i + 3] = __float_as_uint(__fadd_rn(__uint_as_float(r[4 * i + 3]), b.w));
       }
     };
-    // list entry i of (row, half q) lives at s_list[(q * LIST_CAP + i) * BM + row]: the 32 rows of a warp are 32
-    // consecutive 8-byte slots (the row-major layout put them 128 bytes apart: 32-way bank conflicts on every append)
+    // list entry i of (row, quarter q) lives at s_list[(q * LIST_CAP + i) * BM + row]: the 32 rows of a warp are 32
+    // consecutive 8-byte slots.  Every list has ONE writer and one reader, this thread.
     uint2* my_list = s_list + (q * LIST_CAP) * BM + row;
     uint32_t g = 0;
     FZ_TDECL;
     for (int it = 0; it < my_tiles; ++it) {
       const int abuf = it & 1;
-      const long long t = tile_token0(it) + row;
-      const bool valid = t < N;
+      const bool valid = tile_token0(it) + row < (uint32_t)N;
       FZ_DBG(10, it);
       FZ_T();
       mbar_wait(bar(Smem::BAR_ZZ + abuf), (it >> 1) & 1);
       FZ_ACC(1);
       const float zz = s_zz[abuf * BM + row];
       const float margin = vq_margin_measured(zz, s_dz[abuf * BM + row], emax, demax, D);
-      float m = -INFINITY;
+      float m = -INFINITY;                           // running maximum over this quarter's codes
       int n = 0;                                     // list entries; -1: overflow (whole-codebook scan)
       // A flagged chunk joins the list.  Entries a later maximum has put out of reach are dropped: all of them at
       // once when this chunk's maximum beats the previous running maximum by more than the margin, one by one (only
@@ -562,86 +603,90 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant
         FZ_T();
         mbar_wait(bar(Smem::BAR_T_FULL + buf), (g >> 1) & 1);
         FZ_ACC(2);
+        if (nt == 0) FZ_MARK(1 + it * 4);
         tc_fence_after();
-        const uint32_t taddr = tlane + buf * BN;
-        const uint32_t chunk0 = (uint32_t)(nt * (BN / 32) + q * (BN / 64));
-        uint32_t ra[32], rb[32];
-        float cm, m_old;
-        uint32_t mask;
-        TMEM_LD32(ra, taddr);
-        TMEM_LD32(rb, taddr + 32);
+        uint32_t ra[32];
+        TMEM_LD32(ra, tlane + buf * BN);
         TMEM_WAIT_LD32(ra);
-        TMEM_WAIT_LD32(rb);
         // every score of this warp's slice is in registers: the accumulator can be overwritten
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(leader_bar(Smem::BAR_T_EMPTY + buf));
-        add_bias(ra, bias_base + nt * (BN * 4));
-        add_bias(rb, bias_base + nt * (BN * 4) + 128);
-        m_old = m;
-        mask = chunk_flags(ra, margin, m, cm);
-        emit(mask, cm, m_old, chunk0);
-        m_old = m;
-        mask = chunk_flags(rb, margin, m, cm);
-        emit(mask, cm, m_old, chunk0 + 1);
         FZ_ACC(3);
-      }
-      // ---- end of tile: both halves publish (maximum, entries), the q == 0 thread of every row compacts
-      s_m[row * 2 + q] = m;
-      s_ln[row * 2 + q] = n;
-      FZ_DBG(12, it);
-      FZ_T();
-      named_bar_sync(1, 256);
-      FZ_ACC(4);
-      if (q == 0) {
-        const int par = it & 1;
-        FZ_DBG(13, it);
-        if (it >= 2) mbar_wait(bar(Smem::BAR_C_EMPTY + par), ((it >> 1) - 1) & 1);   // consumers are done with tile it-2
+#if !defined(DCVIC_FZ_EXP) || DCVIC_FZ_EXP != 2      // (timing experiments only: results are wrong with DCVIC_FZ_EXP set)
+        add_bias(ra, bias_base + nt * (BN * 4));
+#endif
+        FZ_ACC(4);
+#if !defined(DCVIC_FZ_EXP) || DCVIC_FZ_EXP < 3
+        float cm;
+        const float m_old = m;
+        const uint32_t mask = chunk_flags(ra, margin, m, cm);
+        emit(mask, cm, m_old, (uint32_t)(nt * (BN / kChunk) + q));
+#else
+        m = fmaxf(m, __uint_as_float(ra[lane]));
+#endif
         FZ_ACC(5);
-        const float m1 = s_m[row * 2 + 1];
-        const int n1 = s_ln[row * 2 + 1];
-        const float thr = fmaxf(m, m1) - margin;
-        // (a half whose list overflowed only matters if its maximum is within reach of the row's)
-        bool full = cb_unsafe || !(zz < kVqFp16Zz2Max) || (n < 0 && !(m < thr)) || (n1 < 0 && !(m1 < thr));
-        unsigned short* ck = s_ck + (par * BM + row) * CK_MAX;
-        int w = 0;
-        if (!full) {
-#pragma unroll
-          for (int qq = 0; qq < 2; ++qq) {
-            const int nn = (qq == 0 ? m : m1) < thr ? 0 : (qq == 0 ? n : n1);
-            const uint2* lp = s_list + (qq * LIST_CAP) * BM + row;
+      }
+      // ---- end of tile: the four quarters of a row exchange their maxima; each appends the codes of its surviving
+      // entries to the row's candidate array (slots handed out by an atomic counter: the order does not matter, the
+      // re-rank breaks ties by code index)
+      s_m[row * 4 + q] = m;
+      FZ_MARK(2 + it * 4);
+      FZ_DBG(12, it);
+      named_bar_sync(1 + part, 128);
+      const float4 mq = *reinterpret_cast<const float4*>(s_m + row * 4);
+      // (s_m is written again after the NEXT tile's last N-tile, which the MMA issues only once every epilogue warp
+      // has drained N-tile NT - 3 of that tile, i.e. has left this section - if the tile has that many)
+      if (NT < 3) named_bar_sync(1 + part, 128);
+      const float thr = fmaxf(fmaxf(mq.x, mq.y), fmaxf(mq.z, mq.w)) - margin;
+      const int par = it & 1;
+      FZ_DBG(13, it);
+      if (it >= 2) mbar_wait(bar(Smem::BAR_C_EMPTY + par), ((it >> 1) - 1) & 1);   // consumers are done with tile it-2
+      if (valid) {
+        int* ncp = s_nc + par * BM + row;
+        if (cb_unsafe || !(zz < kVqFp16Zz2Max)) {
+          if (q == 0) {
+            atomicAdd(ncp, kFullFlag);
+            atomicAdd(counters + 9, 1u);              // diagnostics: why a token is scanned in full
+          }
+        } else if (!(m < thr)) {                       // (a quarter whose maximum is out of reach has nothing to add)
+          if (n < 0) {
+            atomicAdd(ncp, kFullFlag);
+            atomicAdd(counters + 6, 1u);
+          } else {
+            uint2 en[LIST_CAP];
+            int cnt = 0;
 #pragma unroll
             for (int i = 0; i < LIST_CAP; ++i) {
-              if (i < nn) {
-                const uint2 en = lp[i * BM];
-                if (!(vq_key_upper(en.x) < thr)) {
-                  const int c0 = (int)(en.x & 0x7Fu) * kChunk;
-                  uint32_t mk = en.y;
-                  while (mk) {
-                    const int b = __ffs(mk) - 1;
-                    mk &= mk - 1;
-                    if (w < CK_MAX) ck[w] = (unsigned short)(c0 + b);
-                    ++w;
-                  }
+              en[i] = make_uint2(0u, 0u);
+              if (i < n) {
+                const uint2 e = my_list[i * BM];
+                if (!(vq_key_upper(e.x) < thr)) { en[i] = e; cnt += __popc(e.y); }
+              }
+            }
+            if (cnt > 0) {
+              int w = atomicAdd(ncp, cnt);
+              if (w <= CK_MAX && w + cnt > CK_MAX) atomicAdd(counters + 7, 1u);
+              unsigned short* ck = s_ck + (par * BM + row) * CK_MAX;
+#pragma unroll
+              for (int i = 0; i < LIST_CAP; ++i) {
+                const int c0 = (int)(en[i].x & 0x7Fu) * kChunk;
+                uint32_t mk = en[i].y;
+                while (mk) {
+                  const int b = __ffs(mk) - 1;
+                  mk &= mk - 1;
+                  if (w < CK_MAX) ck[w] = (unsigned short)(c0 + b);
+                  ++w;
                 }
               }
             }
           }
-          if (w > CK_MAX || w <= 0) {
-            full = true;
-            if (valid) atomicAdd(counters + (w <= 0 ? 8 : 7), 1u);     // diagnostics: why a token is scanned in full
-          }
-        } else if (valid) {
-          atomicAdd(counters + ((n < 0 || n1 < 0) ? 6 : 9), 1u);
         }
-        if (full) ck[0] = 0;
-        s_nc[par * BM + row] = valid ? (full ? -1 : w) : 0;
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar(Smem::BAR_C_FULL + par));
       }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(Smem::BAR_C_FULL + par));
+      FZ_MARK(3 + it * 4);
       FZ_DBG(14, it);
-      FZ_T();
-      named_bar_sync(2, 256);                         // lists may be overwritten by the next tile
       FZ_ACC(6);
     }
     FZ_PUT();
@@ -673,6 +718,9 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant
     };
     const int total_units = my_tiles * NG * 8;
     FZ_TDECL;
+#ifdef DCVIC_FZ_DEBUG
+    int fz_last_it = -1;
+#endif
     // (group, token quad) units are handed out in order through a shared counter: a warp that drew long re-ranks does
     // not hold up its CTA
     for (;;) {
@@ -686,15 +734,34 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant
       FZ_T();
       mbar_wait(bar(Smem::BAR_C_FULL + par), (it >> 1) & 1);
       FZ_ACC(1);
+#ifdef DCVIC_FZ_DEBUG
+      if (it != fz_last_it) { FZ_MARK(1 + it * 4); fz_last_it = it; }
+#endif
       const int r0 = g * GT + 4 * cw;                // first row (token of the CTA tile) of this unit
-      const long long t0 = tile_token0(it) + r0;
+      const uint32_t t0 = tile_token0(it) + r0;
+#if defined(DCVIC_FZ_EXP) && DCVIC_FZ_EXP >= 4
+      const bool live = t0 > 0x7fffffffu;
+#else
+      const bool live = t0 < (uint32_t)N;
+#endif
+      // (a quad is valid or invalid as a whole: N % 4 == 0)
       int nc[4], bk[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         nc[i] = s_nc[par * BM + r0 + i];
         bk[i] = s_ck[(par * BM + r0 + i) * CK_MAX];
+        if (nc[i] <= 0 || nc[i] > CK_MAX) {          // flagged for a whole-codebook scan, too many candidates, or none
+          if (live && nc[i] == 0 && lane == 0) atomicAdd(counters + 8, 1u);
+          nc[i] = -1;
+          bk[i] = 0;
+        }
       }
-      const bool live = nc[0] != 0;                  // (a quad is valid or invalid as a whole: N % 4 == 0)
+#if defined(DCVIC_FZ_EXP) && DCVIC_FZ_EXP >= 3
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { nc[i] = 1; bk[i] = (r0 + i) & 1023; }
+#endif
+      __syncwarp();
+      if (lane < 4) s_nc[par * BM + r0 + lane] = 0;  // for the tile after next (ordered by the C_EMPTY arrival below)
       uint32_t zo[4];
 #pragma unroll
       for (int jj = 0; jj < 4; ++jj) {
@@ -817,6 +884,7 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant
         mbar_arrive(bar(Smem::BAR_C_EMPTY + par));
       }
       FZ_ACC(5);
+      FZ_MARK(3 + it * 4);
     }
     FZ_PUT();
     // loss: one partial per consumer warp, summed in index order by vq_loss_finalize_kernel (deterministic)
@@ -831,6 +899,7 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant
   }
 
   FZ_DBG(30, 0);
+  FZ_MARK(39);
   tc_fence_before();
   __syncthreads();
   cluster_sync();            // no CTA leaves while its peer may still touch its shared memory / barriers

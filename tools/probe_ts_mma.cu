@@ -381,6 +381,124 @@ static void run_smem(unsigned long long* dT, uint32_t* dS, int reps) {
          NN, TS ? "TS" : "SS", reps, bg[0], bg[1], reps ? (double)hT[0] / reps : 0.0);
 }
 
+// ---- tensor-memory port share of the MMA: `nld` warps (4..) of both CTAs stream tcgen05.ld.32x32b.x32 from columns
+// [128, 256) (an accumulator the MMA is not writing) and `nst` further warps stream tcgen05.st.x16 into columns
+// [384, 512) while the leader issues `reps` TS MMAs (D columns [0, 128), A columns [256, 288)).
+#define P_TMEM_LD32(r, taddr)                                                                                            \
+  asm volatile(                                                                                                          \
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,"    \
+      "%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"                                                          \
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),       \
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),            \
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),           \
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])                         \
+      : "r"(taddr)                                                                                                       \
+      : "memory")
+__global__ void __launch_bounds__(1024, 1) mma_tmem_kernel(int reps, int nld, int nst, int bg_iters, unsigned long long* out, uint32_t* sink) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ __align__(8) unsigned long long s_bar;
+  __shared__ uint32_t s_tmem;
+  const uint32_t rank = cluster_ctarank();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    mbar_init(smem_u32(&s_bar), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int i = threadIdx.x; i < 32 * 1024 / 4; i += 1024) reinterpret_cast<uint32_t*>(smem)[i] = 0u;
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(512u));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::);
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  cluster_sync();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = s_tmem;
+  constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+  const uint32_t tl = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+  if (warp >= 4 && warp < 4 + nld) {
+    uint32_t acc = 0;
+    const unsigned long long t0 = clock64();
+    for (int i = 0; i < bg_iters; ++i) {
+      uint32_t r[32];
+      P_TMEM_LD32(r, tl + 128 + (((warp - 4) >> 2) & 3) * 32);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+      for (int j = 0; j < 32; ++j) acc ^= r[j];
+    }
+    const unsigned long long t1 = clock64();
+    if (lane == 0) out[8 + blockIdx.x * 32 + warp] = t1 - t0;
+    if (acc == 0x12345u) sink[0] = acc;
+  } else if (warp >= 4 + nld && warp < 4 + nld + nst) {
+    uint32_t r[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) r[j] = threadIdx.x + j;
+    const unsigned long long t0 = clock64();
+    for (int i = 0; i < bg_iters; ++i) {
+      TMEM_ST16(tl + 384 + (i & 7) * 16, r);
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+    const unsigned long long t1 = clock64();
+    if (lane == 0) out[8 + blockIdx.x * 32 + warp] = t1 - t0;
+  } else if (warp == 0 && reps > 0) {
+    unsigned long long t0 = 0;
+    if (rank == 0 && threadIdx.x == 0) {
+      const uint64_t bd = umma_desc_sw128(smem_u32(smem));
+      const uint32_t one = (gridDim.x > 0) ? 1u : 0u;
+      t0 = clock64();
+      for (int r = 0; r < reps; ++r) {
+        const int k = r & 3;
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                     "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_base),
+                     "r"(tmem_base + 256 + 8 * k), "l"(bd + 2 * k), "r"(idesc), "r"(one) : "memory");
+      }
+      asm volatile(
+          "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+              smem_u32(&s_bar)),
+          "h"((uint16_t)3)
+          : "memory");
+    }
+    mbar_wait(smem_u32(&s_bar), 0);
+    if (rank == 0 && threadIdx.x == 0) out[0] = clock64() - t0;
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  cluster_sync();
+  if (warp == 0) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
+  }
+}
+
+static void run_tmem(unsigned long long* dT, uint32_t* dS, int reps, int nld, int nst) {
+  const int smem = 32 * 1024 + 1024, bg_iters = 6000;
+  CK(cudaFuncSetAttribute(mma_tmem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2);
+  cfg.blockDim = dim3(1024);
+  cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  CK(cudaMemset(dT, 0, 80 * 8));
+  CK(cudaLaunchKernelEx(&cfg, mma_tmem_kernel, reps, nld, nst, bg_iters, dT, dS));
+  CK(cudaDeviceSynchronize());
+  unsigned long long hT[80];
+  CK(cudaMemcpy(hT, dT, sizeof(hT), cudaMemcpyDeviceToHost));
+  unsigned long long mxl = 0, mxs = 0;
+  for (int w = 4; w < 4 + nld; ++w) mxl = hT[8 + w] > mxl ? hT[8 + w] : mxl;
+  for (int w = 4 + nld; w < 4 + nld + nst; ++w) mxs = hT[8 + w] > mxs ? hT[8 + w] : mxs;
+  printf("tmem share, TS MMA 256x128x16 reps=%5d, %2d ld warps %d st warps: ld %.1f B/clk/SM, st %.1f B/clk/SM, MMA %.1f cycles each\n",
+         reps, nld, nst, mxl ? (double)nld * bg_iters * 4096 / (double)mxl : 0.0,
+         mxs ? (double)nst * bg_iters * 2048 / (double)mxs : 0.0, reps ? (double)hT[0] / reps : 0.0);
+}
+
 int main() {
   const int M = 2 * M_CTA;
   __half *hA = (__half*)malloc(M * K * 2), *hB = (__half*)malloc(N * K * 2);
@@ -428,7 +546,7 @@ int main() {
 
   unsigned long long* dT;
   uint32_t* dS;
-  CK(cudaMalloc(&dT, 148 * 8));
+  CK(cudaMalloc(&dT, 148 * 8 + 1024));
   CK(cudaMalloc(&dS, 4));
   for (int nw : {4, 8, 16}) {
     const int iters = 2000;
@@ -450,5 +568,11 @@ int main() {
   run_smem<256, 1>(dT, dS, 3000);
   run_smem<128, 0>(dT, dS, 6000);
   run_smem<128, 1>(dT, dS, 6000);
+  run_tmem(dT, dS, 6000, 0, 0);
+  run_tmem(dT, dS, 6000, 8, 0);
+  run_tmem(dT, dS, 6000, 16, 0);
+  run_tmem(dT, dS, 6000, 16, 4);
+  run_tmem(dT, dS, 6000, 0, 4);
+  run_tmem(dT, dS, 0, 16, 4);
   return bad ? 1 : 0;
 }
