@@ -144,12 +144,16 @@ __device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
 // `margin` of the running maximum (which already includes this chunk).  Flags: d = s - thr on the FMA
 // pipe, sign bits collected with funnel shifts (bit j of the result <=> s[j] >= thr).
 __device__ __forceinline__ uint32_t chunk_flags(const uint32_t (&r)[32], float margin, float& m, float& cm_out) {
-  float a[8];
+  // 32 -> 1 with three-input maxima (FMNMX3): 11 + 4 + 2 instructions
+  auto f = [&](int i) { return __uint_as_float(r[i]); };
+  auto max3 = [](float x, float y, float z) { return fmaxf(fmaxf(x, y), z); };
+  float a[11];
 #pragma unroll
-  for (int j = 0; j < 8; ++j)
-    a[j] = fmaxf(fmaxf(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1])),
-                 fmaxf(__uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])));
-  const float cm = fmaxf(fmaxf(fmaxf(a[0], a[1]), fmaxf(a[2], a[3])), fmaxf(fmaxf(a[4], a[5]), fmaxf(a[6], a[7])));
+  for (int j = 0; j < 10; ++j) a[j] = max3(f(3 * j), f(3 * j + 1), f(3 * j + 2));
+  a[10] = fmaxf(f(30), f(31));
+  const float b0 = max3(a[0], a[1], a[2]), b1 = max3(a[3], a[4], a[5]), b2 = max3(a[6], a[7], a[8]),
+              b3 = fmaxf(a[9], a[10]);
+  const float cm = fmaxf(max3(b0, b1, b2), b3);
   m = fmaxf(m, cm);
   cm_out = cm;
   const float thr = m - margin;

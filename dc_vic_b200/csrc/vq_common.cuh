@@ -138,4 +138,11 @@ int vq_fused_forward(const float* z, const float* E, const float* ee, const floa
                      int D, int HW, int K, bool after_prepare, float beta, int legacy, float* zq, int64_t* idx,
                      float* loss, double* partials, unsigned* counters, cudaStream_t s);
 
+// Shared tail: turn sum((e-z)^2) into the reference's loss scalar (taming quantize.py:291-296: legacy puts beta on
+// the other term; the forward VALUE is mean * (1 + beta) either way, summed in the reference's order).
+__device__ __forceinline__ void write_loss(double total, long long numel, float beta, int legacy, float* loss) {
+  const float m = (float)(total / (double)numel);
+  *loss = legacy ? __fadd_rn(m, __fmul_rn(beta, m)) : __fadd_rn(__fmul_rn(beta, m), m);
+}
+
 }  // namespace dcvic

@@ -63,9 +63,10 @@ constexpr int NZ = DCVIC_FZ_NZ;     // conversion ring stages (8 KB each), a mul
 constexpr int NF = DCVIC_FZ_NF;     // finish ring stages (e_dim * 128 B each)
 constexpr int B_CHUNK = (BN / 2) * BK * 2;   // 8 KB: this CTA's 64 codes x 64 channels
 constexpr int Z_STAGE = BK * GT * 4;         // 8 KB
-constexpr int LIST_CAP = 4;        // list entries per (token, column quarter)
+constexpr int NT_MAX = 8;          // N-tiles per tile: one flag-mask slot per (token, column quarter, N-tile)
 constexpr int CK_MAX = 16;         // candidate codes per token after compaction; more -> whole-codebook scan
-constexpr int MAX_K = 1024;         // -|e|^2/2 table in shared memory (larger codebooks take the two-kernel path)
+constexpr int MAX_K = NT_MAX * BN;  // -|e|^2/2 table and flag-mask slots in shared memory (larger codebooks take the
+                                    // two-kernel path)
 constexpr int NCONS = 8;
 constexpr int NEPI = 16;           // epilogue warps: 4 column quarters x 4 TMEM lane quarters
 constexpr int kFullFlag = 1 << 16; // added to a token's candidate count: whole-codebook scan
@@ -92,8 +93,8 @@ struct Smem {
   __host__ __device__ static constexpr int b_chunks_a(int D) { return (D / BK + 1) / 2; }
   __host__ __device__ static constexpr int b_stage(int D) { return b_chunks_a(D) * B_CHUNK; }
   __host__ __device__ static constexpr int off_bias(int D) { return off_b(D) + NB * b_stage(D); }          // [MAX_K] float
-  __host__ __device__ static constexpr int off_list(int D) { return off_bias(D) + MAX_K * 4; }             // [4][LIST_CAP][BM] uint2
-  __host__ __device__ static constexpr int off_ck(int D) { return off_list(D) + BM * 4 * LIST_CAP * 8; }    // [2][BM][CK_MAX] u16
+  __host__ __device__ static constexpr int off_list(int D) { return off_bias(D) + MAX_K * 4; }             // [4][NT_MAX][BM] u32
+  __host__ __device__ static constexpr int off_ck(int D) { return off_list(D) + BM * 4 * NT_MAX * 4; }      // [2][BM][CK_MAX] u16
   __host__ __device__ static constexpr int off_nc(int D) { return off_ck(D) + 2 * BM * CK_MAX * 2; }        // [2][BM] int
   __host__ __device__ static constexpr int off_zz(int D) { return off_nc(D) + 2 * BM * 4; }                 // [2][BM] float
   __host__ __device__ static constexpr int off_dz(int D) { return off_zz(D) + 2 * BM * 4; }                 // [2][BM] float
@@ -146,6 +147,29 @@ __device__ __forceinline__ float4 lds128(uint32_t a) {
 }
 __device__ __forceinline__ void sts128(uint32_t a, const float4& v) {
   asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+// Bookkeeping in shared memory goes through shared-space instructions on 32-bit addresses: pointers derived from the
+// aligned dynamic-smem base are GENERIC to the compiler (LD.E / ST.E / ATOM.E.GPU on every access otherwise).
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t lds_u16(uint32_t a) {
+  uint16_t v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) {
+  asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+__device__ __forceinline__ void sts_u16(uint32_t a, uint32_t v) {
+  asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((uint16_t)v) : "memory");
+}
+__device__ __forceinline__ uint32_t atoms_add(uint32_t a, uint32_t v) {
+  uint32_t old;
+  asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(a), "r"(v) : "memory");
+  return old;
 }
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
@@ -224,7 +248,8 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant
                 const __grid_constant__ CUtensorMap tm_zc,
                 const __grid_constant__ CUtensorMap tm_zf, const __grid_constant__ CUtensorMap tm_zq,
                 const float* __restrict__ E, const float* __restrict__ ee, const float* __restrict__ emax_ptr, int N, int HW, int K, int num_ptiles, int wait_first,
-                int64_t* __restrict__ idx, double* __restrict__ partials, unsigned* __restrict__ counters) {
+                float beta, int legacy, int64_t* __restrict__ idx, float* __restrict__ loss,
+                double* __restrict__ partials, unsigned* __restrict__ counters) {
   constexpr int KC = D / BK;                 // channel chunks per tile
   constexpr int F_STAGE = D * 128;           // finish stage: [D channels][32 tokens] FP32
   constexpr int NA = Smem::b_chunks_a(D);    // chunks in the first box of an N-tile's slab, KC - NA in the second
@@ -236,14 +261,15 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant
   const uint32_t sbase = smem_u32(smem);
   const uint32_t bar0 = sbase + Smem::off_bar(D);
   auto bar = [&](int slot) { return bar0 + slot * 8; };
-  float* s_bias = reinterpret_cast<float*>(smem + Smem::off_bias(D));
-  uint2* s_list = reinterpret_cast<uint2*>(smem + Smem::off_list(D));
-  unsigned short* s_ck = reinterpret_cast<unsigned short*>(smem + Smem::off_ck(D));
-  int* s_nc = reinterpret_cast<int*>(smem + Smem::off_nc(D));
-  float* s_zz = reinterpret_cast<float*>(smem + Smem::off_zz(D));
-  float* s_dz = reinterpret_cast<float*>(smem + Smem::off_dz(D));     // |z - fp16(z)|^2 per token
-  float* s_m = reinterpret_cast<float*>(smem + Smem::off_m(D));
-  volatile uint32_t* s_tmem = reinterpret_cast<volatile uint32_t*>(smem + Smem::off_tmem(D));
+  // shared-space addresses of the bookkeeping arrays (see lds_u32 above)
+  const uint32_t a_bias = sbase + Smem::off_bias(D);   // [MAX_K] float: -|e|^2/2
+  const uint32_t a_mask = sbase + Smem::off_list(D);   // [4 quarters][NT_MAX][BM] u32 flag masks
+  const uint32_t a_ck = sbase + Smem::off_ck(D);       // [2][BM][CK_MAX] u16 candidate codes
+  const uint32_t a_nc = sbase + Smem::off_nc(D);       // [2][BM] candidate counters
+  const uint32_t a_zz = sbase + Smem::off_zz(D);       // [2][BM] |z|^2
+  const uint32_t a_dz = sbase + Smem::off_dz(D);       // [2][BM] |z - fp16(z)|^2
+  const uint32_t a_m = sbase + Smem::off_m(D);         // [BM][4] quarter maxima
+  const uint32_t a_tmem = sbase + Smem::off_tmem(D);   // [0] TMEM base, [1] tiles converted x 4, [2] next consumer unit
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -257,8 +283,8 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant
   auto leader_bar = [&](int slot) { return map_to_cta(bar(slot), 0); };
 
   if (threadIdx.x == 0) {
-    s_tmem[1] = 0u;
-    s_tmem[2] = 0u;
+    sts_u32(a_tmem + 4, 0u);
+    sts_u32(a_tmem + 8, 0u);
     for (int s = 0; s < NB; ++s) { mbar_init(bar(Smem::BAR_B_FULL + s), 1); mbar_init(bar(Smem::BAR_B_EMPTY + s), 1); }
     for (int s = 0; s < NZ; ++s) { mbar_init(bar(Smem::BAR_Z_FULL + s), 1); mbar_init(bar(Smem::BAR_Z_EMPTY + s), 1); }
     for (int c = 0; c < 8; ++c) mbar_init(bar(Smem::BAR_A_FULL + c), 2 * NG);
@@ -273,7 +299,7 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant
     for (int s = 0; s < NF; ++s) { mbar_init(bar(Smem::BAR_F_FULL + s), 1); mbar_init(bar(Smem::BAR_F_DONE + s), 8); }
     fence_barrier_init();
   }
-  if (threadIdx.x < 2 * BM) s_nc[threadIdx.x] = 0;     // candidate counters (atomic appends; the consumers re-zero them)
+  if (threadIdx.x < 2 * BM) sts_u32(a_nc + threadIdx.x * 4, 0u);     // candidate counters (atomic appends; the consumers re-zero them)
   if (warp == W_MMA) {
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + Smem::off_tmem(D)),
                  "r"(512u));
@@ -284,7 +310,7 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant
   cluster_sync();
   tc_fence_after();
   FZ_MARK(0);
-  const uint32_t tmem_base = *s_tmem;
+  const uint32_t tmem_base = lds_u32(a_tmem);
   // tensor memory: accumulators 2 x 128 columns | A operand 2 x 128 columns
   const uint32_t tmem_acc = tmem_base, tmem_a = tmem_base + 2 * BN;
   // PDL: see vq_tcgen05.cu.  wait_first: the predecessor in the stream may be the producer of z.
@@ -370,7 +396,7 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant
           // may trail the converters by more than one phase of it; a heuristic for the cache, not a data dependence)
           FZ_DBG(3, j);
           FZ_T();
-          while (s_tmem[1] < (uint32_t)(NG * (it + 1))) __nanosleep(64);
+          while (lds_u32(a_tmem + 4) < (uint32_t)(NG * (it + 1))) __nanosleep(64);
           FZ_ACC(1);
           int x, y;
           coords(j, x, y);
@@ -522,12 +548,12 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(leader_bar(Smem::BAR_A_FULL + abuf * 4 + kc));
       }
-      s_zz[abuf * BM + row] = zz;
-      s_dz[abuf * BM + row] = dz2;
+      sts_u32(a_zz + (abuf * BM + row) * 4, __float_as_uint(zz));
+      sts_u32(a_dz + (abuf * BM + row) * 4, __float_as_uint(dz2));
       __syncwarp();
       if (lane == 0) {
         mbar_arrive(bar(Smem::BAR_ZZ + abuf));
-        atomicAdd(const_cast<uint32_t*>(s_tmem) + 1, 1u);
+        atoms_add(a_tmem + 4, 1u);
       }
       FZ_MARK(3 + it * 4);
     }
@@ -545,9 +571,10 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant
     const float emax = emax_ptr[0];
     const bool cb_unsafe = __float_as_uint(emax_ptr[1]) != 0u;
     const float demax = emax_ptr[2];
-    for (int k = threadIdx.x - W_EPI0 * 32; k < K; k += NEPI * 32) s_bias[k] = -0.5f * ee[k];     // exact
+    for (int k = threadIdx.x - W_EPI0 * 32; k < K; k += NEPI * 32)
+      sts_u32(a_bias + k * 4, __float_as_uint(-0.5f * ee[k]));     // exact
     named_bar_sync(5, NEPI * 32);
-    const uint32_t bias_base = sbase + Smem::off_bias(D) + q * kChunk * 4;
+    const uint32_t bias_base = a_bias + q * kChunk * 4;
     // scores of one 32-code chunk += -|e|^2/2 of its codes (the same 32 values for every row: broadcast loads)
     auto add_bias = [&](uint32_t (&r)[32], uint32_t a) {
 #pragma unroll
@@ -559,9 +586,9 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant
         r[4 * i + 3] = __float_as_uint(__fadd_rn(__uint_as_float(r[4 * i + 3]), b.w));
       }
     };
-    // list entry i of (row, quarter q) lives at s_list[(q * LIST_CAP + i) * BM + row]: the 32 rows of a warp are 32
-    // consecutive 8-byte slots.  Every list has ONE writer and one reader, this thread.
-    uint2* my_list = s_list + (q * LIST_CAP) * BM + row;
+    // The flag mask of (row, quarter q, N-tile nt) lives at a_mask + ((q * NT_MAX + nt) * BM + row) * 4: ONE writer and
+    // one reader, this thread; the 32 rows of a warp are 32 consecutive words.  `live` says which slots count.
+    const uint32_t my_mask = a_mask + ((q * NT_MAX) * BM + row) * 4;
     uint32_t g = 0;
     FZ_TDECL;
     for (int it = 0; it < my_tiles; ++it) {
@@ -571,32 +598,11 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant
       FZ_T();
       mbar_wait(bar(Smem::BAR_ZZ + abuf), (it >> 1) & 1);
       FZ_ACC(1);
-      const float zz = s_zz[abuf * BM + row];
-      const float margin = vq_margin_measured(zz, s_dz[abuf * BM + row], emax, demax, D);
+      const float zz = __uint_as_float(lds_u32(a_zz + (abuf * BM + row) * 4));
+      const float margin =
+          vq_margin_measured(zz, __uint_as_float(lds_u32(a_dz + (abuf * BM + row) * 4)), emax, demax, D);
       float m = -INFINITY;                           // running maximum over this quarter's codes
-      int n = 0;                                     // list entries; -1: overflow (whole-codebook scan)
-      // A flagged chunk joins the list.  Entries a later maximum has put out of reach are dropped: all of them at
-      // once when this chunk's maximum beats the previous running maximum by more than the margin, one by one (only
-      // when the list is full) when the running maximum has crept away from them in small steps.
-      auto emit = [&](uint32_t mask, float cm, float m_old, uint32_t chunk) {
-        if (mask != 0u) {
-          if (cm > m_old + margin) n = 0;
-          if (n == LIST_CAP) {
-            const float keep = m - margin;
-            int w = 0;
-#pragma unroll
-            for (int i = 0; i < LIST_CAP; ++i) {
-              const uint2 en = my_list[i * BM];
-              if (!(vq_key_upper(en.x) < keep)) { my_list[w * BM] = en; ++w; }
-            }
-            n = w;
-          }
-          if (n >= 0) {
-            if (n < LIST_CAP) { my_list[n * BM] = make_uint2((__float_as_uint(cm) & 0xFFFFFF80u) | chunk, mask); ++n; }
-            else n = -1;
-          }
-        }
-      };
+      uint32_t live = 0u;                            // N-tiles whose flag mask may hold a candidate
       for (int nt = 0; nt < NT; ++nt, ++g) {
         const uint32_t buf = g & 1;
         FZ_DBG(11, g);
@@ -617,25 +623,28 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant
         add_bias(ra, bias_base + nt * (BN * 4));
 #endif
         FZ_ACC(4);
-#if !defined(DCVIC_FZ_EXP) || DCVIC_FZ_EXP < 3
         float cm;
         const float m_old = m;
         const uint32_t mask = chunk_flags(ra, margin, m, cm);
-        emit(mask, cm, m_old, (uint32_t)(nt * (BN / kChunk) + q));
-#else
-        m = fmaxf(m, __uint_as_float(ra[lane]));
-#endif
+        // A flagged chunk's mask is kept.  When this chunk's maximum beats the previous running maximum by more than
+        // the margin, every earlier mask is out of reach (all its scores are <= m_old) and is dropped.
+        if (mask != 0u) {
+          if (cm > m_old + margin) live = 0u;
+          sts_u32(my_mask + nt * (BM * 4), mask);
+          live |= 1u << nt;
+        }
         FZ_ACC(5);
       }
-      // ---- end of tile: the four quarters of a row exchange their maxima; each appends the codes of its surviving
-      // entries to the row's candidate array (slots handed out by an atomic counter: the order does not matter, the
-      // re-rank breaks ties by code index)
-      s_m[row * 4 + q] = m;
+      // ---- end of tile: the four quarters of a row exchange their maxima; each appends the codes of its live masks
+      // to the row's candidate array (slots handed out by an atomic counter: the order does not matter, the re-rank
+      // breaks ties by code index).  Masks were taken against the running threshold of their time, which is below the
+      // final one: a superset of the codes within the margin of the row maximum.
+      sts_u32(a_m + (row * 4 + q) * 4, __float_as_uint(m));
       FZ_MARK(2 + it * 4);
       FZ_DBG(12, it);
       named_bar_sync(1 + part, 128);
-      const float4 mq = *reinterpret_cast<const float4*>(s_m + row * 4);
-      // (s_m is written again after the NEXT tile's last N-tile, which the MMA issues only once every epilogue warp
+      const float4 mq = lds128(a_m + row * 16);
+      // (a_m is written again after the NEXT tile's last N-tile, which the MMA issues only once every epilogue warp
       // has drained N-tile NT - 3 of that tile, i.e. has left this section - if the tile has that many)
       if (NT < 3) named_bar_sync(1 + part, 128);
       const float thr = fmaxf(fmaxf(mq.x, mq.y), fmaxf(mq.z, mq.w)) - margin;
@@ -643,42 +652,24 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant
       FZ_DBG(13, it);
       if (it >= 2) mbar_wait(bar(Smem::BAR_C_EMPTY + par), ((it >> 1) - 1) & 1);   // consumers are done with tile it-2
       if (valid) {
-        int* ncp = s_nc + par * BM + row;
+        const uint32_t ncp = a_nc + (par * BM + row) * 4;
         if (cb_unsafe || !(zz < kVqFp16Zz2Max)) {
           if (q == 0) {
-            atomicAdd(ncp, kFullFlag);
+            atoms_add(ncp, (uint32_t)kFullFlag);
             atomicAdd(counters + 9, 1u);              // diagnostics: why a token is scanned in full
           }
-        } else if (!(m < thr)) {                       // (a quarter whose maximum is out of reach has nothing to add)
-          if (n < 0) {
-            atomicAdd(ncp, kFullFlag);
-            atomicAdd(counters + 6, 1u);
-          } else {
-            uint2 en[LIST_CAP];
-            int cnt = 0;
-#pragma unroll
-            for (int i = 0; i < LIST_CAP; ++i) {
-              en[i] = make_uint2(0u, 0u);
-              if (i < n) {
-                const uint2 e = my_list[i * BM];
-                if (!(vq_key_upper(e.x) < thr)) { en[i] = e; cnt += __popc(e.y); }
-              }
-            }
-            if (cnt > 0) {
-              int w = atomicAdd(ncp, cnt);
-              if (w <= CK_MAX && w + cnt > CK_MAX) atomicAdd(counters + 7, 1u);
-              unsigned short* ck = s_ck + (par * BM + row) * CK_MAX;
-#pragma unroll
-              for (int i = 0; i < LIST_CAP; ++i) {
-                const int c0 = (int)(en[i].x & 0x7Fu) * kChunk;
-                uint32_t mk = en[i].y;
-                while (mk) {
-                  const int b = __ffs(mk) - 1;
-                  mk &= mk - 1;
-                  if (w < CK_MAX) ck[w] = (unsigned short)(c0 + b);
-                  ++w;
-                }
-              }
+        } else if (live != 0u && !(m < thr)) {         // (a quarter whose maximum is out of reach has nothing to add)
+          int cnt = 0;
+          for (uint32_t lv = live; lv; lv &= lv - 1) cnt += __popc(lds_u32(my_mask + (__ffs(lv) - 1) * (BM * 4)));
+          int w = (int)atoms_add(ncp, (uint32_t)cnt);
+          if (w <= CK_MAX && w + cnt > CK_MAX) atomicAdd(counters + 7, 1u);
+          const uint32_t ck = a_ck + (par * BM + row) * (CK_MAX * 2);
+          for (uint32_t lv = live; lv; lv &= lv - 1) {
+            const int nt = __ffs(lv) - 1;
+            const int c0 = nt * BN + q * kChunk;
+            for (uint32_t mk = lds_u32(my_mask + nt * (BM * 4)); mk; mk &= mk - 1) {
+              if (w < CK_MAX) sts_u16(ck + w * 2, (uint32_t)(c0 + __ffs(mk) - 1));
+              ++w;
             }
           }
         }
@@ -725,7 +716,7 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant
     // not hold up its CTA
     for (;;) {
       int u = 0;
-      if (lane == 0) u = (int)atomicAdd(const_cast<uint32_t*>(s_tmem) + 2, 1u);
+      if (lane == 0) u = (int)atoms_add(a_tmem + 8, 1u);
       u = __shfl_sync(0xffffffffu, u, 0);
       if (u >= total_units) break;
       const int j = u >> 3, cw = u & 7;              // group (in this CTA's sequence), token quad inside it
@@ -748,8 +739,8 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant
       int nc[4], bk[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        nc[i] = s_nc[par * BM + r0 + i];
-        bk[i] = s_ck[(par * BM + r0 + i) * CK_MAX];
+        nc[i] = (int)lds_u32(a_nc + (par * BM + r0 + i) * 4);
+        bk[i] = (int)lds_u16(a_ck + (par * BM + r0 + i) * (CK_MAX * 2));
         if (nc[i] <= 0 || nc[i] > CK_MAX) {          // flagged for a whole-codebook scan, too many candidates, or none
           if (live && nc[i] == 0 && lane == 0) atomicAdd(counters + 8, 1u);
           nc[i] = -1;
@@ -761,7 +752,7 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant
       for (int i = 0; i < 4; ++i) { nc[i] = 1; bk[i] = (r0 + i) & 1023; }
 #endif
       __syncwarp();
-      if (lane < 4) s_nc[par * BM + r0 + lane] = 0;  // for the tile after next (ordered by the C_EMPTY arrival below)
+      if (lane < 4) sts_u32(a_nc + (par * BM + r0 + lane) * 4, 0u);  // for the tile after next (ordered by the C_EMPTY arrival below)
       uint32_t zo[4];
 #pragma unroll
       for (int jj = 0; jj < 4; ++jj) {
@@ -814,10 +805,10 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant
             ++n_rr;
             bd = fmaf(-2.f, dot(er[i]), __fadd_rn(zz, __ldg(ee + bk[i])));
             kb = bk[i];
-            const unsigned short* ck = s_ck + (par * BM + r0 + i) * CK_MAX;
+            const uint32_t ck = a_ck + (par * BM + r0 + i) * (CK_MAX * 2);
 #pragma unroll 1
             for (int ci = 1; ci < nc[i]; ++ci) {
-              const int k0 = ck[ci];
+              const int k0 = (int)lds_u16(ck + ci * 2);
               float4 e0[NH];
               load_row(e0, k0);
               const float d0 = fmaf(-2.f, dot(e0), __fadd_rn(zz, __ldg(ee + k0)));
@@ -875,7 +866,6 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant
           }
         }
         dsq += (double)sq;
-        if (lane < 4) idx[t0 + lane] = (int64_t)(lane == 0 ? bk[0] : lane == 1 ? bk[1] : lane == 2 ? bk[2] : bk[3]);
       }
       fence_proxy_async();                          // generic-proxy writes of the stage -> visible to the TMA store
       __syncwarp();
@@ -883,6 +873,9 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant
         mbar_arrive(bar(Smem::BAR_F_DONE + st));
         mbar_arrive(bar(Smem::BAR_C_EMPTY + par));
       }
+      // (after the fence: the fence would otherwise wait for this global store as well)
+      if (live && lane < 4)
+        idx[t0 + lane] = (int64_t)(lane == 0 ? bk[0] : lane == 1 ? bk[1] : lane == 2 ? bk[2] : bk[3]);
       FZ_ACC(5);
       FZ_MARK(3 + it * 4);
     }
@@ -902,7 +895,26 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant
   FZ_MARK(39);
   tc_fence_before();
   __syncthreads();
+  // Loss: the CTA that finishes last sums every consumer warp's partial in index order (deterministic) - one
+  // device-scope fence and one atomic per CTA instead of a 1-CTA kernel behind this one (3.5 us + a launch gap).
+  __shared__ int s_last;
+  __shared__ double s_scratch[32];
+  if (threadIdx.x == 0) {
+    __threadfence();
+    s_last = atomicAdd(counters + kCtrLoss, 1u) == gridDim.x - 1 ? 1 : 0;
+  }
   cluster_sync();            // no CTA leaves while its peer may still touch its shared memory / barriers
+  if (s_last) {
+    __threadfence();
+    const int n = (int)gridDim.x * NCONS;
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < n; i += NTHREADS) acc += __ldcg(partials + i);
+    const double tot = block_sum(acc, s_scratch);
+    if (threadIdx.x == 0) {
+      write_loss(tot, (long long)N * D, beta, legacy, loss);
+      counters[kCtrLoss] = 0u;
+    }
+  }
   if (warp == W_MMA) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
@@ -945,7 +957,8 @@ static bool map_2d(CUtensorMap* tm, CUtensorMapDataType dt, int esize, const voi
 template <int D>
 static int launch(const CUtensorMap& tcb, const CUtensorMap& tcb2, const CUtensorMap& tzc, const CUtensorMap& tzf, const CUtensorMap& tzq,
                   const float* E, const float* ee, const float* emax, int N, int HW, int K,
-                  int wait_first, int64_t* idx, double* partials, unsigned* counters, int* grid_out, cudaStream_t s) {
+                  int wait_first, float beta, int legacy, int64_t* idx, float* loss, double* partials,
+                  unsigned* counters, cudaStream_t s) {
   const int smem = Smem::bytes(D) + 1024;
   static bool attr_set = false;
   if (!attr_set) {
@@ -970,9 +983,8 @@ static int launch(const CUtensorMap& tcb, const CUtensorMap& tcb2, const CUtenso
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 2;
-  *grid_out = 2 * npairs;
   if (cudaLaunchKernelEx(&cfg, vq_fused_kernel<D>, tcb, tcb2, tzc, tzf, tzq, E, ee, emax, N, HW, K, num_ptiles,
-                         wait_first, idx, partials, counters) != cudaSuccess)
+                         wait_first, beta, legacy, idx, loss, partials, counters) != cudaSuccess)
     return DCVIC_ERR_CUDA;
   return dcvic_launch_status();
 }
@@ -1036,9 +1048,9 @@ int vq_fused_forward(const float* z, const float* E, const float* ee, const floa
       !map_2d(&tzq, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, zq, (uint64_t)HW, (uint64_t)B * D, (uint64_t)HW * 4, GT, D))
     return DCVIC_ERR_CUDA;
   const int wait_first = after_prepare ? 0 : 1;
-  int grid = 0, rc;
+  int rc;
 #define DCVIC_FZ(DD) \
-  launch<DD>(tcb, tcb2, tzc, tzf, tzq, E, ee, emax, N, HW, K, wait_first, idx, partials, counters, &grid, s)
+  launch<DD>(tcb, tcb2, tzc, tzf, tzq, E, ee, emax, N, HW, K, wait_first, beta, legacy, idx, loss, partials, counters, s)
   switch (D) {
     case 64: rc = DCVIC_FZ(64); break;
     case 128: rc = DCVIC_FZ(128); break;
@@ -1047,8 +1059,7 @@ int vq_fused_forward(const float* z, const float* E, const float* ee, const floa
     default: return DCVIC_ERR_UNSUPPORTED;
   }
 #undef DCVIC_FZ
-  if (rc) return rc;
-  return vq_launch_loss_finalize(partials, grid * NCONS, (long long)N * D, beta, legacy, loss, s);
+  return rc;
 }
 
 }  // namespace dcvic

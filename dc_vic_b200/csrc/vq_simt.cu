@@ -130,11 +130,6 @@ int vq_prepare_codebook(const float* codebook, int K, int D, float* ee, float* s
   return dcvic_launch_status();
 }
 
-// Shared tail: turn sum((e-z)^2) into the reference's loss scalar.
-__device__ __forceinline__ void write_loss(double total, long long numel, float beta, int legacy, float* loss) {
-  const float m = (float)(total / (double)numel);
-  *loss = legacy ? __fadd_rn(m, __fmul_rn(beta, m)) : __fadd_rn(__fmul_rn(beta, m), m);
-}
 
 // ------------------------------------------------------------------ narrow fused forward
 // One thread per token, token row in registers, codebook tile (+ |e|^2) in shared memory and
