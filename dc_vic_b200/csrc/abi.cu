@@ -59,6 +59,7 @@ extern "C" int dcvic_vq_forward(const float* z_nchw, const float* codebook, int 
   VqMeta* meta = reinterpret_cast<VqMeta*>(ws + w.off_meta);
   uint2* list = reinterpret_cast<uint2*>(ws + w.off_list);
   __half* cb16 = reinterpret_cast<__half*>(ws + w.off_cb16);
+  float* eperm = reinterpret_cast<float*>(ws + w.off_eperm);
   cudaStream_t s = (cudaStream_t)stream;
   int rc = DCVIC_OK;
 
@@ -67,7 +68,8 @@ extern "C" int dcvic_vq_forward(const float* z_nchw, const float* codebook, int 
   } else {
     const bool prepared = !(flags & (DCVIC_VQ_REUSE_PREP | DCVIC_VQ_STAGE_FINISH_ONLY));
     if (prepared) {
-      rc = vq_prepare_codebook(codebook, K, D, ee, nhee, emax, path == 2 ? cb16 : nullptr, counters, s);
+      rc = vq_prepare_codebook(codebook, K, D, ee, nhee, emax, path == 2 ? cb16 : nullptr,
+                               path == 2 ? eperm : nullptr, counters, s);
       if (rc) return rc;
     }
     if (flags & DCVIC_VQ_STAGE_PREP_ONLY) return rc;
@@ -75,7 +77,7 @@ extern "C" int dcvic_vq_forward(const float* z_nchw, const float* codebook, int 
     const bool do_finish = !(flags & DCVIC_VQ_STAGE_SEARCH_ONLY);
     if (path == 2 && do_search && do_finish && !(flags & DCVIC_VQ_TWO_KERNELS) &&
         vq_fused_supported(z_nchw, zq_nchw, codebook, D, HW, K)) {
-      rc = vq_fused_forward(z_nchw, codebook, ee, emax, cb16, B, D, HW, K, prepared, beta, legacy, zq_nchw, idx, loss,
+      rc = vq_fused_forward(z_nchw, eperm, ee, emax, cb16, B, D, HW, K, prepared, beta, legacy, zq_nchw, idx, loss,
                             partials, counters, s);
     } else if (path == 2) {
       if (do_search)

@@ -28,7 +28,7 @@ struct __align__(16) VqMeta {
 //                           margin of the running maximum when that chunk went by
 struct VqWorkspace {
   size_t off_counters, off_ee, off_nhee, off_emax, off_partials, off_hist, off_cand, off_meta, off_list, off_cb16,
-      total;
+      off_eperm, total;
   int n_tokens;
 };
 
@@ -48,6 +48,7 @@ inline VqWorkspace vq_workspace_layout(int B, int D, int HW, int K) {
   w.off_meta = take(N * sizeof(VqMeta));
   w.off_list = take(N * 2 * kListCap * sizeof(uint2));
   w.off_cb16 = take((size_t)K * (D + kCb16Pad) * sizeof(__half));
+  w.off_eperm = take((size_t)K * D * sizeof(float));      // the codebook in the single-pass kernel's gather order
   w.total = o;
   w.n_tokens = (int)N;
   return w;
@@ -102,8 +103,16 @@ __host__ __device__ __forceinline__ float vq_key_upper(unsigned key) {
 
 // vq_simt.cu
 // scratch: K floats (per-CTA maxima of the prepare kernel)
+// eperm (optional): the FP32 codebook with the channels of every group of four rotated the way the single-pass
+// kernel's consumers visit them (vq_eperm_dest)
 int vq_prepare_codebook(const float* codebook, int K, int D, float* ee, float* scratch, float* emax,
-                        __half* cb16, unsigned* counters, cudaStream_t s);
+                        __half* cb16, float* eperm, unsigned* counters, cudaStream_t s);
+// Consumer lane l = (c >> 2) & 31 holds channels 4 (c >> 2) .. + 3 and visits them in the order (j + (l >> 1)) & 3
+// (conflict-free 16-byte accesses to the swizzled z stage): channel c goes to slot j = (c - (l >> 1)) & 3 of its group.
+__host__ __device__ __forceinline__ int vq_eperm_dest(int c) {
+  const int b = c >> 2, rot = ((b & 31) >> 1) & 3;
+  return 4 * b + (((c & 3) - rot) & 3);
+}
 int vq_narrow_forward(const float* z, const float* E, int B, int D, int HW, int K, float beta, int legacy, float* zq,
                       int64_t* idx, float* loss, double* partials, unsigned* counters, cudaStream_t s);
 int vq_exact_search(const float* z, const float* E, const float* ee, int B, int D, int HW, int K, int* cand,
@@ -134,7 +143,7 @@ int vq_tensor_search(const float* z, const __half* cb16, const float* emax, int 
 // vq_fused.cu: the single-pass wide forward (search + re-rank + gather + straight-through value + loss in one
 // persistent kernel) for e_dim in {64, 128, 192, 256}, K % 128 == 0, K <= 2048, H*W % 32 == 0
 bool vq_fused_supported(const float* z, const float* zq, const float* E, int D, int HW, int K);
-int vq_fused_forward(const float* z, const float* E, const float* ee, const float* emax, const __half* cb16, int B,
+int vq_fused_forward(const float* z, const float* Eperm, const float* ee, const float* emax, const __half* cb16, int B,
                      int D, int HW, int K, bool after_prepare, float beta, int legacy, float* zq, int64_t* idx,
                      float* loss, double* partials, unsigned* counters, cudaStream_t s);
 

@@ -247,7 +247,8 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant__ CUtensorMap tm_cb2,
                 const __grid_constant__ CUtensorMap tm_zc,
                 const __grid_constant__ CUtensorMap tm_zf, const __grid_constant__ CUtensorMap tm_zq,
-                const float* __restrict__ E, const float* __restrict__ ee, const float* __restrict__ emax_ptr, int N, int HW, int K, int num_ptiles, int wait_first,
+                const float* __restrict__ Ep, const float* __restrict__ ee, const float* __restrict__ emax_ptr, int N,
+                int HW, int K, int num_ptiles, int wait_first,
                 float beta, int legacy, int64_t* __restrict__ idx, float* __restrict__ loss,
                 double* __restrict__ partials, unsigned* __restrict__ counters) {
   constexpr int KC = D / BK;                 // channel chunks per tile
@@ -688,196 +689,204 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant
     FZ_DBG(23, 0);
     // Lane l holds 4 consecutive channels per 128-channel block (c = 4l + 128h) of the 4 tokens of its quad: one
     // LDG.128 per codebook row and block, one LDS.128 / STS.128 per channel.  Lane l visits its 4 channels in the
-    // order (j + (l >> 1)) & 3 so that a quarter warp touches 8 different 16-byte pieces of the swizzled stage
-    // (see vq_finish_tma.cu, whose consumer this is).
+    // order (j + (l >> 1)) & 3 so that a quarter warp touches 8 different 16-byte pieces of the swizzled stage; the
+    // codebook copy it gathers from (Ep, written by the prepare kernel) has every group of four channels in exactly
+    // that order, so a row's float4 pairs with the stage's values component by component.
     const int cwarp = warp - W_CONS0;
     const int rot = (lane >> 1) & 3;
     const bool hv[2] = {4 * lane < D, 4 * lane + 128 < D};
-    pdl_wait();                                      // |e|^2 comes from the prepare kernel
+    pdl_wait();                                      // |e|^2 and Ep come from the prepare kernel
     double dsq = 0.0;
     unsigned n_rr = 0, n_fs = 0;
-    auto rotl = [](float4 v, int r) {
-      if (r & 1) v = make_float4(v.y, v.z, v.w, v.x);
-      if (r & 2) v = make_float4(v.z, v.w, v.x, v.y);
-      return v;
-    };
     auto load_row = [&](float4 (&r)[NH], int k) {
-      const float* rowp = E + (size_t)k * D + 4 * lane;
+      const float* rowp = Ep + (size_t)k * D + 4 * lane;
 #pragma unroll
       for (int h = 0; h < NH; ++h)
         r[h] = hv[h] ? __ldg(reinterpret_cast<const float4*>(rowp + 128 * h)) : make_float4(0.f, 0.f, 0.f, 0.f);
     };
-    const int total_units = my_tiles * NG * 8;
+    // this lane's four channel rows of a finish stage (stage base and the quad's 16-byte piece added per unit)
+    uint32_t zrow[4];
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) zrow[jj] = (4 * lane + ((jj + rot) & 3)) * 128;
     FZ_TDECL;
 #ifdef DCVIC_FZ_DEBUG
     int fz_last_it = -1;
 #endif
     // (group, token quad) units are handed out in order through a shared counter: a warp that drew long re-ranks does
-    // not hold up its CTA
+    // not hold up its CTA (a fixed quad per warp cost 25 us on inputs where every fifth token is re-ranked)
+    const int total_units = my_tiles * NG * 8;
     for (;;) {
-      int u = 0;
-      if (lane == 0) u = (int)atoms_add(a_tmem + 8, 1u);
-      u = __shfl_sync(0xffffffffu, u, 0);
-      if (u >= total_units) break;
-      const int j = u >> 3, cw = u & 7;              // group (in this CTA's sequence), token quad inside it
-      const int it = j / NG, g = j % NG, par = it & 1, st = j % NF;
-      FZ_DBG(15, j);
-      FZ_T();
-      mbar_wait(bar(Smem::BAR_C_FULL + par), (it >> 1) & 1);
-      FZ_ACC(1);
+      {
+        int u = 0;
+        if (lane == 0) u = (int)atoms_add(a_tmem + 8, 1u);
+        u = __shfl_sync(0xffffffffu, u, 0);
+        if (u >= total_units) break;
+        const int j = u >> 3, cw = u & 7;            // group (in this CTA's sequence), token quad inside it
+        const int it = j / NG, g = j % NG, par = it & 1, st = j % NF;
+        FZ_DBG(15, j);
+        FZ_T();
+        mbar_wait(bar(Smem::BAR_C_FULL + par), (it >> 1) & 1);
+        FZ_ACC(1);
 #ifdef DCVIC_FZ_DEBUG
-      if (it != fz_last_it) { FZ_MARK(1 + it * 4); fz_last_it = it; }
+        if (it != fz_last_it) { FZ_MARK(1 + it * 4); fz_last_it = it; }
 #endif
-      const int r0 = g * GT + 4 * cw;                // first row (token of the CTA tile) of this unit
-      const uint32_t t0 = tile_token0(it) + r0;
+        uint32_t zoff[4];
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) zoff[jj] = zrow[jj] + (((uint32_t)cw ^ ((zrow[jj] >> 7) & 7u)) << 4);
+        const int rq = g * GT + 4 * cw;              // first row (token of the CTA tile) of this unit
+        const uint32_t t0 = tile_token0(it) + rq;
 #if defined(DCVIC_FZ_EXP) && DCVIC_FZ_EXP >= 4
-      const bool live = t0 > 0x7fffffffu;
+        const bool live = t0 > 0x7fffffffu;
 #else
-      const bool live = t0 < (uint32_t)N;
+        const bool live = t0 < (uint32_t)N;          // (a quad is valid or invalid as a whole: N % 4 == 0)
 #endif
-      // (a quad is valid or invalid as a whole: N % 4 == 0)
-      int nc[4], bk[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        nc[i] = (int)lds_u32(a_nc + (par * BM + r0 + i) * 4);
-        bk[i] = (int)lds_u16(a_ck + (par * BM + r0 + i) * (CK_MAX * 2));
-        if (nc[i] <= 0 || nc[i] > CK_MAX) {          // flagged for a whole-codebook scan, too many candidates, or none
-          if (live && nc[i] == 0 && lane == 0) atomicAdd(counters + 8, 1u);
-          nc[i] = -1;
-          bk[i] = 0;
-        }
-      }
-#if defined(DCVIC_FZ_EXP) && DCVIC_FZ_EXP >= 3
-#pragma unroll
-      for (int i = 0; i < 4; ++i) { nc[i] = 1; bk[i] = (r0 + i) & 1023; }
-#endif
-      __syncwarp();
-      if (lane < 4) sts_u32(a_nc + (par * BM + r0 + lane) * 4, 0u);  // for the tile after next (ordered by the C_EMPTY arrival below)
-      uint32_t zo[4];
-#pragma unroll
-      for (int jj = 0; jj < 4; ++jj) {
-        const int rowc = 4 * lane + ((jj + rot) & 3);
-        zo[jj] = sbase + Smem::OFF_F + st * F_STAGE + rowc * 128 + ((cw ^ (rowc & 7)) << 4);
-      }
-      float4 er[4][NH];
-      if (live) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) load_row(er[i], bk[i]);
-      }
-      FZ_DBG(16, j);
-      FZ_ACC(2);
-      mbar_wait(bar(Smem::BAR_F_FULL + st), (j / NF) & 1);
-      FZ_ACC(3);
-      FZ_DBG(17, j);
-      if (live) {
+        int nc[4], bk[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          if (nc[i] == 1) continue;                  // warp-uniform
-          float4 zg[NH];
-          float zz = 0.f;
+          nc[i] = (int)lds_u32(a_nc + (par * BM + rq + i) * 4);
+          bk[i] = (int)lds_u16(a_ck + (par * BM + rq + i) * (CK_MAX * 2));
+          if (nc[i] <= 0 || nc[i] > CK_MAX) {        // flagged for a whole-codebook scan, too many candidates, or none
+            if (live && nc[i] == 0 && lane == 0) atomicAdd(counters + 8, 1u);
+            nc[i] = -1;
+            bk[i] = 0;
+          }
+        }
+#if defined(DCVIC_FZ_EXP) && DCVIC_FZ_EXP >= 3
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { nc[i] = 1; bk[i] = (rq + i) & 1023; }
+#endif
+        __syncwarp();
+        if (lane < 4) sts_u32(a_nc + (par * BM + rq + lane) * 4, 0u);  // for the tile after next (ordered by the C_EMPTY arrival below)
+        const uint32_t zb = sbase + Smem::OFF_F + st * F_STAGE;
+        float4 er[4][NH];
+        if (live) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) load_row(er[i], bk[i]);
+        }
+        FZ_DBG(16, j);
+        FZ_ACC(2);
+        mbar_wait(bar(Smem::BAR_F_FULL + st), (j / NF) & 1);
+        FZ_ACC(3);
+        FZ_DBG(17, j);
+        if (live) {
+          if ((nc[0] != 1) | (nc[1] != 1) | (nc[2] != 1) | (nc[3] != 1)) {     // warp-uniform
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              if (nc[i] == 1) continue;
+              // the second candidate's row is requested before the token's z is read (most re-ranks have two)
+              const uint32_t ck = a_ck + (par * BM + rq + i) * (CK_MAX * 2);
+              float4 e0[NH];
+              int k0 = 0;
+              if (nc[i] > 1) {
+                k0 = (int)lds_u16(ck + 2);
+                load_row(e0, k0);
+              }
+              float4 zg[NH];                           // this token's z in visiting order
+              float zz = 0.f;
+#pragma unroll
+              for (int h = 0; h < NH; ++h) {
+                float v[4] = {0.f, 0.f, 0.f, 0.f};
+                if (hv[h]) {
+#pragma unroll
+                  for (int jj = 0; jj < 4; ++jj) {
+                    const float4 a = lds128(zb + zoff[jj] + h * 16384);
+                    v[jj] = i == 0 ? a.x : i == 1 ? a.y : i == 2 ? a.z : a.w;
+                  }
+                }
+                zg[h] = make_float4(v[0], v[1], v[2], v[3]);
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) zz = __fadd_rn(zz, __fmul_rn(v[jj], v[jj]));
+              }
+              zz = warp_sum(zz);
+              auto dot = [&](const float4 (&r)[NH]) {
+                float dp = 0.f;
+#pragma unroll
+                for (int h = 0; h < NH; ++h) {
+                  dp = fmaf(zg[h].x, r[h].x, dp); dp = fmaf(zg[h].y, r[h].y, dp);
+                  dp = fmaf(zg[h].z, r[h].z, dp); dp = fmaf(zg[h].w, r[h].w, dp);
+                }
+                return warp_sum(dp);
+              };
+              float bd = FLT_MAX;
+              int kb = 0x7fffffff;
+              if (nc[i] > 1) {
+                ++n_rr;
+                bd = fmaf(-2.f, dot(er[i]), __fadd_rn(zz, __ldg(ee + bk[i])));
+                kb = bk[i];
+#pragma unroll 1
+                for (int ci = 1; ci < nc[i]; ++ci) {
+                  if (ci > 1) {
+                    k0 = (int)lds_u16(ck + ci * 2);
+                    load_row(e0, k0);
+                  }
+                  const float d0 = fmaf(-2.f, dot(e0), __fadd_rn(zz, __ldg(ee + k0)));
+                  if (d0 < bd || (d0 == bd && k0 < kb)) {
+                    bd = d0;
+                    kb = k0;
+#pragma unroll
+                    for (int h = 0; h < NH; ++h) er[i][h] = e0[h];
+                  }
+                }
+              } else {
+                // whole-codebook scan (FP16-unsafe input or more candidates than fit; rare): two rows in flight
+                ++n_fs;
+#pragma unroll 1
+                for (int k = 0; k < K; k += 2) {
+                  float4 e0[NH], e1[NH];
+                  const int k1 = min(k + 1, K - 1);
+                  load_row(e0, k);
+                  load_row(e1, k1);
+                  const float d0 = fmaf(-2.f, dot(e0), __fadd_rn(zz, __ldg(ee + k)));
+                  const float d1 = fmaf(-2.f, dot(e1), __fadd_rn(zz, __ldg(ee + k1)));
+                  if (d0 < bd || (d0 == bd && k < kb)) { bd = d0; kb = k; }
+                  if (d1 < bd || (d1 == bd && k1 < kb)) { bd = d1; kb = k1; }
+                }
+                load_row(er[i], kb);
+              }
+              bk[i] = kb;
+            }
+          }
+          FZ_ACC(4);
+          // ---- z_q = z + (e - z) in place, loss partial
+          float sq = 0.f;
+          float4 za[NH][4];                             // all loads first: one round trip to shared memory per unit
+#pragma unroll
+          for (int h = 0; h < NH; ++h)
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj)
+              za[h][jj] = hv[h] ? lds128(zb + zoff[jj] + h * 16384) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
           for (int h = 0; h < NH; ++h) {
-            float v[4] = {0.f, 0.f, 0.f, 0.f};
-            if (hv[h]) {
+            if (!hv[h]) continue;
 #pragma unroll
-              for (int jj = 0; jj < 4; ++jj) {
-                const float4 a = lds128(zo[jj] + h * 16384);
-                v[jj] = i == 0 ? a.x : i == 1 ? a.y : i == 2 ? a.z : a.w;
-              }
+            for (int jj = 0; jj < 4; ++jj) {
+              const float4 a = za[h][jj];
+              const float4 v0 = er[0][h], v1 = er[1][h], v2 = er[2][h], v3 = er[3][h];
+              const float e0 = jj == 0 ? v0.x : jj == 1 ? v0.y : jj == 2 ? v0.z : v0.w;
+              const float e1 = jj == 0 ? v1.x : jj == 1 ? v1.y : jj == 2 ? v1.z : v1.w;
+              const float e2 = jj == 0 ? v2.x : jj == 1 ? v2.y : jj == 2 ? v2.z : v2.w;
+              const float e3 = jj == 0 ? v3.x : jj == 1 ? v3.y : jj == 2 ? v3.z : v3.w;
+              const float d0 = __fsub_rn(e0, a.x), d1 = __fsub_rn(e1, a.y), d2 = __fsub_rn(e2, a.z),
+                          d3 = __fsub_rn(e3, a.w);
+              sts128(zb + zoff[jj] + h * 16384,
+                     make_float4(__fadd_rn(a.x, d0), __fadd_rn(a.y, d1), __fadd_rn(a.z, d2), __fadd_rn(a.w, d3)));
+              sq = fmaf(d0, d0, sq); sq = fmaf(d1, d1, sq); sq = fmaf(d2, d2, sq); sq = fmaf(d3, d3, sq);
             }
-            zg[h] = rotl(make_float4(v[0], v[1], v[2], v[3]), (4 - rot) & 3);   // back to channel order
-#pragma unroll
-            for (int jj = 0; jj < 4; ++jj) zz = __fadd_rn(zz, __fmul_rn(v[jj], v[jj]));
           }
-          zz = warp_sum(zz);
-          auto dot = [&](const float4 (&r)[NH]) {
-            float dp = 0.f;
-#pragma unroll
-            for (int h = 0; h < NH; ++h) {
-              dp = fmaf(zg[h].x, r[h].x, dp); dp = fmaf(zg[h].y, r[h].y, dp);
-              dp = fmaf(zg[h].z, r[h].z, dp); dp = fmaf(zg[h].w, r[h].w, dp);
-            }
-            return warp_sum(dp);
-          };
-          float bd = FLT_MAX;
-          int kb = 0x7fffffff;
-          if (nc[i] > 1) {
-            ++n_rr;
-            bd = fmaf(-2.f, dot(er[i]), __fadd_rn(zz, __ldg(ee + bk[i])));
-            kb = bk[i];
-            const uint32_t ck = a_ck + (par * BM + r0 + i) * (CK_MAX * 2);
-#pragma unroll 1
-            for (int ci = 1; ci < nc[i]; ++ci) {
-              const int k0 = (int)lds_u16(ck + ci * 2);
-              float4 e0[NH];
-              load_row(e0, k0);
-              const float d0 = fmaf(-2.f, dot(e0), __fadd_rn(zz, __ldg(ee + k0)));
-              if (d0 < bd || (d0 == bd && k0 < kb)) {
-                bd = d0;
-                kb = k0;
-#pragma unroll
-                for (int h = 0; h < NH; ++h) er[i][h] = e0[h];
-              }
-            }
-          } else {
-            // whole-codebook scan (overflowed list or FP16-unsafe input; rare): two rows in flight
-            ++n_fs;
-#pragma unroll 1
-            for (int k = 0; k < K; k += 2) {
-              float4 e0[NH], e1[NH];
-              const int k1 = min(k + 1, K - 1);
-              load_row(e0, k);
-              load_row(e1, k1);
-              const float d0 = fmaf(-2.f, dot(e0), __fadd_rn(zz, __ldg(ee + k)));
-              const float d1 = fmaf(-2.f, dot(e1), __fadd_rn(zz, __ldg(ee + k1)));
-              if (d0 < bd || (d0 == bd && k < kb)) { bd = d0; kb = k; }
-              if (d1 < bd || (d1 == bd && k1 < kb)) { bd = d1; kb = k1; }
-            }
-            load_row(er[i], kb);
-          }
-          bk[i] = kb;
+          dsq += (double)sq;
         }
-        FZ_ACC(4);
-        // ---- z_q = z + (e - z) in place, loss partial
-        float sq = 0.f;
-        float4 za[NH][4];                             // all loads first: one round trip to shared memory per unit
-#pragma unroll
-        for (int h = 0; h < NH; ++h)
-#pragma unroll
-          for (int jj = 0; jj < 4; ++jj)
-            za[h][jj] = hv[h] ? lds128(zo[jj] + h * 16384) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-        for (int h = 0; h < NH; ++h) {
-          if (!hv[h]) continue;
-          const float4 v0 = rotl(er[0][h], rot), v1 = rotl(er[1][h], rot), v2 = rotl(er[2][h], rot),
-                       v3 = rotl(er[3][h], rot);      // visiting order
-#pragma unroll
-          for (int jj = 0; jj < 4; ++jj) {
-            const float4 a = za[h][jj];
-            const float e0 = jj == 0 ? v0.x : jj == 1 ? v0.y : jj == 2 ? v0.z : v0.w;
-            const float e1 = jj == 0 ? v1.x : jj == 1 ? v1.y : jj == 2 ? v1.z : v1.w;
-            const float e2 = jj == 0 ? v2.x : jj == 1 ? v2.y : jj == 2 ? v2.z : v2.w;
-            const float e3 = jj == 0 ? v3.x : jj == 1 ? v3.y : jj == 2 ? v3.z : v3.w;
-            const float d0 = __fsub_rn(e0, a.x), d1 = __fsub_rn(e1, a.y), d2 = __fsub_rn(e2, a.z),
-                        d3 = __fsub_rn(e3, a.w);
-            sts128(zo[jj] + h * 16384,
-                   make_float4(__fadd_rn(a.x, d0), __fadd_rn(a.y, d1), __fadd_rn(a.z, d2), __fadd_rn(a.w, d3)));
-            sq = fmaf(d0, d0, sq); sq = fmaf(d1, d1, sq); sq = fmaf(d2, d2, sq); sq = fmaf(d3, d3, sq);
-          }
+        fence_proxy_async();                          // generic-proxy writes of the stage -> visible to the TMA store
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(bar(Smem::BAR_F_DONE + st));
+          mbar_arrive(bar(Smem::BAR_C_EMPTY + par));
         }
-        dsq += (double)sq;
+        // (after the fence: the fence would otherwise wait for this global store as well)
+        if (live && lane < 4)
+          idx[t0 + lane] = (int64_t)(lane == 0 ? bk[0] : lane == 1 ? bk[1] : lane == 2 ? bk[2] : bk[3]);
+        FZ_ACC(5);
+        FZ_MARK(3 + it * 4);
       }
-      fence_proxy_async();                          // generic-proxy writes of the stage -> visible to the TMA store
-      __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(bar(Smem::BAR_F_DONE + st));
-        mbar_arrive(bar(Smem::BAR_C_EMPTY + par));
-      }
-      // (after the fence: the fence would otherwise wait for this global store as well)
-      if (live && lane < 4)
-        idx[t0 + lane] = (int64_t)(lane == 0 ? bk[0] : lane == 1 ? bk[1] : lane == 2 ? bk[2] : bk[3]);
-      FZ_ACC(5);
-      FZ_MARK(3 + it * 4);
     }
     FZ_PUT();
     // loss: one partial per consumer warp, summed in index order by vq_loss_finalize_kernel (deterministic)

@@ -27,7 +27,7 @@ namespace dcvic {
 __global__ void __launch_bounds__(256) vq_prepare_kernel(const float* __restrict__ E, int K, int D,
                                                           float* __restrict__ ee, float* __restrict__ scratch,
                                                           float* __restrict__ emax, __half* __restrict__ cb16,
-                                                          unsigned* __restrict__ counters) {
+                                                          float* __restrict__ eperm, unsigned* __restrict__ counters) {
   __shared__ float s_m[8];
   __shared__ float s_r[8];
   __shared__ int s_u[8];
@@ -51,6 +51,7 @@ __global__ void __launch_bounds__(256) vq_prepare_kernel(const float* __restrict
       const float dv = v - __half2float(hv);          // exact: the FP16 rounding residual of this element
       res = fmaf(dv, dv, res);
       if (cb16) cb16[at(c)] = hv;
+      if (eperm) eperm[(size_t)k * D + vq_eperm_dest(c)] = v;
     }
     acc = warp_sum(acc);
     res = warp_sum(res);
@@ -115,7 +116,7 @@ __global__ void __launch_bounds__(256) vq_prepare_kernel(const float* __restrict
 }
 
 int vq_prepare_codebook(const float* codebook, int K, int D, float* ee, float* scratch, float* emax, __half* cb16,
-                        unsigned* counters, cudaStream_t s) {
+                        float* eperm, unsigned* counters, cudaStream_t s) {
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(ceil_div_i(K, 8));
   cfg.blockDim = dim3(256);
@@ -125,7 +126,7 @@ int vq_prepare_codebook(const float* codebook, int K, int D, float* ee, float* s
   pdl[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = pdl;
   cfg.numAttrs = 1;
-  if (cudaLaunchKernelEx(&cfg, vq_prepare_kernel, codebook, K, D, ee, scratch, emax, cb16, counters) != cudaSuccess)
+  if (cudaLaunchKernelEx(&cfg, vq_prepare_kernel, codebook, K, D, ee, scratch, emax, cb16, eperm, counters) != cudaSuccess)
     return DCVIC_ERR_CUDA;
   return dcvic_launch_status();
 }
