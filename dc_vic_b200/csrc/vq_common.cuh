@@ -79,11 +79,13 @@ __host__ __device__ __forceinline__ float vq_margin(float zz, float emax) {
 // are exact in FP32 and their FP32 accumulation over D terms is off by at most D 2^-23 |z| |e_k|; the bound applies
 // to the maximum and to the candidate (x2).  On top: 4 ulps of the reference's own FP32 distance (so that every code
 // the reference's rounding could prefer is re-ranked; anything closer than that is a documented near-tie, 1e-6
-// relative being 8 ulps) and 2 % slack.  -|e|^2/2 is added exactly there.
+// relative being 8 ulps) and 2 % slack.
 __host__ __device__ __forceinline__ float vq_margin_measured(float zz, float dz2, float emax, float demax, int D) {
   const float nz = sqrtf(zz), dz = sqrtf(dz2) * 1.000001f;
+  // (+ the constant's way into the accumulator: three FP16 pieces, exact to 2^-25 + 2^-33 |e|^2/2, carried through
+  // e_dim / 16 + 1 FP32 accumulation steps at up to 2^-23 of |e|^2/2 each - x2, maximum and candidate)
   return 2.04f * (dz * (emax + demax) + nz * demax) + (float)D * 2.4e-7f * nz * emax + 4.8e-7f * (zz + emax * emax) +
-         1.0e-30f;
+         (float)(D / 16 + 1) * 1.2e-7f * emax * emax + 1.2e-7f;
 }
 
 // Upper bound of the chunk maximum stored in a list key.  The search keeps the top 25 bits of the FP32 chunk maximum

@@ -62,6 +62,8 @@ constexpr int NZ = DCVIC_FZ_NZ;     // conversion ring stages (8 KB each), a mul
                                     // same converter warp, which therefore meets its barrier phases in order
 constexpr int NF = DCVIC_FZ_NF;     // finish ring stages (e_dim * 128 B each)
 constexpr int B_CHUNK = (BN / 2) * BK * 2;   // 8 KB: this CTA's 64 codes x 64 channels
+constexpr int BP_BYTES = (BN / 2) * 16;      // 1 KB: 64 codes x 8 FP16 (the three pieces of -|e|^2/2 and five zeros)
+constexpr int AP_BYTES = 256;                // two 8-row core matrices: [1, 1, 1, 0 x 5] per row, and zeros
 constexpr int Z_STAGE = BK * GT * 4;         // 8 KB
 constexpr int NT_MAX = 8;          // N-tiles per tile: one flag-mask slot per (token, column quarter, N-tile)
 constexpr int CK_MAX = 16;         // candidate codes per token after compaction; more -> whole-codebook scan
@@ -91,9 +93,11 @@ struct Smem {
   // an N-tile's codebook slab = KC channel chunks, brought by two 3-D boxes: chunks [0, nA) and [nA, KC); a ring
   // stage holds the larger one
   __host__ __device__ static constexpr int b_chunks_a(int D) { return (D / BK + 1) / 2; }
-  __host__ __device__ static constexpr int b_stage(int D) { return b_chunks_a(D) * B_CHUNK; }
-  __host__ __device__ static constexpr int off_bias(int D) { return off_b(D) + NB * b_stage(D); }          // [MAX_K] float
-  __host__ __device__ static constexpr int off_list(int D) { return off_bias(D) + MAX_K * 4; }             // [4][NT_MAX][BM] u32
+  // ... followed by BP_BYTES for this CTA's 64 codes of the N-tile's -|e|^2/2 operand (see the MMA issuer)
+  __host__ __device__ static constexpr int b_slab(int D) { return b_chunks_a(D) * B_CHUNK; }
+  __host__ __device__ static constexpr int b_stage(int D) { return b_slab(D) + BP_BYTES; }
+  __host__ __device__ static constexpr int off_ap(int D) { return off_b(D) + NB * b_stage(D); }            // the ones operand
+  __host__ __device__ static constexpr int off_list(int D) { return off_ap(D) + AP_BYTES; }                // [4][NT_MAX][BM] u32
   __host__ __device__ static constexpr int off_ck(int D) { return off_list(D) + BM * 4 * NT_MAX * 4; }      // [2][BM][CK_MAX] u16
   __host__ __device__ static constexpr int off_nc(int D) { return off_ck(D) + 2 * BM * CK_MAX * 2; }        // [2][BM] int
   __host__ __device__ static constexpr int off_zz(int D) { return off_nc(D) + 2 * BM * 4; }                 // [2][BM] float
@@ -242,10 +246,28 @@ __device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64
       : "memory");
 }
 
+// D[tmem] (+)= A[smem] . B[smem]^T
+__device__ __forceinline__ void umma_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(kIdesc), "r"(accumulate)
+      : "memory");
+}
+// Shared-memory descriptor of an un-swizzled K-major operand: core matrices of 8 rows x 16 bytes (128 contiguous
+// bytes), `lbo` bytes between the two core matrices of a K = 16 step, `sbo` bytes between 8-row groups
+// (validated, strides of 0 included, by tools/probe_ts_mma.cu).
+__device__ __forceinline__ uint64_t umma_desc_none(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
+  return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) |
+         (1ull << 46);
+}
+
 template <int D>
 __global__ void __launch_bounds__(NTHREADS, 1)
 vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant__ CUtensorMap tm_cb2,
-                const __grid_constant__ CUtensorMap tm_zc,
+                const __grid_constant__ CUtensorMap tm_bp, const __grid_constant__ CUtensorMap tm_zc,
                 const __grid_constant__ CUtensorMap tm_zf, const __grid_constant__ CUtensorMap tm_zq,
                 const float* __restrict__ Ep, const float* __restrict__ ee, const float* __restrict__ emax_ptr, int N,
                 int HW, int K, int num_ptiles, int wait_first,
@@ -255,6 +277,7 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant
   constexpr int F_STAGE = D * 128;           // finish stage: [D channels][32 tokens] FP32
   constexpr int NA = Smem::b_chunks_a(D);    // chunks in the first box of an N-tile's slab, KC - NA in the second
   constexpr int B_STAGE = Smem::b_stage(D);
+  constexpr int B_SLAB = Smem::b_slab(D);
   constexpr int OFF_B = Smem::off_b(D);
   constexpr int NH = (D + 127) / 128;        // 128-channel blocks (consumer lanes hold 4 channels of each)
   extern __shared__ uint8_t smem_raw[];
@@ -263,7 +286,7 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant
   const uint32_t bar0 = sbase + Smem::off_bar(D);
   auto bar = [&](int slot) { return bar0 + slot * 8; };
   // shared-space addresses of the bookkeeping arrays (see lds_u32 above)
-  const uint32_t a_bias = sbase + Smem::off_bias(D);   // [MAX_K] float: -|e|^2/2
+  const uint32_t a_ap = sbase + Smem::off_ap(D);       // ones operand of the -|e|^2/2 K-step
   const uint32_t a_mask = sbase + Smem::off_list(D);   // [4 quarters][NT_MAX][BM] u32 flag masks
   const uint32_t a_ck = sbase + Smem::off_ck(D);       // [2][BM][CK_MAX] u16 candidate codes
   const uint32_t a_nc = sbase + Smem::off_nc(D);       // [2][BM] candidate counters
@@ -300,6 +323,12 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant
     for (int s = 0; s < NF; ++s) { mbar_init(bar(Smem::BAR_F_FULL + s), 1); mbar_init(bar(Smem::BAR_F_DONE + s), 8); }
     fence_barrier_init();
   }
+  // ones operand: core matrix 0 = 8 rows of FP16 [1, 1, 1, 0, 0, 0, 0, 0], core matrix 1 = zeros
+  if (threadIdx.x < AP_BYTES / 4) {
+    const int w = threadIdx.x & 3;                   // 32-bit word of a 16-byte row
+    sts_u32(a_ap + threadIdx.x * 4, threadIdx.x >= 32 ? 0u : w == 0 ? 0x3C003C00u : w == 1 ? 0x00003C00u : 0u);
+  }
+  fence_proxy_async();                               // the MMA reads it through the async proxy
   if (threadIdx.x < 2 * BM) sts_u32(a_nc + threadIdx.x * 4, 0u);     // candidate counters (atomic appends; the consumers re-zero them)
   if (warp == W_MMA) {
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + Smem::off_tmem(D)),
@@ -332,6 +361,7 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant
         // codebook (a request costs the issuing thread ~235 cycles whatever its size - tools/probe_tma.cu -, so 8 KB
         // boxes could not feed an MMA that eats one every 218 cycles)
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_cb2) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_bp) : "memory");
         for (int it = 0; it < my_tiles; ++it)
           for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
@@ -341,7 +371,14 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant
               mbar_wait(bar(Smem::BAR_B_EMPTY + stage), phase ^ 1);
               FZ_ACC(1);
               const int nch = part == 0 ? NA : KC - NA;
-              if (leader) mbar_arrive_expect_tx(bar(Smem::BAR_B_FULL + stage), 2 * nch * B_CHUNK);
+              if (leader)
+                mbar_arrive_expect_tx(bar(Smem::BAR_B_FULL + stage), 2 * (nch * B_CHUNK + (part == 0 ? BP_BYTES : 0)));
+              if (part == 0)       // this CTA's 64 codes of the N-tile's -|e|^2/2 operand: 16-byte rows, un-swizzled
+                asm volatile(
+                    "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, "
+                    "{%2, %3}], [%4];" ::"r"(sbase + OFF_B + stage * B_STAGE + B_SLAB),
+                    "l"(&tm_bp), "r"(0), "r"(nt * BN + (int)rank * (BN / 2)), "r"(leader_bar(Smem::BAR_B_FULL + stage))
+                    : "memory");
               asm volatile(
                   "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, "
                   "{%2, %3, %4}], [%5];" ::"r"(sbase + OFF_B + stage * B_STAGE),
@@ -439,6 +476,8 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant
       // fewest instructions per MMA (descriptors advance by constants, channel chunks unrolled, one divergent region
       // per codebook box).
       const uint64_t bd_ring = umma_desc_sw128(sbase + OFF_B);     // stage 0; a stage further: + B_STAGE / 16
+      const uint64_t bp_ring = umma_desc_none(sbase + OFF_B + B_SLAB, 0, 128);
+      const uint64_t ad_ones = umma_desc_none(a_ap, 128, 0);
       int stage = 0;
       uint32_t phase = 0;
       uint32_t g = 0;
@@ -473,11 +512,16 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant
             tc_fence_after();
             if (issuer) {
               const uint64_t bds = bd_ring + (uint64_t)(uint32_t)(stage * (B_STAGE >> 4));
+              // The N-tile's first MMA overwrites the buffer with -|e_k|^2/2 for every row: a K = 16 step in the SS
+              // form, ones operand [1, 1, 1, 0 ...] x the three FP16 pieces of the constant (un-swizzled K-major
+              // operands; a stride of 0 makes every 8-row group read the same core matrix, and the codes' second core
+              // matrix - whatever it holds - meets the ones operand's zeros).  The epilogue pays nothing for it.
+              if (part == 0) umma_ss(d, ad_ones, bp_ring + (uint64_t)(uint32_t)(stage * (B_STAGE >> 4)), rt_zero);
 #pragma unroll
               for (int c = c0; c < c1; ++c) {
                 const uint64_t bd = bds + (uint64_t)((c - c0) * (B_CHUNK >> 4));
                 const uint32_t a = a0 + c * (BK / 2);
-                umma_ts(d, a, bd, c == 0 ? rt_zero : rt_one);     // the N-tile's first MMA overwrites the buffer
+                umma_ts(d, a, bd, rt_one);
                 umma_ts(d, a + 8, bd + 2, rt_one);
                 umma_ts(d, a + 16, bd + 4, rt_one);
                 umma_ts(d, a + 24, bd + 6, rt_one);
@@ -572,21 +616,6 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant
     const float emax = emax_ptr[0];
     const bool cb_unsafe = __float_as_uint(emax_ptr[1]) != 0u;
     const float demax = emax_ptr[2];
-    for (int k = threadIdx.x - W_EPI0 * 32; k < K; k += NEPI * 32)
-      sts_u32(a_bias + k * 4, __float_as_uint(-0.5f * ee[k]));     // exact
-    named_bar_sync(5, NEPI * 32);
-    const uint32_t bias_base = a_bias + q * kChunk * 4;
-    // scores of one 32-code chunk += -|e|^2/2 of its codes (the same 32 values for every row: broadcast loads)
-    auto add_bias = [&](uint32_t (&r)[32], uint32_t a) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float4 b = lds128(a + i * 16);
-        r[4 * i] = __float_as_uint(__fadd_rn(__uint_as_float(r[4 * i]), b.x));
-        r[4 * i + 1] = __float_as_uint(__fadd_rn(__uint_as_float(r[4 * i + 1]), b.y));
-        r[4 * i + 2] = __float_as_uint(__fadd_rn(__uint_as_float(r[4 * i + 2]), b.z));
-        r[4 * i + 3] = __float_as_uint(__fadd_rn(__uint_as_float(r[4 * i + 3]), b.w));
-      }
-    };
     // The flag mask of (row, quarter q, N-tile nt) lives at a_mask + ((q * NT_MAX + nt) * BM + row) * 4: ONE writer and
     // one reader, this thread; the 32 rows of a warp are 32 consecutive words.  `live` says which slots count.
     const uint32_t my_mask = a_mask + ((q * NT_MAX) * BM + row) * 4;
@@ -620,9 +649,6 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(leader_bar(Smem::BAR_T_EMPTY + buf));
         FZ_ACC(3);
-#if !defined(DCVIC_FZ_EXP) || DCVIC_FZ_EXP != 2      // (timing experiments only: results are wrong with DCVIC_FZ_EXP set)
-        add_bias(ra, bias_base + nt * (BN * 4));
-#endif
         FZ_ACC(4);
         float cm;
         const float m_old = m;
@@ -885,7 +911,7 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant
         if (live && lane < 4)
           idx[t0 + lane] = (int64_t)(lane == 0 ? bk[0] : lane == 1 ? bk[1] : lane == 2 ? bk[2] : bk[3]);
         FZ_ACC(5);
-        FZ_MARK(3 + it * 4);
+        if ((u & 31) >= 24) FZ_MARK(3 + it * 4);     // (the tile's last eight units; a mark per unit perturbs)
       }
     }
     FZ_PUT();
@@ -964,7 +990,7 @@ static bool map_2d(CUtensorMap* tm, CUtensorMapDataType dt, int esize, const voi
 }
 
 template <int D>
-static int launch(const CUtensorMap& tcb, const CUtensorMap& tcb2, const CUtensorMap& tzc, const CUtensorMap& tzf, const CUtensorMap& tzq,
+static int launch(const CUtensorMap& tcb, const CUtensorMap& tcb2, const CUtensorMap& tbp, const CUtensorMap& tzc, const CUtensorMap& tzf, const CUtensorMap& tzq,
                   const float* E, const float* ee, const float* emax, int N, int HW, int K,
                   int wait_first, float beta, int legacy, int64_t* idx, float* loss, double* partials,
                   unsigned* counters, cudaStream_t s) {
@@ -992,7 +1018,7 @@ static int launch(const CUtensorMap& tcb, const CUtensorMap& tcb2, const CUtenso
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 2;
-  if (cudaLaunchKernelEx(&cfg, vq_fused_kernel<D>, tcb, tcb2, tzc, tzf, tzq, E, ee, emax, N, HW, K, num_ptiles,
+  if (cudaLaunchKernelEx(&cfg, vq_fused_kernel<D>, tcb, tcb2, tbp, tzc, tzf, tzq, E, ee, emax, N, HW, K, num_ptiles,
                          wait_first, beta, legacy, idx, loss, partials, counters) != cudaSuccess)
     return DCVIC_ERR_CUDA;
   return dcvic_launch_status();
@@ -1033,7 +1059,7 @@ int vq_fused_forward(const float* z, const float* E, const float* ee, const floa
                      const __half* cb16, int B, int D, int HW, int K, bool after_prepare, float beta, int legacy,
                      float* zq, int64_t* idx, float* loss, double* partials, unsigned* counters, cudaStream_t s) {
   using namespace fz;
-  CUtensorMap tcb, tcb2, tzc, tzf, tzq;
+  CUtensorMap tcb, tcb2, tbp, tzc, tzf, tzq;
   const int N = B * HW;
   {
     EncodeTiledFn encode = encode_fn();
@@ -1052,6 +1078,19 @@ int vq_fused_forward(const float* z, const float* E, const float* ee, const floa
         return DCVIC_ERR_CUDA;
     }
   }
+  {
+    // -|e|^2/2 operand: the first 8 FP16 of every code's row of the pad chunk (chunk e_dim / 64 of the chunk-major
+    // codebook: the prepare kernel's three-way split and zeros), 64 codes per box, 16-byte rows, no swizzle
+    EncodeTiledFn encode = encode_fn();
+    const cuuint64_t gdim[2] = {8, (cuuint64_t)K};
+    const cuuint64_t gstride[1] = {(cuuint64_t)BK * 2};
+    const cuuint32_t box[2] = {8, (cuuint32_t)(BN / 2)};
+    const cuuint32_t estr[2] = {1, 1};
+    if (encode(&tbp, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(cb16) + (size_t)(D / BK) * K * BK, gdim,
+               gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return DCVIC_ERR_CUDA;
+  }
   if (!map_2d(&tzc, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, z, (uint64_t)HW, (uint64_t)B * D, (uint64_t)HW * 4, GT, BK) ||
       !map_2d(&tzf, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, z, (uint64_t)HW, (uint64_t)B * D, (uint64_t)HW * 4, GT, D) ||
       !map_2d(&tzq, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, zq, (uint64_t)HW, (uint64_t)B * D, (uint64_t)HW * 4, GT, D))
@@ -1059,7 +1098,7 @@ int vq_fused_forward(const float* z, const float* E, const float* ee, const floa
   const int wait_first = after_prepare ? 0 : 1;
   int rc;
 #define DCVIC_FZ(DD) \
-  launch<DD>(tcb, tcb2, tzc, tzf, tzq, E, ee, emax, N, HW, K, wait_first, beta, legacy, idx, loss, partials, counters, s)
+  launch<DD>(tcb, tcb2, tbp, tzc, tzf, tzq, E, ee, emax, N, HW, K, wait_first, beta, legacy, idx, loss, partials, counters, s)
   switch (D) {
     case 64: rc = DCVIC_FZ(64); break;
     case 128: rc = DCVIC_FZ(128); break;

@@ -73,7 +73,7 @@ __device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64
 
 __global__ void __launch_bounds__(128, 1)
 probe_kernel(const __half* __restrict__ A /* [256][K] */, const __half* __restrict__ B /* [N][K] */,
-             float* __restrict__ D /* [256][N] */) {
+             float* __restrict__ D /* [256][N] */, int mode) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   __shared__ __align__(8) unsigned long long s_bar;
@@ -100,6 +100,23 @@ probe_kernel(const __half* __restrict__ A /* [256][K] */, const __half* __restri
     const uint4 v = *reinterpret_cast<const uint4*>(B + (size_t)(rank * 64 + row) * K + piece * 8);
     *reinterpret_cast<uint4*>(smem + row * 128 + ((piece ^ (row & 7)) << 4)) = v;
   }
+  // mode 1 / 2: a per-column constant c[n] = h + m + l enters the accumulator through ONE extra K = 16 step in the SS
+  // form with un-swizzled K-major operands (core matrix = 8 rows x 16 bytes, contiguous): B' row n = [h, m, l, 0 x 13],
+  // A' row = [1, 1, 1, 0 x 13] for every row - mode 1 keeps ONE 8-row core matrix and a stride of 0 between 8-row groups.
+  if (mode) {
+    __half* bp = reinterpret_cast<__half*>(smem + 8192);          // B' k-core 0: 64 rows x 8 halves, then 1 KB of zeros
+    for (int i = threadIdx.x; i < 64 * 8 * 2; i += 128) {
+      const int row = (i >> 3) & 63, col = i & 7, n = rank * 64 + row;
+      float v = 0.f;
+      if (i < 64 * 8) v = col == 0 ? (float)(n % 5 - 2) : col == 1 ? (float)(n % 3) : col == 2 ? 1.f : 0.f;
+      bp[i] = __float2half(v);
+    }
+    __half* ap = reinterpret_cast<__half*>(smem + 12288);         // A' k-core 0 (8 or 128 rows), zeros from + 2048
+    for (int i = threadIdx.x; i < 128 * 8 * 2; i += 128) {
+      const int col = i & 7;
+      ap[i] = __float2half(i < 128 * 8 && col < 3 ? 1.f : 0.f);
+    }
+  }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   // A: row = rank*128 + threadIdx.x -> TMEM lane threadIdx.x, columns tmem_a + c (channels 2c, 2c+1)
   {
@@ -121,8 +138,20 @@ probe_kernel(const __half* __restrict__ A /* [256][K] */, const __half* __restri
   if (rank == 0 && threadIdx.x == 0) {
     const uint64_t bd = umma_desc_sw128(smem_u32(smem));
     const uint32_t one = (gridDim.x > 0) ? 1u : 0u, zero = (gridDim.x > 100000) ? 1u : 0u;   // run-time values
+    if (mode) {
+      auto desc_none = [](uint32_t addr, uint32_t lbo, uint32_t sbo) {
+        return (uint64_t)((addr & 0x3FFFF) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) |
+               (1ull << 46);
+      };
+      // (mode 1: the codes' second core matrix is the first one again - stride 0 - and meets the zeros of A')
+      const uint64_t bpd = desc_none(smem_u32(smem) + 8192, mode == 1 ? 0 : 1024, 128);
+      const uint64_t apd = desc_none(smem_u32(smem) + 12288, 2048, mode == 1 ? 0 : 128);
+      asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                   "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+                   "l"(apd), "l"(bpd), "r"(kIdesc), "r"(zero) : "memory");
+    }
 #pragma unroll
-    for (int k = 0; k < K / 16; ++k) umma_ts(tmem_d, tmem_a + 8 * k, bd + 2 * k, k == 0 ? zero : one);
+    for (int k = 0; k < K / 16; ++k) umma_ts(tmem_d, tmem_a + 8 * k, bd + 2 * k, (k == 0 && !mode) ? zero : one);
     asm volatile(
         "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
             smem_u32(&s_bar)),
@@ -520,7 +549,8 @@ int main() {
   CK(cudaMemcpy(dA, hA, M * K * 2, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(dB, hB, N * K * 2, cudaMemcpyHostToDevice));
   CK(cudaMemset(dD, 0xFF, M * N * 4));
-  const int smem = 64 * 128 + 1024;
+  const int smem = 24 * 1024 + 1024;
+  CK(cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(2);
   cfg.blockDim = dim3(128);
@@ -532,17 +562,28 @@ int main() {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  CK(cudaLaunchKernelEx(&cfg, probe_kernel, (const __half*)dA, (const __half*)dB, dD));
-  CK(cudaDeviceSynchronize());
   float* out = (float*)malloc(M * N * 4);
-  CK(cudaMemcpy(out, dD, M * N * 4, cudaMemcpyDeviceToHost));
   int bad = 0;
-  for (int i = 0; i < M * N; ++i)
-    if (out[i] != ref[i]) {
-      if (bad < 8) printf("mismatch m=%d n=%d got %g want %g\n", i / N, i % N, out[i], ref[i]);
-      ++bad;
+  for (int mode = 0; mode < 3; ++mode) {
+    CK(cudaMemset(dD, 0xFF, M * N * 4));
+    CK(cudaLaunchKernelEx(&cfg, probe_kernel, (const __half*)dA, (const __half*)dB, dD, mode));
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(out, dD, M * N * 4, cudaMemcpyDeviceToHost));
+    int badm = 0;
+    for (int i = 0; i < M * N; ++i) {
+      const int n = i % N;
+      const float want = ref[i] + (mode ? (float)((n % 5 - 2) + (n % 3) + 1) : 0.f);
+      if (out[i] != want) {
+        if (badm < 4) printf("mode %d mismatch m=%d n=%d got %g want %g\n", mode, i / N, n, out[i], want);
+        ++badm;
+      }
     }
-  printf("TS-MMA cta_group::2 A-in-TMEM: %d mismatches of %d -> %s\n", bad, M * N, bad ? "FAIL" : "OK");
+    printf("TS-MMA cta_group::2 A-in-TMEM%s: %d mismatches of %d -> %s\n",
+           mode == 0 ? "" : mode == 1 ? " + column constant by an SS K-step (A' = one core matrix, SBO 0)"
+                                      : " + column constant by an SS K-step (A' = 128 rows)",
+           badm, M * N, badm ? "FAIL" : "OK");
+    if (mode == 0) bad = badm;
+  }
 
   unsigned long long* dT;
   uint32_t* dS;
