@@ -270,7 +270,7 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant
                 const __grid_constant__ CUtensorMap tm_bp, const __grid_constant__ CUtensorMap tm_zc,
                 const __grid_constant__ CUtensorMap tm_zf, const __grid_constant__ CUtensorMap tm_zq,
                 const float* __restrict__ Ep, const float* __restrict__ ee, const float* __restrict__ emax_ptr, int N,
-                int HW, int K, int num_ptiles, int wait_first,
+                int HW, int K, int num_gp, int wait_first,
                 float beta, int legacy, int64_t* __restrict__ idx, float* __restrict__ loss,
                 double* __restrict__ partials, unsigned* __restrict__ counters) {
   constexpr int KC = D / BK;                 // channel chunks per tile
@@ -300,10 +300,18 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant
   const bool leader = rank == 0;
   const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
   const int NT = K / BN;
-  const int my_tiles = pair < num_ptiles ? (num_ptiles - pair + npairs - 1) / npairs : 0;
-  // first token of this CTA's half of its it-th tile
-  // (< N + 2 * BM: 32-bit unsigned arithmetic throughout - the TMA / MMA warps live on 24 registers)
-  auto tile_token0 = [&](int it) { return ((uint32_t)(pair + it * npairs) * 2u + rank) * (uint32_t)BM; };
+  // Work split: the tokens go in "group pairs" of 64 (a group of 32 for either CTA), and CTA pair p takes the
+  // contiguous run of group pairs [p * num_gp / npairs, (p + 1) * num_gp / npairs): tiles of 4 group pairs, of which
+  // only the LAST may be partial.  Every pair gets the same work to within one group (whole 256-token tiles dealt
+  // round-robin left 34 of 74 pairs with a fourth tile on the headline shape and the other 40 idle meanwhile); in a
+  // partial tile the warps of the missing groups only keep the barriers going.
+  const int gp_lo = (int)((long long)pair * num_gp / npairs), gp_hi = (int)((long long)(pair + 1) * num_gp / npairs);
+  const int my_groups = gp_hi - gp_lo;               // groups of 32 tokens this CTA handles
+  const int my_tiles = (my_groups + NG - 1) / NG;
+  auto tile_groups = [&](int it) { return min(NG, my_groups - it * NG); };
+  // first token of this CTA's group g of its it-th tile
+  // (< N + 64: 32-bit unsigned arithmetic throughout - the TMA / MMA warps live on 24 registers)
+  auto group_token0 = [&](int it, int g) { return ((uint32_t)(gp_lo + it * NG + g) * 2u + rank) * (uint32_t)GT; };
   auto leader_bar = [&](int slot) { return map_to_cta(bar(slot), 0); };
 
   if (threadIdx.x == 0) {
@@ -393,20 +401,20 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant
       // ===================== conversion ring: z chunks [64 ch x 32 tokens], order (tile, chunk, group) ================
       if (lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_zc) : "memory");
-        int s = 0;
         FZ_TDECL;
         for (int it = 0; it < my_tiles; ++it) {
-          const uint32_t t0 = tile_token0(it);
+          const int ng = tile_groups(it);
 #pragma unroll 1
           for (int kc = 0; kc < KC; ++kc)
 #pragma unroll 1
-            for (int g = 0; g < NG; ++g, ++s) {
+            for (int g = 0; g < ng; ++g) {
+              const int s = (it * KC + kc) * NG + g;    // (the converters' numbering; a partial tile - the last - skips slots)
               const int st = s % NZ;
               FZ_DBG(2, s);
               FZ_T();
               mbar_wait(bar(Smem::BAR_Z_EMPTY + st), ((s / NZ) & 1) ^ 1);
               FZ_ACC(1);
-              const uint32_t tg = t0 + g * GT;          // (groups beyond N: out-of-bounds box, zero fill)
+              const uint32_t tg = group_token0(it, g);   // (a group beyond N: out-of-bounds box, zero fill)
               mbar_arrive_expect_tx(bar(Smem::BAR_Z_FULL + st), Z_STAGE);
               tma_load_2d_cta(sbase + Smem::OFF_Z + st * Z_STAGE, &tm_zc, (int)(tg % (uint32_t)HW),
                               (int)(tg / (uint32_t)HW) * D + kc * BK,
@@ -421,10 +429,10 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant
       if (lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_zf) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_zq) : "memory");
-        const int total = my_tiles * NG;
+        const int total = my_groups;
         FZ_TDECL;
         auto coords = [&](int j, int& x, int& y) {
-          const uint32_t tg = tile_token0(j / NG) + (j % NG) * GT;
+          const uint32_t tg = group_token0(j / NG, j % NG);
           x = (int)(tg % (uint32_t)HW);
           y = (int)(tg / (uint32_t)HW) * D;
         };
@@ -555,6 +563,14 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant
       FZ_ACC(1);
       FZ_MARK(1 + it * 4);
       tc_fence_after();
+      if (g >= tile_groups(it)) {                    // partial (last) tile: nothing to convert, the barriers still count us
+        if (lane == 0) {
+          for (int kc = 0; kc < KC; ++kc) mbar_arrive_cluster(leader_bar(Smem::BAR_A_FULL + abuf * 4 + kc));
+          mbar_arrive(bar(Smem::BAR_ZZ + abuf));
+          atoms_add(a_tmem + 4, 1u);
+        }
+        continue;
+      }
       float zz = 0.f, dz2 = 0.f;
 #pragma unroll 1
       for (int kc = 0; kc < KC; ++kc) {
@@ -623,7 +639,8 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant
     FZ_TDECL;
     for (int it = 0; it < my_tiles; ++it) {
       const int abuf = it & 1;
-      const bool valid = tile_token0(it) + row < (uint32_t)N;
+      const bool have = part < tile_groups(it);       // (partial tile: this lane quarter's group may be missing)
+      const bool valid = have && group_token0(it, part) + lane < (uint32_t)N;
       FZ_DBG(10, it);
       FZ_T();
       mbar_wait(bar(Smem::BAR_ZZ + abuf), (it >> 1) & 1);
@@ -640,6 +657,11 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant
         mbar_wait(bar(Smem::BAR_T_FULL + buf), (g >> 1) & 1);
         FZ_ACC(2);
         if (nt == 0) FZ_MARK(1 + it * 4);
+        if (!have) {                                   // nothing to read: hand the accumulator straight back
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(leader_bar(Smem::BAR_T_EMPTY + buf));
+          continue;
+        }
         tc_fence_after();
         uint32_t ra[32];
         TMEM_LD32(ra, tlane + buf * BN);
@@ -740,7 +762,7 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant
 #endif
     // (group, token quad) units are handed out in order through a shared counter: a warp that drew long re-ranks does
     // not hold up its CTA (a fixed quad per warp cost 25 us on inputs where every fifth token is re-ranked)
-    const int total_units = my_tiles * NG * 8;
+    const int total_units = my_groups * 8;
     for (;;) {
       {
         int u = 0;
@@ -760,7 +782,7 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj) zoff[jj] = zrow[jj] + (((uint32_t)cw ^ ((zrow[jj] >> 7) & 7u)) << 4);
         const int rq = g * GT + 4 * cw;              // first row (token of the CTA tile) of this unit
-        const uint32_t t0 = tile_token0(it) + rq;
+        const uint32_t t0 = group_token0(it, g) + 4 * cw;
 #if defined(DCVIC_FZ_EXP) && DCVIC_FZ_EXP >= 4
         const bool live = t0 > 0x7fffffffu;
 #else
@@ -823,29 +845,42 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant
 #pragma unroll
                 for (int jj = 0; jj < 4; ++jj) zz = __fadd_rn(zz, __fmul_rn(v[jj], v[jj]));
               }
-              zz = warp_sum(zz);
-              auto dot = [&](const float4 (&r)[NH]) {
+              auto part = [&](const float4 (&r)[NH]) {     // this lane's share of z . e
                 float dp = 0.f;
 #pragma unroll
                 for (int h = 0; h < NH; ++h) {
                   dp = fmaf(zg[h].x, r[h].x, dp); dp = fmaf(zg[h].y, r[h].y, dp);
                   dp = fmaf(zg[h].z, r[h].z, dp); dp = fmaf(zg[h].w, r[h].w, dp);
                 }
-                return warp_sum(dp);
+                return dp;
               };
+              auto dot = [&](const float4 (&r)[NH]) { return warp_sum(part(r)); };
               float bd = FLT_MAX;
               int kb = 0x7fffffff;
               if (nc[i] > 1) {
                 ++n_rr;
-                bd = fmaf(-2.f, dot(er[i]), __fadd_rn(zz, __ldg(ee + bk[i])));
+                // |z|^2 and the first two candidates' products go through the butterfly together (three dependent
+                // 5-step shuffle chains one after the other were most of a re-rank's latency)
+                const float ee_a = __ldg(ee + bk[i]), ee_b = __ldg(ee + k0);
+                float pa = part(er[i]), pb = part(e0);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                  zz += __shfl_xor_sync(0xffffffffu, zz, o);
+                  pa += __shfl_xor_sync(0xffffffffu, pa, o);
+                  pb += __shfl_xor_sync(0xffffffffu, pb, o);
+                }
+                bd = fmaf(-2.f, pa, __fadd_rn(zz, ee_a));
                 kb = bk[i];
 #pragma unroll 1
                 for (int ci = 1; ci < nc[i]; ++ci) {
+                  float d0;
                   if (ci > 1) {
                     k0 = (int)lds_u16(ck + ci * 2);
                     load_row(e0, k0);
+                    d0 = fmaf(-2.f, dot(e0), __fadd_rn(zz, __ldg(ee + k0)));
+                  } else {
+                    d0 = fmaf(-2.f, pb, __fadd_rn(zz, ee_b));
                   }
-                  const float d0 = fmaf(-2.f, dot(e0), __fadd_rn(zz, __ldg(ee + k0)));
                   if (d0 < bd || (d0 == bd && k0 < kb)) {
                     bd = d0;
                     kb = k0;
@@ -856,6 +891,7 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant
               } else {
                 // whole-codebook scan (FP16-unsafe input or more candidates than fit; rare): two rows in flight
                 ++n_fs;
+                zz = warp_sum(zz);
 #pragma unroll 1
                 for (int k = 0; k < K; k += 2) {
                   float4 e0[NH], e1[NH];
@@ -1001,9 +1037,9 @@ static int launch(const CUtensorMap& tcb, const CUtensorMap& tcb2, const CUtenso
       return DCVIC_ERR_CUDA;
     attr_set = true;
   }
-  const int num_ptiles = (N + 2 * BM - 1) / (2 * BM);
+  const int num_gp = (N + 2 * GT - 1) / (2 * GT);          // group pairs: 64 tokens, 32 for either CTA of a pair
   const int max_pairs = kNumSMs / 2;
-  const int npairs = num_ptiles < max_pairs ? num_ptiles : max_pairs;
+  const int npairs = num_gp < max_pairs ? num_gp : max_pairs;       // (small inputs: one group pair per CTA pair)
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(2 * npairs);
   cfg.blockDim = dim3(NTHREADS);
@@ -1018,7 +1054,7 @@ static int launch(const CUtensorMap& tcb, const CUtensorMap& tcb2, const CUtenso
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 2;
-  if (cudaLaunchKernelEx(&cfg, vq_fused_kernel<D>, tcb, tcb2, tbp, tzc, tzf, tzq, E, ee, emax, N, HW, K, num_ptiles,
+  if (cudaLaunchKernelEx(&cfg, vq_fused_kernel<D>, tcb, tcb2, tbp, tzc, tzf, tzq, E, ee, emax, N, HW, K, num_gp,
                          wait_first, beta, legacy, idx, loss, partials, counters) != cudaSuccess)
     return DCVIC_ERR_CUDA;
   return dcvic_launch_status();
