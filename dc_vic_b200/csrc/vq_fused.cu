@@ -78,10 +78,16 @@ constexpr int NWARPS = W_CONS0 + NCONS;
 constexpr int NTHREADS = NWARPS * 32;
 // registers: 32 warps launch with 64 each = the whole file, and setmaxnreg can only move registers WITHIN the launch
 // allocation (a total above it leaves the last warpgroup waiting for ever): TMA / MMA warps drop to 24, converters
-// to 40, the epilogue warps keep their 64, consumers take 96: 128 * (24 + 40 + 4 * 64 + 2 * 96) = 65,536
+// take 56 (at 40 their loop spilled and recomputed its swizzled addresses), the epilogue warps keep their 64,
+// consumers take 88: 128 * (24 + 56 + 4 * 64 + 2 * 88) = 65,536
 #define FZ_REGS_AUX 24
-#define FZ_REGS_CONV 40
-#define FZ_REGS_CONS 96
+#ifndef FZ_REGS_CONV
+#define FZ_REGS_CONV 56
+#endif
+#ifndef FZ_REGS_CONS
+#define FZ_REGS_CONS 88
+#endif
+static_assert(128 * (FZ_REGS_AUX + FZ_REGS_CONV + 4 * 64 + 2 * FZ_REGS_CONS) <= 65536, "register file");
 static_assert(NTHREADS == 1024, "register budget above assumes 32 warps");
 
 
@@ -194,9 +200,22 @@ constexpr int FZ_REC = 48;          // ints per warp: [0] progress, [1..6] cycle
   } while (0)
 #endif
 // time marks: the SM clock (low 32 bits) when a warp passes a point; tools/debug_fused.py draws the tile timeline
+#ifdef DCVIC_FZ_NO_CMARKS   // (tools/fused_span.py: wall-clock marks only)
+#define FZ_MARK(k)
+#else
 #define FZ_MARK(k)                                                                             \
   do {                                                                                         \
     if (g_fz_dbg && (threadIdx.x & 31) == 0 && (k) < 40) FZ_SLOT(8 + (k)) = (int)clock64();    \
+  } while (0)
+#endif
+// wall-clock marks (ns, low 32 bits of %globaltimer): comparable ACROSS SMs, unlike the SM clock
+#define FZ_GMARK(k)                                                                            \
+  do {                                                                                         \
+    if (g_fz_dbg && (threadIdx.x & 31) == 0) {                                                 \
+      unsigned long long t_;                                                                   \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                                   \
+      FZ_SLOT(8 + (k)) = (int)t_;                                                              \
+    }                                                                                          \
   } while (0)
 #ifdef DCVIC_FZ_MARKS_ONLY
 #define FZ_TDECL
@@ -226,6 +245,7 @@ constexpr int FZ_REC = 48;          // ints per warp: [0] progress, [1..6] cycle
 #else
 #define FZ_DBG(code, val)
 #define FZ_MARK(k)
+#define FZ_GMARK(k)
 #define FZ_TDECL
 #define FZ_T()
 #define FZ_ACC(k)
@@ -296,6 +316,7 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant
   const uint32_t a_tmem = sbase + Smem::off_tmem(D);   // [0] TMEM base, [1] tiles converted x 4, [2] next consumer unit
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  FZ_GMARK(33);                                      // kernel entry
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
   const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
@@ -348,12 +369,14 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant
   cluster_sync();
   tc_fence_after();
   FZ_MARK(0);
+  FZ_GMARK(34);                                      // set-up done
   const uint32_t tmem_base = lds_u32(a_tmem);
   // tensor memory: accumulators 2 x 128 columns | A operand 2 x 128 columns
   const uint32_t tmem_acc = tmem_base, tmem_a = tmem_base + 2 * BN;
   // PDL: see vq_tcgen05.cu.  wait_first: the predecessor in the stream may be the producer of z.
   if (wait_first) pdl_wait();
   pdl_launch_dependents();
+  FZ_GMARK(35);                                      // predecessor complete
 
   if (warp < 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(FZ_REGS_AUX));
@@ -379,6 +402,13 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant
               mbar_wait(bar(Smem::BAR_B_EMPTY + stage), phase ^ 1);
               FZ_ACC(1);
               const int nch = part == 0 ? NA : KC - NA;
+#ifdef DCVIC_FZ_HALFB   // experiment: half the codebook traffic (the second box is not loaded; wrong results)
+              if (part == 1) {
+                if (leader) mbar_arrive(bar(Smem::BAR_B_FULL + stage));
+                if (++stage == NB) { stage = 0; phase ^= 1; }
+                continue;
+              }
+#endif
               if (leader)
                 mbar_arrive_expect_tx(bar(Smem::BAR_B_FULL + stage), 2 * (nch * B_CHUNK + (part == 0 ? BP_BYTES : 0)));
               if (part == 0)       // this CTA's 64 codes of the N-tile's -|e|^2/2 operand: 16-byte rows, un-swizzled
@@ -414,7 +444,11 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant
               FZ_T();
               mbar_wait(bar(Smem::BAR_Z_EMPTY + st), ((s / NZ) & 1) ^ 1);
               FZ_ACC(1);
+#if defined(DCVIC_FZ_X) && (DCVIC_FZ_X & 4)   // experiment: conversion loads from L2 (one group, over and over)
+              const uint32_t tg = rank * (uint32_t)GT;
+#else
               const uint32_t tg = group_token0(it, g);   // (a group beyond N: out-of-bounds box, zero fill)
+#endif
               mbar_arrive_expect_tx(bar(Smem::BAR_Z_FULL + st), Z_STAGE);
               tma_load_2d_cta(sbase + Smem::OFF_Z + st * Z_STAGE, &tm_zc, (int)(tg % (uint32_t)HW),
                               (int)(tg / (uint32_t)HW) * D + kc * BK,
@@ -446,8 +480,12 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant
           FZ_ACC(1);
           int x, y;
           coords(j, x, y);
+#if defined(DCVIC_FZ_X) && (DCVIC_FZ_X & 2)   // experiment: no second read of z
+          mbar_arrive(bar(Smem::BAR_F_FULL + st));
+#else
           mbar_arrive_expect_tx(bar(Smem::BAR_F_FULL + st), F_STAGE);
           tma_load_2d_cta(sbase + Smem::OFF_F + st * F_STAGE, &tm_zf, x, y, bar(Smem::BAR_F_FULL + st));
+#endif
           if (j % NG == 0) FZ_MARK(1 + it * 4);
         };
         for (int j = 0; j < total && j < NF; ++j) load(j);
@@ -459,7 +497,9 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant
           FZ_ACC(2);
           int x, y;
           coords(j, x, y);
+#if !defined(DCVIC_FZ_X) || !(DCVIC_FZ_X & 1)  // (experiment bit 1: no z_q stores)
           tma_store_2d(&tm_zq, x, y, sbase + Smem::OFF_F + st * F_STAGE);
+#endif
           bulk_commit();
           if (j % NG == 0) FZ_MARK(2 + (j / NG) * 4);
           if (j % NG == NG - 1) FZ_MARK(3 + (j / NG) * 4);
@@ -674,7 +714,13 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant
         FZ_ACC(4);
         float cm;
         const float m_old = m;
+#ifdef DCVIC_FZ_EPIFREE   // experiment: what the kernel costs without the flag arithmetic (wrong results)
+        cm = __uint_as_float(ra[0] ^ ra[31]);
+        m = fmaxf(m, cm);
+        const uint32_t mask = nt == 0 ? 1u : 0u;
+#else
         const uint32_t mask = chunk_flags(ra, margin, m, cm);
+#endif
         // A flagged chunk's mask is kept.  When this chunk's maximum beats the previous running maximum by more than
         // the margin, every earlier mask is out of reach (all its scores are <= m_old) and is dropped.
         if (mask != 0u) {
@@ -807,9 +853,29 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant
         if (lane < 4) sts_u32(a_nc + (par * BM + rq + lane) * 4, 0u);  // for the tile after next (ordered by the C_EMPTY arrival below)
         const uint32_t zb = sbase + Smem::OFF_F + st * F_STAGE;
         float4 er[4][NH];
+        // Second candidates: the row of the quad's first re-ranked token is requested together with the first
+        // candidates' rows (and the |e|^2 values with them); inside the re-rank loop every token requests its
+        // successor's before it reduces its own - one L2 round trip per unit instead of one per re-ranked token.
+        const uint32_t ck0 = a_ck + (par * BM + rq) * (CK_MAX * 2);
+        int jr = -1;
+#pragma unroll
+        for (int i = 3; i >= 0; --i)
+          if (nc[i] > 1) jr = i;
+        float4 e2[NH];
+        int k2 = 0;
+        float ee1[4] = {0.f, 0.f, 0.f, 0.f}, ee2 = 0.f;
+#pragma unroll
+        for (int h = 0; h < NH; ++h) e2[h] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (live) {
 #pragma unroll
           for (int i = 0; i < 4; ++i) load_row(er[i], bk[i]);
+          if (jr >= 0) {
+            k2 = (int)lds_u16(ck0 + jr * (CK_MAX * 2) + 2);
+            load_row(e2, k2);
+            ee2 = __ldg(ee + k2);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) ee1[i] = __ldg(ee + bk[i]);
+          }
         }
         FZ_DBG(16, j);
         FZ_ACC(2);
@@ -821,13 +887,23 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               if (nc[i] == 1) continue;
-              // the second candidate's row is requested before the token's z is read (most re-ranks have two)
-              const uint32_t ck = a_ck + (par * BM + rq + i) * (CK_MAX * 2);
-              float4 e0[NH];
-              int k0 = 0;
+              const uint32_t ck = ck0 + i * (CK_MAX * 2);
+              // (e2, k2, ee2 hold this token's second candidate.)  The next re-ranked token's is requested now:
+              int jn = -1;
+              float4 e2n[NH];
+              int k2n = 0;
+              float ee2n = 0.f;
+#pragma unroll
+              for (int h = 0; h < NH; ++h) e2n[h] = make_float4(0.f, 0.f, 0.f, 0.f);
               if (nc[i] > 1) {
-                k0 = (int)lds_u16(ck + 2);
-                load_row(e0, k0);
+#pragma unroll
+                for (int t = 3; t > i; --t)
+                  if (nc[t] > 1) jn = t;
+                if (jn >= 0) {
+                  k2n = (int)lds_u16(ck0 + jn * (CK_MAX * 2) + 2);
+                  load_row(e2n, k2n);
+                  ee2n = __ldg(ee + k2n);
+                }
               }
               float4 zg[NH];                           // this token's z in visiting order
               float zz = 0.f;
@@ -861,32 +937,42 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant
                 ++n_rr;
                 // |z|^2 and the first two candidates' products go through the butterfly together (three dependent
                 // 5-step shuffle chains one after the other were most of a re-rank's latency)
-                const float ee_a = __ldg(ee + bk[i]), ee_b = __ldg(ee + k0);
-                float pa = part(er[i]), pb = part(e0);
+                float pa = part(er[i]), pb = part(e2);
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) {
                   zz += __shfl_xor_sync(0xffffffffu, zz, o);
                   pa += __shfl_xor_sync(0xffffffffu, pa, o);
                   pb += __shfl_xor_sync(0xffffffffu, pb, o);
                 }
-                bd = fmaf(-2.f, pa, __fadd_rn(zz, ee_a));
+                bd = fmaf(-2.f, pa, __fadd_rn(zz, ee1[i]));
                 kb = bk[i];
-#pragma unroll 1
-                for (int ci = 1; ci < nc[i]; ++ci) {
-                  float d0;
-                  if (ci > 1) {
-                    k0 = (int)lds_u16(ck + ci * 2);
-                    load_row(e0, k0);
-                    d0 = fmaf(-2.f, dot(e0), __fadd_rn(zz, __ldg(ee + k0)));
-                  } else {
-                    d0 = fmaf(-2.f, pb, __fadd_rn(zz, ee_b));
+                {
+                  const float d0 = fmaf(-2.f, pb, __fadd_rn(zz, ee2));
+                  if (d0 < bd || (d0 == bd && k2 < kb)) {
+                    bd = d0;
+                    kb = k2;
+#pragma unroll
+                    for (int h = 0; h < NH; ++h) er[i][h] = e2[h];
                   }
+                }
+#pragma unroll 1
+                for (int ci = 2; ci < nc[i]; ++ci) {
+                  float4 e0[NH];
+                  const int k0 = (int)lds_u16(ck + ci * 2);
+                  load_row(e0, k0);
+                  const float d0 = fmaf(-2.f, dot(e0), __fadd_rn(zz, __ldg(ee + k0)));
                   if (d0 < bd || (d0 == bd && k0 < kb)) {
                     bd = d0;
                     kb = k0;
 #pragma unroll
                     for (int h = 0; h < NH; ++h) er[i][h] = e0[h];
                   }
+                }
+                if (jn >= 0) {
+                  k2 = k2n;
+                  ee2 = ee2n;
+#pragma unroll
+                  for (int h = 0; h < NH; ++h) e2[h] = e2n[h];
                 }
               } else {
                 // whole-codebook scan (FP16-unsafe input or more candidates than fit; rare): two rows in flight
@@ -964,6 +1050,7 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant
 
   FZ_DBG(30, 0);
   FZ_MARK(39);
+  FZ_GMARK(36);                                      // role loop left
   tc_fence_before();
   __syncthreads();
   // Loss: the CTA that finishes last sums every consumer warp's partial in index order (deterministic) - one
@@ -990,6 +1077,7 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
   }
+  FZ_GMARK(37);                                      // kernel exit
 }
 
 // ------------------------------------------------------------------ host side
@@ -1039,7 +1127,18 @@ static int launch(const CUtensorMap& tcb, const CUtensorMap& tcb2, const CUtenso
   }
   const int num_gp = (N + 2 * GT - 1) / (2 * GT);          // group pairs: 64 tokens, 32 for either CTA of a pair
   const int max_pairs = kNumSMs / 2;
-  const int npairs = num_gp < max_pairs ? num_gp : max_pairs;       // (small inputs: one group pair per CTA pair)
+  int npairs = num_gp < max_pairs ? num_gp : max_pairs;             // (small inputs: one group pair per CTA pair)
+#ifdef DCVIC_FZ_WHOLE_TILES   // (measured: 57.6 us against 55.1 - the finish of a FULL last tile is a longer tail)
+  // A partial tile costs a whole pass over the codebook (MMA time and 0.5 MB of L2 traffic per CTA pair), and the
+  // kernel runs at the L2's throughput: with two or more tiles per pair, use the FEWEST pairs that keep the number of
+  // rounds (64 pairs x 4 whole tiles on the headline shape instead of 74 x (3 + a partial one): 256 codebook passes
+  // instead of 296).
+  {
+    const int gp_per_pair = (num_gp + max_pairs - 1) / max_pairs;
+    const int rounds = (gp_per_pair + NG - 1) / NG;
+    if (rounds >= 2) npairs = (num_gp + rounds * NG - 1) / (rounds * NG);
+  }
+#endif
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(2 * npairs);
   cfg.blockDim = dim3(NTHREADS);
