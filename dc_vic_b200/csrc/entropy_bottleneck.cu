@@ -201,6 +201,61 @@ __global__ void __launch_bounds__(kEbThreads) eb_forward_kernel(const float* __r
   }
 }
 
+// Evaluation mode (no noise): the input of the likelihood is round(x - med) + med, i.e. per channel a function of an
+// INTEGER.  The CTA evaluates the channel's likelihood once for the symbols -kEbTabR .. kEbTabR - 1 (one thread per
+// entry, the same arithmetic as the direct kernel, so every value is the one the direct kernel would produce) and
+// the latents become a table look-up: 12 B of HBM traffic and a handful of instructions per latent instead of 49
+// SFU operations (the direct kernel is bound by the SFU pipe at 0.12 of HBM).  Symbols outside the table (|x - med|
+// >= kEbTabR: far in the tails) are evaluated directly.  A CTA takes `chunk` consecutive float4 of its channel
+// (kEbTabPerThread per thread) so that building the table is < 1 % of its work.
+constexpr int kEbTabR = 64;
+constexpr int kEbTabPerThread = 16;
+__global__ void __launch_bounds__(kEbThreads) eb_forward_table_kernel(const float* __restrict__ x, EbParamPtrs P, int B,
+                                                                       int C, int HW, float lik_bound,
+                                                                       float* __restrict__ x_hat,
+                                                                       float* __restrict__ lik) {
+  __shared__ float sp[72];
+  __shared__ float tab[2 * kEbTabR];
+  const int c = blockIdx.y;
+  eb_load_params(P, c, sp);
+  __syncthreads();
+  const float med = sp[MED];
+  if (threadIdx.x < 2 * kEbTabR) {
+    const float outputs = __fadd_rn((float)((int)threadIdx.x - kEbTabR), med);
+    float lower, upper;
+    eb_logits_pair(sp, outputs, lower, upper);
+    tab[threadIdx.x] = fmaxf(eb_lik_fast(lower, upper), lik_bound);
+  }
+  __syncthreads();
+  const long long per_ch4 = (long long)B * HW / 4;               // float4 per channel (H*W % 4 == 0)
+  const int hw4 = HW / 4;
+  const long long q0 = (long long)blockIdx.x * (kEbThreads * kEbTabPerThread);
+#pragma unroll 4
+  for (int i = 0; i < kEbTabPerThread; ++i) {
+    const long long q = q0 + (long long)i * kEbThreads + threadIdx.x;
+    if (q >= per_ch4) break;
+    const long long b = q / hw4, p4 = q % hw4;
+    const size_t o = ((size_t)b * C + c) * HW + (size_t)p4 * 4;
+    const float4 v4 = ldg_stream(reinterpret_cast<const float4*>(x + o));
+    const float v[4] = {v4.x, v4.y, v4.z, v4.w};
+    float xh[4], lk[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float d = rintf(__fsub_rn(v[k], med));
+      xh[k] = __fadd_rn(d, med);
+      if (fabsf(d) < (float)kEbTabR) {                           // (NaN fails the test and takes the direct path)
+        lk[k] = tab[(int)d + kEbTabR];
+      } else {
+        float lower, upper;
+        eb_logits_pair(sp, xh[k], lower, upper);
+        lk[k] = fmaxf(eb_lik_fast(lower, upper), lik_bound);
+      }
+    }
+    if (lik) stg_stream(reinterpret_cast<float4*>(lik + o), make_float4(lk[0], lk[1], lk[2], lk[3]));
+    if (x_hat) stg_stream(reinterpret_cast<float4*>(x_hat + o), make_float4(xh[0], xh[1], xh[2], xh[3]));
+  }
+}
+
 // forward + backward through logits for one input, accumulating parameter grads (wrt the
 // TRANSFORMED params) into acc[58]; returns d out / d x * gout.
 __device__ __forceinline__ float eb_logits_backward(const float* sp, float x, float gout, float* acc) {
@@ -460,7 +515,11 @@ extern "C" int dcvic_eb_forward(const float* x, const float* noise, const float*
   dim3 grid(ceil_div_i(per_ch, kEbThreads * kEbPerThread), C);
   auto misaligned = [](const void* p) { return p && (reinterpret_cast<uintptr_t>(p) & 15) != 0; };
   const bool vec = HW % 4 == 0 && !misaligned(x) && !misaligned(noise) && !misaligned(x_hat) && !misaligned(lik);
-  if (vec)
+  // evaluation mode with enough latents per channel to pay for a table of 128 symbols per CTA: the look-up kernel
+  if (vec && !noise && lik && per_ch >= 16 * 2 * kEbTabR) {
+    dim3 tgrid(ceil_div_i(per_ch / 4, kEbThreads * kEbTabPerThread), C);
+    eb_forward_table_kernel<<<tgrid, kEbThreads, 0, (cudaStream_t)stream>>>(x, P, B, C, HW, lik_bound, x_hat, lik);
+  } else if (vec)
     eb_forward_kernel<4><<<grid, kEbThreads, 0, (cudaStream_t)stream>>>(x, noise, P, B, C, HW, lik_bound, x_hat_mode,
                                                                          x_hat, lik);
   else

@@ -704,8 +704,13 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant
         }
         tc_fence_after();
         uint32_t ra[32];
+#ifdef DCVIC_FZ_NOLD      // experiment: the pipeline without the accumulator read-out (TMEM read bandwidth)
+#pragma unroll
+        for (int i_ = 0; i_ < 32; ++i_) ra[i_] = (uint32_t)(g + i_);
+#else
         TMEM_LD32(ra, tlane + buf * BN);
         TMEM_WAIT_LD32(ra);
+#endif
         // every score of this warp's slice is in registers: the accumulator can be overwritten
         tc_fence_before();
         __syncwarp();
