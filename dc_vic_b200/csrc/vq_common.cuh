@@ -41,8 +41,9 @@ inline VqWorkspace vq_workspace_layout(int B, int D, int HW, int K) {
   w.off_ee = take((size_t)K * sizeof(float));
   w.off_nhee = take((size_t)K * sizeof(float));
   w.off_emax = take(4 * sizeof(float));
-  // loss partials: one per finish warp (4 tokens each), or 16 per persistent CTA of the TMA finish
-  w.off_partials = take((N / 4 + 8 + (size_t)kNumSMs * 16) * sizeof(double));
+  // loss partials: one per finish warp (4 tokens each), 16 per persistent CTA of the TMA finish, or 24 per CTA of the
+  // single-pass kernel (consumer warps + helping epilogue warps)
+  w.off_partials = take((N / 4 + 8 + (size_t)kNumSMs * 32) * sizeof(double));
   w.off_hist = take((size_t)K * sizeof(unsigned));
   w.off_cand = take(N * sizeof(int));
   w.off_meta = take(N * sizeof(VqMeta));

@@ -35,6 +35,8 @@
 #include <float.h>
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "vq_common.cuh"
 #include "sm100_ptx.cuh"
 
@@ -71,6 +73,7 @@ constexpr int MAX_K = NT_MAX * BN;  // -|e|^2/2 table and flag-mask slots in sha
                                     // two-kernel path)
 constexpr int NCONS = 8;
 constexpr int NEPI = 16;           // epilogue warps: 4 column quarters x 4 TMEM lane quarters
+constexpr int NFIN = NCONS + NEPI; // warps that may run the finish (loss partial slots per CTA)
 constexpr int kFullFlag = 1 << 16; // added to a token's candidate count: whole-codebook scan
 static_assert(NZ % NG == 0, "a conversion-ring stage must always belong to the same converter warp");
 constexpr int W_TMAB = 0, W_ZLOAD = 1, W_FIN = 2, W_MMA = 3, W_CONV0 = 4, W_EPI0 = 8, W_CONS0 = W_EPI0 + NEPI;
@@ -313,7 +316,7 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant
   const uint32_t a_zz = sbase + Smem::off_zz(D);       // [2][BM] |z|^2
   const uint32_t a_dz = sbase + Smem::off_dz(D);       // [2][BM] |z - fp16(z)|^2
   const uint32_t a_m = sbase + Smem::off_m(D);         // [BM][4] quarter maxima
-  const uint32_t a_tmem = sbase + Smem::off_tmem(D);   // [0] TMEM base, [1] tiles converted x 4, [2] next consumer unit
+  const uint32_t a_tmem = sbase + Smem::off_tmem(D);   // [0] TMEM base, [1] tiles converted x 4, [2] next consumer unit, [3] finish groups requested
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   FZ_GMARK(33);                                      // kernel entry
@@ -338,6 +341,7 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant
   if (threadIdx.x == 0) {
     sts_u32(a_tmem + 4, 0u);
     sts_u32(a_tmem + 8, 0u);
+    sts_u32(a_tmem + 12, 0u);
     for (int s = 0; s < NB; ++s) { mbar_init(bar(Smem::BAR_B_FULL + s), 1); mbar_init(bar(Smem::BAR_B_EMPTY + s), 1); }
     for (int s = 0; s < NZ; ++s) { mbar_init(bar(Smem::BAR_Z_FULL + s), 1); mbar_init(bar(Smem::BAR_Z_EMPTY + s), 1); }
     for (int c = 0; c < 8; ++c) mbar_init(bar(Smem::BAR_A_FULL + c), 2 * NG);
@@ -377,6 +381,320 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant
   if (wait_first) pdl_wait();
   pdl_launch_dependents();
   FZ_GMARK(35);                                      // predecessor complete
+
+  // ------------------------------------------------------------------------------------------------------------------
+  // The finish of (group, token quad) units drawn from a shared counter: FP32 re-rank of the tokens with more than one
+  // candidate, z + (e - z) in place in the finish stage, loss partial, indices.  The consumer warps run it with TOK = 4
+  // (the quad in one pass, 88 registers); the epilogue warps, once their own work is done, with TOK = 2 (two passes of
+  // two tokens each fit the 64 registers they have).
+  // Lane l holds 4 consecutive channels per 128-channel block (c = 4l + 128h) of the pass's tokens: one LDG.128 per
+  // codebook row and block, one LDS / STS per channel.  Lane l visits its 4 channels in the order (j + (l >> 1)) & 3 so
+  // that a quarter warp touches 8 different 16-byte pieces of the swizzled stage; the codebook copy it gathers from
+  // (Ep, written by the prepare kernel) has every group of four channels in exactly that order, so a row's float4
+  // pairs with the stage's values component by component.
+  auto consume = [&](auto tok_c, const int slot) {
+    constexpr int TOK = decltype(tok_c)::value;
+    constexpr int NPASS = 4 / TOK;
+    const int rot = (lane >> 1) & 3;
+    const bool hv[2] = {4 * lane < D, 4 * lane + 128 < D};
+    double dsq = 0.0;
+    unsigned n_rr = 0, n_fs = 0;
+    auto load_row = [&](float4 (&r)[NH], int k) {
+      const float* rowp = Ep + (size_t)k * D + 4 * lane;
+#pragma unroll
+      for (int h = 0; h < NH; ++h)
+        r[h] = hv[h] ? __ldg(reinterpret_cast<const float4*>(rowp + 128 * h)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+    auto comp = [](const float4& v, int jj) { return jj == 0 ? v.x : jj == 1 ? v.y : jj == 2 ? v.z : v.w; };
+    // the pass's TOK tokens of one channel: the quad's 16-byte piece, or one half of it
+    auto ldz = [&](uint32_t a, float (&v)[TOK]) {
+      if constexpr (TOK == 4) {
+        const float4 t = lds128(a);
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+      } else {
+        asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v[0]), "=f"(v[1]) : "r"(a));
+      }
+    };
+    auto stz = [&](uint32_t a, const float (&v)[TOK]) {
+      if constexpr (TOK == 4) {
+        sts128(a, make_float4(v[0], v[1], v[2], v[3]));
+      } else {
+        asm volatile("st.shared.v2.f32 [%0], {%1,%2};" ::"r"(a), "f"(v[0]), "f"(v[1]) : "memory");
+      }
+    };
+    // this lane's four channel rows of a finish stage (stage base and the quad's 16-byte piece added per unit)
+    uint32_t zrow[4];
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) zrow[jj] = (4 * lane + ((jj + rot) & 3)) * 128;
+    FZ_TDECL;
+#ifdef DCVIC_FZ_DEBUG
+    int fz_last_it = -1;
+#endif
+    // (group, token quad) units are handed out in order through a shared counter: a warp that drew long re-ranks does
+    // not hold up its CTA (a fixed quad per warp cost 25 us on inputs where every fifth token is re-ranked)
+    const int total_units = my_groups * 8;
+    for (;;) {
+      int u = 0;
+      if (lane == 0) u = (int)atoms_add(a_tmem + 8, 1u);
+      u = __shfl_sync(0xffffffffu, u, 0);
+      if (u >= total_units) break;
+      const int j = u >> 3, cw = u & 7;            // group (in this CTA's sequence), token quad inside it
+      const int it = j / NG, g = j % NG, par = it & 1, st = j % NF;
+      FZ_DBG(15, j);
+      FZ_T();
+      mbar_wait(bar(Smem::BAR_C_FULL + par), (it >> 1) & 1);
+      FZ_ACC(1);
+#ifdef DCVIC_FZ_DEBUG
+      if (it != fz_last_it) { FZ_MARK(1 + it * 4); fz_last_it = it; }
+#endif
+      uint32_t zoff[4];
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) zoff[jj] = zrow[jj] + (((uint32_t)cw ^ ((zrow[jj] >> 7) & 7u)) << 4);
+      const uint32_t tq = group_token0(it, g) + 4 * cw;
+#if defined(DCVIC_FZ_EXP) && DCVIC_FZ_EXP >= 4
+      const bool live = tq > 0x7fffffffu;
+#else
+      const bool live = tq < (uint32_t)N;          // (a quad is valid or invalid as a whole: N % 4 == 0)
+#endif
+      const uint32_t zb = sbase + Smem::OFF_F + st * F_STAGE;
+      int kfin[4] = {0, 0, 0, 0};
+#pragma unroll
+      for (int sub = 0; sub < NPASS; ++sub) {
+        const int rq = g * GT + 4 * cw + sub * TOK;     // first row (token of the CTA tile) of this pass
+        const uint32_t zsub = (uint32_t)(sub * TOK * 4);
+        int nc[TOK], bk[TOK];
+#pragma unroll
+        for (int i = 0; i < TOK; ++i) {
+          nc[i] = (int)lds_u32(a_nc + (par * BM + rq + i) * 4);
+          bk[i] = (int)lds_u16(a_ck + (par * BM + rq + i) * (CK_MAX * 2));
+          if (nc[i] <= 0 || nc[i] > CK_MAX) {        // flagged for a whole-codebook scan, too many candidates, or none
+            if (live && nc[i] == 0 && lane == 0) atomicAdd(counters + 8, 1u);
+            nc[i] = -1;
+            bk[i] = 0;
+          }
+        }
+#if defined(DCVIC_FZ_EXP) && DCVIC_FZ_EXP >= 3
+#pragma unroll
+        for (int i = 0; i < TOK; ++i) { nc[i] = 1; bk[i] = (rq + i) & 1023; }
+#endif
+        __syncwarp();
+        if (lane < TOK) sts_u32(a_nc + (par * BM + rq + lane) * 4, 0u);  // for the tile after next (ordered by the C_EMPTY arrival below)
+        float4 er[TOK][NH];
+        // Second candidates: the row of the pass's first re-ranked token is requested together with the first
+        // candidates' rows (and the |e|^2 values with them); inside the re-rank loop every token requests its
+        // successor's before it reduces its own - one L2 round trip per pass instead of one per re-ranked token.
+        const uint32_t ck0 = a_ck + (par * BM + rq) * (CK_MAX * 2);
+        int jr = -1;
+#pragma unroll
+        for (int i = TOK - 1; i >= 0; --i)
+          if (nc[i] > 1) jr = i;
+        float4 e2[NH];
+        int k2 = 0;
+        float ee1[TOK], ee2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < TOK; ++i) ee1[i] = 0.f;
+#pragma unroll
+        for (int h = 0; h < NH; ++h) e2[h] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (live) {
+#pragma unroll
+          for (int i = 0; i < TOK; ++i) load_row(er[i], bk[i]);
+          if (jr >= 0) {
+            k2 = (int)lds_u16(ck0 + jr * (CK_MAX * 2) + 2);
+            load_row(e2, k2);
+            ee2 = __ldg(ee + k2);
+#pragma unroll
+            for (int i = 0; i < TOK; ++i) ee1[i] = __ldg(ee + bk[i]);
+          }
+        }
+        if (sub == 0) {
+          FZ_DBG(16, j);
+          FZ_ACC(2);
+          // (With the 16 helper warps drawing units as well, one of 24 warps can be TWO rounds of the finish ring ahead
+          // of a straggler, where the barrier's parity repeats - it hung: first make sure this group's load has been
+          // requested at all, a monotonic count, then wait for its phase.  Eight warps cannot get that far ahead.)
+#ifdef DCVIC_FZ_HELPERS
+          while (lds_u32(a_tmem + 12) <= (uint32_t)j) __nanosleep(32);
+#endif
+          mbar_wait(bar(Smem::BAR_F_FULL + st), (j / NF) & 1);
+          FZ_ACC(3);
+          FZ_DBG(17, j);
+        }
+        if (live) {
+          bool any_rr = false;
+#pragma unroll
+          for (int i = 0; i < TOK; ++i) any_rr |= nc[i] != 1;
+          if (any_rr) {                                  // warp-uniform
+#pragma unroll
+            for (int i = 0; i < TOK; ++i) {
+              if (nc[i] == 1) continue;
+              const uint32_t ck = ck0 + i * (CK_MAX * 2);
+              // (e2, k2, ee2 hold this token's second candidate.)  The next re-ranked token's is requested now:
+              int jn = -1;
+              float4 e2n[NH];
+              int k2n = 0;
+              float ee2n = 0.f;
+#pragma unroll
+              for (int h = 0; h < NH; ++h) e2n[h] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (nc[i] > 1) {
+#pragma unroll
+                for (int t = TOK - 1; t > i; --t)
+                  if (nc[t] > 1) jn = t;
+                if (jn >= 0) {
+                  k2n = (int)lds_u16(ck0 + jn * (CK_MAX * 2) + 2);
+                  load_row(e2n, k2n);
+                  ee2n = __ldg(ee + k2n);
+                }
+              }
+              float4 zg[NH];                           // this token's z in visiting order
+              float zz = 0.f;
+#pragma unroll
+              for (int h = 0; h < NH; ++h) {
+                float v[4] = {0.f, 0.f, 0.f, 0.f};
+                if (hv[h]) {
+#pragma unroll
+                  for (int jj = 0; jj < 4; ++jj) {
+                    float t[TOK];
+                    ldz(zb + zoff[jj] + zsub + h * 16384, t);
+                    v[jj] = t[i];
+                  }
+                }
+                zg[h] = make_float4(v[0], v[1], v[2], v[3]);
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) zz = __fadd_rn(zz, __fmul_rn(v[jj], v[jj]));
+              }
+              auto part = [&](const float4 (&r)[NH]) {     // this lane's share of z . e
+                float dp = 0.f;
+#pragma unroll
+                for (int h = 0; h < NH; ++h) {
+                  dp = fmaf(zg[h].x, r[h].x, dp); dp = fmaf(zg[h].y, r[h].y, dp);
+                  dp = fmaf(zg[h].z, r[h].z, dp); dp = fmaf(zg[h].w, r[h].w, dp);
+                }
+                return dp;
+              };
+              auto dot = [&](const float4 (&r)[NH]) { return warp_sum(part(r)); };
+              float bd = FLT_MAX;
+              int kb = 0x7fffffff;
+              if (nc[i] > 1) {
+                ++n_rr;
+                // |z|^2 and the first two candidates' products go through the butterfly together (three dependent
+                // 5-step shuffle chains one after the other were most of a re-rank's latency)
+                float pa = part(er[i]), pb = part(e2);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                  zz += __shfl_xor_sync(0xffffffffu, zz, o);
+                  pa += __shfl_xor_sync(0xffffffffu, pa, o);
+                  pb += __shfl_xor_sync(0xffffffffu, pb, o);
+                }
+                bd = fmaf(-2.f, pa, __fadd_rn(zz, ee1[i]));
+                kb = bk[i];
+                {
+                  const float d0 = fmaf(-2.f, pb, __fadd_rn(zz, ee2));
+                  if (d0 < bd || (d0 == bd && k2 < kb)) {
+                    bd = d0;
+                    kb = k2;
+#pragma unroll
+                    for (int h = 0; h < NH; ++h) er[i][h] = e2[h];
+                  }
+                }
+#pragma unroll 1
+                for (int ci = 2; ci < nc[i]; ++ci) {
+                  float4 e0[NH];
+                  const int k0 = (int)lds_u16(ck + ci * 2);
+                  load_row(e0, k0);
+                  const float d0 = fmaf(-2.f, dot(e0), __fadd_rn(zz, __ldg(ee + k0)));
+                  if (d0 < bd || (d0 == bd && k0 < kb)) {
+                    bd = d0;
+                    kb = k0;
+#pragma unroll
+                    for (int h = 0; h < NH; ++h) er[i][h] = e0[h];
+                  }
+                }
+                if (jn >= 0) {
+                  k2 = k2n;
+                  ee2 = ee2n;
+#pragma unroll
+                  for (int h = 0; h < NH; ++h) e2[h] = e2n[h];
+                }
+              } else {
+                // whole-codebook scan (FP16-unsafe input or more candidates than fit; rare): two rows in flight
+                ++n_fs;
+                zz = warp_sum(zz);
+#pragma unroll 1
+                for (int k = 0; k < K; k += 2) {
+                  float4 e0[NH], e1[NH];
+                  const int k1 = min(k + 1, K - 1);
+                  load_row(e0, k);
+                  load_row(e1, k1);
+                  const float d0 = fmaf(-2.f, dot(e0), __fadd_rn(zz, __ldg(ee + k)));
+                  const float d1 = fmaf(-2.f, dot(e1), __fadd_rn(zz, __ldg(ee + k1)));
+                  if (d0 < bd || (d0 == bd && k < kb)) { bd = d0; kb = k; }
+                  if (d1 < bd || (d1 == bd && k1 < kb)) { bd = d1; kb = k1; }
+                }
+                load_row(er[i], kb);
+              }
+              bk[i] = kb;
+            }
+          }
+          if (sub == NPASS - 1) FZ_ACC(4);
+          // ---- z_q = z + (e - z) in place, loss partial
+          float sq = 0.f;
+          float za[NH][4][TOK];                         // all loads first: one round trip to shared memory per pass
+#pragma unroll
+          for (int h = 0; h < NH; ++h)
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+              if (hv[h]) {
+                ldz(zb + zoff[jj] + zsub + h * 16384, za[h][jj]);
+              } else {
+#pragma unroll
+                for (int i = 0; i < TOK; ++i) za[h][jj][i] = 0.f;
+              }
+            }
+#pragma unroll
+          for (int h = 0; h < NH; ++h) {
+            if (!hv[h]) continue;
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+              float o[TOK];
+#pragma unroll
+              for (int i = 0; i < TOK; ++i) {
+                const float a = za[h][jj][i];
+                const float d = __fsub_rn(comp(er[i][h], jj), a);
+                o[i] = __fadd_rn(a, d);
+                sq = fmaf(d, d, sq);
+              }
+              stz(zb + zoff[jj] + zsub + h * 16384, o);
+            }
+          }
+          dsq += (double)sq;
+        }
+#pragma unroll
+        for (int i = 0; i < TOK; ++i) kfin[sub * TOK + i] = bk[i];
+      }
+      fence_proxy_async();                          // generic-proxy writes of the stage -> visible to the TMA store
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(bar(Smem::BAR_F_DONE + st));
+        mbar_arrive(bar(Smem::BAR_C_EMPTY + par));
+      }
+      // (after the fence: the fence would otherwise wait for this global store as well)
+      if (live && lane < 4)
+        idx[tq + lane] = (int64_t)(lane == 0 ? kfin[0] : lane == 1 ? kfin[1] : lane == 2 ? kfin[2] : kfin[3]);
+      FZ_ACC(5);
+      if ((u & 31) >= 24) FZ_MARK(3 + it * 4);     // (the tile's last eight units; a mark per unit perturbs)
+    }
+    FZ_PUT();
+    // loss: one partial per finishing warp, summed in index order by the last CTA (deterministic for a given
+    // assignment of units to warps)
+    {
+      const double wsum = warp_sum(dsq);
+      if (lane == 0) partials[(size_t)blockIdx.x * NFIN + slot] = wsum;
+    }
+    if (lane == 0) {
+      if (n_rr) atomicAdd(counters + kCtrRerank, n_rr);
+      if (n_fs) atomicAdd(counters + kCtrOverflow, n_fs);
+    }
+  };
 
   if (warp < 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(FZ_REGS_AUX));
@@ -486,6 +804,7 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant
           mbar_arrive_expect_tx(bar(Smem::BAR_F_FULL + st), F_STAGE);
           tma_load_2d_cta(sbase + Smem::OFF_F + st * F_STAGE, &tm_zf, x, y, bar(Smem::BAR_F_FULL + st));
 #endif
+          sts_u32(a_tmem + 12, (uint32_t)(j + 1));   // groups requested so far (see the finish's wait for its stage)
           if (j % NG == 0) FZ_MARK(1 + it * 4);
         };
         for (int j = 0; j < total && j < NF; ++j) load(j);
@@ -781,276 +1100,23 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant
       FZ_ACC(6);
     }
     FZ_PUT();
+    // Experiment (-DDCVIC_FZ_HELPERS; off: measured 58.9 us against 54.8): their own work done, the sixteen epilogue
+    // warps help with the finish, two tokens per pass in their 64 registers.  The consumers run behind the MMA by
+    // construction and the tail after the last MMA is 7-9 us of eight warps working through dependent L2 / shared-
+    // memory round trips with the other 24 idle.  The tail did shrink (11.4 -> 9.9 us), but the second instance of
+    // the finish takes the kernel from 4,544 to 6,368 instructions (72 -> 102 KB) and the MMA phase grew by 3 us.
+#ifdef DCVIC_FZ_HELPERS
+    consume(std::integral_constant<int, 2>{}, NCONS + (warp - W_EPI0));
+#else
+    if (lane == 0) partials[(size_t)blockIdx.x * NFIN + NCONS + (warp - W_EPI0)] = 0.0;
+#endif
   } else {
-    // ===================== consumers: FP32 re-rank, z + (e - z) in place, loss, indices =====================
+    // ===================== consumers: the finish, four tokens per pass =====================
     FZ_DBG(22, 0);
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(FZ_REGS_CONS));
     FZ_DBG(23, 0);
-    // Lane l holds 4 consecutive channels per 128-channel block (c = 4l + 128h) of the 4 tokens of its quad: one
-    // LDG.128 per codebook row and block, one LDS.128 / STS.128 per channel.  Lane l visits its 4 channels in the
-    // order (j + (l >> 1)) & 3 so that a quarter warp touches 8 different 16-byte pieces of the swizzled stage; the
-    // codebook copy it gathers from (Ep, written by the prepare kernel) has every group of four channels in exactly
-    // that order, so a row's float4 pairs with the stage's values component by component.
-    const int cwarp = warp - W_CONS0;
-    const int rot = (lane >> 1) & 3;
-    const bool hv[2] = {4 * lane < D, 4 * lane + 128 < D};
     pdl_wait();                                      // |e|^2 and Ep come from the prepare kernel
-    double dsq = 0.0;
-    unsigned n_rr = 0, n_fs = 0;
-    auto load_row = [&](float4 (&r)[NH], int k) {
-      const float* rowp = Ep + (size_t)k * D + 4 * lane;
-#pragma unroll
-      for (int h = 0; h < NH; ++h)
-        r[h] = hv[h] ? __ldg(reinterpret_cast<const float4*>(rowp + 128 * h)) : make_float4(0.f, 0.f, 0.f, 0.f);
-    };
-    // this lane's four channel rows of a finish stage (stage base and the quad's 16-byte piece added per unit)
-    uint32_t zrow[4];
-#pragma unroll
-    for (int jj = 0; jj < 4; ++jj) zrow[jj] = (4 * lane + ((jj + rot) & 3)) * 128;
-    FZ_TDECL;
-#ifdef DCVIC_FZ_DEBUG
-    int fz_last_it = -1;
-#endif
-    // (group, token quad) units are handed out in order through a shared counter: a warp that drew long re-ranks does
-    // not hold up its CTA (a fixed quad per warp cost 25 us on inputs where every fifth token is re-ranked)
-    const int total_units = my_groups * 8;
-    for (;;) {
-      {
-        int u = 0;
-        if (lane == 0) u = (int)atoms_add(a_tmem + 8, 1u);
-        u = __shfl_sync(0xffffffffu, u, 0);
-        if (u >= total_units) break;
-        const int j = u >> 3, cw = u & 7;            // group (in this CTA's sequence), token quad inside it
-        const int it = j / NG, g = j % NG, par = it & 1, st = j % NF;
-        FZ_DBG(15, j);
-        FZ_T();
-        mbar_wait(bar(Smem::BAR_C_FULL + par), (it >> 1) & 1);
-        FZ_ACC(1);
-#ifdef DCVIC_FZ_DEBUG
-        if (it != fz_last_it) { FZ_MARK(1 + it * 4); fz_last_it = it; }
-#endif
-        uint32_t zoff[4];
-#pragma unroll
-        for (int jj = 0; jj < 4; ++jj) zoff[jj] = zrow[jj] + (((uint32_t)cw ^ ((zrow[jj] >> 7) & 7u)) << 4);
-        const int rq = g * GT + 4 * cw;              // first row (token of the CTA tile) of this unit
-        const uint32_t t0 = group_token0(it, g) + 4 * cw;
-#if defined(DCVIC_FZ_EXP) && DCVIC_FZ_EXP >= 4
-        const bool live = t0 > 0x7fffffffu;
-#else
-        const bool live = t0 < (uint32_t)N;          // (a quad is valid or invalid as a whole: N % 4 == 0)
-#endif
-        int nc[4], bk[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          nc[i] = (int)lds_u32(a_nc + (par * BM + rq + i) * 4);
-          bk[i] = (int)lds_u16(a_ck + (par * BM + rq + i) * (CK_MAX * 2));
-          if (nc[i] <= 0 || nc[i] > CK_MAX) {        // flagged for a whole-codebook scan, too many candidates, or none
-            if (live && nc[i] == 0 && lane == 0) atomicAdd(counters + 8, 1u);
-            nc[i] = -1;
-            bk[i] = 0;
-          }
-        }
-#if defined(DCVIC_FZ_EXP) && DCVIC_FZ_EXP >= 3
-#pragma unroll
-        for (int i = 0; i < 4; ++i) { nc[i] = 1; bk[i] = (rq + i) & 1023; }
-#endif
-        __syncwarp();
-        if (lane < 4) sts_u32(a_nc + (par * BM + rq + lane) * 4, 0u);  // for the tile after next (ordered by the C_EMPTY arrival below)
-        const uint32_t zb = sbase + Smem::OFF_F + st * F_STAGE;
-        float4 er[4][NH];
-        // Second candidates: the row of the quad's first re-ranked token is requested together with the first
-        // candidates' rows (and the |e|^2 values with them); inside the re-rank loop every token requests its
-        // successor's before it reduces its own - one L2 round trip per unit instead of one per re-ranked token.
-        const uint32_t ck0 = a_ck + (par * BM + rq) * (CK_MAX * 2);
-        int jr = -1;
-#pragma unroll
-        for (int i = 3; i >= 0; --i)
-          if (nc[i] > 1) jr = i;
-        float4 e2[NH];
-        int k2 = 0;
-        float ee1[4] = {0.f, 0.f, 0.f, 0.f}, ee2 = 0.f;
-#pragma unroll
-        for (int h = 0; h < NH; ++h) e2[h] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (live) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) load_row(er[i], bk[i]);
-          if (jr >= 0) {
-            k2 = (int)lds_u16(ck0 + jr * (CK_MAX * 2) + 2);
-            load_row(e2, k2);
-            ee2 = __ldg(ee + k2);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) ee1[i] = __ldg(ee + bk[i]);
-          }
-        }
-        FZ_DBG(16, j);
-        FZ_ACC(2);
-        mbar_wait(bar(Smem::BAR_F_FULL + st), (j / NF) & 1);
-        FZ_ACC(3);
-        FZ_DBG(17, j);
-        if (live) {
-          if ((nc[0] != 1) | (nc[1] != 1) | (nc[2] != 1) | (nc[3] != 1)) {     // warp-uniform
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              if (nc[i] == 1) continue;
-              const uint32_t ck = ck0 + i * (CK_MAX * 2);
-              // (e2, k2, ee2 hold this token's second candidate.)  The next re-ranked token's is requested now:
-              int jn = -1;
-              float4 e2n[NH];
-              int k2n = 0;
-              float ee2n = 0.f;
-#pragma unroll
-              for (int h = 0; h < NH; ++h) e2n[h] = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (nc[i] > 1) {
-#pragma unroll
-                for (int t = 3; t > i; --t)
-                  if (nc[t] > 1) jn = t;
-                if (jn >= 0) {
-                  k2n = (int)lds_u16(ck0 + jn * (CK_MAX * 2) + 2);
-                  load_row(e2n, k2n);
-                  ee2n = __ldg(ee + k2n);
-                }
-              }
-              float4 zg[NH];                           // this token's z in visiting order
-              float zz = 0.f;
-#pragma unroll
-              for (int h = 0; h < NH; ++h) {
-                float v[4] = {0.f, 0.f, 0.f, 0.f};
-                if (hv[h]) {
-#pragma unroll
-                  for (int jj = 0; jj < 4; ++jj) {
-                    const float4 a = lds128(zb + zoff[jj] + h * 16384);
-                    v[jj] = i == 0 ? a.x : i == 1 ? a.y : i == 2 ? a.z : a.w;
-                  }
-                }
-                zg[h] = make_float4(v[0], v[1], v[2], v[3]);
-#pragma unroll
-                for (int jj = 0; jj < 4; ++jj) zz = __fadd_rn(zz, __fmul_rn(v[jj], v[jj]));
-              }
-              auto part = [&](const float4 (&r)[NH]) {     // this lane's share of z . e
-                float dp = 0.f;
-#pragma unroll
-                for (int h = 0; h < NH; ++h) {
-                  dp = fmaf(zg[h].x, r[h].x, dp); dp = fmaf(zg[h].y, r[h].y, dp);
-                  dp = fmaf(zg[h].z, r[h].z, dp); dp = fmaf(zg[h].w, r[h].w, dp);
-                }
-                return dp;
-              };
-              auto dot = [&](const float4 (&r)[NH]) { return warp_sum(part(r)); };
-              float bd = FLT_MAX;
-              int kb = 0x7fffffff;
-              if (nc[i] > 1) {
-                ++n_rr;
-                // |z|^2 and the first two candidates' products go through the butterfly together (three dependent
-                // 5-step shuffle chains one after the other were most of a re-rank's latency)
-                float pa = part(er[i]), pb = part(e2);
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                  zz += __shfl_xor_sync(0xffffffffu, zz, o);
-                  pa += __shfl_xor_sync(0xffffffffu, pa, o);
-                  pb += __shfl_xor_sync(0xffffffffu, pb, o);
-                }
-                bd = fmaf(-2.f, pa, __fadd_rn(zz, ee1[i]));
-                kb = bk[i];
-                {
-                  const float d0 = fmaf(-2.f, pb, __fadd_rn(zz, ee2));
-                  if (d0 < bd || (d0 == bd && k2 < kb)) {
-                    bd = d0;
-                    kb = k2;
-#pragma unroll
-                    for (int h = 0; h < NH; ++h) er[i][h] = e2[h];
-                  }
-                }
-#pragma unroll 1
-                for (int ci = 2; ci < nc[i]; ++ci) {
-                  float4 e0[NH];
-                  const int k0 = (int)lds_u16(ck + ci * 2);
-                  load_row(e0, k0);
-                  const float d0 = fmaf(-2.f, dot(e0), __fadd_rn(zz, __ldg(ee + k0)));
-                  if (d0 < bd || (d0 == bd && k0 < kb)) {
-                    bd = d0;
-                    kb = k0;
-#pragma unroll
-                    for (int h = 0; h < NH; ++h) er[i][h] = e0[h];
-                  }
-                }
-                if (jn >= 0) {
-                  k2 = k2n;
-                  ee2 = ee2n;
-#pragma unroll
-                  for (int h = 0; h < NH; ++h) e2[h] = e2n[h];
-                }
-              } else {
-                // whole-codebook scan (FP16-unsafe input or more candidates than fit; rare): two rows in flight
-                ++n_fs;
-                zz = warp_sum(zz);
-#pragma unroll 1
-                for (int k = 0; k < K; k += 2) {
-                  float4 e0[NH], e1[NH];
-                  const int k1 = min(k + 1, K - 1);
-                  load_row(e0, k);
-                  load_row(e1, k1);
-                  const float d0 = fmaf(-2.f, dot(e0), __fadd_rn(zz, __ldg(ee + k)));
-                  const float d1 = fmaf(-2.f, dot(e1), __fadd_rn(zz, __ldg(ee + k1)));
-                  if (d0 < bd || (d0 == bd && k < kb)) { bd = d0; kb = k; }
-                  if (d1 < bd || (d1 == bd && k1 < kb)) { bd = d1; kb = k1; }
-                }
-                load_row(er[i], kb);
-              }
-              bk[i] = kb;
-            }
-          }
-          FZ_ACC(4);
-          // ---- z_q = z + (e - z) in place, loss partial
-          float sq = 0.f;
-          float4 za[NH][4];                             // all loads first: one round trip to shared memory per unit
-#pragma unroll
-          for (int h = 0; h < NH; ++h)
-#pragma unroll
-            for (int jj = 0; jj < 4; ++jj)
-              za[h][jj] = hv[h] ? lds128(zb + zoff[jj] + h * 16384) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-          for (int h = 0; h < NH; ++h) {
-            if (!hv[h]) continue;
-#pragma unroll
-            for (int jj = 0; jj < 4; ++jj) {
-              const float4 a = za[h][jj];
-              const float4 v0 = er[0][h], v1 = er[1][h], v2 = er[2][h], v3 = er[3][h];
-              const float e0 = jj == 0 ? v0.x : jj == 1 ? v0.y : jj == 2 ? v0.z : v0.w;
-              const float e1 = jj == 0 ? v1.x : jj == 1 ? v1.y : jj == 2 ? v1.z : v1.w;
-              const float e2 = jj == 0 ? v2.x : jj == 1 ? v2.y : jj == 2 ? v2.z : v2.w;
-              const float e3 = jj == 0 ? v3.x : jj == 1 ? v3.y : jj == 2 ? v3.z : v3.w;
-              const float d0 = __fsub_rn(e0, a.x), d1 = __fsub_rn(e1, a.y), d2 = __fsub_rn(e2, a.z),
-                          d3 = __fsub_rn(e3, a.w);
-              sts128(zb + zoff[jj] + h * 16384,
-                     make_float4(__fadd_rn(a.x, d0), __fadd_rn(a.y, d1), __fadd_rn(a.z, d2), __fadd_rn(a.w, d3)));
-              sq = fmaf(d0, d0, sq); sq = fmaf(d1, d1, sq); sq = fmaf(d2, d2, sq); sq = fmaf(d3, d3, sq);
-            }
-          }
-          dsq += (double)sq;
-        }
-        fence_proxy_async();                          // generic-proxy writes of the stage -> visible to the TMA store
-        __syncwarp();
-        if (lane == 0) {
-          mbar_arrive(bar(Smem::BAR_F_DONE + st));
-          mbar_arrive(bar(Smem::BAR_C_EMPTY + par));
-        }
-        // (after the fence: the fence would otherwise wait for this global store as well)
-        if (live && lane < 4)
-          idx[t0 + lane] = (int64_t)(lane == 0 ? bk[0] : lane == 1 ? bk[1] : lane == 2 ? bk[2] : bk[3]);
-        FZ_ACC(5);
-        if ((u & 31) >= 24) FZ_MARK(3 + it * 4);     // (the tile's last eight units; a mark per unit perturbs)
-      }
-    }
-    FZ_PUT();
-    // loss: one partial per consumer warp, summed in index order by vq_loss_finalize_kernel (deterministic)
-    {
-      const double wsum = warp_sum(dsq);
-      if (lane == 0) partials[(size_t)blockIdx.x * NCONS + cwarp] = wsum;
-    }
-    if (lane == 0) {
-      if (n_rr) atomicAdd(counters + kCtrRerank, n_rr);
-      if (n_fs) atomicAdd(counters + kCtrOverflow, n_fs);
-    }
+    consume(std::integral_constant<int, 4>{}, warp - W_CONS0);
   }
 
   FZ_DBG(30, 0);
@@ -1069,7 +1135,7 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant
   cluster_sync();            // no CTA leaves while its peer may still touch its shared memory / barriers
   if (s_last) {
     __threadfence();
-    const int n = (int)gridDim.x * NCONS;
+    const int n = (int)gridDim.x * NFIN;
     double acc = 0.0;
     for (int i = threadIdx.x; i < n; i += NTHREADS) acc += __ldcg(partials + i);
     const double tot = block_sum(acc, s_scratch);
