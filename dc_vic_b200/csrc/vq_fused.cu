@@ -1069,7 +1069,9 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant
       const float thr = fmaxf(fmaxf(mq.x, mq.y), fmaxf(mq.z, mq.w)) - margin;
       const int par = it & 1;
       FZ_DBG(13, it);
+      FZ_ACC(6);
       if (it >= 2) mbar_wait(bar(Smem::BAR_C_EMPTY + par), ((it >> 1) - 1) & 1);   // consumers are done with tile it-2
+      FZ_ACC(4);                                     // (slot 4: waiting for the consumers)
       if (valid) {
         const uint32_t ncp = a_nc + (par * BM + row) * 4;
         if (cb_unsafe || !(zz < kVqFp16Zz2Max)) {

@@ -54,7 +54,7 @@ ROLES = {0: ("tmaB", ["wait B_EMPTY"]), 1: ("zload", ["wait Z_EMPTY"]),
          2: ("fin", ["wait converted", "wait F_DONE", "wait read-out", "drain"]),
          3: ("mma", ["wait T_EMPTY", "wait A_FULL", "wait B_FULL"]),
          4: ("conv", ["wait A_EMPTY", "wait Z_FULL"]),
-         8: ("epi", ["wait ZZ", "wait T_FULL", "tcgen05.ld+release", "bias", "flags+emit", "tile end"]),
+         8: ("epi", ["wait ZZ", "wait T_FULL", "tcgen05.ld+release", "wait C_EMPTY", "flags+emit", "tile end"]),
          24: ("cons", ["wait C_FULL", "rows issue", "wait F_FULL", "re-rank", "z_q+arrive"])}
 for b in range(min(grid, 2)):
     print(f"CTA {b}:")

@@ -23,19 +23,8 @@ G = os.path.join(ROOT, "gpurun_out")
 P = os.path.join(ROOT, "profiles")
 
 
-def raw(rep):
-    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-    rows = list(csv.reader(io.StringIO(out)))
-    return [dict(zip(rows[0], r)) for r in rows[2:]]
-
-
 def num(s):
     return float(s.replace(",", "")) if s not in ("", None) else 0.0
-
-
-def to_bytes(d, key):
-    v, unit = num(d[key]), None
-    return v
 
 
 bench = os.path.join(G, f"{tag}_bench.json")
