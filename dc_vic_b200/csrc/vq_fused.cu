@@ -140,6 +140,35 @@ __device__ __forceinline__ void tma_load_2d_cta(uint32_t dst, const CUtensorMap*
       "l"(map), "r"(x), "r"(y), "r"(bar)
       : "memory");
 }
+// L2 eviction-priority hints (createpolicy): z is read twice by this kernel (conversion, then the finish about one
+// tile time later) and z_q is never read again.  Bits of DCVIC_FZ_HINTS: 1 conversion loads evict_last, 2 z_q stores
+// evict_first, 4 finish loads evict_first.  All three: 1.5-2 us per launch (0 = none, for A/B runs).
+#ifndef DCVIC_FZ_HINTS
+#define DCVIC_FZ_HINTS 7
+#endif
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void tma_load_2d_cta_hint(uint32_t dst, const CUtensorMap* map, int x, int y, uint32_t bar,
+                                                     uint64_t pol) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], "
+      "[%4], %5;" ::"r"(dst),
+      "l"(map), "r"(x), "r"(y), "r"(bar), "l"(pol)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_2d_hint(const CUtensorMap* map, int x, int y, uint32_t src, uint64_t pol) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%1, %2}], [%3], %4;" ::"l"(map),
+               "r"(x), "r"(y), "r"(src), "l"(pol)
+               : "memory");
+}
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, int x, int y, uint32_t src) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(map), "r"(x),
                "r"(y), "r"(src)
@@ -768,9 +797,15 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant
               const uint32_t tg = group_token0(it, g);   // (a group beyond N: out-of-bounds box, zero fill)
 #endif
               mbar_arrive_expect_tx(bar(Smem::BAR_Z_FULL + st), Z_STAGE);
+#if DCVIC_FZ_HINTS & 1
+              tma_load_2d_cta_hint(sbase + Smem::OFF_Z + st * Z_STAGE, &tm_zc, (int)(tg % (uint32_t)HW),
+                                   (int)(tg / (uint32_t)HW) * D + kc * BK, bar(Smem::BAR_Z_FULL + st),
+                                   l2_policy_evict_last());
+#else
               tma_load_2d_cta(sbase + Smem::OFF_Z + st * Z_STAGE, &tm_zc, (int)(tg % (uint32_t)HW),
                               (int)(tg / (uint32_t)HW) * D + kc * BK,
                               bar(Smem::BAR_Z_FULL + st));
+#endif
             }
           FZ_MARK(3 + it * 4);
         }
@@ -802,7 +837,12 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant
           mbar_arrive(bar(Smem::BAR_F_FULL + st));
 #else
           mbar_arrive_expect_tx(bar(Smem::BAR_F_FULL + st), F_STAGE);
+#if DCVIC_FZ_HINTS & 4
+          tma_load_2d_cta_hint(sbase + Smem::OFF_F + st * F_STAGE, &tm_zf, x, y, bar(Smem::BAR_F_FULL + st),
+                               l2_policy_evict_first());
+#else
           tma_load_2d_cta(sbase + Smem::OFF_F + st * F_STAGE, &tm_zf, x, y, bar(Smem::BAR_F_FULL + st));
+#endif
 #endif
           sts_u32(a_tmem + 12, (uint32_t)(j + 1));   // groups requested so far (see the finish's wait for its stage)
           if (j % NG == 0) FZ_MARK(1 + it * 4);
@@ -817,14 +857,20 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant
           int x, y;
           coords(j, x, y);
 #if !defined(DCVIC_FZ_X) || !(DCVIC_FZ_X & 1)  // (experiment bit 1: no z_q stores)
+#if DCVIC_FZ_HINTS & 2
+          tma_store_2d_hint(&tm_zq, x, y, sbase + Smem::OFF_F + st * F_STAGE, l2_policy_evict_first());
+#else
           tma_store_2d(&tm_zq, x, y, sbase + Smem::OFF_F + st * F_STAGE);
+#endif
 #endif
           bulk_commit();
           if (j % NG == 0) FZ_MARK(2 + (j / NG) * 4);
           if (j % NG == NG - 1) FZ_MARK(3 + (j / NG) * 4);
           if (j + NF < total) {
             FZ_T();
+#if !defined(DCVIC_FZ_X) || !(DCVIC_FZ_X & 8)  // (experiment bit 8: refill without waiting for the read-out - racy)
             bulk_wait_read_all();                    // the stage has been read out: refill it
+#endif
             FZ_ACC(3);
             load(j + NF);
           }

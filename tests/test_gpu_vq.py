@@ -399,7 +399,10 @@ def test_decode_tokens_with_post_quant_conv_and_code_losses():
         lat_r = O.post_quant_latent(idx_r, E, pq.weight.detach(), pq.bias.detach())
         idx, lat, acc = D.decode_tokens(logits.to(DEV), E.to(DEV), gt.to(DEV), post_quant_conv=pq.to(DEV))
         assert torch.equal(idx.cpu(), idx_r)
-        assert torch.allclose(lat.cpu(), lat_r, rtol=1e-6, atol=1e-6)          # 4 fused multiply-adds vs cuDNN's order
+        # D fused multiply-adds per output against the CPU conv of the oracle, whose summation order depends on the
+        # host's thread count / oneDNN kernel choice (seen to differ by a few 1e-6 once in ~50 runs): FP32 sum of <= 8
+        # O(1) products
+        assert torch.allclose(lat.cpu(), lat_r, rtol=1e-5, atol=1e-5), float((lat.cpu() - lat_r).abs().max())
         assert abs(float(acc) - float((idx_r == gt).float().mean())) < 1e-7
         for gamma, red in ((0.0, "mean"), (2.0, "mean"), (1.0, "sum"), (0.5, "mean")):
             lr = logits.clone().requires_grad_(True)
