@@ -33,6 +33,7 @@
 //               ((|z|^2 + |e|^2) - 2 z.e, lowest index on ties); z + (e - z) overwrites z in the stage; loss partials.
 #include <cuda.h>
 #include <float.h>
+#include <stdio.h>
 #include <stdlib.h>
 
 #include <type_traits>
@@ -71,6 +72,21 @@ constexpr int NT_MAX = 8;          // N-tiles per tile: one flag-mask slot per (
 constexpr int CK_MAX = 16;         // candidate codes per token after compaction; more -> whole-codebook scan
 constexpr int MAX_K = NT_MAX * BN;  // -|e|^2/2 table and flag-mask slots in shared memory (larger codebooks take the
                                     // two-kernel path)
+// Cluster size: 2 = one CTA pair per cluster.  4 (experiment, -DDCVIC_FZ_CLUSTER=4) = two pairs that walk the codebook
+// in lockstep: pair 0's CTAs load every codebook slab once and TMA-multicast it to the CTA of the same parity in pair 1
+// (half the L2 -> SM codebook traffic: 156 of the 450 MB a launch moves through the L2).
+#ifndef DCVIC_FZ_CLUSTER
+#define DCVIC_FZ_CLUSTER 2
+#endif
+constexpr int CL = DCVIC_FZ_CLUSTER;
+// (cluster of 4) how a multicast load reports to the MMA issuer: 0 = it completes on the barrier of the CTA it lands
+// in and a non-leader forwards that to its leader (plain .multicast::cluster); 1 = the .cta_group::2 form, whose
+// barrier operand names the pair's leader - one hop less
+#ifndef DCVIC_FZ_MC_DIRECT
+#define DCVIC_FZ_MC_DIRECT 0
+#endif
+constexpr bool kMcDirect = DCVIC_FZ_MC_DIRECT != 0;
+static_assert(CL == 2 || CL == 4, "cluster of one or two CTA pairs");
 constexpr int NCONS = 8;
 constexpr int NEPI = 16;           // epilogue warps: 4 column quarters x 4 TMEM lane quarters
 constexpr int NFIN = NCONS + NEPI; // warps that may run the finish (loss partial slots per CTA)
@@ -349,29 +365,40 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   FZ_GMARK(33);                                      // kernel entry
-  const uint32_t rank = cluster_ctarank();
+  const uint32_t crank = cluster_ctarank();          // 0 .. CL - 1
+  const uint32_t rank = crank & 1u;                  // inside the CTA pair: 0 = leader (issues the MMAs)
+  const uint32_t pbase = crank & ~1u;                // cluster rank of this pair's leader
   const bool leader = rank == 0;
-  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const int cl = blockIdx.x / CL, ncl = gridDim.x / CL, pin = (int)(crank >> 1);   // cluster, pair inside it
   const int NT = K / BN;
   // Work split: the tokens go in "group pairs" of 64 (a group of 32 for either CTA), and CTA pair p takes the
   // contiguous run of group pairs [p * num_gp / npairs, (p + 1) * num_gp / npairs): tiles of 4 group pairs, of which
   // only the LAST may be partial.  Every pair gets the same work to within one group (whole 256-token tiles dealt
   // round-robin left 34 of 74 pairs with a fourth tile on the headline shape and the other 40 idle meanwhile); in a
   // partial tile the warps of the missing groups only keep the barriers going.
-  const int gp_lo = (int)((long long)pair * num_gp / npairs), gp_hi = (int)((long long)(pair + 1) * num_gp / npairs);
+  // (Cluster of two pairs: the cluster's run is halved between its pairs, and BOTH walk as many tiles as the larger
+  // half needs - they share the codebook ring's phases; a pair's surplus tile has no groups.)
+  const int c_lo = (int)((long long)cl * num_gp / ncl), c_n = (int)((long long)(cl + 1) * num_gp / ncl) - c_lo;
+  constexpr int PP = CL / 2;
+  const int gp_lo = c_lo + pin * c_n / PP, gp_hi = c_lo + (pin + 1) * c_n / PP;
   const int my_groups = gp_hi - gp_lo;               // groups of 32 tokens this CTA handles
-  const int my_tiles = (my_groups + NG - 1) / NG;
-  auto tile_groups = [&](int it) { return min(NG, my_groups - it * NG); };
+  const int my_tiles = ((c_n + PP - 1) / PP + NG - 1) / NG;
+  auto tile_groups = [&](int it) { return max(0, min(NG, my_groups - it * NG)); };
   // first token of this CTA's group g of its it-th tile
   // (< N + 64: 32-bit unsigned arithmetic throughout - the TMA / MMA warps live on 24 registers)
   auto group_token0 = [&](int it, int g) { return ((uint32_t)(gp_lo + it * NG + g) * 2u + rank) * (uint32_t)GT; };
-  auto leader_bar = [&](int slot) { return map_to_cta(bar(slot), 0); };
+  auto leader_bar = [&](int slot) { return map_to_cta(bar(slot), pbase); };
 
   if (threadIdx.x == 0) {
     sts_u32(a_tmem + 4, 0u);
     sts_u32(a_tmem + 8, 0u);
     sts_u32(a_tmem + 12, 0u);
-    for (int s = 0; s < NB; ++s) { mbar_init(bar(Smem::BAR_B_FULL + s), 1); mbar_init(bar(Smem::BAR_B_EMPTY + s), 1); }
+    // (cluster of two pairs: every CTA's B_FULL counts its own half's bytes, a leader's also its peer's forwarded
+    // arrival; B_EMPTY counts the MMA commits of both pairs)
+    for (int s = 0; s < NB; ++s) {
+      mbar_init(bar(Smem::BAR_B_FULL + s), CL == 4 && leader && !kMcDirect ? 2 : 1);
+      mbar_init(bar(Smem::BAR_B_EMPTY + s), CL / 2);
+    }
     for (int s = 0; s < NZ; ++s) { mbar_init(bar(Smem::BAR_Z_FULL + s), 1); mbar_init(bar(Smem::BAR_Z_EMPTY + s), 1); }
     for (int c = 0; c < 8; ++c) mbar_init(bar(Smem::BAR_A_FULL + c), 2 * NG);
     for (int b = 0; b < 2; ++b) {
@@ -756,6 +783,52 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant
                 continue;
               }
 #endif
+              if constexpr (CL == 4) {
+                // Two pairs in lockstep: every CTA arms its OWN barrier for its half's bytes; pair 0's CTAs issue the
+                // loads, multicast to themselves and to the CTA of the same parity in pair 1 (data and complete_tx land
+                // at the same offsets in both).  A non-leader's warp 3 forwards its barrier's completion to its leader.
+                if constexpr (kMcDirect) {
+                  if (leader)
+                    mbar_arrive_expect_tx(bar(Smem::BAR_B_FULL + stage), 2 * (nch * B_CHUNK + (part == 0 ? BP_BYTES : 0)));
+                  if (pin == 0) {
+                    const uint16_t mask = (uint16_t)((1u << crank) | (1u << (crank + 2)));
+                    const uint32_t lb = leader_bar(Smem::BAR_B_FULL + stage);
+                    if (part == 0)
+                      asm volatile(
+                          "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+                          ".multicast::cluster [%0], [%1, {%2, %3}], [%4], %5;" ::"r"(sbase + OFF_B + stage * B_STAGE + B_SLAB),
+                          "l"(&tm_bp), "r"(0), "r"(nt * BN + (int)rank * (BN / 2)), "r"(lb), "h"(mask)
+                          : "memory");
+                    asm volatile(
+                        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+                        ".multicast::cluster [%0], [%1, {%2, %3, %4}], [%5], %6;" ::"r"(sbase + OFF_B + stage * B_STAGE),
+                        "l"(part == 0 ? &tm_cb : &tm_cb2), "r"(0), "r"(nt * BN + (int)rank * (BN / 2)),
+                        "r"(part == 0 ? 0 : NA), "r"(lb), "h"(mask)
+                        : "memory");
+                  }
+                  if (++stage == NB) { stage = 0; phase ^= 1; }
+                  continue;
+                }
+                const uint32_t fb = bar(Smem::BAR_B_FULL + stage);
+                mbar_arrive_expect_tx(fb, nch * B_CHUNK + (part == 0 ? BP_BYTES : 0));
+                if (pin == 0) {
+                  const uint16_t mask = (uint16_t)((1u << crank) | (1u << (crank + 2)));
+                  if (part == 0)
+                    asm volatile(
+                        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster "
+                        "[%0], [%1, {%2, %3}], [%4], %5;" ::"r"(sbase + OFF_B + stage * B_STAGE + B_SLAB),
+                        "l"(&tm_bp), "r"(0), "r"(nt * BN + (int)rank * (BN / 2)), "r"(fb), "h"(mask)
+                        : "memory");
+                  asm volatile(
+                      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster "
+                      "[%0], [%1, {%2, %3, %4}], [%5], %6;" ::"r"(sbase + OFF_B + stage * B_STAGE),
+                      "l"(part == 0 ? &tm_cb : &tm_cb2), "r"(0), "r"(nt * BN + (int)rank * (BN / 2)),
+                      "r"(part == 0 ? 0 : NA), "r"(fb), "h"(mask)
+                      : "memory");
+                }
+                if (++stage == NB) { stage = 0; phase ^= 1; }
+                continue;
+              }
               if (leader)
                 mbar_arrive_expect_tx(bar(Smem::BAR_B_FULL + stage), 2 * (nch * B_CHUNK + (part == 0 ? BP_BYTES : 0)));
               if (part == 0)       // this CTA's 64 codes of the N-tile's -|e|^2/2 operand: 16-byte rows, un-swizzled
@@ -883,6 +956,7 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant
     } else if (leader) {
       // ===================== MMA issuer: whole warp walks the loop, one elected lane issues =====================
       const bool issuer = elect_one();
+      const uint16_t pair_mask = (uint16_t)(3u << pbase);   // this pair's two CTAs in the cluster
       const uint32_t rt_one = my_tiles > 0 ? 1u : 0u;   // 1, but not a compile-time constant (see vq_tcgen05.cu)
       const uint32_t rt_zero = my_tiles < 0 ? 1u : 0u;  // 0, likewise
       // The loop below is the kernel's pacemaker and shares its scheduler with seven busy warps: it is kept to the
@@ -939,17 +1013,31 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant
                 umma_ts(d, a + 16, bd + 4, rt_one);
                 umma_ts(d, a + 24, bd + 6, rt_one);
               }
-              umma_commit<2>(bar(Smem::BAR_B_EMPTY + stage));
-              if (part == (KC > NA ? 1 : 0)) umma_commit<2>(bar(Smem::BAR_T_FULL + buf));
+              umma_commit<2>(bar(Smem::BAR_B_EMPTY + stage), CL == 4 ? (uint16_t)0xF : pair_mask);   // (every loader)
+              if (part == (KC > NA ? 1 : 0)) umma_commit<2>(bar(Smem::BAR_T_FULL + buf), pair_mask);
             }
             if (++stage == NB) { stage = 0; phase ^= 1; }
           }
         }
-        if (issuer) umma_commit<2>(bar(Smem::BAR_A_EMPTY + abuf));
+        if (issuer) umma_commit<2>(bar(Smem::BAR_A_EMPTY + abuf), pair_mask);
         FZ_MARK(3 + it * 4);
         __syncwarp();
       }
       FZ_PUT();
+    } else if (CL == 4 && !kMcDirect) {
+      // ===================== non-leader, warp 3 (cluster of two pairs): forward "my half has landed" =====================
+      // The multicast loads complete on the barrier of the CTA they land in; the MMA issuer waits on ITS barrier, which
+      // counts its own half (bytes) and this arrival.
+      if (lane == 0) {
+        int stage = 0;
+        uint32_t phase = 0;
+        const int n = my_tiles * NT * (KC > NA ? 2 : 1);
+        for (int i = 0; i < n; ++i) {
+          mbar_wait(bar(Smem::BAR_B_FULL + stage), phase);
+          mbar_arrive_cluster_release(leader_bar(Smem::BAR_B_FULL + stage));
+          if (++stage == NB) { stage = 0; phase ^= 1; }
+        }
+      }
     }
   } else if (warp < W_EPI0) {
     // ===================== converters: FP32 ring stage -> FP16 A operand in tensor memory =====================
@@ -1245,8 +1333,35 @@ static int launch(const CUtensorMap& tcb, const CUtensorMap& tcb2, const CUtenso
     attr_set = true;
   }
   const int num_gp = (N + 2 * GT - 1) / (2 * GT);          // group pairs: 64 tokens, 32 for either CTA of a pair
-  const int max_pairs = kNumSMs / 2;
+  int max_pairs = kNumSMs / 2;
+  if (CL == 4) {
+    // clusters of four must fit a GPC: fewer than 148 / 4 of them may be co-resident, and a second wave would double
+    // the kernel's time
+    static int max_clusters = 0;
+    if (max_clusters == 0) {
+      cudaLaunchConfig_t q{};
+      q.gridDim = dim3(kNumSMs / CL * CL);
+      q.blockDim = dim3(NTHREADS);
+      q.dynamicSmemBytes = smem;
+      cudaLaunchAttribute qa[1];
+      qa[0].id = cudaLaunchAttributeClusterDimension;
+      qa[0].val.clusterDim.x = CL;
+      qa[0].val.clusterDim.y = 1;
+      qa[0].val.clusterDim.z = 1;
+      q.attrs = qa;
+      q.numAttrs = 1;
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, vq_fused_kernel<D>, &q) != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        n = kNumSMs / CL / 2;
+      }
+      max_clusters = n < kNumSMs / CL ? n : kNumSMs / CL;
+      if (getenv("DCVIC_FZ_VERBOSE")) fprintf(stderr, "vq_fused: %d clusters of %d co-resident (occupancy query: %d)\n", max_clusters, CL, n);
+    }
+    max_pairs = max_clusters * (CL / 2);
+  }
   int npairs = num_gp < max_pairs ? num_gp : max_pairs;             // (small inputs: one group pair per CTA pair)
+  if (CL == 4) npairs = (npairs + 1) / 2 * 2;                       // whole clusters
 #ifdef DCVIC_FZ_WHOLE_TILES   // (measured: 57.6 us against 55.1 - the finish of a FULL last tile is a longer tail)
   // A partial tile costs a whole pass over the codebook (MMA time and 0.5 MB of L2 traffic per CTA pair), and the
   // kernel runs at the L2's throughput: with two or more tiles per pair, use the FEWEST pairs that keep the number of
@@ -1265,7 +1380,7 @@ static int launch(const CUtensorMap& tcb, const CUtensorMap& tcb2, const CUtenso
   cfg.stream = s;
   cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.x = CL;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
