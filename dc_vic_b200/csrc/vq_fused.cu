@@ -434,6 +434,21 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant
   // tensor memory: accumulators 2 x 128 columns | A operand 2 x 128 columns
   const uint32_t tmem_acc = tmem_base, tmem_a = tmem_base + 2 * BN;
   // PDL: see vq_tcgen05.cu.  wait_first: the predecessor in the stream may be the producer of z.
+#ifndef DCVIC_FZ_NO_PREFETCH
+  // While the predecessor in the stream finishes (it may be writing z), ask the L2 for this CTA's first tile of z: a
+  // prefetch only moves lines into the L2, which stays coherent with whatever the predecessor still writes, and the
+  // conversion ring's first loads then hit the L2 instead of paying an HBM round trip with the tensor cores idle.
+  if (wait_first && warp == W_ZLOAD && lane == 0 && my_tiles > 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_zf) : "memory");
+    const int ng = tile_groups(0);
+    for (int g = 0; g < ng; ++g) {
+      const uint32_t tg = group_token0(0, g);
+      asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(&tm_zf),
+                   "r"((int)(tg % (uint32_t)HW)), "r"((int)(tg / (uint32_t)HW) * D)
+                   : "memory");
+    }
+  }
+#endif
   if (wait_first) pdl_wait();
   pdl_launch_dependents();
   FZ_GMARK(35);                                      // predecessor complete
