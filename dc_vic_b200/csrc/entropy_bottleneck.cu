@@ -209,7 +209,10 @@ __global__ void __launch_bounds__(kEbThreads) eb_forward_kernel(const float* __r
 // >= kEbTabR: far in the tails) are evaluated directly.  A CTA takes `chunk` consecutive float4 of its channel
 // (kEbTabPerThread per thread) so that building the table is < 1 % of its work.
 constexpr int kEbTabR = 64;
-constexpr int kEbTabPerThread = 16;
+#ifndef DCVIC_EB_TAB_PER_THREAD
+#define DCVIC_EB_TAB_PER_THREAD 16
+#endif
+constexpr int kEbTabPerThread = DCVIC_EB_TAB_PER_THREAD;
 __global__ void __launch_bounds__(kEbThreads) eb_forward_table_kernel(const float* __restrict__ x, EbParamPtrs P, int B,
                                                                        int C, int HW, float lik_bound,
                                                                        float* __restrict__ x_hat,
@@ -230,13 +233,11 @@ __global__ void __launch_bounds__(kEbThreads) eb_forward_table_kernel(const floa
   const long long per_ch4 = (long long)B * HW / 4;               // float4 per channel (H*W % 4 == 0)
   const int hw4 = HW / 4;
   const long long q0 = (long long)blockIdx.x * (kEbThreads * kEbTabPerThread);
-#pragma unroll 4
-  for (int i = 0; i < kEbTabPerThread; ++i) {
-    const long long q = q0 + (long long)i * kEbThreads + threadIdx.x;
-    if (q >= per_ch4) break;
+  auto offset_of = [&](long long q) {
     const long long b = q / hw4, p4 = q % hw4;
-    const size_t o = ((size_t)b * C + c) * HW + (size_t)p4 * 4;
-    const float4 v4 = ldg_stream(reinterpret_cast<const float4*>(x + o));
+    return ((size_t)b * C + c) * HW + (size_t)p4 * 4;
+  };
+  auto finish = [&](size_t o, const float4& v4) {
     const float v[4] = {v4.x, v4.y, v4.z, v4.w};
     float xh[4], lk[4];
 #pragma unroll
@@ -253,6 +254,28 @@ __global__ void __launch_bounds__(kEbThreads) eb_forward_table_kernel(const floa
     }
     if (lik) stg_stream(reinterpret_cast<float4*>(lik + o), make_float4(lk[0], lk[1], lk[2], lk[3]));
     if (x_hat) stg_stream(reinterpret_cast<float4*>(x_hat + o), make_float4(xh[0], xh[1], xh[2], xh[3]));
+  };
+  if (q0 + (long long)kEbThreads * kEbTabPerThread <= per_ch4) {
+    // whole chunk in range (all but a channel's last CTA): four loads in flight per thread before any is used
+#pragma unroll 1
+    for (int i = 0; i < kEbTabPerThread; i += 4) {
+      size_t o[4];
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        o[u] = offset_of(q0 + (long long)(i + u) * kEbThreads + threadIdx.x);
+        v[u] = ldg_stream(reinterpret_cast<const float4*>(x + o[u]));
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) finish(o[u], v[u]);
+    }
+  } else {
+    for (int i = 0; i < kEbTabPerThread; ++i) {
+      const long long q = q0 + (long long)i * kEbThreads + threadIdx.x;
+      if (q >= per_ch4) break;
+      const size_t o = offset_of(q);
+      finish(o, ldg_stream(reinterpret_cast<const float4*>(x + o)));
+    }
   }
 }
 
