@@ -31,6 +31,16 @@
 //   warps 24-31 consumers (the finish): (group, token quad) units.  First candidates' codebook rows are requested
 //               before the group's z has arrived; tokens with more than one candidate are re-ranked in FP32
 //               ((|z|^2 + |e|^2) - 2 z.e, lowest index on ties); z + (e - z) overwrites z in the stage; loss partials.
+//
+// Compile-time switches (python -m dc_vic_b200.build --variant <name> -D...; a variant library is only ever loaded
+// through DCVIC_B200_LIB).  Measurement aids that produce WRONG results, used for the what-if table in DESIGN 4.1:
+//   DCVIC_FZ_EXP=3|4 (no re-rank | consumers idle), DCVIC_FZ_EPIFREE (no flag arithmetic), DCVIC_FZ_X bits 1|2|4|8
+//   (no z_q stores | no second read of z | conversion loads from the L2 | refill a finish stage without waiting for
+//   its read-out), DCVIC_FZ_HALFB (half the codebook bytes), DCVIC_FZ_NOLD (no accumulator read-out).
+// Correct variants that measured slower and are off: DCVIC_FZ_WHOLE_TILES, DCVIC_FZ_HELPERS, DCVIC_FZ_CLUSTER=4
+//   (+ DCVIC_FZ_MC_DIRECT=1), DCVIC_FZ_HINTS=0, DCVIC_FZ_NO_PREFETCH; ring depths DCVIC_FZ_NB / NZ / NF and the
+//   register split FZ_REGS_CONV / FZ_REGS_CONS are tunables.  -DDCVIC_FZ_DEBUG (+ _TIMING_ONLY / _MARKS_ONLY /
+//   DCVIC_FZ_NO_CMARKS) builds the instrumented kernels of tools/debug_fused.py and tools/fused_span.py.
 #include <cuda.h>
 #include <float.h>
 #include <stdio.h>
