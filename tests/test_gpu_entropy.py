@@ -248,29 +248,33 @@ def test_entropy_bottleneck_forward(train):
     assert torch.equal(a[0].cpu(), b[0]) and rel_err(a[1], b[1]) < REL
 
 
-def test_entropy_bottleneck_eval_table_path():
+@pytest.mark.parametrize("shape", [(16, 24, 32, 32), (20, 24, 36, 36), (6, 24, 36, 36)])
+def test_entropy_bottleneck_eval_table_path(shape):
     """Evaluation forward with >= 4096 latents per channel takes the look-up kernel (one likelihood table per channel
-    and CTA): equal to the oracle within tolerance, and BIT-equal to the direct kernel (the same input in 2048-latent
+    and CTA): equal to the oracle within tolerance, and BIT-equal to the direct kernel (the same input in two-image
     slices, which stay below the switch), including symbols outside the table (|x - med| >= 64) and the likelihood
-    bound in the far tails."""
+    bound in the far tails.  The shapes cover a CTA whose chunk is entirely in range (batched loads), one that is cut
+    short by the end of the channel, and both in one launch."""
     torch.manual_seed(11)
-    ref = O.SteEntropyBottleneck(channels=24)
+    C = shape[1]
+    ref = O.SteEntropyBottleneck(channels=C)
     with torch.no_grad():
         for n, p in ref.named_parameters():
             if n != "quantiles":
                 p.add_(0.1 * torch.randn_like(p))
-        ref.quantiles[:, 0, 1] += 0.3 * torch.randn(24)
-    ours = D.SteEntropyBottleneck(channels=24)
+        ref.quantiles[:, 0, 1] += 0.3 * torch.randn(C)
+    ours = D.SteEntropyBottleneck(channels=C)
     ours.load_state_dict(ref.state_dict())
     ours.to(DEV)
-    x = 3 * torch.randn(16, 24, 32, 32)
+    x = 3 * torch.randn(*shape)
+    assert shape[0] * shape[2] * shape[3] >= 4096 and 2 * shape[2] * shape[3] < 4096
     x.view(-1)[::97] *= 40.0                     # far tails: beyond the table, down to the likelihood bound
     x.view(-1)[5::1013] = 63.5
     x.view(-1)[7::1013] = -64.5
     with torch.no_grad():
         xh_r, lk_r = ref(x, is_train=False)
         xh, lk = ours(x.to(DEV), is_train=False)
-        parts = [ours(x[i:i + 2].to(DEV), is_train=False) for i in range(0, 16, 2)]     # 2048 per channel: direct kernel
+        parts = [ours(x[i:i + 2].to(DEV), is_train=False) for i in range(0, shape[0], 2)]    # direct kernel
     assert torch.equal(xh.cpu(), xh_r)
     assert rel_err(lk, lk_r) < REL
     assert float(lk.min()) == float(torch.tensor(1e-9)) and float((lk.cpu() == lk.cpu().min()).sum()) > 0
