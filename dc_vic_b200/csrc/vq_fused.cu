@@ -373,7 +373,10 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant
   const uint32_t a_m = sbase + Smem::off_m(D);         // [BM][4] quarter maxima
   const uint32_t a_tmem = sbase + Smem::off_tmem(D);   // [0] TMEM base, [1] tiles converted x 4, [2] next consumer unit, [3] finish groups requested
 
+  __shared__ int s_last;
+  __shared__ double s_scratch[32];                   // [0, NFIN): loss partial per finishing warp; reused by the final sum
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x < 32) s_scratch[threadIdx.x] = 0.0;
   FZ_GMARK(33);                                      // kernel entry
   const uint32_t crank = cluster_ctarank();          // 0 .. CL - 1
   const uint32_t rank = crank & 1u;                  // inside the CTA pair: 0 = leader (issues the MMAs)
@@ -769,7 +772,7 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant
     // assignment of units to warps)
     {
       const double wsum = warp_sum(dsq);
-      if (lane == 0) partials[(size_t)blockIdx.x * NFIN + slot] = wsum;
+      if (lane == 0) s_scratch[slot] = wsum;           // (summed per CTA at the exit, in slot order)
     }
     if (lane == 0) {
       if (n_rr) atomicAdd(counters + kCtrRerank, n_rr);
@@ -1268,8 +1271,6 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant
     // the finish takes the kernel from 4,544 to 6,368 instructions (72 -> 102 KB) and the MMA phase grew by 3 us.
 #ifdef DCVIC_FZ_HELPERS
     consume(std::integral_constant<int, 2>{}, NCONS + (warp - W_EPI0));
-#else
-    if (lane == 0) partials[(size_t)blockIdx.x * NFIN + NCONS + (warp - W_EPI0)] = 0.0;
 #endif
   } else {
     // ===================== consumers: the finish, four tokens per pass =====================
@@ -1285,18 +1286,20 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant
   FZ_GMARK(36);                                      // role loop left
   tc_fence_before();
   __syncthreads();
-  // Loss: the CTA that finishes last sums every consumer warp's partial in index order (deterministic) - one
+  // Loss: every CTA sums its finishing warps' partials (shared memory, slot order) into one value; the CTA that
+  // finishes last sums those in index order (deterministic for a given assignment of units to warps) - one
   // device-scope fence and one atomic per CTA instead of a 1-CTA kernel behind this one (3.5 us + a launch gap).
-  __shared__ int s_last;
-  __shared__ double s_scratch[32];
   if (threadIdx.x == 0) {
+    double cta = 0.0;                                // this CTA's finishing warps, in slot order
+    for (int w = 0; w < NFIN; ++w) cta += s_scratch[w];
+    partials[blockIdx.x] = cta;
     __threadfence();
     s_last = atomicAdd(counters + kCtrLoss, 1u) == gridDim.x - 1 ? 1 : 0;
   }
   cluster_sync();            // no CTA leaves while its peer may still touch its shared memory / barriers
   if (s_last) {
     __threadfence();
-    const int n = (int)gridDim.x * NFIN;
+    const int n = (int)gridDim.x;
     double acc = 0.0;
     for (int i = threadIdx.x; i < n; i += NTHREADS) acc += __ldcg(partials + i);
     const double tot = block_sum(acc, s_scratch);
