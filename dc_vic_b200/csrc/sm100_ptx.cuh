@@ -125,6 +125,43 @@ __device__ __forceinline__ void umma_commit(uint32_t bar, uint16_t cta_mask = 3)
                : "memory")
 
 
+// 16 consecutive 32-bit columns of this thread's TMEM lane
+#define TMEM_LD16(r, taddr)                                                                                        \
+  asm volatile(                                                                                                    \
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"      \
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),  \
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])                    \
+      : "r"(taddr)                                                                                                 \
+      : "memory")
+#define TMEM_WAIT_LD16(r)                                                                                          \
+  asm volatile("tcgen05.wait::ld.sync.aligned;"                                                                    \
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),   \
+                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]),          \
+                 "+r"(r[15])                                                                                       \
+               :                                                                                                   \
+               : "memory")
+
+// chunk_flags for a 16-code slice: maximum, running maximum, 16-bit flag mask (bit j <=> s[j] >= m - margin)
+__device__ __forceinline__ uint32_t chunk_flags16(const uint32_t (&r)[16], float margin, float& m, float& cm_out) {
+  auto f = [&](int i) { return __uint_as_float(r[i]); };
+  auto max3 = [](float x, float y, float z) { return fmaxf(fmaxf(x, y), z); };
+  const float a0 = max3(f(0), f(1), f(2)), a1 = max3(f(3), f(4), f(5)), a2 = max3(f(6), f(7), f(8)),
+              a3 = max3(f(9), f(10), f(11)), a4 = max3(f(12), f(13), f(14));
+  const float cm = fmaxf(max3(a0, a1, a2), max3(a3, a4, f(15)));
+  m = fmaxf(m, cm);
+  cm_out = cm;
+  const float thr = m - margin;
+  uint32_t neg[2] = {0u, 0u};
+#pragma unroll
+  for (int j = 7; j >= 0; --j)
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      const float d = __fsub_rn(__uint_as_float(r[c * 8 + j]), thr);
+      neg[c] = __funnelshift_l(__float_as_uint(d), neg[c], 1);
+    }
+  return ~(neg[0] | (neg[1] << 8)) & 0xFFFFu;
+}
+
 // true in exactly one lane of a converged warp
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;

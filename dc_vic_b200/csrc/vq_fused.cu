@@ -37,7 +37,7 @@
 //   DCVIC_FZ_EXP=3|4 (no re-rank | consumers idle), DCVIC_FZ_EPIFREE (no flag arithmetic), DCVIC_FZ_X bits 1|2|4|8
 //   (no z_q stores | no second read of z | conversion loads from the L2 | refill a finish stage without waiting for
 //   its read-out), DCVIC_FZ_HALFB (half the codebook bytes), DCVIC_FZ_NOLD (no accumulator read-out).
-// Correct variants that measured slower and are off: DCVIC_FZ_WHOLE_TILES, DCVIC_FZ_HELPERS, DCVIC_FZ_CLUSTER=4
+// Correct variants that measured slower and are off: DCVIC_FZ_WHOLE_TILES, DCVIC_FZ_HELPERS, DCVIC_FZ_SUB64, DCVIC_FZ_CLUSTER=4
 //   (+ DCVIC_FZ_MC_DIRECT=1), DCVIC_FZ_HINTS=0, DCVIC_FZ_NO_PREFETCH; ring depths DCVIC_FZ_NB / NZ / NF and the
 //   register split FZ_REGS_CONV / FZ_REGS_CONS are tunables.  -DDCVIC_FZ_DEBUG (+ _TIMING_ONLY / _MARKS_ONLY /
 //   DCVIC_FZ_NO_CMARKS) builds the instrumented kernels of tools/debug_fused.py and tools/fused_span.py.
@@ -56,6 +56,11 @@ namespace fz {
 
 using namespace tc;
 
+#if defined(DCVIC_FZ_SUB64) && DCVIC_FZ_SUB64
+#define DCVIC_FZ_SUB64_EARLY 1
+#else
+#define DCVIC_FZ_SUB64_EARLY 0
+#endif
 constexpr int BM = 128;   // tokens per CTA tile
 constexpr int BN = 128;   // codes per N-tile (UMMA N); 64 per CTA of the pair
 constexpr int BK = 64;    // channels per chunk (64 fp16 = one SWIZZLE_128B row)
@@ -79,7 +84,11 @@ constexpr int BP_BYTES = (BN / 2) * 16;      // 1 KB: 64 codes x 8 FP16 (the thr
 constexpr int AP_BYTES = 256;                // two 8-row core matrices: [1, 1, 1, 0 x 5] per row, and zeros
 constexpr int Z_STAGE = BK * GT * 4;         // 8 KB
 constexpr int NT_MAX = 8;          // N-tiles per tile: one flag-mask slot per (token, column quarter, N-tile)
+#if DCVIC_FZ_SUB64_EARLY   // (the four extra barriers of that experiment need 32 bytes)
+constexpr int CK_MAX = 15;
+#else
 constexpr int CK_MAX = 16;         // candidate codes per token after compaction; more -> whole-codebook scan
+#endif
 constexpr int MAX_K = NT_MAX * BN;  // -|e|^2/2 table and flag-mask slots in shared memory (larger codebooks take the
                                     // two-kernel path)
 // Cluster size: 2 = one CTA pair per cluster.  4 (experiment, -DDCVIC_FZ_CLUSTER=4) = two pairs that walk the codebook
@@ -88,6 +97,14 @@ constexpr int MAX_K = NT_MAX * BN;  // -|e|^2/2 table and flag-mask slots in sha
 #ifndef DCVIC_FZ_CLUSTER
 #define DCVIC_FZ_CLUSTER 2
 #endif
+// Accumulator pipeline: 0 = two 128-column buffers, one per N-tile; 1 (experiment) = FOUR 64-column buffers: every
+// 128-code slab of the ring is multiplied as two 64-code MMAs (rows 0-31 / 32-63 of either CTA's half), so the issuer
+// can run three sub-tiles ahead of the slowest epilogue warp instead of one N-tile
+#ifndef DCVIC_FZ_SUB64
+#define DCVIC_FZ_SUB64 0
+#endif
+constexpr bool kSub64 = DCVIC_FZ_SUB64 != 0;
+constexpr int NACC = kSub64 ? 4 : 2;                    // accumulator buffers
 constexpr int CL = DCVIC_FZ_CLUSTER;
 // (cluster of 4) how a multicast load reports to the MMA issuer: 0 = it completes on the barrier of the CTA it lands
 // in and a non-leader forwards that to its leader (plain .multicast::cluster); 1 = the .cta_group::2 form, whose
@@ -146,9 +163,9 @@ struct Smem {
   static constexpr int BAR_Z_EMPTY = BAR_Z_FULL + NZ;       // [NZ]
   static constexpr int BAR_A_FULL = BAR_Z_EMPTY + NZ;       // [2][4] leader only: chunk kc of A buffer b is written
   static constexpr int BAR_A_EMPTY = BAR_A_FULL + 8;        // [2] the tile's MMAs have read A buffer b
-  static constexpr int BAR_T_FULL = BAR_A_EMPTY + 2;        // [2]
-  static constexpr int BAR_T_EMPTY = BAR_T_FULL + 2;        // [2] leader only
-  static constexpr int BAR_ZZ = BAR_T_EMPTY + 2;            // [2]
+  static constexpr int BAR_T_FULL = BAR_A_EMPTY + 2;        // [NACC]
+  static constexpr int BAR_T_EMPTY = BAR_T_FULL + NACC;     // [NACC] leader only
+  static constexpr int BAR_ZZ = BAR_T_EMPTY + NACC;         // [2]
   static constexpr int BAR_C_FULL = BAR_ZZ + 2;             // [2]
   static constexpr int BAR_C_EMPTY = BAR_C_FULL + 2;        // [2]
   static constexpr int BAR_F_FULL = BAR_C_EMPTY + 2;        // [NF]
@@ -311,7 +328,8 @@ constexpr int FZ_REC = 48;          // ints per warp: [0] progress, [1..6] cycle
 #endif
 
 // kind::f16 instruction descriptor: D = F32, A = B = F16, both K-major, N = 128, M = 256 (cta_group::2)
-constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
+constexpr uint32_t kIdesc =
+    (1u << 4) | ((uint32_t)((kSub64 ? BN / 2 : BN) >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
 
 // D[tmem] (+)= A[tmem] . B[smem]^T
 __device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t accumulate) {
@@ -418,6 +436,10 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant
       mbar_init(bar(Smem::BAR_A_EMPTY + b), 1);
       mbar_init(bar(Smem::BAR_T_FULL + b), 1);
       mbar_init(bar(Smem::BAR_T_EMPTY + b), 2 * NEPI);
+      if (kSub64) {
+        mbar_init(bar(Smem::BAR_T_FULL + 2 + b), 1);
+        mbar_init(bar(Smem::BAR_T_EMPTY + 2 + b), 2 * NEPI);
+      }
       mbar_init(bar(Smem::BAR_ZZ + b), NG);
       mbar_init(bar(Smem::BAR_C_FULL + b), NEPI);
       mbar_init(bar(Smem::BAR_C_EMPTY + b), NG * 8);          // one arrival per (group, quad) unit
@@ -1001,6 +1023,62 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant
         const int abuf = it & 1;
         const uint32_t a0 = tmem_a + abuf * BM;           // 128 columns per A buffer
         for (int nt = 0; nt < NT; ++nt, ++g) {
+          if constexpr (kSub64) {
+            // Two 64-code MMAs per slab (rows 0-31, then 32-63, of either CTA's half) into four 64-column buffers:
+            // accumulator column j of sub-tile `sub` is code nt * 128 + (j / 32) * 64 + sub * 32 + j % 32.
+            constexpr int NPARTS = KC > NA ? 2 : 1;
+            constexpr int c0s[2] = {0, NA}, c1s[2] = {NA, KC};
+            int st[2];
+            uint32_t ph[2];
+#pragma unroll
+            for (int part = 0; part < NPARTS; ++part) {
+              st[part] = stage;
+              ph[part] = phase;
+              if (++stage == NB) { stage = 0; phase ^= 1; }
+            }
+#pragma unroll
+            for (int sub = 0; sub < 2; ++sub) {
+              const uint32_t sidx = g * 2 + sub, buf = sidx & 3;
+              FZ_DBG(5, sidx);
+              FZ_T();
+              if (sidx >= 4) mbar_wait(bar(Smem::BAR_T_EMPTY + buf), ((sidx >> 2) - 1) & 1);
+              FZ_ACC(1);
+              const uint32_t d = tmem_acc + buf * (BN / 2);
+#pragma unroll
+              for (int part = 0; part < NPARTS; ++part) {
+                const int c0 = c0s[part], c1 = c1s[part];
+                if (sub == 0) {
+                  FZ_T();
+                  mbar_wait(bar(Smem::BAR_B_FULL + st[part]), ph[part]);
+                  FZ_ACC(3);
+                  if (nt == 0) {
+                    FZ_T();
+#pragma unroll
+                    for (int c = c0; c < c1; ++c) mbar_wait(bar(Smem::BAR_A_FULL + abuf * 4 + c), (it >> 1) & 1);
+                    FZ_ACC(2);
+                  }
+                }
+                tc_fence_after();
+                if (issuer) {
+                  const uint64_t bds = bd_ring + (uint64_t)(uint32_t)(st[part] * (B_STAGE >> 4) + sub * (4096 >> 4));
+                  if (part == 0)
+                    umma_ss(d, ad_ones, bp_ring + (uint64_t)(uint32_t)(st[0] * (B_STAGE >> 4) + sub * (512 >> 4)), rt_zero);
+#pragma unroll
+                  for (int c = c0; c < c1; ++c) {
+                    const uint64_t bd = bds + (uint64_t)((c - c0) * (B_CHUNK >> 4));
+                    const uint32_t a = a0 + c * (BK / 2);
+                    umma_ts(d, a, bd, rt_one);
+                    umma_ts(d, a + 8, bd + 2, rt_one);
+                    umma_ts(d, a + 16, bd + 4, rt_one);
+                    umma_ts(d, a + 24, bd + 6, rt_one);
+                  }
+                  if (sub == 1) umma_commit<2>(bar(Smem::BAR_B_EMPTY + st[part]), CL == 4 ? (uint16_t)0xF : pair_mask);
+                  if (part == NPARTS - 1) umma_commit<2>(bar(Smem::BAR_T_FULL + buf), pair_mask);
+                }
+              }
+            }
+            continue;
+          }
           const uint32_t buf = g & 1;
           FZ_DBG(5, g);
           FZ_T();
@@ -1171,6 +1249,39 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant
           vq_margin_measured(zz, __uint_as_float(lds_u32(a_dz + (abuf * BM + row) * 4)), emax, demax, D);
       float m = -INFINITY;                           // running maximum over this quarter's codes
       uint32_t live = 0u;                            // N-tiles whose flag mask may hold a candidate
+      if constexpr (kSub64) {
+        // 64-column buffers: this warp reads 16 columns of every sub-tile (q >> 1: which CTA's half of the slab, q & 1:
+        // which 16 of that half's 32 codes); masks are 16 bits at a_mask + ((q * 16 + slot) * BM + row) * 2
+        for (int sl = 0; sl < 2 * NT; ++sl) {
+          const uint32_t sidx = g * 2 + (uint32_t)sl, buf = sidx & 3;
+          FZ_T();
+          mbar_wait(bar(Smem::BAR_T_FULL + buf), (sidx >> 2) & 1);
+          FZ_ACC(2);
+          if (!have) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(leader_bar(Smem::BAR_T_EMPTY + buf));
+            continue;
+          }
+          tc_fence_after();
+          uint32_t rb[16];
+          TMEM_LD16(rb, tmem_acc + ((uint32_t)(part * 32) << 16) + buf * (BN / 2) + q * 16);
+          TMEM_WAIT_LD16(rb);
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(leader_bar(Smem::BAR_T_EMPTY + buf));
+          FZ_ACC(3);
+          float cm;
+          const float m_old = m;
+          const uint32_t mask = chunk_flags16(rb, margin, m, cm);
+          if (mask != 0u) {
+            if (cm > m_old + margin) live = 0u;
+            sts_u16(a_mask + ((q * 16 + sl) * BM + row) * 2, mask);
+            live |= 1u << sl;
+          }
+          FZ_ACC(5);
+        }
+        g += NT;
+      } else {   // (braces: with `else for (...) {...}` nvcc 12.9 dropped the statement AFTER the loop in the SUB64 build)
       for (int nt = 0; nt < NT; ++nt, ++g) {
         const uint32_t buf = g & 1;
         FZ_DBG(11, g);
@@ -1216,6 +1327,7 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant
         }
         FZ_ACC(5);
       }
+      }
       // ---- end of tile: the four quarters of a row exchange their maxima; each appends the codes of its live masks
       // to the row's candidate array (slots handed out by an atomic counter: the order does not matter, the re-rank
       // breaks ties by code index).  Masks were taken against the running threshold of their time, which is below the
@@ -1242,15 +1354,22 @@ vq_fused_kernel(const __grid_constant__ CUtensorMap tm_cb, const __grid_constant
             atomicAdd(counters + 9, 1u);              // diagnostics: why a token is scanned in full
           }
         } else if (live != 0u && !(m < thr)) {         // (a quarter whose maximum is out of reach has nothing to add)
+          // (64-column buffers: slot sl = 2 nt + sub holds 16 codes from nt * 128 + (q >> 1) * 64 + sub * 32 + (q & 1) * 16)
+          auto slot_mask = [&](int sl) {
+            return kSub64 ? lds_u16(a_mask + ((q * 16 + sl) * BM + row) * 2) : lds_u32(my_mask + sl * (BM * 4));
+          };
+          auto slot_code0 = [&](int sl) {
+            return kSub64 ? (sl >> 1) * BN + (q >> 1) * (BN / 2) + (sl & 1) * 32 + (q & 1) * 16 : sl * BN + q * kChunk;
+          };
           int cnt = 0;
-          for (uint32_t lv = live; lv; lv &= lv - 1) cnt += __popc(lds_u32(my_mask + (__ffs(lv) - 1) * (BM * 4)));
+          for (uint32_t lv = live; lv; lv &= lv - 1) cnt += __popc(slot_mask(__ffs(lv) - 1));
           int w = (int)atoms_add(ncp, (uint32_t)cnt);
           if (w <= CK_MAX && w + cnt > CK_MAX) atomicAdd(counters + 7, 1u);
           const uint32_t ck = a_ck + (par * BM + row) * (CK_MAX * 2);
           for (uint32_t lv = live; lv; lv &= lv - 1) {
             const int nt = __ffs(lv) - 1;
-            const int c0 = nt * BN + q * kChunk;
-            for (uint32_t mk = lds_u32(my_mask + nt * (BM * 4)); mk; mk &= mk - 1) {
+            const int c0 = slot_code0(nt);
+            for (uint32_t mk = slot_mask(nt); mk; mk &= mk - 1) {
               if (w < CK_MAX) sts_u16(ck + w * 2, (uint32_t)(c0 + __ffs(mk) - 1));
               ++w;
             }
